@@ -1,0 +1,100 @@
+/* libmqb200 -- C ABI of the B200-native MobileQuant hot path.
+ *
+ * The reference (saic-fi/MobileQuant) has no FFI on this path: its boundary is the Python module surface of
+ * mobilellm/quantization/qmodule.py and algorithm.py.  This header is the thin C ABI that sits *behind* that
+ * surface (mobilequant_b200/quantization/*.py binds it with ctypes).  Conventions follow the reference's only
+ * C ABI, capp/api/libllmod.h:10-17,42-133: extern "C", every call returns an int status (0 = OK), an opaque
+ * context created by mq_setup / freed by mq_release (magic + refcount validated, capp/src/libllmod.cpp:23-65),
+ * per-context last-error text, and no C++ exception ever crosses the boundary.
+ *
+ * Ownership: every device buffer is allocated and owned by the caller (PyTorch); the library receives raw device
+ * pointers, element counts and a cudaStream_t (passed as void*).  All calls are asynchronous on that stream and
+ * never synchronise.  One host thread per context.
+ *
+ * Each entry point cites the reference code whose arithmetic it replaces ("qm" = mobilellm/quantization/qmodule.py,
+ * "alg" = mobilellm/quantization/algorithm.py, "hm" = mobilellm/model/hf_model.py).
+ */
+#ifndef MQB200_H
+#define MQB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQB200_VERSION 100 /* major*100 + minor */
+
+enum mq_status_code { /* mirrors libllmod_status_code, capp/api/libllmod.h:10-17 */
+  MQ_NO_ERROR = 0,
+  MQ_INVALID_CONTEXT,
+  MQ_INVALID_ARGUMENT,
+  MQ_FAILED_ALLOCATION,
+  MQ_RUNTIME_ERROR,
+  MQ_INTERNAL_ERROR,
+};
+
+/* Quantizer description == QuantConfig (qm:81-107) restricted to what reaches a kernel. */
+typedef struct mq_qcfg {
+  int32_t bitwidth;     /* 2..16; >16 means pass-through and never reaches the library (qm:252) */
+  int32_t is_symmetric; /* qm:45-54 */
+} mq_qcfg;
+
+int mq_version(void);
+const char* mq_get_error_description(int errorcode);                 /* libllmod.h:119 */
+const char* mq_get_last_error_extra_info(int errorcode, void* ctx);  /* libllmod.h:133 */
+int mq_setup(void** ctx, int device);                                /* libllmod.h:42  */
+int mq_ref_context(void* ctx);                                       /* libllmod.h:67  */
+int mq_release(void* ctx);                                           /* libllmod.h:73  */
+int mq_device_sm_count(void* ctx, int* out);
+
+/* ---- K1: static fake-quant, Quantizer.forward with cached scale/offset (qm:279-295) -------------------------
+ * y = (clamp(rne(x/scale)+offset, qmin, qmax) - offset) * scale.  scale/offset are DEVICE pointers:
+ *   group == 0 : one (scale, offset) for the whole tensor (per-tensor activations, LRL parameters)
+ *   group  > 0 : element i uses scale[i / group] (per-channel weights: group = in_features)
+ * y and/or codes may be NULL.  codes receives the integer code as int32 (exact when offset is an integer).     */
+int mq_fq_fwd(void* ctx, const float* x, float* y, int32_t* codes, int64_t n, const float* scale,
+              const float* offset, int64_t group, float qmin, float qmax, void* stream);
+
+/* Backward of the above as autograd derives it from qm:17-21,286-290:
+ *   gx = g*m;  gscale = sum g*(m*(rne(u)-u) + (1-m)*(qc-o));  goffset = -sum g*(1-m)*scale,   u = x/scale.
+ * gscale/goffset (may be NULL) are per-group DEVICE accumulators that are OVERWRITTEN (deterministic two-stage
+ * reduction in ctx workspace).  Only group == 0 supports gscale/goffset.                                        */
+int mq_fq_bwd(void* ctx, const float* x, const float* g, float* gx, int64_t n, const float* scale,
+              const float* offset, int64_t group, float qmin, float qmax, float* gscale, float* goffset,
+              void* stream);
+
+/* ---- K8: range statistics, generate_act_range.py:55-69 (per tensor) / :57-63 (per channel) -------------------
+ * minmax[0] = min(minmax[0], min x), minmax[1] = max(minmax[1], max x) when accumulate != 0, else overwritten.
+ * rows variant: x is [rows, cols]; per_row != 0 reduces over cols (weights, qm:30) else over rows (per-channel
+ * activation stats); out_min/out_max have rows or cols entries.                                                 */
+int mq_minmax(void* ctx, const float* x, int64_t n, float* minmax, int accumulate, void* stream);
+int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_row, float* out_min,
+                 float* out_max, int accumulate, void* stream);
+
+/* ---- K2: weight prep = LET transform (alg:60-96) + dynamic/LWC Quantizer.forward (qm:262-290) -----------------
+ * W' = (W {* or /} col_fac[k]) {/ or *} row_fac[n]   (modes: 0 none, 1 divide, 2 multiply; NULL when mode 0).
+ *   ln.weight / s (alg:60) is rows=1, col_mode=1;  fc.weight * s (alg:68) col_mode=2;  fc1/q: row_mode=1 (alg:77,93);
+ *   k_proj: row_mode=2 (alg:95).
+ * (mn,mx) = per tensor (per_channel == 0) or per row; mx *= sig_up[g]; mn *= sig_low[g] (NULL = no LWC)
+ * scale/offset per group from qm:40-61; outputs (any may be NULL):
+ *   w_fq   fp32 fake-quantised W'            (what QLinear.forward feeds F.linear, qm:347-353)
+ *   codes  int8 storage: asymmetric -> uint8 codes, symmetric -> int8 codes; bitwidth 4 with pack4 != 0 packs two
+ *          codes per byte (low nibble = even k)
+ *   scale_out/offset_out [groups]; colsum int32 [rows] = sum_k code  (zero-point correction of the int GEMM)
+ *   wt_out fp32 W' before quantisation (the temp_weight of alg:68, kept for the backward)                       */
+int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const float* col_fac, int col_mode,
+                 const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
+                 mq_qcfg cfg, float* w_fq, void* codes, int pack4, float* scale_out, float* offset_out,
+                 int32_t* colsum, float* wt_out, void* stream);
+
+/* Backward of mq_wprep_fwd: given g = dL/dw_fq produce dL/dcol_fac [cols], dL/drow_fac [rows], dL/dsig_up,
+ * dL/dsig_low [groups] (any may be NULL), including the amin/amax paths of qm:264-275 (gradient of a min/max is
+ * split evenly among tied elements, as torch.amin/amax do).  scratch: rows*cols floats owned by the caller.     */
+int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_t cols, const float* col_fac,
+                 int col_mode, const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
+                 mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
+                 float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQB200_H */

@@ -1,0 +1,104 @@
+// Shared device/host helpers for libmqb200 (sm_100a only).
+//
+// Numerics contract (DESIGN.md "Arithmetic"): every parity-critical fp32 operation is written with an
+// explicit round-to-nearest intrinsic (__fdiv_rn, __fmul_rn, __fadd_rn, rintf) so that ptxas can never
+// contract it into an FMA or replace a division by a reciprocal multiply.  The reference computes
+// clamp(round(x / scale) + offset, qmin, qmax) with torch fp32 ops (mobilellm/quantization/qmodule.py:286-290);
+// torch.round is round-half-to-even == rintf == cvt.rni.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#define MQ_CLIPMIN 1e-5f   // qmodule.py:11
+#define MQ_CLIPMAX 1e6f    // qmodule.py:12
+
+namespace mq {
+
+constexpr int kWarp = 32;
+
+struct Ctx;  // defined in api.cu
+
+// ---- exact fp32 primitives -------------------------------------------------------------------------------------
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+// q = clamp(rne(x / s) + o, qmin, qmax)       (qmodule.py:286-287)
+__device__ __forceinline__ float quant_code(float x, float s, float o, float qmin, float qmax) {
+  float q = fadd(rintf(fdiv(x, s)), o);
+  return fminf(fmaxf(q, qmin), qmax);
+}
+// x^ = (q - o) * s                            (qmodule.py:290)
+__device__ __forceinline__ float dequant(float q, float s, float o) { return fmul(fsub(q, o), s); }
+
+__device__ __forceinline__ float fake_quant(float x, float s, float o, float qmin, float qmax) {
+  return dequant(quant_code(x, s, o, qmin, qmax), s, o);
+}
+
+// scale/offset from (min,max)                  (qmodule.py:40-61)
+__device__ __forceinline__ void scale_offset_from_minmax(float mn, float mx, int bits, bool symmetric, float& s,
+                                                         float& o, float& qmin, float& qmax) {
+  float alpha, beta;
+  if (symmetric) {
+    alpha = fmaxf(fabsf(mn), fabsf(mx));
+    beta = 0.f;
+    qmin = -(float)(1 << (bits - 1));
+    qmax = (float)((1 << (bits - 1)) - 1);
+  } else {
+    alpha = fsub(mx, mn);
+    beta = mn;
+    qmin = 0.f;
+    qmax = (float)((1 << bits) - 1);
+  }
+  s = fdiv(alpha, qmax);
+  s = fminf(fmaxf(s, MQ_CLIPMIN), MQ_CLIPMAX);
+  // offset = -(beta / scale).round(); symmetric: -(0/scale).round() = -0 -> 0
+  o = symmetric ? 0.f : -rintf(fdiv(beta, s));
+}
+
+// ---- ordered-int encoding so float min/max can use integer atomics ---------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// ---- warp / block reductions -----------------------------------------------------------------------------------
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+struct OpMin { template <typename T> __device__ T operator()(T a, T b) const { return a < b ? a : b; } };
+struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { return a > b ? a : b; } };
+struct OpSum { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+struct OpFMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct OpFMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// Block reduce over blockDim.x threads (multiple of 32, <= 1024). Result valid in every thread.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T* smem /* >= 32 entries */) {
+  v = warp_reduce(v, op);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  T r = smem[0];
+  for (int i = 1; i < nw; ++i) r = op(r, smem[i]);
+  return r;
+}
+
+// ---- vector ld/st ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace mq

@@ -1,0 +1,137 @@
+"""Tensor-level wrappers over the C ABI (include/mqb200.h).  These are the only callers of libmqb200 in the package."""
+import ctypes
+from ctypes import c_int, c_int32, c_int64, c_float, c_void_p
+import torch
+from . import _lib
+from ._lib import mq_qcfg, ptr, check, stream_ptr, MQError
+
+_P = c_void_p
+_protos_done = False
+
+
+def _protos():
+    global _protos_done
+    if _protos_done:
+        return _lib.load()
+    lib = _lib.load()
+    lib.mq_fq_fwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_float, c_float, _P]
+    lib.mq_fq_bwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_float, c_float, _P, _P, _P]
+    lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
+    lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
+    lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
+                                 _P, _P, c_int, _P, _P, _P, _P, _P]
+    lib.mq_wprep_bwd.argtypes = [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
+                                 _P, _P, _P, _P, _P, _P]
+    _protos_done = True
+    return lib
+
+
+def _h(t):
+    return _lib.ctx(t.device.index)
+
+
+F32 = torch.float32
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------------------
+def fq_fwd(x, scale, offset, qmin, qmax, group=0, want_y=True, want_codes=False):
+    lib = _protos()
+    x = x.contiguous()
+    y = torch.empty_like(x) if want_y else None
+    codes = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_codes else None
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(lib.mq_fq_fwd(h, ptr(x, F32), ptr(y), ptr(codes), x.numel(), ptr(scale, F32), ptr(offset, F32),
+                            int(group), float(qmin), float(qmax), stream_ptr()), h)
+    return y, codes
+
+
+def fq_bwd(x, g, scale, offset, qmin, qmax, group=0, want_gx=True, want_gparams=True):
+    lib = _protos()
+    x = x.contiguous(); g = g.contiguous()
+    gx = torch.empty_like(x) if want_gx else None
+    gs = torch.empty((), dtype=F32, device=x.device) if want_gparams else None
+    go = torch.empty((), dtype=F32, device=x.device) if want_gparams else None
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(lib.mq_fq_bwd(h, ptr(x, F32), ptr(g, F32), ptr(gx), x.numel(), ptr(scale, F32), ptr(offset, F32),
+                            int(group), float(qmin), float(qmax), ptr(gs), ptr(go), stream_ptr()), h)
+    return gx, gs, go
+
+
+# ---- K8 ---------------------------------------------------------------------------------------------------------
+def minmax(x, out=None, accumulate=False):
+    """out: float32[2] CUDA tensor = [min, max] (running when accumulate)."""
+    lib = _protos()
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(2, dtype=F32, device=x.device); accumulate = False
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(lib.mq_minmax(h, ptr(x, F32), x.numel(), ptr(out, F32), int(accumulate), stream_ptr()), h)
+    return out
+
+
+def minmax_2d(x2d, per_row, out_min=None, out_max=None, accumulate=False):
+    lib = _protos()
+    x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    n = rows if per_row else cols
+    if out_min is None:
+        out_min = torch.empty(n, dtype=F32, device=x2d.device); out_max = torch.empty_like(out_min); accumulate = False
+    h = _h(x2d)
+    with torch.cuda.device(x2d.device):
+        check(lib.mq_minmax_2d(h, ptr(x2d, F32), rows, cols, int(per_row), ptr(out_min, F32), ptr(out_max, F32),
+                               int(accumulate), stream_ptr()), h)
+    return out_min, out_max
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------------------
+MODE_NONE, MODE_DIV, MODE_MUL = 0, 1, 2
+
+
+def wprep_fwd(w, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac=None, row_mode=0, sig_up=None,
+              sig_low=None, want_fq=True, want_codes=False, pack4=False, want_wt=False):
+    """Returns dict(w_fq, codes, scale, offset, colsum, wt).  w is [rows, cols] (a norm weight is [1, H])."""
+    lib = _protos()
+    w = w.contiguous()
+    rows, cols = w.shape
+    dev = w.device
+    groups = rows if per_channel else 1
+    out = dict(w_fq=torch.empty_like(w) if want_fq else None, codes=None, colsum=None,
+               scale=torch.empty(groups, dtype=F32, device=dev), offset=torch.empty(groups, dtype=F32, device=dev),
+               wt=torch.empty_like(w) if want_wt else None)
+    if want_codes:
+        ncode = rows * cols // 2 if pack4 else rows * cols
+        out["codes"] = torch.empty(ncode, dtype=torch.int8 if symmetric else torch.uint8, device=dev)
+        out["codes"] = out["codes"].view(rows, -1)
+        out["colsum"] = torch.empty(rows, dtype=torch.int32, device=dev)
+    h = _h(w)
+    cfg = mq_qcfg(int(bits), int(bool(symmetric)))
+    with torch.cuda.device(dev):
+        check(lib.mq_wprep_fwd(h, ptr(w, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac), int(row_mode),
+                               ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(out["w_fq"]),
+                               ptr(out["codes"]), int(bool(pack4)), ptr(out["scale"]), ptr(out["offset"]),
+                               ptr(out["colsum"]), ptr(out["wt"]), stream_ptr()), h)
+    return out
+
+
+def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac=None, row_mode=0, sig_up=None,
+              sig_low=None, need_col=True, need_row=True, need_sig=True):
+    lib = _protos()
+    w = w.contiguous(); g = g.contiguous()
+    rows, cols = w.shape
+    dev = w.device
+    groups = rows if per_channel else 1
+    g_col = torch.empty(cols, dtype=F32, device=dev) if (need_col and col_mode) else None
+    g_row = torch.empty(rows, dtype=F32, device=dev) if (need_row and row_mode) else None
+    g_up = torch.empty(groups, dtype=F32, device=dev) if (need_sig and sig_up is not None) else None
+    g_low = torch.empty(groups, dtype=F32, device=dev) if (need_sig and sig_low is not None) else None
+    scratch = torch.empty_like(w) if g_col is not None else None
+    h = _h(w)
+    cfg = mq_qcfg(int(bits), int(bool(symmetric)))
+    with torch.cuda.device(dev):
+        check(lib.mq_wprep_bwd(h, ptr(w, F32), ptr(g, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac),
+                               int(row_mode), ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(g_col),
+                               ptr(g_row), ptr(g_up), ptr(g_low), ptr(scratch), stream_ptr()), h)
+    return g_col, g_row, g_up, g_low

@@ -1,0 +1,173 @@
+"""K1 / K8 / K2 CUDA kernels (through the C ABI) against the CPU oracle and the reference-generated goldens.
+Bar: forward values and integer codes bit-exact; gradients to fp32 summation round-off (tolerance stated)."""
+import os
+import torch
+import pytest
+from oracle import fakequant_ref as fr
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_fq_static_golden(cuda, golden_dir):
+    from mobilequant_b200 import kernels as K
+    for c in _load(golden_dir, "quantizer.pt"):
+        if c["lwc"]:
+            continue
+        x = c["x"].to(cuda); s = c["scale"].to(cuda).reshape(()); o = c["offset"].to(cuda).reshape(())
+        y, codes = K.fq_fwd(x, s, o, c["qmin"], c["qmax"], want_codes=True)
+        assert torch.equal(y.cpu(), c["y"])
+        ref_codes = fr.quant_codes(c["x"], c["scale"], c["offset"], c["qmin"], c["qmax"]).to(torch.int32)
+        assert torch.equal(codes.cpu(), ref_codes)
+        gx, gs, go = K.fq_bwd(x, c["gy"].to(cuda), s, o, c["qmin"], c["qmax"])
+        assert torch.equal(gx.cpu(), c["gx"])
+        # sums over up to ~10k elements: fp32 order-of-summation tolerance
+        assert torch.allclose(gs.cpu(), c["g_scale"], rtol=2e-5, atol=1e-4)
+        assert torch.allclose(go.cpu(), c["g_offset"], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096, 1 << 20, (1 << 22) + 5])
+def test_fq_sizes_and_unaligned(cuda, n):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, generator=g) * 3
+    s, o, qmin, qmax = fr.scale_offset_from_minmax(-2.5, 4.0, 8, False)
+    y, codes = K.fq_fwd(x.to(cuda), s.to(cuda), o.to(cuda), qmin, qmax, want_codes=True)
+    assert torch.equal(y.cpu(), fr.fake_quant(x, s, o, qmin, qmax))
+    assert torch.equal(codes.cpu().float(), fr.quant_codes(x, s, o, qmin, qmax))
+    # a misaligned view takes the scalar path
+    if n > 8:
+        xv = x.to(cuda)[1:]
+        y2, _ = K.fq_fwd(xv, s.to(cuda), o.to(cuda), qmin, qmax)
+        assert torch.equal(y2.cpu(), fr.fake_quant(x[1:], s, o, qmin, qmax))
+
+
+def test_fq_fractional_offset_lrl(cuda):
+    """After LRL steps scale/offset are arbitrary floats: same arithmetic, non-integer codes."""
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(5, 300, 64, generator=g)
+    s = torch.tensor(0.0123457); o = torch.tensor(127.00037)
+    xr = x.clone().requires_grad_(True); sr = s.clone().requires_grad_(True); orr = o.clone().requires_grad_(True)
+    yr = fr.fake_quant(xr, sr, orr, 0, 255)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    y, _ = K.fq_fwd(x.to(cuda), s.to(cuda), o.to(cuda), 0, 255)
+    assert torch.equal(y.cpu(), yr.detach())
+    gx, gs, go = K.fq_bwd(x.to(cuda), gy.to(cuda), s.to(cuda), o.to(cuda), 0, 255)
+    assert torch.equal(gx.cpu(), xr.grad)
+    assert torch.allclose(gs.cpu(), sr.grad, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(go.cpu(), orr.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_fq_per_channel_groups(cuda):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(64, 96, generator=g) * 0.05
+    mn, mx = fr.tensor_minmax(w, True)
+    s, o, qmin, qmax = fr.scale_offset_from_minmax(mn, mx, 4, True)
+    y, codes = K.fq_fwd(w.to(cuda), s.reshape(-1).to(cuda), o.reshape(-1).to(cuda), qmin, qmax, group=96,
+                        want_codes=True)
+    assert torch.equal(y.cpu(), fr.fake_quant(w, s, o, qmin, qmax))
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, (1 << 21) + 3])
+def test_minmax(cuda, n):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, generator=g)
+    out = K.minmax(x.to(cuda))
+    assert out.cpu().tolist() == [x.min().item(), x.max().item()]
+    x2 = torch.randn(n, generator=g) * 2
+    K.minmax(x2.to(cuda), out, accumulate=True)      # running update, generate_act_range.py:69
+    assert out.cpu().tolist() == [min(x.min().item(), x2.min().item()), max(x.max().item(), x2.max().item())]
+
+
+def test_minmax_2d(cuda):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(777, 130, generator=g)
+    mn, mx = K.minmax_2d(x.to(cuda), per_row=True)
+    assert torch.equal(mn.cpu(), x.amin(1)) and torch.equal(mx.cpu(), x.amax(1))
+    mn, mx = K.minmax_2d(x.to(cuda), per_row=False)
+    assert torch.equal(mn.cpu(), x.amin(0)) and torch.equal(mx.cpu(), x.amax(0))
+
+
+def test_wprep_golden_lwc(cuda, golden_dir):
+    """LWC weight quantizer forward (bit-exact vs the reference Quantizer) and bound-factor gradients."""
+    from mobilequant_b200 import kernels as K
+    for c in _load(golden_dir, "quantizer.pt"):
+        if not c["lwc"]:
+            continue
+        w = c["x"].to(cuda)
+        up = c["up"].clone().requires_grad_(True); low = c["low"].clone().requires_grad_(True)
+        su, sl = torch.sigmoid(up), torch.sigmoid(low)
+        out = K.wprep_fwd(w, c["bits"], c["sym"], c["per_channel"], sig_up=su.detach().reshape(-1).to(cuda),
+                          sig_low=sl.detach().reshape(-1).to(cuda), want_codes=c["bits"] <= 8)
+        assert torch.equal(out["w_fq"].cpu(), c["y"]), (c["bits"], c["sym"], c["per_channel"])
+        assert torch.equal(out["scale"].cpu(), c["scale"].reshape(-1))
+        assert torch.equal(out["offset"].cpu(), c["offset"].reshape(-1) + 0.0)
+        if c["bits"] <= 8:
+            ref_codes = fr.quant_codes(c["x"], c["scale"], c["offset"], c["qmin"], c["qmax"]).to(torch.int64)
+            assert torch.equal(out["codes"].cpu().to(torch.int64), ref_codes)
+            assert torch.equal(out["colsum"].cpu().to(torch.int64), ref_codes.sum(1))
+        _, _, g_su, g_sl = K.wprep_bwd(w, c["gy"].to(cuda), c["bits"], c["sym"], c["per_channel"],
+                                       sig_up=su.detach().reshape(-1).to(cuda), sig_low=sl.detach().reshape(-1).to(cuda))
+        su.backward(g_su.cpu().reshape(su.shape)); sl.backward(g_sl.cpu().reshape(sl.shape))
+        assert torch.allclose(up.grad, c["g_up"], rtol=1e-4, atol=1e-5), (up.grad - c["g_up"]).abs().max()
+        assert torch.allclose(low.grad, c["g_low"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("bits,sym,per_ch,col_mode,row_mode", [
+    (8, False, False, 2, 0),   # q/k/v/w1 under ln smoothing (alg:68)
+    (8, False, False, 2, 1),   # w3: * fc1 scale, / fc2 scale (alg:68,77)
+    (8, False, True, 2, 0),    # w2 per-channel (alg:87)
+    (4, True, True, 2, 2),     # k_proj under q-k smoothing (alg:95), W4 symmetric
+    (16, False, False, 1, 0),  # norm weight / scale (alg:60)
+])
+def test_wprep_let_fwd_bwd(cuda, bits, sym, per_ch, col_mode, row_mode):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(bits * 100 + col_mode * 10 + row_mode)
+    rows, cols = (1, 256) if bits == 16 else (96, 160)
+    w = torch.randn(rows, cols, generator=g) * 0.02
+    cf = (1 + 0.2 * torch.randn(cols, generator=g)).requires_grad_(True)
+    rf = (1 + 0.2 * torch.randn(rows, generator=g)).requires_grad_(True)
+    groups = rows if per_ch else 1
+    up = (4 + 0.5 * torch.randn(groups, 1, generator=g)).requires_grad_(True)
+    low = (4 + 0.5 * torch.randn(groups, 1, generator=g)).requires_grad_(True)
+    su, sl = torch.sigmoid(up), torch.sigmoid(low)
+    wt = fr.let_weight(w, cf, col_mode, rf if row_mode else None, row_mode)
+    y = fr.dynamic_fake_quant(wt, bits, sym, per_ch, su if per_ch else su.reshape(-1)[0], sl if per_ch else sl.reshape(-1)[0])
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    d = lambda t: t.detach().reshape(-1).to(cuda).contiguous()
+    out = K.wprep_fwd(w.to(cuda), bits, sym, per_ch, d(cf), col_mode, d(rf) if row_mode else None, row_mode, d(su), d(sl),
+                      want_wt=True)
+    assert torch.equal(out["wt"].cpu(), wt.detach())
+    assert torch.equal(out["w_fq"].cpu(), y.detach())
+    g_col, g_row, g_up, g_low = K.wprep_bwd(w.to(cuda), gy.to(cuda), bits, sym, per_ch, d(cf), col_mode,
+                                            d(rf) if row_mode else None, row_mode, d(su), d(sl))
+    tol = dict(rtol=2e-4, atol=2e-5)
+    assert torch.allclose(g_col.cpu(), cf.grad, **tol), (g_col.cpu() - cf.grad).abs().max()
+    if row_mode:
+        assert torch.allclose(g_row.cpu(), rf.grad, **tol), (g_row.cpu() - rf.grad).abs().max()
+    gsu = torch.autograd.grad(su, up, g_up.cpu().reshape(su.shape))[0]
+    gsl = torch.autograd.grad(sl, low, g_low.cpu().reshape(sl.shape))[0]
+    assert torch.allclose(gsu, up.grad, **tol), (gsu - up.grad).abs().max()
+    assert torch.allclose(gsl, low.grad, **tol)
+
+
+def test_wprep_pack4(cuda):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(32, 64, generator=g) * 0.02
+    out = K.wprep_fwd(w.to(cuda), 4, True, True, want_codes=True, pack4=True)
+    codes, _, _ = fr.weight_codes(w, 4, True, True)
+    packed = out["codes"].cpu().view(torch.uint8).to(torch.int64)
+    lo = packed & 0xF; hi = packed >> 4
+    sext = lambda v: torch.where(v >= 8, v - 16, v)
+    un = torch.stack([sext(lo), sext(hi)], dim=-1).reshape(32, 64)
+    assert torch.equal(un, codes)
