@@ -88,11 +88,13 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
 
 /* Backward of mq_wprep_fwd: given g = dL/dw_fq produce dL/dcol_fac [cols], dL/drow_fac [rows], dL/dsig_up,
  * dL/dsig_low [groups] (any may be NULL), including the amin/amax paths of qm:264-275 (gradient of a min/max is
- * split evenly among tied elements, as torch.amin/amax do).  scratch: rows*cols floats owned by the caller.     */
+ * split evenly among tied elements, as torch.amin/amax do).  g_wt (may be NULL) receives dL/dW' [rows, cols] for
+ * callers that built W' themselves (Quantizer.forward on an arbitrary tensor).  scratch: rows*cols floats owned by
+ * the caller, needed only with g_col_fac.                                                                       */
 int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_t cols, const float* col_fac,
                  int col_mode, const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
                  mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
-                 float* scratch, void* stream);
+                 float* g_wt, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

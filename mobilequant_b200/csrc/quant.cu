@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(256) wprep_bwd_apply_kernel(const float* __res
                                                                const float* __restrict__ sig_low, int per_channel,
                                                                int bits, int sym, const GroupGrad* __restrict__ gg,
                                                                float* __restrict__ col_contrib /*[rows,cols] or NULL*/,
-                                                               float* __restrict__ g_row_fac /*[rows] or NULL*/) {
+                                                               float* __restrict__ g_row_fac /*[rows] or NULL*/,
+                                                               float* __restrict__ g_wt /*[rows,cols] or NULL*/) {
   __shared__ float redf[32];
   const int64_t row = blockIdx.x;
   const int64_t gi = per_channel ? row : 0;
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(256) wprep_bwd_apply_kernel(const float* __res
     float dwp = e.gx;
     if (wp == gmx) dwp += sh.share_mx;
     if (wp == gmn) dwp += sh.share_mn;
+    if (g_wt) g_wt[row * cols + k] = dwp;
     float gt = dwp;                                 // dL/dt
     if (la.row_mode == 1) { gt = fdiv(dwp, r); acc_r -= fmul(dwp, fdiv(wp, r)); }
     else if (la.row_mode == 2) { gt = fmul(dwp, r); acc_r += fmul(dwp, t); }
@@ -571,7 +573,7 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
 int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_t cols, const float* col_fac,
                  int col_mode, const float* row_fac, int row_mode, const float* sig_up, const float* sig_low,
                  int per_channel, mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
-                 float* scratch, void* stream) {
+                 float* g_wt, float* scratch, void* stream) {
   MQ_CTX(c, ctx);
   if (int e = wprep_check(c, w, rows, cols, col_fac, col_mode, row_fac, row_mode, cfg)) return e;
   MQ_REQUIRE(c, g != nullptr, "g is NULL");
@@ -600,10 +602,10 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   wprep_bwd_group_kernel<<<ggrid, 256, 0, st>>>(row_mn, row_mx, sig_up, sig_low, per_channel, cfg.bitwidth,
                                                 cfg.is_symmetric, rows, row_gs, row_cmn, row_cmx, gg, g_sig_up,
                                                 g_sig_low);
-  if (g_col_fac || g_row_fac) {
+  if (g_col_fac || g_row_fac || g_wt) {
     wprep_bwd_apply_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
                                                            per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
-                                                           g_col_fac ? scratch : nullptr, g_row_fac);
+                                                           g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
   }
   if (g_col_fac) {
     unsigned gx = (unsigned)((cols + 127) / 128);

@@ -21,7 +21,7 @@ def _protos():
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
                                  _P, _P, c_int, _P, _P, _P, _P, _P]
     lib.mq_wprep_bwd.argtypes = [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
-                                 _P, _P, _P, _P, _P, _P]
+                                 _P, _P, _P, _P, _P, _P, _P]
     _protos_done = True
     return lib
 
@@ -117,7 +117,7 @@ def wprep_fwd(w, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac
 
 
 def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac=None, row_mode=0, sig_up=None,
-              sig_low=None, need_col=True, need_row=True, need_sig=True):
+              sig_low=None, need_col=True, need_row=True, need_sig=True, need_wt=False):
     lib = _protos()
     w = w.contiguous(); g = g.contiguous()
     rows, cols = w.shape
@@ -128,10 +128,13 @@ def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_
     g_up = torch.empty(groups, dtype=F32, device=dev) if (need_sig and sig_up is not None) else None
     g_low = torch.empty(groups, dtype=F32, device=dev) if (need_sig and sig_low is not None) else None
     scratch = torch.empty_like(w) if g_col is not None else None
+    g_wt = torch.empty_like(w) if need_wt else None
     h = _h(w)
     cfg = mq_qcfg(int(bits), int(bool(symmetric)))
     with torch.cuda.device(dev):
         check(lib.mq_wprep_bwd(h, ptr(w, F32), ptr(g, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac),
                                int(row_mode), ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(g_col),
-                               ptr(g_row), ptr(g_up), ptr(g_low), ptr(scratch), stream_ptr()), h)
+                               ptr(g_row), ptr(g_up), ptr(g_low), ptr(g_wt), ptr(scratch), stream_ptr()), h)
+    if need_wt:
+        return g_col, g_row, g_up, g_low, g_wt
     return g_col, g_row, g_up, g_low

@@ -1,0 +1,589 @@
+"""MobileQuant calibration loops, GPU-resident (drop-in mirror of mobilellm/quantization/algorithm.py: same public
+names, argument meaning, parameter names and checkpoint layout).
+
+Differences in *execution*, not in semantics:
+  * LET is not materialised with ATen ops: smooth_lm_temporary attaches a `let` descriptor to each module and the
+    weight quantizer's fused kernel applies  W * s[k] (/ or *) r[n]  + min/max + LWC + fake-quant in one pass
+    (mq_wprep_fwd) and reduces dL/dW^ straight into the per-channel LET / LWC gradients (mq_wprep_bwd).
+  * calibration activations (inps / fp_inps / quant_inps, alg:445-449) stay resident in HBM (180 GB on a B200 holds
+    512 x 1024 x 2048 fp32 x 3 = 13 GB); the reference shuttles them CPU<->GPU every step (alg:477,532,573).
+  * the reference's layer-sharding over GPUs (utils/parallel_utils.py) is replaced by sample-sharded data parallelism:
+    one process per GPU, gradients of the 0.3-1.0 M learnable scalars all-reduced over NCCL each step
+    (== the reference run with --batch_size world_size, alg:532-533).
+"""
+import copy, gc, math, os
+from collections import OrderedDict
+import torch
+import torch.nn as nn
+import torch.distributed as dist
+from .qmodule import QLinear, QLayerNorm, QRMSNorm, QMatMul, QSiLU, QGELU, MODE_DIV, MODE_MUL
+from ..utils.optim import NativeScalerWithGradNormCount
+
+CLIPMIN, CLIPMAX = 1e-5, 1e6
+
+
+class TruncateFunction(torch.autograd.Function):          # alg:27-42
+    @staticmethod
+    def forward(ctx, input, threshold):
+        t = input.clone()
+        small = t.abs() < threshold
+        t[small] = t[small].sign() * threshold
+        return t
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.clone(), None
+
+
+def truncate_number(number, threshold=1e-2):
+    return TruncateFunction.apply(number, threshold)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LET: temporary (per training step) and in-place (fuse) variants, alg:47-144
+# ---------------------------------------------------------------------------------------------------------------
+def _let(module):
+    if getattr(module, "let", None) is None:
+        module.let = {}
+    return module.let
+
+
+def _has_bias(m):
+    return getattr(m, "bias", None) is not None
+
+
+def smooth_ln_fcs_temporary(ln, fcs, scales, shifts, use_shift=True):
+    """alg:47-68: ln.w / s, ln.b -> (b - shift)/s ; fc.W * s, fc.b + W @ shift."""
+    fcs = fcs if isinstance(fcs, list) else [fcs]
+    ln.use_temporary_parameter = True
+    ln.let = dict(col_fac=scales, col_mode=MODE_DIV)
+    if _has_bias(ln):
+        ln.temp_bias = (ln.bias - shifts) / scales
+    else:
+        ln.temp_bias = (-1 * shifts) / scales if use_shift else None
+    for fc in fcs:
+        fc.use_temporary_parameter = True
+        fc.let = dict(col_fac=scales, col_mode=MODE_MUL)
+        if use_shift:
+            fc.temp_bias = fc.bias + fc.weight @ shifts if _has_bias(fc) else fc.weight @ shifts
+        else:                                   # shift == 0: W @ 0 adds an exact zero, skip the GEMV
+            fc.temp_bias = fc.bias if _has_bias(fc) else None
+
+
+def smooth_fc_fc_temporary(fc1, fc2, scales, shifts, use_shift=True):
+    """alg:71-87: fc1.W' / s[n], fc1.b' -> (b' - shift)/s ; fc2.W * s[k], fc2.b + W @ shift."""
+    fc1.use_temporary_parameter = True
+    fc2.use_temporary_parameter = True
+    l1 = _let(fc1)
+    l1.update(row_fac=scales, row_mode=MODE_DIV)
+    b1 = getattr(fc1, "temp_bias", None) if hasattr(fc1, "temp_bias") else fc1.bias
+    if b1 is not None:
+        fc1.temp_bias = (b1 - shifts) / scales.view(-1)
+    else:
+        fc1.temp_bias = (-1 * shifts) / scales.view(-1) if use_shift else None
+    fc2.let = dict(col_fac=scales, col_mode=MODE_MUL)
+    if use_shift:
+        fc2.temp_bias = fc2.bias + fc2.weight @ shifts if _has_bias(fc2) else fc2.weight @ shifts
+    else:
+        fc2.temp_bias = fc2.bias if _has_bias(fc2) else None
+
+
+def smooth_q_k_temporary(q_proj, k_proj, scales):
+    """alg:90-96: q / s[n], k * s[n] (weights and biases)."""
+    q_proj.use_temporary_parameter = True
+    k_proj.use_temporary_parameter = True
+    _let(q_proj).update(row_fac=scales, row_mode=MODE_DIV)
+    _let(k_proj).update(row_fac=scales, row_mode=MODE_MUL)
+    if getattr(q_proj, "temp_bias", None) is not None:
+        q_proj.temp_bias = q_proj.temp_bias / scales.view(-1)
+    if getattr(k_proj, "temp_bias", None) is not None:
+        k_proj.temp_bias = k_proj.temp_bias * scales.view(-1)
+
+
+def _set_bias(m, value):
+    if _has_bias(m):
+        m.bias.copy_(value)
+    else:
+        if hasattr(m, "bias"):
+            del m.bias
+        m.register_buffer("bias", value)
+
+
+def smooth_ln_fcs_inplace(ln, fcs, scales, shifts):       # alg:99-120
+    fcs = fcs if isinstance(fcs, list) else [fcs]
+    ln.use_temporary_parameter = False
+    _set_bias(ln, ((ln.bias - shifts) / scales) if _has_bias(ln) else (-1 * shifts) / scales)
+    ln.weight.div_(scales)
+    for fc in fcs:
+        fc.use_temporary_parameter = False
+        _set_bias(fc, (fc.bias + fc.weight @ shifts) if _has_bias(fc) else fc.weight @ shifts)
+        fc.weight.mul_(scales.view(1, -1))
+
+
+def smooth_fc_fc_inplace(fc1, fc2, scales, shifts):       # alg:123-135
+    fc1.use_temporary_parameter = False
+    fc2.use_temporary_parameter = False
+    fc1.bias.sub_(shifts)
+    fc1.bias.div_(scales.view(-1))
+    fc1.weight.div_(scales.view(-1, 1))
+    _set_bias(fc2, (fc2.bias + fc2.weight @ shifts) if _has_bias(fc2) else fc2.weight @ shifts)
+    fc2.weight.mul_(scales.view(1, -1))
+
+
+def smooth_q_k_inplace(q_proj, k_proj, scales):           # alg:138-144
+    q_proj.use_temporary_parameter = False
+    k_proj.use_temporary_parameter = False
+    q_proj.weight.div_(scales.view(-1, 1))
+    q_proj.bias.div_(scales.view(-1))
+    k_proj.weight.mul_(scales.view(-1, 1))
+    k_proj.bias.mul_(scales.view(-1))
+
+
+def _truncate_let(model, use_shift):
+    template = "smooth" if use_shift else "smooth_scale"
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if template in name:
+                p.data = truncate_number(p)               # alg:190-193
+
+
+def _let_plan(model, config, original_omniquant):
+    """Which (ln, fcs) / (fc1, fc2) / (q, k) pairs exist for this block -- alg:195-220."""
+    at, mlp = model.self_attn, model.mlp
+    plan = dict(ln=[], fcfc=[], qk=None)
+    three = config.num_linears_per_mlp == 3
+    if config.shared_attention_norm:
+        plan["ln"].append((model.input_layernorm, [at.q_proj, at.k_proj, at.v_proj, mlp.w1] + ([mlp.w3] if three else []), "qkv"))
+    else:
+        plan["ln"].append((model.input_layernorm, [at.q_proj, at.k_proj, at.v_proj], "qkv"))
+        plan["ln"].append((model.post_attention_layernorm, [mlp.w1] + ([mlp.w3] if three else []), "fc1"))
+    if at.v_proj.weight.shape[0] == at.o_proj.weight.shape[1]:
+        plan["fcfc"].append((at.v_proj, at.o_proj, "out"))
+    if three and not original_omniquant:
+        plan["fcfc"].append((mlp.w3, mlp.w2, "fc2"))
+    if at.q_proj.weight.shape[0] == at.k_proj.weight.shape[0]:
+        plan["qk"] = (at.q_proj, at.k_proj)
+    return plan
+
+
+def smooth_lm_temporary(model, config, use_let, use_shift=False, original_omniquant=False):
+    """alg:187-233 for one decoder block."""
+    for m in model.modules():
+        if isinstance(m, (QLinear, QRMSNorm, QLayerNorm)):
+            m.let = None
+            if hasattr(m, "temp_bias"):
+                del m.temp_bias
+    if use_let:
+        _truncate_let(model, use_shift)
+        plan = _let_plan(model, config, original_omniquant)
+        for ln, fcs, key in plan["ln"]:
+            smooth_ln_fcs_temporary(ln, fcs, getattr(model, f"{key}_smooth_scale"), getattr(model, f"{key}_smooth_shift"), use_shift)
+        for fc1, fc2, key in plan["fcfc"]:
+            smooth_fc_fc_temporary(fc1, fc2, getattr(model, f"{key}_smooth_scale"), getattr(model, f"{key}_smooth_shift"), use_shift)
+        if plan["qk"] is not None:
+            smooth_q_k_temporary(plan["qk"][0], plan["qk"][1], model.qkt_smooth_scale)
+    for m in model.modules():
+        if isinstance(m, QLinear):
+            m.use_temporary_parameter = True
+            if not hasattr(m, "temp_bias"):
+                m.temp_bias = m.bias
+
+
+@torch.no_grad()
+def smooth_lm_inplace(model, config, use_let, use_shift=False, original_omniquant=False):
+    """alg:147-184: fuse LET into the weights and clamp every weight to its learned LWC range."""
+    if use_let:
+        _truncate_let(model, use_shift)
+        plan = _let_plan(model, config, original_omniquant)
+        for ln, fcs, key in plan["ln"]:
+            smooth_ln_fcs_inplace(ln, fcs, getattr(model, f"{key}_smooth_scale"), getattr(model, f"{key}_smooth_shift"))
+        for fc1, fc2, key in plan["fcfc"]:
+            smooth_fc_fc_inplace(fc1, fc2, getattr(model, f"{key}_smooth_scale"), getattr(model, f"{key}_smooth_shift"))
+        if plan["qk"] is not None:
+            smooth_q_k_inplace(plan["qk"][0], plan["qk"][1], model.qkt_smooth_scale)
+    for m in model.modules():
+        if isinstance(m, (QLinear, QRMSNorm, QLayerNorm)):
+            m.weight.data = m.weight_quantizer.run_lwc(m.weight)
+            m.use_temporary_parameter = False
+            m.let = None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter groups -- alg:239-292
+# ---------------------------------------------------------------------------------------------------------------
+def let_parameters(model, use_shift=False):
+    template = "smooth" if use_shift else "smooth_scale"
+    return iter([p for n, p in model.named_parameters() if n.find(template) > -1])
+
+
+def lwc_parameters(model):
+    return iter([p for n, p in model.named_parameters() if n.find("bound_factor") > -1])
+
+
+def lrl_parameters(model):
+    out = []
+    for n, p in model.named_parameters():
+        if n.find("quantizer.offset") > -1:
+            out.append(p)
+        if n.find("quantizer.scale") > -1:
+            out.append(p)
+    return iter(out)
+
+
+def _is_quant_param(n, template):
+    return n.find("bound_factor") > -1 or n.find(template) > -1 or n.find("quantizer.offset") > -1 or n.find("quantizer.scale") > -1
+
+
+def get_parameters(model, use_shift=False):
+    template = "smooth" if use_shift else "smooth_scale"
+    return iter([p for n, p in model.named_parameters() if _is_quant_param(n, template)])
+
+
+def quant_state_dict(model, destination=None, prefix="", keep_vars=False, use_shift=False):
+    destination = OrderedDict() if destination is None else destination
+    template = "smooth" if use_shift else "smooth_scale"
+    for n, p in model.named_parameters():
+        if _is_quant_param(n, template):
+            destination[prefix + n] = p if keep_vars else p.detach()
+    return destination
+
+
+def clear_temp_variable(model):
+    for m in model.modules():
+        if isinstance(m, (QLinear, QLayerNorm, QRMSNorm)):
+            for a in ("temp_weight", "temp_bias"):
+                if hasattr(m, a):
+                    delattr(m, a)
+            m.let = None
+
+
+def get_lr(max_lr, min_lr, it, warmup_iters, max_iters):
+    """alg:296-307: linear warm-up then cosine decay."""
+    if it < warmup_iters:
+        return max_lr * it / warmup_iters
+    if it > max_iters:
+        return min_lr
+    decay_ratio = (it - warmup_iters) / (max_iters - warmup_iters)
+    assert 0 <= decay_ratio <= 1
+    coeff = 0.5 * (1.0 + math.cos(math.pi * decay_ratio))
+    return min_lr + coeff * (max_lr - min_lr)
+
+
+class LayerList(nn.Module):                               # alg:313-322
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = layers
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None):
+        for i in range(len(self.layers)):
+            out = self.layers[i](hidden_states, attention_mask, position_ids)
+            hidden_states = out[0]
+        return out
+
+
+def _each_q(module):
+    for slot in ("input", "input2", "weight", "output"):
+        q = getattr(module, f"{slot}_quantizer", None)
+        if q is not None:
+            yield slot, q
+
+
+def enable_quant(args, model):
+    """alg:325-351."""
+    for m in model.modules():
+        if isinstance(m, (QLinear, QRMSNorm, QLayerNorm, QMatMul, QSiLU, QGELU)):
+            for slot, q in _each_q(m):
+                q.enable = True
+                if slot == "weight" and args.lwc:
+                    q.enable_lwc(m.weight)
+    return model
+
+
+def disable_quant(model):
+    """alg:354-378."""
+    for m in model.modules():
+        if isinstance(m, (QLinear, QRMSNorm, QLayerNorm, QMatMul, QSiLU, QGELU)):
+            for slot, q in _each_q(m):
+                q.enable = False
+                if slot == "weight":
+                    q.disable_lwc()
+    return model
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# shared pieces of the two loops
+# ---------------------------------------------------------------------------------------------------------------
+def _dp():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _catch_first_layer_inputs(model, layers, dataloader, nsamples, seqlen, device, dtype):
+    """alg:409-441 / 617-645: run the embedding, stop at layer 0, keep its inputs + mask + position ids."""
+    inps = torch.zeros((nsamples, seqlen, model.config.hidden_size), dtype=dtype, device=device)
+    cache = {"i": 0}
+
+    class Catcher(nn.Module):
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+
+        def forward(self, inp, **kwargs):
+            inps[cache["i"]] = inp
+            cache["i"] += 1
+            cache["attention_mask"] = kwargs["attention_mask"]
+            cache["position_ids"] = kwargs["position_ids"]
+            raise ValueError
+
+    layers[0] = Catcher(layers[0])
+    with torch.no_grad():
+        for batch in dataloader:
+            if cache["i"] >= nsamples:
+                break
+            try:
+                model(batch[0].to(device))
+            except ValueError:
+                pass
+    layers[0] = layers[0].module
+    return inps, cache.get("attention_mask"), cache.get("position_ids")
+
+
+def _register_let(layer, pairs, device, dtype):
+    """alg:484-496 / 692-706."""
+    if layer.self_attn.q_proj.weight.shape[0] == layer.self_attn.k_proj.weight.shape[0]:
+        layer.register_parameter("qkt_smooth_scale", nn.Parameter(torch.ones(layer.self_attn.q_proj.out_features, device=device, dtype=dtype)))
+    for name, module in layer.named_modules():
+        if isinstance(module, QLinear):
+            for key in pairs:
+                if key in name:
+                    layer.register_parameter(f"{pairs[key]}_smooth_shift", nn.Parameter(torch.zeros(module.in_features, device=device, dtype=dtype)))
+                    layer.register_parameter(f"{pairs[key]}_smooth_scale", nn.Parameter(torch.ones(module.in_features, device=device, dtype=dtype)))
+
+
+def _drop_learned(layer):
+    for name in [n for n, _ in layer.named_parameters() if n.find("bound_factor") > -1 or n.find("smooth") > -1]:
+        obj = layer
+        parts = name.split(".")
+        for p in parts[:-1]:
+            obj = getattr(obj, p)
+        delattr(obj, parts[-1])
+
+
+def _allreduce_grads(params, world):
+    """Data-parallel exchange: SUM of the learnable-scalar gradients over NCCL, then the batch mean (alg:459)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def _train_step(args, loss, optimizer, loss_scaler, params_fn, world):
+    optimizer.zero_grad()
+    if world > 1:
+        loss.backward()
+        _allreduce_grads(list(params_fn()), world)
+        return loss_scaler.step_only(optimizer, parameters=params_fn())
+    return loss_scaler(loss, optimizer, parameters=params_fn())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def omniquant(args, model, dataloader, logger, device=None):
+    """Block-wise calibration, alg:381-584."""
+    logger.info("Starting ...")
+    use_cache = model.config.use_cache
+    model.config.use_cache = False
+    if device is None:
+        device = next(model.parameters()).device
+    device = torch.device(device)
+    rank, world = _dp()
+    layers = model.model.layers
+    model.model.embed_tokens = model.model.embed_tokens.to(device)
+    model.model.norm = model.model.norm.to(device)
+    pairs = {"q_proj": "qkv", "w1": "fc1"}
+    if layers[0].self_attn.v_proj.weight.shape[0] == layers[0].self_attn.o_proj.weight.shape[1]:
+        pairs["o_proj"] = "out"
+    if model.config.num_linears_per_mlp == 3 and not args.original_omniquant:
+        pairs["w2"] = "fc2"
+    layers[0] = layers[0].to(device)
+    if not (args.deactive_amp and args.epochs > 0):
+        raise NotImplementedError("the B200 path calibrates in fp32 (the reference's W8A8/W4A8 recipes all set "
+                                  "--deactive_amp, ptq/mobilequant.py:122-123)")
+    dtype = torch.float32
+    inps, attention_mask, position_ids = _catch_first_layer_inputs(model, layers, dataloader, args.nsamples, args.seqlen, device, dtype)
+    quant_inps = inps
+    fp_inps = inps.clone()
+    fp_inps_2 = inps.clone() if args.aug_loss else None
+    attention_mask_batch = attention_mask.repeat(args.batch_size, 1, 1, 1) if attention_mask is not None else None
+    loss_func = torch.nn.MSELoss()
+    omni_parameters = torch.load(args.resume) if args.resume else {}
+    steps_per_epoch = args.nsamples // args.batch_size
+    gsteps = steps_per_epoch // world                       # global optimiser steps per epoch (world micro-batches each)
+    my_batches = [g * world + rank for g in range(gsteps)]  # micro-batches owned by this rank
+    my_samples = [k for j in my_batches for k in range(j * args.batch_size, (j + 1) * args.batch_size)] if world > 1 \
+        else list(range(args.nsamples))
+
+    for i in range(len(layers)):
+        logger.info(f"=== Start quantize layer {i} ===")
+        qlayer = layers[i].to(device)
+        disable_quant(qlayer)
+        if args.epochs > 0:
+            with torch.no_grad():
+                for j in my_samples:
+                    fp_inps[j] = qlayer(fp_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
+                    if args.aug_loss:
+                        fp_inps_2[j] = qlayer(quant_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
+        enable_quant(args, qlayer)
+        if args.let:
+            _register_let(qlayer, pairs, device, dtype)
+        if args.resume:
+            qlayer.load_state_dict(omni_parameters[i], strict=False)
+        if args.epochs > 0:
+            groups = [{"params": let_parameters(qlayer, args.use_shift), "lr": args.let_lr},
+                      {"params": lwc_parameters(qlayer), "lr": args.lwc_lr}]
+            if args.lrl:
+                groups.append({"params": lrl_parameters(qlayer), "lr": args.lrl_lr})
+            optimizer = torch.optim.AdamW(groups, weight_decay=args.wd)
+            loss_scaler = NativeScalerWithGradNormCount()
+            max_iters = args.epochs * gsteps
+            warmup_iters = args.warmup_epochs * gsteps
+            for epochs in range(args.epochs):
+                loss_list, norm_list = [], []
+                for g, j in enumerate(my_batches):
+                    index = j * args.batch_size
+                    it = epochs * gsteps + g
+                    optimizer.param_groups[0]["lr"] = get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters)
+                    optimizer.param_groups[1]["lr"] = get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters)
+                    if args.lrl:
+                        optimizer.param_groups[2]["lr"] = get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters)
+                    smooth_lm_temporary(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
+                    quant_out = qlayer(quant_inps[index:index + args.batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+                    loss = loss_func(fp_inps[index:index + args.batch_size], quant_out)
+                    if args.aug_loss:
+                        loss += loss_func(fp_inps_2[index:index + args.batch_size], quant_out)
+                    loss_list.append(loss.detach())
+                    norm = _train_step(args, loss, optimizer, loss_scaler, lambda: get_parameters(qlayer, args.use_shift), world)
+                    norm_list.append(norm.detach())
+                loss_mean = torch.stack(loss_list).mean().item()
+                if not math.isfinite(loss_mean):
+                    raise FloatingPointError(f"layer {i} epoch {epochs}: loss is not finite")   # reference: pdb (alg:536-538)
+                norm_mean = torch.stack(norm_list).mean().item()
+                logger.info(f"layer {i} iter {epochs} loss:{loss_mean} norm:{norm_mean} max memory_allocated {torch.cuda.max_memory_allocated(device) / 1024**2} ")
+            clear_temp_variable(qlayer)
+            del optimizer
+        if args.epochs > 0:
+            omni_parameters[i] = quant_state_dict(qlayer)
+            if rank == 0:
+                torch.save(omni_parameters, os.path.join(args.output_dir, "quant_parameters.pth"))
+        smooth_lm_inplace(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
+        _drop_learned(qlayer)
+        if args.epochs > 0:
+            with torch.no_grad():
+                for j in my_samples:
+                    quant_inps[j] = qlayer(quant_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
+        layers[i] = qlayer
+    del inps, quant_inps, fp_inps, fp_inps_2
+    gc.collect()
+    model.config.use_cache = use_cache
+    return model
+
+
+def e2equant(args, model, dataloader, logger, device=None):
+    """End-to-end calibration, alg:587-787."""
+    logger.info("Starting ...")
+    use_cache = model.config.use_cache
+    model.config.use_cache = False
+    rank, world = _dp()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    model.to(device)                                       # replaces map_layers_to_multi_gpus (alg:593)
+    layers = model.model.layers
+    pairs = {"q_proj": "qkv", "w1": "fc1"}
+    if layers[0].self_attn.v_proj.weight.shape[0] == layers[0].self_attn.o_proj.weight.shape[1]:
+        pairs["o_proj"] = "out"
+    if model.config.num_linears_per_mlp == 3:
+        pairs["w2"] = "fc2"
+    if not (args.deactive_amp and args.epochs > 0):
+        raise NotImplementedError("the B200 path calibrates in fp32 (--deactive_amp)")
+    dtype = torch.float32
+    inps, attention_mask, position_ids = _catch_first_layer_inputs(model, layers, dataloader, args.nsamples, args.seqlen, device, dtype)
+    quant_inps = inps
+    fp_inps = inps.clone()
+    fp_inps_2 = inps.clone() if args.aug_loss else None
+    attention_mask_batch = attention_mask.repeat(args.batch_size, 1, 1, 1) if attention_mask is not None else None
+    loss_func = torch.nn.MSELoss()
+    e2e_parameters = torch.load(args.resume) if args.resume else {}
+    batch_size = args.batch_size
+    steps_per_epoch = args.nsamples // batch_size
+    gsteps = steps_per_epoch // world
+    my_batches = [g * world + rank for g in range(gsteps)]
+    disable_quant(model)
+    backbone = LayerList(layers)
+
+    if args.epochs > 0:
+        with torch.no_grad():
+            for j in my_batches:                            # FP targets of this rank's shard only
+                index = j * batch_size
+                fp_inps[index:index + batch_size] = backbone(fp_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+                if args.aug_loss:
+                    fp_inps_2[index:index + batch_size] = backbone(quant_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+    enable_quant(args, model)
+    if args.let:
+        for i in range(len(layers)):
+            _register_let(layers[i], pairs, device, dtype)
+            if args.resume:
+                layers[i].load_state_dict(e2e_parameters[i], strict=False)
+
+    optimizer = None
+    if args.epochs > 0:
+        optimizer = torch.optim.AdamW([{"params": let_parameters(model, args.use_shift), "lr": args.let_lr},
+                                       {"params": lwc_parameters(model), "lr": args.lwc_lr},
+                                       {"params": lrl_parameters(model), "lr": args.lrl_lr}], weight_decay=args.wd)
+        loss_scaler = NativeScalerWithGradNormCount()
+        max_iters = args.epochs * gsteps
+        warmup_iters = args.warmup_epochs * gsteps
+        for epochs in range(args.epochs):
+            loss_list, norm_list = [], []
+            for g, j in enumerate(my_batches):
+                index = j * batch_size
+                it = epochs * gsteps + g
+                optimizer.param_groups[0]["lr"] = get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters)
+                optimizer.param_groups[1]["lr"] = get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters)
+                optimizer.param_groups[2]["lr"] = get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters)
+                for k in range(len(layers)):
+                    smooth_lm_temporary(layers[k], model.config, args.let, args.use_shift)
+                quant_out = backbone(quant_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+                loss = loss_func(fp_inps[index:index + batch_size], quant_out)
+                if args.aug_loss:
+                    loss += loss_func(fp_inps_2[index:index + batch_size], quant_out)
+                loss_list.append(loss.detach())
+                norm = _train_step(args, loss, optimizer, loss_scaler, lambda: get_parameters(model, args.use_shift), world)
+                norm_list.append(norm.detach())
+            loss_mean = torch.stack(loss_list).mean().item()
+            if not math.isfinite(loss_mean):
+                raise FloatingPointError(f"epoch {epochs}: loss is not finite")
+            norm_mean = torch.stack(norm_list).mean().item()
+            logger.info(f"Epoch {epochs} loss:{loss_mean} norm:{norm_mean} max memory_allocated {torch.cuda.max_memory_allocated(device) / 1024**2} ")
+            for k in range(len(layers)):
+                e2e_parameters[k] = quant_state_dict(layers[k])
+            if rank == 0:
+                torch.save(e2e_parameters, os.path.join(args.output_dir, "parameters.pth"))
+
+    for i in range(len(layers)):
+        e2e_parameters[i] = OrderedDict((k, v.clone()) for k, v in quant_state_dict(layers[i]).items())
+        smooth_lm_inplace(layers[i], model.config, args.let, args.use_shift)
+        _drop_learned(layers[i])
+    if rank == 0:
+        torch.save(e2e_parameters, os.path.join(args.output_dir, "parameters.pth"))
+    del optimizer, inps, quant_inps, fp_inps, fp_inps_2
+    gc.collect()
+    model.config.use_cache = use_cache
+    return model

@@ -1,0 +1,70 @@
+"""autograd.Function wrappers: forward AND backward are single fused CUDA kernels from libmqb200 (no torch elementwise
+chains; the reference spends ~8 launches forward / ~10 backward per Quantizer call)."""
+import torch
+from .. import kernels as K
+
+
+class StaticFakeQuantFn(torch.autograd.Function):
+    """Quantizer.forward with cached scale/offset (qmodule.py:279-295).  scale/offset: 0-d (per tensor) or one entry
+    per row of the last dimension (cached per-channel weight quantizer)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, offset, qmin, qmax):
+        group = 0 if scale.numel() == 1 else x.shape[-1]
+        s = scale.detach().reshape(-1).float().contiguous()
+        o = offset.detach().reshape(-1).float().contiguous()
+        xc = x.detach().float().contiguous()
+        y, _ = K.fq_fwd(xc, s, o, qmin, qmax, group=group)
+        ctx.save_for_backward(xc, s, o)
+        ctx.meta = (qmin, qmax, group, scale.shape, offset.shape, x.dtype)
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, s, o = ctx.saved_tensors
+        qmin, qmax, group, sshape, oshape, xdtype = ctx.meta
+        need_x, need_s, need_o = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if (need_s or need_o) and group != 0:
+            raise NotImplementedError("learnable per-channel static scales are not part of any MobileQuant recipe")
+        gx, gs, go = K.fq_bwd(xc, g.float().contiguous(), s, o, qmin, qmax, group=group, want_gx=need_x,
+                              want_gparams=need_s or need_o)
+        return (gx.to(xdtype) if need_x else None, gs.reshape(sshape) if need_s else None,
+                go.reshape(oshape) if need_o else None, None, None)
+
+
+class LetLwcWeightQuantFn(torch.autograd.Function):
+    """LET transform (algorithm.py:60-96) + dynamic / LWC Quantizer.forward (qmodule.py:262-290) in one pass over the
+    weight.  Returns (w_fq, scale, offset); scale/offset are not differentiable outputs (the reference re-derives them
+    every forward)."""
+
+    @staticmethod
+    def forward(ctx, w, col_fac, col_mode, row_fac, row_mode, sig_up, sig_low, bits, symmetric, per_channel):
+        w2 = w.detach().float().contiguous()
+        cf = None if col_fac is None else col_fac.detach().reshape(-1).float().contiguous()
+        rf = None if row_fac is None else row_fac.detach().reshape(-1).float().contiguous()
+        su = None if sig_up is None else sig_up.detach().reshape(-1).float().contiguous()
+        sl = None if sig_low is None else sig_low.detach().reshape(-1).float().contiguous()
+        out = K.wprep_fwd(w2, bits, symmetric, per_channel, cf, col_mode, rf, row_mode, su, sl)
+        ctx.save_for_backward(w2, cf, rf, su, sl)
+        ctx.meta = (col_mode, row_mode, bits, symmetric, per_channel,
+                    None if col_fac is None else col_fac.shape, None if row_fac is None else row_fac.shape,
+                    None if sig_up is None else sig_up.shape, None if sig_low is None else sig_low.shape, w.dtype)
+        ctx.mark_non_differentiable(out["scale"], out["offset"])
+        return out["w_fq"].to(w.dtype), out["scale"], out["offset"]
+
+    @staticmethod
+    def backward(ctx, g, _gs, _go):
+        w2, cf, rf, su, sl = ctx.saved_tensors
+        col_mode, row_mode, bits, symmetric, per_channel, cshape, rshape, ushape, lshape, wdtype = ctx.meta
+        n = ctx.needs_input_grad
+        need_w = n[0]
+        if need_w and (col_mode or row_mode):
+            raise NotImplementedError("dL/dW through a fused LET transform is never needed (weights are frozen)")
+        res = K.wprep_bwd(w2, g.float().contiguous(), bits, symmetric, per_channel, cf, col_mode, rf, row_mode, su, sl,
+                          need_col=n[1], need_row=n[3], need_sig=n[5] or n[6], need_wt=need_w)
+        g_col, g_row, g_up, g_low = res[:4]
+        g_w = res[4].to(wdtype) if need_w else None
+        return (g_w, g_col.reshape(cshape) if (n[1] and g_col is not None) else None, None,
+                g_row.reshape(rshape) if (n[3] and g_row is not None) else None, None,
+                g_up.reshape(ushape) if (n[5] and g_up is not None) else None,
+                g_low.reshape(lshape) if (n[6] and g_low is not None) else None, None, None, None)

@@ -142,7 +142,7 @@ def test_wprep_let_fwd_bwd(cuda, bits, sym, per_ch, col_mode, row_mode):
     wt = fr.let_weight(w, cf, col_mode, rf if row_mode else None, row_mode)
     y = fr.dynamic_fake_quant(wt, bits, sym, per_ch, su if per_ch else su.reshape(-1)[0], sl if per_ch else sl.reshape(-1)[0])
     gy = torch.randn(y.shape, generator=g)
-    y.backward(gy)
+    y.backward(gy, retain_graph=True)
     d = lambda t: t.detach().reshape(-1).to(cuda).contiguous()
     out = K.wprep_fwd(w.to(cuda), bits, sym, per_ch, d(cf), col_mode, d(rf) if row_mode else None, row_mode, d(su), d(sl),
                       want_wt=True)
