@@ -52,6 +52,11 @@ def _has_bias(m):
     return getattr(m, "bias", None) is not None
 
 
+def _plain(t):
+    """A non-Parameter alias (assigning an nn.Parameter to a module attribute would register it as a parameter)."""
+    return t.view_as(t) if isinstance(t, nn.Parameter) else t
+
+
 def smooth_ln_fcs_temporary(ln, fcs, scales, shifts, use_shift=True):
     """alg:47-68: ln.w / s, ln.b -> (b - shift)/s ; fc.W * s, fc.b + W @ shift."""
     fcs = fcs if isinstance(fcs, list) else [fcs]
@@ -67,7 +72,7 @@ def smooth_ln_fcs_temporary(ln, fcs, scales, shifts, use_shift=True):
         if use_shift:
             fc.temp_bias = fc.bias + fc.weight @ shifts if _has_bias(fc) else fc.weight @ shifts
         else:                                   # shift == 0: W @ 0 adds an exact zero, skip the GEMV
-            fc.temp_bias = fc.bias if _has_bias(fc) else None
+            fc.temp_bias = _plain(fc.bias) if _has_bias(fc) else None
 
 
 def smooth_fc_fc_temporary(fc1, fc2, scales, shifts, use_shift=True):
@@ -85,7 +90,7 @@ def smooth_fc_fc_temporary(fc1, fc2, scales, shifts, use_shift=True):
     if use_shift:
         fc2.temp_bias = fc2.bias + fc2.weight @ shifts if _has_bias(fc2) else fc2.weight @ shifts
     else:
-        fc2.temp_bias = fc2.bias if _has_bias(fc2) else None
+        fc2.temp_bias = _plain(fc2.bias) if _has_bias(fc2) else None
 
 
 def smooth_q_k_temporary(q_proj, k_proj, scales):
@@ -186,7 +191,7 @@ def smooth_lm_temporary(model, config, use_let, use_shift=False, original_omniqu
         if isinstance(m, QLinear):
             m.use_temporary_parameter = True
             if not hasattr(m, "temp_bias"):
-                m.temp_bias = m.bias
+                m.temp_bias = _plain(m.bias)
 
 
 @torch.no_grad()
