@@ -96,6 +96,22 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
                  mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
                  float* g_wt, float* scratch, void* stream);
 
+/* ---- K3/K7: integer GEMM with fused requantisation epilogue == QLinear.forward on codes (qm:341-358) ------------
+ * acc = A[M,K] (u8/s8 codes, row-major) x B[N,K]^T (u8/s8 weight codes from mq_wprep_fwd), s32 accumulate on
+ * tcgen05 tensor cores.  Zero points are removed exactly in the epilogue:
+ *   I = acc - ow[n]*rowsum[m] + c0[n],  c0[n] = K*ox*ow[n] - ox*colsum[n];   y = float(I)*sxw[n] (+ bias[n])
+ * mode 0 QUANT : out = clamp(rne(y/so[n]) + oo[n], 0, qmax) as u8 (out_bits 8) or u16 (16), ld = ldo elements;
+ *                rowsum_out[m] (optional, zero-initialised by the caller) += sum_n code  (for the next GEMM)
+ * mode 1 ACTMUL: B rows are interleaved per 256-row tile as [128 rows of w1 | the same 128 rows of w3];
+ *                out[m, j] = Q_w2in( lut[Q_w1out(y1)] * dequant(Q_w3out(y3)) )  u8, N/2 columns (HFMLP, hm:1057-1060 with
+ *                QSiLU/QGELU qm:739-753,790-799 folded into the 256-entry lut)
+ * mode 2 RESID : resid[m,n] += dequant(Q_out(y))   fp32 in place (o_proj / w2 + residual add, hm:1257,1270)
+ * mode 3 F32   : out = y (fp32);  mode 4 I32: out = I (int32)                                                   */
+int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
+             const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias, int mode,
+             const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo, int32_t* rowsum_out,
+             const float* lut, float s2, float o2, float qmax2, float* resid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

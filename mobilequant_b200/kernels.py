@@ -22,6 +22,8 @@ def _protos():
                                  _P, _P, c_int, _P, _P, _P, _P, _P]
     lib.mq_wprep_bwd.argtypes = [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
                                  _P, _P, _P, _P, _P, _P, _P]
+    lib.mq_qgemm.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
+                             c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, _P]
     _protos_done = True
     return lib
 
@@ -138,3 +140,35 @@ def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_
     if need_wt:
         return g_col, g_row, g_up, g_low, g_wt
     return g_col, g_row, g_up, g_low
+
+
+# ---- K3/K7 ------------------------------------------------------------------------------------------------------
+EPI_QUANT, EPI_ACTMUL, EPI_RESID, EPI_F32, EPI_I32 = 0, 1, 2, 3, 4
+
+
+def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out_bits=8, out=None, ldo=None,
+          rowsum_out=None, lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None):
+    """a: [M,K] uint8/int8 codes, b: [N,K] uint8/int8 codes.  See include/mqb200.h:mq_qgemm."""
+    lib = _protos()
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K
+    dev = a.device
+    if out is None and mode != EPI_RESID:
+        if mode == EPI_QUANT:
+            out = torch.empty(M, N, dtype=torch.uint8 if out_bits == 8 else torch.int16, device=dev)
+        elif mode == EPI_ACTMUL:
+            out = torch.empty(M, N // 2, dtype=torch.uint8, device=dev)
+        elif mode == EPI_F32:
+            out = torch.empty(M, N, dtype=F32, device=dev)
+        else:
+            out = torch.empty(M, N, dtype=torch.int32, device=dev)
+    if ldo is None:
+        ldo = resid.shape[-1] if mode == EPI_RESID else out.shape[-1]
+    h = _h(a)
+    with torch.cuda.device(dev):
+        check(lib.mq_qgemm(h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K,
+                           ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias),
+                           int(mode), ptr(so), ptr(oo), float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out),
+                           ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), stream_ptr()), h)
+    return resid if mode == EPI_RESID else out

@@ -1,0 +1,107 @@
+"""tcgen05 integer GEMM + fused epilogues (mq_qgemm) against the exact-integer oracle (oracle/int_ref.py)."""
+import numpy as np
+import pytest
+import torch
+from oracle import int_ref as ir
+
+pytestmark = pytest.mark.gpu
+
+
+def _prep(M, N, K, seed, a_signed=False, b_signed=False, per_channel=False):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(-128 if a_signed else 0, 128 if a_signed else 256, size=(M, K)).astype(np.int8 if a_signed else np.uint8)
+    b = rng.integers(-128 if b_signed else 0, 128 if b_signed else 256, size=(N, K)).astype(np.int8 if b_signed else np.uint8)
+    ox = 0 if a_signed else int(rng.integers(0, 256))
+    ow = np.zeros(N, np.int64) if b_signed else (rng.integers(0, 256, size=N) if per_channel else np.full(N, rng.integers(0, 256)))
+    sx = np.float32(rng.uniform(0.01, 0.05))
+    sw = (rng.uniform(1e-4, 3e-4, size=N) if per_channel else np.full(N, rng.uniform(1e-4, 3e-4))).astype(np.float32)
+    return a, b, ox, ow.astype(np.int64), sx, sw
+
+
+def _dev(a, b, ox, ow, sx, sw, K, cuda):
+    ta, tb = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+    rowsum = ta.to(torch.int32).sum(1).to(torch.int32)
+    colsum = torch.from_numpy(b.astype(np.int64).sum(1))
+    c0 = (K * ox * torch.from_numpy(ow) - ox * colsum).to(torch.int32).to(cuda)
+    sxw = torch.from_numpy((np.float32(sx) * sw).astype(np.float32)).to(cuda)
+    return ta, tb, rowsum, sxw, torch.from_numpy(ow).to(torch.int32).to(cuda), c0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (256, 512, 2048), (100, 96, 352), (1000, 2560, 2048), (384, 2048, 5632)])
+@pytest.mark.parametrize("signed", [False, True])
+def test_qgemm_exact_integer(cuda, M, N, K, signed):
+    from mobilequant_b200 import kernels as Kn
+    a, b, ox, ow, sx, sw = _prep(M, N, K, M + N + K, b_signed=signed)
+    ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
+    out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_I32)
+    ref = ir.int_acc(a, b, ox, ow)
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_qgemm_quant_epilogue(cuda, bits):
+    from mobilequant_b200 import kernels as Kn
+    M, N, K = 300, 768, 1024
+    a, b, ox, ow, sx, sw = _prep(M, N, K, 7 + bits, per_channel=True)
+    ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
+    rng = np.random.default_rng(3)
+    bias = rng.normal(0, 0.5, size=N).astype(np.float32)
+    y = ir.qlinear_y(a, sx, ox, b, sw, ow, bias)
+    qmax = 2 ** bits - 1
+    so = np.full(N, (y.max() - y.min()) / qmax * 0.9, np.float32); so[N // 2:] *= np.float32(1.3)   # two output quantizers
+    oo = np.rint(-y.min() / so).astype(np.float32)
+    ref = ir.quant_codes(y, so.reshape(1, -1), oo.reshape(1, -1), 0, qmax).astype(np.int64)
+    rs_out = torch.zeros(M, dtype=torch.int32, device=cuda)
+    out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_QUANT, bias=torch.from_numpy(bias).to(cuda),
+                   so=torch.from_numpy(so).to(cuda), oo=torch.from_numpy(oo).to(cuda), qmax=qmax, out_bits=bits, rowsum_out=rs_out)
+    got = out.cpu().numpy()
+    got = got.astype(np.int64) if bits == 8 else got.view(np.uint16).astype(np.int64)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(rs_out.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+def test_qgemm_resid_epilogue(cuda):
+    from mobilequant_b200 import kernels as Kn
+    M, N, K = 260, 512, 768
+    a, b, ox, ow, sx, sw = _prep(M, N, K, 11)
+    ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
+    y = ir.qlinear_y(a, sx, ox, b, sw, ow)
+    so = np.float32((y.max() - y.min()) / 65535); oo = np.float32(np.rint(-y.min() / so))
+    rng = np.random.default_rng(5)
+    h = rng.normal(0, 1, size=(M, N)).astype(np.float32)
+    ref = (h + ir.dequant(ir.quant_codes(y, so, oo, 0, 65535), so, oo)).astype(np.float32)
+    th = torch.from_numpy(h.copy()).to(cuda)
+    Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_RESID, so=torch.full((N,), float(so), device=cuda),
+             oo=torch.full((N,), float(oo), device=cuda), qmax=65535, resid=th)
+    assert np.array_equal(th.cpu().numpy(), ref)
+
+
+def test_qgemm_actmul_epilogue(cuda):
+    """Fused w1||w3 GEMM + activation LUT * gate + w2 input quantizer."""
+    from mobilequant_b200 import kernels as Kn
+    M, I, K = 200, 384, 512
+    rng = np.random.default_rng(21)
+    a, b1, ox, ow1, sx, sw1 = _prep(M, I, K, 31)
+    _, b3, _, ow3, _, sw3 = _prep(M, I, K, 32)
+    y1 = ir.qlinear_y(a, sx, ox, b1, sw1, ow1); y3 = ir.qlinear_y(a, sx, ox, b3, sw3, ow3)
+    so1 = np.float32((y1.max() - y1.min()) / 255); oo1 = np.float32(np.rint(-y1.min() / so1))
+    so3 = np.float32((y3.max() - y3.min()) / 255); oo3 = np.float32(np.rint(-y3.min() / so3))
+    lut = rng.normal(0, 1, size=256).astype(np.float32)
+    q1 = ir.quant_codes(y1, so1, oo1, 0, 255).astype(np.int64)
+    u = ir.dequant(ir.quant_codes(y3, so3, oo3, 0, 255), so3, oo3)
+    prod = (lut[q1] * u).astype(np.float32)
+    s2 = np.float32((prod.max() - prod.min()) / 255); o2 = np.float32(np.rint(-prod.min() / s2))
+    ref = ir.quant_codes(prod, s2, o2, 0, 255).astype(np.int64)
+    # interleave per 256-row tile: [128 rows w1 | 128 rows w3]
+    nb = I // 128
+    b = np.concatenate([np.concatenate([b1[i * 128:(i + 1) * 128], b3[i * 128:(i + 1) * 128]]) for i in range(nb)])
+    il = lambda v1, v3: np.concatenate([np.concatenate([v1[i * 128:(i + 1) * 128], v3[i * 128:(i + 1) * 128]]) for i in range(nb)])
+    ow = il(ow1, ow3); sw = il(sw1, sw3)
+    ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
+    so = torch.from_numpy(il(np.full(I, so1, np.float32), np.full(I, so3, np.float32))).to(cuda)
+    oo = torch.from_numpy(il(np.full(I, oo1, np.float32), np.full(I, oo3, np.float32))).to(cuda)
+    rs_out = torch.zeros(M, dtype=torch.int32, device=cuda)
+    out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qmax=255, lut=torch.from_numpy(lut).to(cuda),
+                   s2=float(s2), o2=float(o2), qmax2=255, rowsum_out=rs_out)
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(rs_out.cpu().numpy().astype(np.int64), ref.sum(1))
