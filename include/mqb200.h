@@ -112,6 +112,30 @@ int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, 
              const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo, int32_t* rowsum_out,
              const float* lut, float s2, float o2, float qmax2, float* resid, void* stream);
 
+/* ---- K4: QRMSNorm.forward (qm:515-531, L2-norm form hm:187-195) / QLayerNorm.forward (qm:625-642) on codes ---------
+ * x fp32 residual stream [rows, H] -> 16-bit input quantizer -> norm with the fake-quantised weight w_fq (from
+ * mq_wprep_fwd) -> 8-bit output quantizer: codes u8 [rows, H] and rowsum[rows] = sum of the codes.               */
+int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, float s_in, float o_in, float qmax_in,
+             const float* w_fq, const float* bias, float alpha, float eps, float s_out, float o_out, float qmax_out,
+             uint8_t* codes, int32_t* rowsum, void* stream);
+
+/* ---- K5: RoPE between two quantizers (hm:486-501 + qm:455-459) ------------------------------------------------------
+ * qkv: u8 codes [B*T, ldq] of the fused q|k|v projection.  in_qparams / out_qparams are HOST arrays
+ * {s_q,o_q,s_k,o_k,s_v,o_v}: projection output quantizers, then qk_bmm.input / qk_bmm.input2 / pv_bmm.input2.
+ * cos/sin: device [T, rot] (hm:308-318).  Outputs: q [B,nh,T,hd], k [B,nkv,T,hd], vt [B,nkv,hd,T] u8 codes and the
+ * per-row code sums rsq [B,nh,T], rsk [B,nkv,T].                                                                 */
+int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int nkv, int hd, int rot, const float* in_qparams,
+             const float* out_qparams, const float* cos, const float* sin, uint8_t* q, uint8_t* k, uint8_t* vt, int32_t* rsq,
+             int32_t* rsk, void* stream);
+
+/* ---- K6: quantised causal attention (HFAttention.forward hm:510-534 with QMatMul qm:453-466) -----------------------
+ * qparams (HOST) = {o_q, o_k, o_v, s_q*s_k, s_s, o_s, qmax_s, s_p, qmax_p, s_p*s_v, s_out, o_out}; lut (device u32
+ * [qmax_s+1]) = rne(2^31 * exp(-k * s_s / sqrt(hd))).  out: u8 codes [B*T, nh*hd]; rowsum_out[B*T] (optional,
+ * zero-initialised by the caller) accumulates the emitted codes for the o_proj zero-point correction.            */
+int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, const int32_t* rsq, const int32_t* rsk, int B,
+             int T, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out, int32_t* rowsum_out,
+             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

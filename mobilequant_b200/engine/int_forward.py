@@ -1,0 +1,270 @@
+"""The statically-quantised integer forward (W8A8 / W4A8) of the unified decoder.
+
+In the reference this stage does not exist in executable form: `eval/harness_eval.py --mode custom` (:81-89) *simulates*
+it in fp32 (fake-quant, qm:285-290) and the true integer execution is handed to Qualcomm QNN after AIMET export
+(device/export.py:311-363).  IntEngine compiles a calibrated model -- fused weights (alg:147-184), default_qcfg.json
+(qm:957-962) and act_dict.json (qm:908-937) -- into integer tensors + per-column epilogue constants and runs every
+decoder block on integer codes with the libmqb200 kernels:
+
+    h (fp32 residual) --qnorm--> u8 --qgemm(QKV)--> u8 --qrope--> q,k,vT u8 --qattn--> u8 --qgemm(o_proj)+resid--> h
+    h --qnorm--> u8 --qgemm(w1||w3)+act LUT*gate--> u8 --qgemm(w2)+resid--> h
+
+Embedding lookup, the final (unquantised) norm and lm_head stay in floating point, as in the reference (qm:843-845).
+"""
+import math
+import numpy as np
+import torch
+from .. import kernels as K
+from ..quantization.qmodule import compute_scale_offset_from_min_max
+
+
+def _sq(act_dict, qcfg, name, slot):
+    """(scale, offset, qmax) python floats of a static activation quantizer (qm:216-245 from act_dict.json)."""
+    c = qcfg[name][slot]
+    bits, sym = int(c["bitwidth"]), c["is_symmetric"] in ("True", "true")
+    if sym:
+        raise NotImplementedError("symmetric activation quantizers are not used by any MobileQuant recipe")
+    if slot == "input2" and slot not in act_dict[name]:
+        mn, mx = 0.0, 1.0
+    else:
+        mn, mx = act_dict[name][slot]
+    s, o, _, _, qmin, qmax = compute_scale_offset_from_min_max(mn, mx, bits, sym)
+    o = float(o)
+    if o != round(o):
+        raise ValueError(f"{name}.{slot}: offset {o} is not integral; reload ranges through act_dict.json (qm:60)")
+    return float(s), o + 0.0, float(qmax)
+
+
+def _f64_sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x.astype(np.float64)))
+
+
+class IntEngine:
+    def __init__(self, model, qcfg, act_dict, device=None):
+        """model: float HFForCausalLM holding the *fused* weights (LET folded, LWC-clamped) -- e.g. the output of
+        ptq.mobilequant.quantize / create_fp_model, or any float checkpoint for plain static PTQ."""
+        self.cfg = cfg = model.config
+        self.device = dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("IntEngine runs on a CUDA device only (no CPU fallback)")
+        self.nh, self.nkv = cfg.num_attention_heads, cfg.num_key_value_heads
+        self.hd = cfg.head_dim if cfg.head_dim is not None else cfg.hidden_size // cfg.num_attention_heads
+        self.rot = int(cfg.partial_rotary_factor * self.hd)
+        self.H, self.I = cfg.hidden_size, cfg.intermediate_size
+        self.Ipad = (self.I + 127) // 128 * 128
+        self.layernorm = cfg.norm_class.lower() == "layernorm"
+        if cfg.num_linears_per_mlp != 3 or cfg.shared_attention_norm or cfg.parallel_residual:
+            raise NotImplementedError("IntEngine covers the gated-MLP pre-norm block of the three evaluated families")
+        self.embed = model.model.embed_tokens.weight.detach().float().to(dev)
+        self.final_norm = model.model.norm.to(dev).float()
+        self.lm_head = model.lm_head.weight.detach().float().to(dev)
+        self.layers = [self._build_layer(model.model.layers[i], f"model.layers.{i}", qcfg, act_dict) for i in range(cfg.num_hidden_layers)]
+        self._rope_cache = {}
+        self._bufs = {}
+
+    # ---- build ------------------------------------------------------------------------------------------------------
+    def _wq(self, w, c, want_fq=False):
+        bits, sym, pc = int(c["bitwidth"]), c["is_symmetric"] in ("True", "true"), c["is_per_channel"] in ("True", "true")
+        w = w.detach().float().to(self.device).contiguous()
+        w2 = w.reshape(1, -1) if w.dim() == 1 else w
+        out = K.wprep_fwd(w2, bits, sym, pc, want_fq=want_fq, want_codes=bits <= 8)
+        out["sym"] = sym
+        out["rows"] = w2.shape[0]
+        return out
+
+    def _percol(self, wq_list, sx, ox, Kdim, out_q, biases, pad_to=None):
+        """Concatenate several quantised weight matrices along N and derive the per-column epilogue constants."""
+        codes, sw, ow, cs, so, oo, bias = [], [], [], [], [], [], []
+        signed = wq_list[0]["sym"]
+        for wq, oq, b in zip(wq_list, out_q, biases):
+            n = wq["rows"]
+            codes.append(wq["codes"].view(torch.int8 if signed else torch.uint8))
+            sw.append(wq["scale"].expand(n) if wq["scale"].numel() == 1 else wq["scale"])
+            ow.append(wq["offset"].expand(n) if wq["offset"].numel() == 1 else wq["offset"])
+            cs.append(wq["colsum"])
+            so.append(torch.full((n,), oq[0], device=self.device)); oo.append(torch.full((n,), oq[1], device=self.device))
+            bias.append(torch.zeros(n, device=self.device) if b is None else b.detach().float().to(self.device))
+        codes = torch.cat(codes); sw = torch.cat(sw).float(); ow = torch.cat(ow).to(torch.int64); cs = torch.cat(cs).to(torch.int64)
+        sxw = (torch.tensor(sx, dtype=torch.float32, device=self.device) * sw).contiguous()
+        c0 = (Kdim * int(ox) * ow - int(ox) * cs)
+        assert c0.abs().max().item() < 2 ** 31
+        bias = torch.cat(bias)
+        return dict(codes=codes.contiguous(), sxw=sxw, ow=ow.to(torch.int32).contiguous(), c0=c0.to(torch.int32).contiguous(),
+                    bias=bias.contiguous() if bias.abs().max().item() > 0 else None, so=torch.cat(so).contiguous(),
+                    oo=torch.cat(oo).contiguous(), qmax=out_q[0][2], N=codes.shape[0], K=Kdim)
+
+    def _build_layer(self, layer, p, qcfg, act):
+        L = {}
+        at, mlp = layer.self_attn, layer.mlp
+        for tag, mod, name in (("n1", layer.input_layernorm, p + ".input_layernorm"), ("n2", layer.post_attention_layernorm, p + ".post_attention_layernorm")):
+            wq = self._wq(mod.weight, qcfg[name]["weight"], want_fq=True)
+            b = getattr(mod, "bias", None)
+            b = None if b is None or float(b.detach().abs().max()) == 0.0 else b.detach().float().to(self.device).contiguous()
+            L[tag] = dict(w_fq=wq["w_fq"].reshape(-1).contiguous(), bias=b, qin=_sq(act, qcfg, name, "input"), qout=_sq(act, qcfg, name, "output"),
+                          eps=float(getattr(mod, "eps", 1e-5)))
+        pa = p + ".self_attn."
+        x1 = L["n1"]["qout"]
+        qo = [_sq(act, qcfg, pa + n, "output") for n in ("q_proj", "k_proj", "v_proj")]
+        L["qkv"] = self._percol([self._wq(m.weight, qcfg[pa + n]["weight"]) for m, n in ((at.q_proj, "q_proj"), (at.k_proj, "k_proj"), (at.v_proj, "v_proj"))],
+                                x1[0], x1[1], self.H, qo, [getattr(at.q_proj, "bias", None), getattr(at.k_proj, "bias", None), getattr(at.v_proj, "bias", None)])
+        qk_in, qk_in2, qk_out = (_sq(act, qcfg, pa + "qk_bmm", s) for s in ("input", "input2", "output"))
+        pv_in, pv_in2, pv_out = (_sq(act, qcfg, pa + "pv_bmm", s) for s in ("input", "input2", "output"))
+        if pv_in[1] != 0.0:
+            raise NotImplementedError("pv_bmm.input_quantizer offset must be 0 (softmax output range starts at 0)")
+        L["rope_in"] = [(q[0], q[1]) for q in qo]
+        L["rope_out"] = [(qk_in[0], qk_in[1]), (qk_in2[0], qk_in2[1]), (pv_in2[0], pv_in2[1])]
+        f = np.float32
+        L["attn"] = [qk_in[1], qk_in2[1], pv_in2[1], float(f(qk_in[0]) * f(qk_in2[0])), qk_out[0], qk_out[1], qk_out[2], pv_in[0], pv_in[2],
+                     float(f(pv_in[0]) * f(pv_in2[0])), pv_out[0], pv_out[1]]
+        k = np.arange(int(qk_out[2]) + 1, dtype=np.float64)
+        lut = np.rint(np.exp(-k * np.float64(f(qk_out[0])) / np.sqrt(np.float64(self.hd))) * 2.0 ** 31).astype(np.uint32)
+        L["attn_lut"] = torch.from_numpy(lut.view(np.int32)).to(self.device)
+        L["o"] = self._percol([self._wq(at.o_proj.weight, qcfg[pa + "o_proj"]["weight"])], pv_out[0], pv_out[1], self.nh * self.hd,
+                              [_sq(act, qcfg, pa + "o_proj", "output")], [getattr(at.o_proj, "bias", None)])
+        # ---- MLP: w1 || w3 interleaved per 128 rows (padded to a multiple of 128), activation folded into a LUT
+        pm = p + ".mlp."
+        x2 = L["n2"]["qout"]
+        q1, q3 = _sq(act, qcfg, pm + "w1", "output"), _sq(act, qcfg, pm + "w3", "output")
+        w1 = self._wq(mlp.w1.weight, qcfg[pm + "w1"]["weight"]); w3 = self._wq(mlp.w3.weight, qcfg[pm + "w3"]["weight"])
+        pc1 = self._percol([w1], x2[0], x2[1], self.H, [q1], [getattr(mlp.w1, "bias", None)])
+        pc3 = self._percol([w3], x2[0], x2[1], self.H, [q3], [getattr(mlp.w3, "bias", None)])
+        L["w13"] = self._interleave(pc1, pc3)
+        act_q = qcfg[pm + "act_fn"]
+        q_aout = _sq(act, qcfg, pm + "act_fn", "output")
+        c = np.arange(256, dtype=np.float32)
+        xg = ((c - f(q1[1])) * f(q1[0])).astype(np.float32)
+        if "input2" in act_q:                                   # QSiLU
+            q_in2 = _sq(act, qcfg, pm + "act_fn", "input2")
+            sg = _f64_sigmoid(xg).astype(np.float32)
+            sgq = np.clip(np.rint(sg / f(q_in2[0])).astype(np.float32) + f(q_in2[1]), 0, f(q_in2[2])).astype(np.float32)
+            sgq = ((sgq - f(q_in2[1])) * f(q_in2[0])).astype(np.float32)
+            a = (xg * sgq).astype(np.float32)
+        else:                                                   # QGELU (erf form, qm:794)
+            xd = xg.astype(np.float64)
+            a = (0.5 * xd * (1.0 + np.vectorize(math.erf)(xd / np.sqrt(2.0)))).astype(np.float32)
+        aq = np.clip(np.rint(a / f(q_aout[0])).astype(np.float32) + f(q_aout[1]), 0, f(q_aout[2])).astype(np.float32)
+        L["act_lut"] = torch.from_numpy(((aq - f(q_aout[1])) * f(q_aout[0])).astype(np.float32)).to(self.device)
+        w2_in = _sq(act, qcfg, pm + "w2", "input")
+        L["w2_in"] = w2_in
+        w2 = self._wq(mlp.w2.weight, qcfg[pm + "w2"]["weight"])
+        L["w2"] = self._percol([self._pad_cols(w2)], w2_in[0], w2_in[1], self.Ipad, [_sq(act, qcfg, pm + "w2", "output")], [getattr(mlp.w2, "bias", None)])
+        return L
+
+    def _pad_cols(self, wq):
+        """Pad K (=intermediate) to Ipad with the row's zero point so that padded columns contribute exactly 0."""
+        if self.Ipad == self.I:
+            return wq
+        rows = wq["rows"]
+        codes = wq["codes"]
+        off = wq["offset"].expand(rows) if wq["offset"].numel() == 1 else wq["offset"]
+        pad = off.to(codes.dtype).view(-1, 1).expand(rows, self.Ipad - self.I)
+        wq = dict(wq)
+        wq["codes"] = torch.cat([codes, pad], dim=1).contiguous()
+        wq["colsum"] = (wq["colsum"].to(torch.int64) + off.to(torch.int64) * (self.Ipad - self.I)).to(torch.int32)
+        return wq
+
+    def _interleave(self, a, b):
+        """[128 rows of w1 | 128 rows of w3] per 256-row GEMM tile; rows beyond I are zero-point padding."""
+        I, Ipad = self.I, self.Ipad
+
+        def pad(t, fill):
+            if Ipad == I:
+                return t
+            extra = torch.full((Ipad - I,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+            return torch.cat([t, extra])
+
+        def il(x, y):
+            return torch.stack([x.view(Ipad // 128, 128, *x.shape[1:]), y.view(Ipad // 128, 128, *y.shape[1:])], dim=1).reshape(2 * Ipad, *x.shape[1:]).contiguous()
+
+        out = dict(N=2 * Ipad, K=a["K"], qmax=a["qmax"])
+        out["codes"] = il(pad(a["codes"], 0), pad(b["codes"], 0))
+        for k, fill in (("sxw", 0.0), ("ow", 0), ("c0", 0), ("so", 1.0), ("oo", 0.0)):
+            out[k] = il(pad(a[k], fill), pad(b[k], fill))
+        if a["bias"] is None and b["bias"] is None:
+            out["bias"] = None
+        else:
+            z = lambda d: d["bias"] if d["bias"] is not None else torch.zeros(I, device=self.device)
+            out["bias"] = il(pad(z(a), 0.0), pad(z(b), 0.0))
+        return out
+
+    # ---- run --------------------------------------------------------------------------------------------------------
+    def _rope(self, T):
+        if T not in self._rope_cache:
+            from ..model.hf_model import rope_cos_sin
+            pos = torch.arange(T, device=self.device).unsqueeze(0)
+            cos, sin = rope_cos_sin(pos, self.rot, self.cfg.rope_theta, self.device, torch.float32)
+            self._rope_cache[T] = (cos[0].contiguous(), sin[0].contiguous())
+        return self._rope_cache[T]
+
+    def set_rope_tables(self, T, cos, sin):
+        """Tests pass the oracle's tables so that both sides use bit-identical cos/sin."""
+        self._rope_cache[T] = (cos.to(self.device).float().contiguous(), sin.to(self.device).float().contiguous())
+
+    def _buffers(self, B, T):
+        key = (B, T)
+        if key not in self._bufs:
+            M, dev = B * T, self.device
+            u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+            i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+            self._bufs[key] = dict(x=u8(M, self.H), rs=i32(M), qkv=u8(M, (self.nh + 2 * self.nkv) * self.hd),
+                                   rope=dict(q=u8(B, self.nh, T, self.hd), k=u8(B, self.nkv, T, self.hd), vt=u8(B, self.nkv, self.hd, T),
+                                             rsq=i32(B, self.nh, T), rsk=i32(B, self.nkv, T)),
+                                   attn=u8(M, self.nh * self.hd), rs_attn=i32(M), act=u8(M, self.Ipad), rs_act=i32(M))
+        return self._bufs[key]
+
+    def _gemm(self, a, g, rowsum, mode, **kw):
+        return K.qgemm(a, g["codes"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"], **kw)
+
+    @torch.no_grad()
+    def block(self, h, L, B, T, bufs, trace=None):
+        """One decoder block on the fp32 residual stream h [B*T, H] (updated in place)."""
+        cos, sin = self._rope(T)
+        K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
+        self._gemm(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, out=bufs["qkv"], out_bits=8)
+        K.qrope(bufs["qkv"], B, T, self.nh, self.nkv, self.hd, self.rot, L["rope_in"], L["rope_out"], cos, sin, bufs["rope"])
+        bufs["rs_attn"].zero_()
+        K.qattn(bufs["rope"], B, T, self.nh, self.nkv, self.hd, L["attn"], L["attn_lut"], bufs["attn"], bufs["rs_attn"])
+        if trace is not None:
+            trace.update(x1=bufs["x"].clone(), qkv=bufs["qkv"].clone(), q=bufs["rope"]["q"].clone(), k=bufs["rope"]["k"].clone(),
+                         vt=bufs["rope"]["vt"].clone(), attn=bufs["attn"].clone())
+        self._gemm(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, resid=h)
+        if trace is not None:
+            trace.update(h_mid=h.clone())
+        K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
+        bufs["rs_act"].zero_()
+        w2in = L["w2_in"]
+        self._gemm(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1], qmax2=w2in[2],
+                   rowsum_out=bufs["rs_act"])
+        if trace is not None:
+            trace.update(x2=bufs["x"].clone(), act=bufs["act"].clone())
+        self._gemm(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, resid=h)
+        return h
+
+    @torch.no_grad()
+    def backbone(self, h, B, T, trace_layer=None):
+        bufs = self._buffers(B, T)
+        trace = None
+        for i, L in enumerate(self.layers):
+            tr = {} if trace_layer == i else None
+            self.block(h, L, B, T, bufs, tr)
+            if tr is not None:
+                trace = tr
+        return (h, trace) if trace_layer is not None else h
+
+    @torch.no_grad()
+    def forward(self, input_ids, return_logits=True, last_token_only=False):
+        """input_ids: LongTensor [B, T] on the engine's device.  Returns logits [B, T, V] (or the final hidden state)."""
+        B, T = input_ids.shape
+        h = torch.nn.functional.embedding(input_ids, self.embed)
+        if self.cfg.normalize_embed:
+            h = h * (self.H ** 0.5)
+        h = h.reshape(B * T, self.H).contiguous()
+        h = self.backbone(h, B, T).view(B, T, self.H)
+        if not return_logits:
+            return h
+        if last_token_only:
+            h = h[:, -1:, :]
+        hn = self.final_norm(h)
+        return torch.nn.functional.linear(hn, self.lm_head)
+
+    __call__ = forward

@@ -24,6 +24,10 @@ def _protos():
                                  _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qgemm.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
                              c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, _P]
+    lib.mq_qnorm.argtypes = [_P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float,
+                             c_float, c_float, _P, _P, _P]
+    lib.mq_qrope.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
+    lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
     _protos_done = True
     return lib
 
@@ -172,3 +176,57 @@ def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255
                            int(mode), ptr(so), ptr(oo), float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out),
                            ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), stream_ptr()), h)
     return resid if mode == EPI_RESID else out
+
+
+# ---- K4 / K5 / K6 (integer engine) ---------------------------------------------------------------------------------
+def _host_floats(vals):
+    arr = (c_float * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def qnorm(x, qin, w_fq, bias, qout, layernorm=False, eps=1e-5, codes=None, rowsum=None):
+    """x fp32 [rows, H]; qin/qout = (scale, offset, qmax) python floats.  Returns (codes u8, rowsum int32)."""
+    lib = _protos()
+    rows, H = x.shape
+    if codes is None:
+        codes = torch.empty(rows, H, dtype=torch.uint8, device=x.device)
+    if rowsum is None:
+        rowsum = torch.empty(rows, dtype=torch.int32, device=x.device)
+    h = _h(x)
+    import math
+    with torch.cuda.device(x.device):
+        check(lib.mq_qnorm(h, ptr(x, F32), rows, H, int(layernorm), float(qin[0]), float(qin[1]), float(qin[2]), ptr(w_fq, F32),
+                           ptr(bias), float(math.sqrt(H)), float(eps), float(qout[0]), float(qout[1]), float(qout[2]),
+                           ptr(codes), ptr(rowsum), stream_ptr()), h)
+    return codes, rowsum
+
+
+def qrope(qkv, B, T, nh, nkv, hd, rot, qin, qout, cos, sin, bufs=None):
+    """qkv u8 [B*T, ldq]; qin/qout: 3 x (scale, offset).  Returns dict(q, k, vt, rsq, rsk)."""
+    lib = _protos()
+    dev = qkv.device
+    if bufs is None:
+        bufs = dict(q=torch.empty(B, nh, T, hd, dtype=torch.uint8, device=dev), k=torch.empty(B, nkv, T, hd, dtype=torch.uint8, device=dev),
+                    vt=torch.empty(B, nkv, hd, T, dtype=torch.uint8, device=dev),
+                    rsq=torch.empty(B, nh, T, dtype=torch.int32, device=dev), rsk=torch.empty(B, nkv, T, dtype=torch.int32, device=dev))
+    h = _h(qkv)
+    pin = _host_floats([v for so in qin for v in so]); pout = _host_floats([v for so in qout for v in so])
+    with torch.cuda.device(dev):
+        check(lib.mq_qrope(h, ptr(qkv), qkv.shape[-1], B, T, nh, nkv, hd, rot, ctypes.cast(pin, _P), ctypes.cast(pout, _P),
+                           ptr(cos, F32), ptr(sin, F32), ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]),
+                           ptr(bufs["rsk"]), stream_ptr()), h)
+    return bufs
+
+
+def qattn(bufs, B, T, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
+    """qparams = [o_q, o_k, o_v, s_q*s_k, s_s, o_s, qmax_s, s_p, qmax_p, s_p*s_v, s_out, o_out] (python floats)."""
+    lib = _protos()
+    dev = bufs["q"].device
+    if out is None:
+        out = torch.empty(B * T, nh * hd, dtype=torch.uint8, device=dev)
+    h = _h(out)
+    pq = _host_floats(qparams)
+    with torch.cuda.device(dev):
+        check(lib.mq_qattn(h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
+                           ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
+    return out

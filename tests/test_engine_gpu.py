@@ -1,0 +1,114 @@
+"""Integer engine kernels (qnorm / qrope / qattn) and the whole IntEngine against the exact-integer oracle
+(bit-exact codes), plus the LSB-flip distance to the reference's fp32 fake-quant forward (golden logits)."""
+import numpy as np
+import pytest
+import torch
+from oracle import int_ref as ir
+from oracle import model_ref as mr
+from helpers import load_golden, MODEL_GOLDENS, product_model
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.mark.parametrize("layernorm,H,rows", [(False, 128, 37), (False, 2048, 64), (True, 256, 50)])
+def test_qnorm(cuda, layernorm, H, rows):
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(H + rows)
+    x = (rng.normal(0, 1.5, size=(rows, H)) * rng.uniform(0.2, 3, size=(rows, 1))).astype(f32)
+    w = rng.normal(0, 1, size=H).astype(f32)
+    bias = rng.normal(0, 0.1, size=H).astype(f32) if layernorm else None
+    qin = (f32((x.max() - x.min()) * 0.9 / 65535), f32(np.rint(-x.min() * 0.9 / ((x.max() - x.min()) * 0.9 / 65535))), f32(65535))
+    qout = (f32(8.0 / 255), f32(128), f32(255))
+    ref = ir.qnorm_int(x, qin, w, bias, qout, layernorm, 1e-5)
+    codes, rs = K.qnorm(torch.from_numpy(x).to(cuda), qin, torch.from_numpy(w).to(cuda), None if bias is None else torch.from_numpy(bias).to(cuda),
+                        qout, layernorm, 1e-5)
+    assert np.array_equal(codes.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+@pytest.mark.parametrize("B,T,nh,nkv,hd,rot", [(2, 48, 4, 2, 32, 32), (1, 100, 8, 8, 64, 16), (2, 64, 4, 1, 64, 64)])
+def test_qrope(cuda, B, T, nh, nkv, hd, rot):
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(T + hd)
+    N = (nh + 2 * nkv) * hd
+    qkv = rng.integers(0, 256, size=(B * T, N)).astype(np.uint8)
+    qin = [(f32(0.031), f32(120)), (f32(0.027), f32(131)), (f32(0.011), f32(127))]
+    qout = [(f32(0.033), f32(125)), (f32(0.029), f32(128)), (f32(0.012), f32(126))]
+    cos, sin = ir.rope_tables(T, rot)
+    q, k, v = ir.qrope_int(qkv, B, T, nh, nkv, hd, rot, qin, qout, cos, sin)
+    out = K.qrope(torch.from_numpy(qkv).to(cuda), B, T, nh, nkv, hd, rot, qin, qout, torch.from_numpy(cos).to(cuda), torch.from_numpy(sin).to(cuda))
+    assert np.array_equal(out["q"].cpu().numpy().astype(np.int64), q)
+    assert np.array_equal(out["k"].cpu().numpy().astype(np.int64), k)
+    assert np.array_equal(out["vt"].cpu().numpy().astype(np.int64), v.transpose(0, 1, 3, 2))
+    assert np.array_equal(out["rsq"].cpu().numpy().astype(np.int64), q.sum(-1))
+    assert np.array_equal(out["rsk"].cpu().numpy().astype(np.int64), k.sum(-1))
+
+
+@pytest.mark.parametrize("B,T,nh,nkv,hd", [(1, 64, 2, 1, 64), (2, 100, 4, 2, 32), (1, 200, 4, 4, 64), (1, 130, 2, 1, 128), (1, 96, 2, 1, 256)])
+def test_qattn(cuda, B, T, nh, nkv, hd):
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(T * hd)
+    q = rng.integers(0, 256, size=(B, nh, T, hd)).astype(np.uint8)
+    k = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)
+    v = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)
+    qq, qk, qv = (f32(0.02), f32(126)), (f32(0.018), f32(131)), (f32(0.015), f32(124))
+    smax = 255 * 255 * hd * 0.02 * 0.018 * 0.12
+    qs = (f32(2 * smax / 65535), f32(32768), f32(65535))
+    qp = (f32(1.0 / 65535), f32(0), f32(65535))
+    qo = (f32(0.7 / 255), f32(128), f32(255))
+    ref = ir.qattn_int(q.astype(np.int64), k.astype(np.int64), v.astype(np.int64), nh, nkv, qq, qk, qv, qs, qp, qo)
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    bufs = dict(q=dev(q), k=dev(k), vt=dev(np.ascontiguousarray(v.transpose(0, 1, 3, 2))),
+                rsq=dev(q.astype(np.int32).sum(-1).astype(np.int32)), rsk=dev(k.astype(np.int32).sum(-1).astype(np.int32)))
+    lut = dev(ir.exp_lut(qs[0], hd, qs[2]).view(np.int32))
+    params = [qq[1], qk[1], qv[1], f32(qq[0]) * f32(qk[0]), qs[0], qs[1], qs[2], qp[0], qp[2], f32(qp[0]) * f32(qv[0]), qo[0], qo[1]]
+    rs = torch.zeros(B * T, dtype=torch.int32, device=cuda)
+    out = K.qattn(bufs, B, T, nh, nkv, hd, params, lut, rowsum_out=rs)
+    got = out.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, ref), f"{(got != ref).mean():.4f} mismatching"
+    assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+@pytest.mark.parametrize("tag", MODEL_GOLDENS)
+def test_engine_bit_exact_vs_integer_oracle(cuda, tag):
+    """Every integer tensor of a block (norm / qkv / rope / attention / activation codes) and the fp32 residual stream
+    after all layers are bit-identical to the CPU restatement."""
+    from mobilequant_b200.engine import IntEngine
+    g = load_golden(f"model_{tag}.pt")
+    model = product_model(g)
+    eng = IntEngine(model, g["qcfg"], g["act_dict"], cuda)
+    ids = torch.cat(g["samples"][:2], dim=0)
+    B, T = ids.shape
+    im = ir.IntModel(g["state_dict"], g["cfg"], mr.recipe_from_qcfg_json(g["qcfg"]), g["act_dict"])
+    cos, sin = ir.rope_tables(T, im.rot, g["cfg"].get("rope_theta", 10000.0))
+    eng.set_rope_tables(T, torch.from_numpy(cos), torch.from_numpy(sin))
+    h_ref, tr_ref = im.backbone(im.embed(ids.numpy()), B, T, cos, sin, trace_layer=0)
+    h = torch.nn.functional.embedding(ids.to(cuda), eng.embed)
+    if eng.cfg.normalize_embed:
+        h = h * (eng.H ** 0.5)
+    h, tr = eng.backbone(h.reshape(B * T, -1).contiguous(), B, T, trace_layer=0)
+    n = lambda t: t.cpu().numpy().astype(np.int64)
+    assert np.array_equal(n(tr["x1"]), tr_ref["x1"])
+    assert np.array_equal(n(tr["qkv"]), tr_ref["qkv"])
+    assert np.array_equal(n(tr["q"]), tr_ref["q"]) and np.array_equal(n(tr["k"]), tr_ref["k"])
+    assert np.array_equal(n(tr["vt"]), tr_ref["v"].transpose(0, 1, 3, 2))
+    assert np.array_equal(n(tr["attn"]), tr_ref["attn"])
+    assert np.array_equal(tr["h_mid"].cpu().numpy(), tr_ref["h_mid"])
+    assert np.array_equal(n(tr["x2"]), tr_ref["x2"])
+    assert np.array_equal(n(tr["act"])[:, :eng.I], tr_ref["act"])
+    assert np.array_equal(h.cpu().numpy(), h_ref)
+
+
+@pytest.mark.parametrize("tag", MODEL_GOLDENS)
+def test_engine_vs_reference_fake_quant(cuda, tag):
+    """Distance of the integer forward to the reference's fp32 fake-quant forward (golden logits written by the
+    unmodified reference): codes may flip by one LSB where the fp32 GEMM of the reference rounds differently."""
+    from mobilequant_b200.engine import IntEngine
+    g = load_golden(f"model_{tag}.pt")
+    eng = IntEngine(product_model(g), g["qcfg"], g["act_dict"], cuda)
+    logits = eng(g["samples"][0].to(cuda)).cpu()
+    ref = g["logits_fq"]
+    scale = ref.abs().max().item()
+    assert (logits - ref).abs().max().item() < 0.03 * scale
+    assert (logits - ref).abs().mean().item() < 3e-3 * scale
