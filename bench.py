@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Headline benchmark of the MobileQuant hot path on B200 (contract: task statement / BASELINE.json).
+
+Workload (config.workload): statically-quantised W8A8 integer forward of TinyLlama-1.1B shapes, batch x seq 1024
+synthetic prompts, random-init weights (no checkpoints offline): embeddings -> 22 integer decoder blocks (IntEngine)
+-> final norm -> lm_head over all positions -> arg-max of the last position.  metric = int8 tokens/s.
+
+  value  : device-timed (CUDA events), token ids already resident in HBM
+  e2e    : same through the public API with pinned-host token ids H2D and the next-token ids D2H every step
+  calib  : MobileQuant e2e calibration (LET+LWC+LRL, module path) samples/s on the same model (second half of the metric)
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+`--impl reference` times the reference's own CPU implementation of this forward (the fp32 fake-quant simulation,
+eval/harness_eval.py --mode custom recipe) as restated in oracle/model_ref.py, on the host cores.
+"""
+import argparse, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "tinyllama-1.1b"
+SEQ = 1024
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=8, help="sequences per GPU per step")
+    p.add_argument("--seqlen", type=int, default=SEQ)
+    p.add_argument("--model", default=MODEL)
+    p.add_argument("--layers", type=int, default=None, help="debug: override num_hidden_layers")
+    p.add_argument("--no-calib", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seq", type=int, default=1, help="sequences in the bounded CPU sample")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def model_cfg(args):
+    from mobilequant_b200.model.hf_config import named_config
+    over = {}
+    if args.layers:
+        over["num_hidden_layers"] = args.layers
+    return named_config(args.model, **over)
+
+
+def synth_ids(n, T, vocab, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(3, vocab, (n, T), generator=g)       # reference's random-id convention, device/export.py:116
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU path for this forward (fp32 fake-quant simulation), oracle port, all host threads."""
+    import torch
+    from oracle import model_ref as mr
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cfg = model_cfg(args)
+    cd = {k: getattr(cfg, k) for k in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                                       "num_key_value_heads", "hidden_act", "head_dim", "norm_class", "num_linears_per_mlp",
+                                       "partial_rotary_factor", "rope_theta", "normalize_embed", "layer_norm_eps")}
+    torch.manual_seed(1337)
+    from mobilequant_b200.model import HFForCausalLM
+    sd = {k: v.detach() for k, v in HFForCausalLM(cfg).float().state_dict().items()}
+    T = args.seqlen
+    ids = synth_ids(args.cpu_seq, T, cfg.vocab_size, 1337)
+    act = mr.act_range(sd, cd, [ids[:1]])
+    qs = mr.QState(mr.default_recipe(cd, 8, False, False, 8), act)
+    times = []
+    with torch.no_grad():
+        warm = min(args.warmup, 1)              # a CPU step is ~10 s: one warm-up pass (page-in, thread pool) is enough
+        for i in range(warm + args.steps):
+            t0 = time.perf_counter()
+            logits, _ = mr.model_forward(sd, cd, ids, qs, quant=True)
+            nxt = logits[:, -1].argmax(-1)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    tot = sum(times)
+    v = args.steps * ids.numel() / tot
+    line = {"impl": "reference", "metric": "int8_tok_per_s", "value": v, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warm, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} W8A8 static fake-quant forward (reference CPU path), {args.cpu_seq} x seq{T} per step",
+                       "timing": "host wall clock, inputs larger than LLC (4.4 GB fp32 weights)"},
+            "cpu_baseline": {"value": v, "unit": "tok/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.cpu_seq} sequence(s) x {T} tokens per step, {args.steps} steps"},
+            "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mobilequant_b200 import kernels as K
+    from mobilequant_b200.model import HFForCausalLM
+    from mobilequant_b200.engine import IntEngine
+    from mobilequant_b200.quantization import qmodule as Q
+    from mobilequant_b200.ptq.generate_act_range import get_act_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True          # as ptq/mobilequant.py:91 (only the fp lm_head / teacher use it)
+    cfg = model_cfg(args)
+    T, B = args.seqlen, args.batch
+    torch.manual_seed(1337)
+    with torch.device(dev):
+        model = HFForCausalLM(cfg).float()
+    model.eval()
+    # activation ranges from a short calibration pass on synthetic ids (config 1 of BASELINE.json, on the GPU; with
+    # several ranks the two samples are sharded and the packed ranges all-reduced, identical on every replica)
+    act = get_act_range(model, [synth_ids(1, T, cfg.vocab_size, 7 + i) for i in range(2)])
+    from mobilequant_b200.ptq.generate_qcfg import default_qcfg
+    qcfg = default_qcfg(cfg, Q.QuantConfig(bitwidth=8), Q.QuantConfig(bitwidth=8))
+    eng = IntEngine(model, qcfg, act, dev)
+    ids_host = synth_ids(B, T, cfg.vocab_size, 1000 + rank).pin_memory()
+    ids_dev = ids_host.to(dev)
+    out_host = torch.empty(B, dtype=torch.int64).pin_memory()
+
+    def step_resident():
+        logits = eng(ids_dev)
+        return logits[:, -1].argmax(-1)
+
+    def step_e2e():
+        d = ids_host.to(dev, non_blocking=True)
+        nxt = eng(d)[:, -1].argmax(-1)
+        out_host.copy_(nxt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return nxt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    K.reset_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = K.launch_count()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e_dev = timed(step_e2e, args.steps)
+    tokens_step = B * T * world
+    value = tokens_step * args.steps / (ms / 1e3)
+    e2e = tokens_step * args.steps / (ms_e2e_dev / 1e3)
+
+    line = {"metric": "int8_tok_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{args.model} W8A8 static-quant integer forward, batch {B} x seq {T} per GPU, random-init weights",
+                       "global_batch": B * world, "seq_len": T, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+                       "l2": "inputs larger than L2: 1.1 GB int8 weights + 1 GB logits streamed per step"},
+            "clocks": clk.summary(), "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": ids_host.numel() * 8 * world,
+                    "d2h_bytes_per_step": out_host.numel() * 8 * world}}
+
+    if rank == 0:
+        line["roofline"], line["kernel_shares"] = roofline(eng, ids_dev, B, T)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(model, cfg, act, T, args.cpu_seq)
+        if not args.no_calib and world == 1:
+            del eng
+            torch.cuda.empty_cache()
+            line["calib"] = calib_throughput(model, qcfg, act, cfg, T, dev)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline(eng, ids, B, T):
+    """Per-kernel-class device time of one forward (CUDA events around every launch) and the roofline entry of the
+    dominant kernel (the tcgen05 int8 GEMM)."""
+    import torch
+    from mobilequant_b200 import kernels as K
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peaks = json.load(open(pth))
+    K.enable_event_timing(True)
+    eng(ids)
+    torch.cuda.synchronize()
+    per = K.collect_event_timing()
+    K.enable_event_timing(False)
+    tot = sum(v["ms"] for v in per.values())
+    shares = {k: {"ms": round(v["ms"], 4), "launches": v["n"], "share": round(v["ms"] / tot, 4)} for k, v in per.items()}
+    g = per["qgemm"]
+    M = B * T
+    cfg = eng.cfg
+    ops = 2.0 * M * (eng.H * (eng.nh + 2 * eng.nkv) * eng.hd + eng.nh * eng.hd * eng.H + 2 * eng.Ipad * eng.H + eng.Ipad * eng.H) * cfg.num_hidden_layers
+    achieved = ops / (g["ms"] / 1e3) / 1e12
+    bf16 = peaks.get("bf16_tflops")
+    peak = 2.0 * bf16 if bf16 else 2 * 1590.0
+    # library INT8 proxy measured in the same run
+    a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=ids.device)
+    b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=ids.device)
+    for _ in range(3):
+        torch._int_mm(a, b.t())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        torch._int_mm(a, b.t())
+    e1.record(); torch.cuda.synchronize()
+    lib = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
+    rl = {"kernel": "qgemm_kernel<256> (tcgen05 kind::i8)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s",
+          "frac": achieved / peak, "traffic": None,
+          "peak_source": ("2 x measured bf16 burst (MEASURED_PEAKS.json): int8 issues at twice the bf16 rate on sm_100"
+                          if bf16 else "2 x fallback bf16 1.59 PF"),
+          "avg_launch_ms": g["ms"] / g["n"], "launches_per_step": g["n"], "ops_per_step": ops,
+          "int8_library_proxy_tops": lib, "frac_of_library_proxy": achieved / lib, "frac_of_spec_4500": achieved / 4500.0}
+    return rl, shares
+
+
+def calib_throughput(model, qcfg, act, cfg, T, dev, nsamples=4):
+    """MobileQuant e2e calibration (LET + LWC + LRL, experiments/w8a8/main/e2e_llama-s1024-ep60.sh learning rates) on the
+    module path: FP-target pass + one optimiser step per sample."""
+    import types, tempfile, torch
+    from mobilequant_b200.quantization import qmodule as Q, algorithm as A
+
+    class _L:
+        def info(self, *a, **k):
+            pass
+    Q.create_sim_qmodel(model, Q.QuantConfig(bitwidth=8), Q.QuantConfig(bitwidth=8))
+    for p in model.parameters():
+        p.requires_grad = False
+    Q.update_quant_cfg(model)
+    Q.set_scale_and_offset(model, act, "parameter")
+    out = tempfile.mkdtemp()
+    args = types.SimpleNamespace(nsamples=nsamples, seqlen=T, batch_size=1, epochs=1, warmup_epochs=0, deactive_amp=True, let=True,
+                                 lwc=True, lrl=True, use_shift=False, aug_loss=False, let_lr=1e-3, lwc_lr=1e-2, lrl_lr=1e-6,
+                                 let_min_lr=1e-4, lwc_min_lr=1e-3, lrl_min_lr=1e-7, wd=0.0, resume=None, cache_in_gpu=True,
+                                 original_omniquant=False, dtype=torch.float32, output_dir=out)
+    loader = [(synth_ids(1, T, cfg.vocab_size, 50 + i), None) for i in range(nsamples)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    A.e2equant(args, model, loader, _L(), device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": nsamples / dt, "unit": "samples/s", "samples": nsamples, "seconds": dt,
+            "what": "e2equant LET+LWC+LRL, bs 1, seq %d, 1 epoch, includes FP-target pass, fuse and parameters.pth save" % T,
+            "path": "module path (fused quantizer kernels + cuBLAS TF32 GEMMs); projected 512 samples: %.1f s" % (512 * dt / nsamples)}
+
+
+def cpu_baseline(model, cfg, act, T, nseq):
+    """The oracle port of the reference's fp32 fake-quant forward on the host cores, bounded sample."""
+    import torch
+    from oracle import model_ref as mr
+    torch.set_num_threads(os.cpu_count() or 1)
+    cd = {k: getattr(cfg, k) for k in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                                       "num_key_value_heads", "hidden_act", "head_dim", "norm_class", "num_linears_per_mlp",
+                                       "partial_rotary_factor", "rope_theta", "normalize_embed", "layer_norm_eps")}
+    from mobilequant_b200.quantization import qmodule as Q
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if "quantizer" not in k and "smooth" not in k}
+    qs = mr.QState(mr.default_recipe(cd, 8, False, False, 8), act)
+    ids = synth_ids(nseq, T, cfg.vocab_size, 1337)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        logits, _ = mr.model_forward(sd, cd, ids, qs, quant=True)
+        logits[:, -1].argmax(-1)
+        dt = time.perf_counter() - t0
+    return {"value": ids.numel() / dt, "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{nseq} sequence(s) x {T} tokens, one fp32 fake-quant forward (oracle/model_ref.py), {dt:.1f} s"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

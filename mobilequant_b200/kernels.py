@@ -36,6 +36,46 @@ def _h(t):
     return _lib.ctx(t.device.index)
 
 
+# ---- launch accounting (bench.py: "gpu_launches", per-kernel-class device time) ----------------------------------
+_launches = 0
+_timing = None
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def enable_event_timing(on):
+    global _timing
+    _timing = {} if on else None
+
+
+def collect_event_timing():
+    """{name: {"ms": total device ms, "n": calls}}; call after torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in (_timing or {}).items():
+        out[name] = {"ms": sum(a.elapsed_time(b) for a, b in evs), "n": len(evs)}
+    return out
+
+
+def _launch(name, fn, *args):
+    global _launches
+    _launches += 1
+    if _timing is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _timing.setdefault(name, []).append((e0, e1))
+    return rc
+
+
 F32 = torch.float32
 
 
@@ -47,7 +87,7 @@ def fq_fwd(x, scale, offset, qmin, qmax, group=0, want_y=True, want_codes=False)
     codes = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_codes else None
     h = _h(x)
     with torch.cuda.device(x.device):
-        check(lib.mq_fq_fwd(h, ptr(x, F32), ptr(y), ptr(codes), x.numel(), ptr(scale, F32), ptr(offset, F32),
+        check(_launch("fq_fwd", lib.mq_fq_fwd, h, ptr(x, F32), ptr(y), ptr(codes), x.numel(), ptr(scale, F32), ptr(offset, F32),
                             int(group), float(qmin), float(qmax), stream_ptr()), h)
     return y, codes
 
@@ -60,7 +100,7 @@ def fq_bwd(x, g, scale, offset, qmin, qmax, group=0, want_gx=True, want_gparams=
     go = torch.empty((), dtype=F32, device=x.device) if want_gparams else None
     h = _h(x)
     with torch.cuda.device(x.device):
-        check(lib.mq_fq_bwd(h, ptr(x, F32), ptr(g, F32), ptr(gx), x.numel(), ptr(scale, F32), ptr(offset, F32),
+        check(_launch("fq_bwd", lib.mq_fq_bwd, h, ptr(x, F32), ptr(g, F32), ptr(gx), x.numel(), ptr(scale, F32), ptr(offset, F32),
                             int(group), float(qmin), float(qmax), ptr(gs), ptr(go), stream_ptr()), h)
     return gx, gs, go
 
@@ -74,7 +114,7 @@ def minmax(x, out=None, accumulate=False):
         out = torch.empty(2, dtype=F32, device=x.device); accumulate = False
     h = _h(x)
     with torch.cuda.device(x.device):
-        check(lib.mq_minmax(h, ptr(x, F32), x.numel(), ptr(out, F32), int(accumulate), stream_ptr()), h)
+        check(_launch("minmax", lib.mq_minmax, h, ptr(x, F32), x.numel(), ptr(out, F32), int(accumulate), stream_ptr()), h)
     return out
 
 
@@ -87,7 +127,7 @@ def minmax_2d(x2d, per_row, out_min=None, out_max=None, accumulate=False):
         out_min = torch.empty(n, dtype=F32, device=x2d.device); out_max = torch.empty_like(out_min); accumulate = False
     h = _h(x2d)
     with torch.cuda.device(x2d.device):
-        check(lib.mq_minmax_2d(h, ptr(x2d, F32), rows, cols, int(per_row), ptr(out_min, F32), ptr(out_max, F32),
+        check(_launch("minmax_2d", lib.mq_minmax_2d, h, ptr(x2d, F32), rows, cols, int(per_row), ptr(out_min, F32), ptr(out_max, F32),
                                int(accumulate), stream_ptr()), h)
     return out_min, out_max
 
@@ -115,7 +155,7 @@ def wprep_fwd(w, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac
     h = _h(w)
     cfg = mq_qcfg(int(bits), int(bool(symmetric)))
     with torch.cuda.device(dev):
-        check(lib.mq_wprep_fwd(h, ptr(w, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac), int(row_mode),
+        check(_launch("wprep_fwd", lib.mq_wprep_fwd, h, ptr(w, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac), int(row_mode),
                                ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(out["w_fq"]),
                                ptr(out["codes"]), int(bool(pack4)), ptr(out["scale"]), ptr(out["offset"]),
                                ptr(out["colsum"]), ptr(out["wt"]), stream_ptr()), h)
@@ -138,7 +178,7 @@ def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_
     h = _h(w)
     cfg = mq_qcfg(int(bits), int(bool(symmetric)))
     with torch.cuda.device(dev):
-        check(lib.mq_wprep_bwd(h, ptr(w, F32), ptr(g, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac),
+        check(_launch("wprep_bwd", lib.mq_wprep_bwd, h, ptr(w, F32), ptr(g, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac),
                                int(row_mode), ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(g_col),
                                ptr(g_row), ptr(g_up), ptr(g_low), ptr(g_wt), ptr(scratch), stream_ptr()), h)
     if need_wt:
@@ -171,7 +211,7 @@ def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255
         ldo = resid.shape[-1] if mode == EPI_RESID else out.shape[-1]
     h = _h(a)
     with torch.cuda.device(dev):
-        check(lib.mq_qgemm(h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K,
+        check(_launch("qgemm", lib.mq_qgemm, h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K,
                            ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias),
                            int(mode), ptr(so), ptr(oo), float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out),
                            ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), stream_ptr()), h)
@@ -195,7 +235,7 @@ def qnorm(x, qin, w_fq, bias, qout, layernorm=False, eps=1e-5, codes=None, rowsu
     h = _h(x)
     import math
     with torch.cuda.device(x.device):
-        check(lib.mq_qnorm(h, ptr(x, F32), rows, H, int(layernorm), float(qin[0]), float(qin[1]), float(qin[2]), ptr(w_fq, F32),
+        check(_launch("qnorm", lib.mq_qnorm, h, ptr(x, F32), rows, H, int(layernorm), float(qin[0]), float(qin[1]), float(qin[2]), ptr(w_fq, F32),
                            ptr(bias), float(math.sqrt(H)), float(eps), float(qout[0]), float(qout[1]), float(qout[2]),
                            ptr(codes), ptr(rowsum), stream_ptr()), h)
     return codes, rowsum
@@ -212,7 +252,7 @@ def qrope(qkv, B, T, nh, nkv, hd, rot, qin, qout, cos, sin, bufs=None):
     h = _h(qkv)
     pin = _host_floats([v for so in qin for v in so]); pout = _host_floats([v for so in qout for v in so])
     with torch.cuda.device(dev):
-        check(lib.mq_qrope(h, ptr(qkv), qkv.shape[-1], B, T, nh, nkv, hd, rot, ctypes.cast(pin, _P), ctypes.cast(pout, _P),
+        check(_launch("qrope", lib.mq_qrope, h, ptr(qkv), qkv.shape[-1], B, T, nh, nkv, hd, rot, ctypes.cast(pin, _P), ctypes.cast(pout, _P),
                            ptr(cos, F32), ptr(sin, F32), ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]),
                            ptr(bufs["rsk"]), stream_ptr()), h)
     return bufs
@@ -227,6 +267,6 @@ def qattn(bufs, B, T, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
     h = _h(out)
     pq = _host_floats(qparams)
     with torch.cuda.device(dev):
-        check(lib.mq_qattn(h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
+        check(_launch("qattn", lib.mq_qattn, h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
                            ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
     return out

@@ -11,6 +11,14 @@ def generate_qcfg(model, weight_qcfg, act_qcfg, use_8bit_softmax_input=False, us
     return export_qcfg(model)
 
 
+def default_qcfg(config, weight_qcfg, act_qcfg, **kw):
+    """default_qcfg.json content for an architecture without materialising its weights (meta device)."""
+    import torch
+    with torch.device("meta"):
+        shell = HFForCausalLM(config)
+    return generate_qcfg(shell, weight_qcfg, act_qcfg, **kw)
+
+
 def add_quant_args(p):
     p.add_argument("--weight_bitwidth", type=int, default=4)
     p.add_argument("--weight_group_size", type=int, default=-1)
