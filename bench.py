@@ -35,6 +35,9 @@ def parse():
     p.add_argument("--no-calib", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seq", type=int, default=1, help="sequences in the bounded CPU sample")
+    p.add_argument("--profile-step", action="store_true",
+                   help="ncu helper: run the warm-up, then ONE step between cudaProfilerStart/Stop and exit (use with "
+                        "`ncu --profile-from-start off`); prints no bench line")
     return p.parse_args()
 
 
@@ -203,6 +206,13 @@ def run_ours(args):
 
     for _ in range(max(3, args.warmup)):
         step_resident()
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     K.reset_launch_count()
     with ClockSampler(local) as clk:
         ms = timed(step_resident, args.steps)
