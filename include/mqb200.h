@@ -100,17 +100,20 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
  * acc = A[M,K] (u8/s8 codes, row-major) x B[N,K]^T (u8/s8 weight codes from mq_wprep_fwd), s32 accumulate on
  * tcgen05 tensor cores.  Zero points are removed exactly in the epilogue:
  *   I = acc - ow[n]*rowsum[m] + c0[n],  c0[n] = K*ox*ow[n] - ox*colsum[n];   y = float(I)*sxw[n] (+ bias[n])
- * mode 0 QUANT : out = clamp(rne(y/so[n]) + oo[n], 0, qmax) as u8 (out_bits 8) or u16 (16), ld = ldo elements;
+ * so/oo describe the (per-tensor, qm:216-245) output quantizers of the fused column segments: one (scale, integral offset)
+ * entry per group of `qgroup` consecutive columns (qgroup % 32 == 0; e.g. the fused q|k|v projection has three segments).
+ * mode 0 QUANT : out = clamp(rne(y/so[g]) + oo[g], 0, qmax) as u8 (out_bits 8) or u16 (16), ld = ldo elements;
  *                rowsum_out[m] (optional, zero-initialised by the caller) += sum_n code  (for the next GEMM)
  * mode 1 ACTMUL: B rows are interleaved per 256-row tile as [128 rows of w1 | the same 128 rows of w3];
  *                out[m, j] = Q_w2in( lut[Q_w1out(y1)] * dequant(Q_w3out(y3)) )  u8, N/2 columns (HFMLP, hm:1057-1060 with
- *                QSiLU/QGELU qm:739-753,790-799 folded into the 256-entry lut)
- * mode 2 RESID : resid[m,n] += dequant(Q_out(y))   fp32 in place (o_proj / w2 + residual add, hm:1257,1270)
+ *                QSiLU/QGELU qm:739-753,790-799 folded into the 256-entry lut); qgroup must divide 128
+ * mode 2 RESID : resid[m,n] += dequant(Q_out(y))   fp32 in place (o_proj / w2 + residual add, hm:1257,1270); the add is
+ *                performed by the L2 (TMA reduce-add, round-to-nearest; subnormal sums flush to zero)
  * mode 3 F32   : out = y (fp32);  mode 4 I32: out = I (int32)                                                   */
 int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
              const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias, int mode,
              const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo, int32_t* rowsum_out,
-             const float* lut, float s2, float o2, float qmax2, float* resid, void* stream);
+             const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup, void* stream);
 
 /* ---- K4: QRMSNorm.forward (qm:515-531, L2-norm form hm:187-195) / QLayerNorm.forward (qm:625-642) on codes ---------
  * x fp32 residual stream [rows, H] -> 16-bit input quantizer -> norm with the fake-quantised weight w_fq (from
@@ -129,12 +132,22 @@ int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int n
              int32_t* rsk, void* stream);
 
 /* ---- K6: quantised causal attention (HFAttention.forward hm:510-534 with QMatMul qm:453-466) -----------------------
- * qparams (HOST) = {o_q, o_k, o_v, s_q*s_k, s_s, o_s, qmax_s, s_p, qmax_p, s_p*s_v, s_out, o_out}; lut (device u32
- * [qmax_s+1]) = rne(2^31 * exp(-k * s_s / sqrt(hd))).  out: u8 codes [B*T, nh*hd]; rowsum_out[B*T] (optional,
- * zero-initialised by the caller) accumulates the emitted codes for the o_proj zero-point correction.            */
+ * qparams (HOST) = {o_q, o_k, o_v, s_q*s_k, s_s, o_s, qmax_s, s_p, qmax_p, s_p*s_v, s_out, o_out}; lut (device u32[512])
+ * is the two-level exp table A[256] | B[256], A[i] = rne(2^31 exp(-256 i a)), B[j] = rne(2^31 exp(-j a)),
+ * a = s_s / sqrt(hd): exp(-k a) for a 16-bit code distance k is evaluated as (A[k >> 8] * B[k & 255]) >> 31.
+ * out: u8 codes [B*T, nh*hd]; rowsum_out[B*T] (optional, zero-initialised by the caller) accumulates the emitted codes
+ * for the o_proj zero-point correction.  Offsets must be integral (ranges reloaded through act_dict.json, qm:60).   */
 int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, const int32_t* rsq, const int32_t* rsk, int B,
              int T, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out, int32_t* rowsum_out,
              void* stream);
+
+/* ---- test hook ---------------------------------------------------------------------------------------------------
+ * The integer-engine kernels requantise with a branch-free exact division (RN(a/b) from RN(1/b) and two FMAs, a
+ * third/fourth for scales whose significand is all ones) instead of the IEEE division + rint of qm:286.  This entry
+ * point checks that path against __fdiv_rn / rintf on n pseudo-random operand pairs and writes the number of
+ * disagreements to *mismatches (device u64).  mode 0: random scales; 1: `fixed_scale` with integer-valued numerators;
+ * 2: all-ones significands.                                                                                         */
+int mq_selftest_div(void* ctx, int64_t n, uint64_t seed, int mode, float fixed_scale, uint64_t* mismatches, void* stream);
 
 #ifdef __cplusplus
 }

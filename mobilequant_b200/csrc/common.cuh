@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include <type_traits>
 
 #define MQ_CLIPMIN 1e-5f   // qmodule.py:11
 #define MQ_CLIPMAX 1e6f    // qmodule.py:12
@@ -56,6 +57,61 @@ __device__ __forceinline__ void scale_offset_from_minmax(float mn, float mx, int
   s = fminf(fmaxf(s, MQ_CLIPMIN), MQ_CLIPMAX);
   // offset = -(beta / scale).round(); symmetric: -(0/scale).round() = -0 -> 0
   o = symmetric ? 0.f : -rintf(fdiv(beta, s));
+}
+
+// ---- branch-free exact requantisation (integer engine kernels) ----------------------------------------------------
+// RN(a / b) without the XU pipe or a slow-path branch, given rb = RN(1/b) (host: 1.0f/b in IEEE fp32, device:
+// __frcp_rn).  q0 = a*rb is within 1 ulp of a/b; one Newton step on the exact FMA residual gives the correctly rounded
+// quotient (Markstein) -- except when b's significand is all ones, where RN(1/b) is not accurate enough and a second
+// step is needed (`five`, decided once per scale on the host / per kernel).  Valid for normal-range operands
+// (activation and score magnitudes); tests/test_quant_kernels_gpu.py::test_div_rn_exact checks it against __fdiv_rn.
+template <bool FIVE>
+__device__ __forceinline__ float div_rn(float a, float b, float rb) {
+  float q = __fmul_rn(a, rb);
+  float r = __fmaf_rn(-q, b, a);
+  q = __fmaf_rn(r, rb, q);
+  if (FIVE) {
+    r = __fmaf_rn(-q, b, a);
+    q = __fmaf_rn(r, rb, q);
+  }
+  return q;
+}
+__host__ __device__ __forceinline__ bool mantissa_all_ones(float b) {
+#ifdef __CUDA_ARCH__
+  return (__float_as_uint(b) & 0x7fffffu) == 0x7fffffu;
+#else
+  union { float f; uint32_t u; } v; v.f = b; return (v.u & 0x7fffffu) == 0x7fffffu;
+#endif
+}
+constexpr float kRoundMagic = 12582912.f;        // 1.5 * 2^23: x + magic rounds x to an integer (RNE) for |x| < 2^22
+constexpr int kRoundMagicBits = 0x4B400000;
+
+// Static quantizer with an INTEGRAL offset, prepared once: code = clamp(rne(x/s)+o, 0, qmax) computed as
+// rne(clamp(x/s, -o, qmax-o)) + o (identical because rne is monotone and the bounds are integers).
+struct QParam {
+  float s, rs, lo, hi;
+  int ioff;                                       // int(o) - kRoundMagicBits
+  bool five;                                      // s has an all-ones significand: callers take the FIVE=true path
+};
+__device__ __forceinline__ QParam make_qparam(float s, float o, float qmax) {
+  QParam p;
+  p.s = s; p.rs = __frcp_rn(s); p.lo = -o; p.hi = __fsub_rn(qmax, o); p.ioff = (int)o - kRoundMagicBits;
+  p.five = mantissa_all_ones(s);
+  return p;
+}
+// rounded, clamped quotient as (magic + n): __float_as_int(m) + ioff is the code, __fsub_rn(m, magic) is n = code - o
+template <bool FIVE>
+__device__ __forceinline__ float quant_magic(float x, const QParam& p) {
+  float q = div_rn<FIVE>(x, p.s, p.rs);
+  q = fminf(fmaxf(q, p.lo), p.hi);
+  return __fadd_rn(q, kRoundMagic);
+}
+template <bool FIVE>
+__device__ __forceinline__ int quant_int(float x, const QParam& p) { return __float_as_int(quant_magic<FIVE>(x, p)) + p.ioff; }
+// run body(std::true_type / std::false_type) on the exact-division variant the scales need (uniform branch)
+template <typename F>
+__device__ __forceinline__ void dispatch_five(bool five, F&& body) {
+  if (five) body(std::true_type{}); else body(std::false_type{});
 }
 
 // ---- ordered-int encoding so float min/max can use integer atomics ---------------------------------------------

@@ -11,78 +11,120 @@ namespace mq {
 //   r = clamp(rne(x/s_in)+o_in, 0, qmax_in) - o_in ; x^ = r*s_in ; nrm = sqrt(float(sum r^2)) * s_in  (sum exact, u64)
 //   t = w_fq * (alpha * (x^ / max(nrm, 1e-12))) (+ bias) ; code = clamp(rne(t/s_out)+o_out, 0, qmax_out)
 // QLayerNorm.forward (qm:625-642): mean/var from the exact integer sums (double), y = ((x^-mean)*rstd)*w + b.
-// One warp per row, the row stays in registers (H <= 32*kMaxPerLane); emits u8 codes + their row sum.
+// One warp per row.  NV > 0: the row's de-offset integers r stay in registers (H == 128*NV) so x is read once;
+// NV == 0: generic H, second pass re-reads the row through L1/L2.  All requantisation is the branch-free exact
+// division of common.cuh (the previous version was bound by the XU pipe: MUFU.RCP + FRND + F2I per element).
 // =====================================================================================================================
-constexpr int kNormMaxVec = 16;   // float4 per lane -> H <= 2048*... 32 lanes * 16 * 4 = 2048... extended by loop below
+struct NormArgs {
+  const float* x; int64_t rows; int H;
+  float s_in, o_in, qmax_in;
+  const float* w_fq; const float* bias;
+  float alpha, eps, s_out, o_out, qmax_out;
+  uint8_t* codes; int32_t* rowsum;
+};
 
-template <bool kLayerNorm>
-__global__ void __launch_bounds__(128) qnorm_kernel(const float* __restrict__ x, int64_t rows, int H, float s_in, float o_in,
-                                                     float qmax_in, const float* __restrict__ w_fq,
-                                                     const float* __restrict__ bias, float alpha, float eps, float s_out,
-                                                     float o_out, float qmax_out, uint8_t* __restrict__ codes,
-                                                     int32_t* __restrict__ rowsum) {
+template <bool kLayerNorm, int NV>
+__global__ void __launch_bounds__(128) qnorm_kernel(const NormArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* xr = x + row * H;
-  // pass 1: integer statistics (row is re-read from L1/L2 in pass 2; H*4 bytes per warp)
+  if (row >= a.rows) return;
+  const int H = a.H;
+  const float* xr = a.x + row * H;
+  const QParam qi = make_qparam(a.s_in, a.o_in, a.qmax_in);
+  const QParam qo = make_qparam(a.s_out, a.o_out, a.qmax_out);
+  constexpr int NR = NV > 0 ? NV : 1;
+  float rr[NR][4];                               // r = code - o_in as exact fp32 integers
+  // ---- pass 1: integer statistics
   unsigned long long s2 = 0; long long s1 = 0;
-  for (int k = lane * 4; k < H; k += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + k);
-    float r0 = fsub(quant_code(v.x, s_in, o_in, 0.f, qmax_in), o_in), r1 = fsub(quant_code(v.y, s_in, o_in, 0.f, qmax_in), o_in);
-    float r2 = fsub(quant_code(v.z, s_in, o_in, 0.f, qmax_in), o_in), r3 = fsub(quant_code(v.w, s_in, o_in, 0.f, qmax_in), o_in);
-    long long i0 = (long long)r0, i1 = (long long)r1, i2 = (long long)r2, i3 = (long long)r3;
-    s2 += (unsigned long long)(i0 * i0) + (unsigned long long)(i1 * i1) + (unsigned long long)(i2 * i2) + (unsigned long long)(i3 * i3);
-    s1 += i0 + i1 + i2 + i3;
-  }
+  auto stats = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    auto one = [&](float4 v, float (&r)[4]) {
+      r[0] = __fsub_rn(quant_magic<FIVE>(v.x, qi), kRoundMagic); r[1] = __fsub_rn(quant_magic<FIVE>(v.y, qi), kRoundMagic);
+      r[2] = __fsub_rn(quant_magic<FIVE>(v.z, qi), kRoundMagic); r[3] = __fsub_rn(quant_magic<FIVE>(v.w, qi), kRoundMagic);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = __float2int_rn(r[j]);
+        s2 += (unsigned long long)((long long)i * i);
+        if (kLayerNorm) s1 += i;
+      }
+    };
+    if (NV > 0) {
+#pragma unroll
+      for (int it = 0; it < NR; ++it) one(ldg4_stream(xr + it * 128 + lane * 4), rr[it]);
+    } else {
+      float tmp[4];
+      for (int k = lane * 4; k < H; k += 128) one(ldg4(xr + k), tmp);
+    }
+  };
+  dispatch_five(qi.five, stats);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    if (kLayerNorm) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
   }
-  float denom = 1.f, mean = 0.f, rstd = 1.f;
+  float denom = 1.f, rdenom = 1.f, mean = 0.f, rstd = 1.f;
+  bool five = qo.five | qi.five;
   if (kLayerNorm) {
     const double m = (double)s1 / (double)H;
     const double var = (double)s2 / (double)H - m * m;
-    mean = (float)(m * (double)s_in);
-    rstd = (float)(1.0 / sqrt(var * (double)s_in * (double)s_in + (double)eps));
+    mean = (float)(m * (double)a.s_in);
+    rstd = (float)(1.0 / sqrt(var * (double)a.s_in * (double)a.s_in + (double)a.eps));
   } else {
-    denom = fmaxf(fmul(__fsqrt_rn(__ull2float_rn(s2)), s_in), 1e-12f);
+    denom = fmaxf(fmul(__fsqrt_rn(__ull2float_rn(s2)), a.s_in), 1e-12f);
+    rdenom = __frcp_rn(denom);
+    five |= mantissa_all_ones(denom);           // warp-uniform: one row per warp
   }
+  // ---- pass 2: normalise, requantise, emit codes + row sum
   int csum = 0;
-  for (int k = lane * 4; k < H; k += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + k);
-    float4 w = __ldg(reinterpret_cast<const float4*>(w_fq + k));
-    float xv[4] = {v.x, v.y, v.z, v.w}, wv[4] = {w.x, w.y, w.z, w.w};
-    uint32_t packed = 0;
+  auto emit = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    auto one = [&](const float (&r)[4], int k) {
+      const float4 w = ldg4(a.w_fq + k);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.bias) { const float4 b = ldg4(a.bias + k); bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w; }
+      uint32_t packed = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xh = dequant(quant_code(xv[j], s_in, o_in, 0.f, qmax_in), s_in, o_in);
-      float t;
-      if (kLayerNorm) {
-        t = fmul(fmul(fsub(xh, mean), rstd), wv[j]);
-        if (bias) t = fadd(t, __ldg(bias + k + j));
-      } else {
-        t = fmul(wv[j], fmul(alpha, fdiv(xh, denom)));
-        if (bias) t = fadd(t, __ldg(bias + k + j));
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmul(r[j], a.s_in);
+        float t;
+        if (kLayerNorm) t = fmul(fmul(fsub(xh, mean), rstd), wv[j]);
+        else t = fmul(wv[j], fmul(a.alpha, div_rn<FIVE>(xh, denom, rdenom)));
+        if (a.bias) t = fadd(t, bv[j]);
+        packed |= (uint32_t)quant_int<FIVE>(t, qo) << (8 * j);
       }
-      const int c = (int)quant_code(t, s_out, o_out, 0.f, qmax_out);
-      csum += c;
-      packed |= (uint32_t)c << (8 * j);
+      csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+      *reinterpret_cast<uint32_t*>(a.codes + row * H + k) = packed;
+    };
+    if (NV > 0) {
+#pragma unroll
+      for (int it = 0; it < NR; ++it) one(rr[it], it * 128 + lane * 4);
+    } else {
+      for (int k = lane * 4; k < H; k += 128) {
+        const float4 v = ldg4(xr + k);
+        float r[4];
+        r[0] = __fsub_rn(quant_magic<FIVE>(v.x, qi), kRoundMagic); r[1] = __fsub_rn(quant_magic<FIVE>(v.y, qi), kRoundMagic);
+        r[2] = __fsub_rn(quant_magic<FIVE>(v.z, qi), kRoundMagic); r[3] = __fsub_rn(quant_magic<FIVE>(v.w, qi), kRoundMagic);
+        one(r, k);
+      }
     }
-    *reinterpret_cast<uint32_t*>(codes + row * H + k) = packed;
-  }
+  };
+  dispatch_five(five, emit);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
-  if (lane == 0 && rowsum) rowsum[row] = csum;
+  if (lane == 0 && a.rowsum) a.rowsum[row] = csum;
 }
 
 // =====================================================================================================================
 // K5: de-quantise q/k/v projection codes, RoPE (hm:338-367, partial rotary hm:489-501), re-quantise with the qk_bmm /
 // pv_bmm input quantizers (qm:455-459) and write the attention layouts:
 //   q  [B, nh, T, hd] u8      k [B, nkv, T, hd] u8      vT [B, nkv, hd, T] u8   (+ per-token code sums of q and k rows)
-// One CTA per 32 tokens; V goes through a shared-memory transpose so that vT rows are written 32 bytes at a time.
+// One CTA per 16 tokens.  A thread owns 4 consecutive head dims (one 32-bit word of codes) of one (token, head) and
+// reads the partner word for rotate_half; the lanes of one (token, head) are adjacent so the code sum is a shuffle
+// reduction.  V goes through a shared-memory transpose so that vT rows are written 16 bytes at a time.
 // =====================================================================================================================
+constexpr int kRopeTok = 16;
+
 struct RopeArgs {
   const uint8_t* qkv;     // [M, ldq] codes of the fused q|k|v projection
   int ldq;
@@ -95,79 +137,100 @@ struct RopeArgs {
   int32_t *rsq, *rsk;     // [B, nh, T], [B, nkv, T] code sums over hd
 };
 
-__global__ void __launch_bounds__(256) qrope_kernel(const RopeArgs a) {
-  extern __shared__ uint8_t vs[];                       // [32 tokens][nkv*hd + 4]
-  const int tok0 = blockIdx.x * 32;
+__device__ __forceinline__ void unpack4(uint32_t w, float s, float o, float (&x)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = dequant(__uint2float_rn((w >> (8 * j)) & 255u), s, o);
+}
+
+template <bool FIVE>
+__device__ __forceinline__ void qrope_body(const RopeArgs& a, uint8_t* vs) {
+  const int tok0 = blockIdx.x * kRopeTok;
   const int M = a.B * a.T;
   const int half = a.rot / 2;
-  const int vstride = a.nkv * a.hd + 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ---- q and k: one warp per (token, head), lanes over the head dim
+  const int words = a.hd / 4;                            // 32-bit words per head
+  const int wpt = words > 32 ? words / 32 : 1;           // words per thread (hd = 256 -> 2)
+  const int lpi = words / wpt;                           // lanes per (token, head): 8, 16 or 32
+  const QParam qq = make_qparam(a.sq, a.oq, 255.f), qk = make_qparam(a.sk, a.ok, 255.f), qv = make_qparam(a.sv, a.ov, 255.f);
+  // ---- q and k
   const int heads_qk = a.nh + a.nkv;
-  for (int item = warp; item < 32 * heads_qk; item += 8) {
-    const int tl = item / heads_qk, hh = item % heads_qk;
+  const int items = kRopeTok * heads_qk * lpi;           // multiple of 8
+  for (int it = threadIdx.x; it < ((items + 31) & ~31); it += blockDim.x) {
+    const bool active = it < items;
+    const int sub = it % lpi, th = it / lpi;
+    const int tl = th / heads_qk, hh = th % heads_qk;
     const int tok = tok0 + tl;
-    if (tok >= M) continue;
-    const int b = tok / a.T, t = tok % a.T;
-    const bool is_q = hh < a.nh;
-    const int h = is_q ? hh : hh - a.nh;
-    const uint8_t* src = a.qkv + int64_t(tok) * a.ldq + (is_q ? h * a.hd : a.nh * a.hd + h * a.hd);
-    const float s_in = is_q ? a.sq_in : a.sk_in, o_in = is_q ? a.oq_in : a.ok_in;
-    const float s_o = is_q ? a.sq : a.sk, o_o = is_q ? a.oq : a.ok;
-    uint8_t* dst = is_q ? a.q + ((int64_t(b) * a.nh + h) * a.T + t) * a.hd : a.k + ((int64_t(b) * a.nkv + h) * a.T + t) * a.hd;
+    const bool ok = active && tok < M;
     int csum = 0;
-    for (int d = lane; d < a.hd; d += 32) {
-      float out;
-      const float xd = dequant((float)src[d], s_in, o_in);
-      if (d < a.rot) {
-        const float c = __ldg(a.cos + int64_t(t) * a.rot + d), s = __ldg(a.sin + int64_t(t) * a.rot + d);
-        // q_embed = (q * cos) + (rotate_half(q) * sin); rotate_half = cat(-x2, x1)
-        const float other = dequant((float)src[d < half ? d + half : d - half], s_in, o_in);
-        const float rh = d < half ? -other : other;
-        out = fadd(fmul(xd, c), fmul(rh, s));
-      } else {
-        out = xd;
-      }
-      const int code = (int)quant_code(out, s_o, o_o, 0.f, 255.f);
-      dst[d] = (uint8_t)code;
-      csum += code;
-    }
+    if (ok) {
+      const int b = tok / a.T, t = tok % a.T;
+      const bool is_q = hh < a.nh;
+      const int h = is_q ? hh : hh - a.nh;
+      const uint8_t* src = a.qkv + int64_t(tok) * a.ldq + hh * a.hd;      // q heads then k heads are contiguous in the row
+      const float s_in = is_q ? a.sq_in : a.sk_in, o_in = is_q ? a.oq_in : a.ok_in;
+      const QParam& qo = is_q ? qq : qk;
+      uint8_t* dst = is_q ? a.q + ((int64_t(b) * a.nh + h) * a.T + t) * a.hd : a.k + ((int64_t(b) * a.nkv + h) * a.T + t) * a.hd;
+      for (int wi = 0; wi < wpt; ++wi) {
+        const int d = (sub + wi * lpi) * 4;
+        float x[4], out[4];
+        unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + d)), s_in, o_in, x);
+        if (d < a.rot) {
+          // q_embed = (q * cos) + (rotate_half(q) * sin); rotate_half = cat(-x2, x1)
+          const int dp = d < half ? d + half : d - half;
+          float y[4];
+          unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + dp)), s_in, o_in, y);
+          const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
+          const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
-    for (int dd = 16; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
-    if (lane == 0) {
-      if (is_q) a.rsq[(int64_t(b) * a.nh + h) * a.T + t] = csum;
-      else a.rsk[(int64_t(b) * a.nkv + h) * a.T + t] = csum;
+          for (int j = 0; j < 4; ++j) out[j] = fadd(fmul(x[j], cv[j]), fmul(d < half ? -y[j] : y[j], sv[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[j] = x[j];
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(out[j], qo) << (8 * j);
+        *reinterpret_cast<uint32_t*>(dst + d) = packed;
+        csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+      }
+    }
+    for (int dd = lpi >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
+    if (ok && sub == 0) {
+      const int b = tok / a.T, t = tok % a.T;
+      if (hh < a.nh) a.rsq[(int64_t(b) * a.nh + hh) * a.T + t] = csum;
+      else a.rsk[(int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t] = csum;
     }
   }
   // ---- v: requant into smem, then transposed store
   const int vw = a.nkv * a.hd;
-  for (int idx = threadIdx.x; idx < 32 * vw; idx += 256) {
-    const int tl = idx / vw, c = idx % vw;
+  const int vstride = vw + 4;
+  for (int idx = threadIdx.x; idx < kRopeTok * (vw / 4); idx += blockDim.x) {
+    const int tl = idx / (vw / 4), c = (idx % (vw / 4)) * 4;
     const int tok = tok0 + tl;
-    uint8_t code = 0;
+    uint32_t packed = 0;
     if (tok < M) {
-      const float xv = dequant((float)a.qkv[int64_t(tok) * a.ldq + (a.nh + a.nkv) * a.hd + c], a.sv_in, a.ov_in);
-      code = (uint8_t)quant_code(xv, a.sv, a.ov, 0.f, 255.f);
+      float x[4];
+      unpack4(__ldg(reinterpret_cast<const uint32_t*>(a.qkv + int64_t(tok) * a.ldq + (a.nh + a.nkv) * a.hd + c)), a.sv_in, a.ov_in, x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(x[j], qv) << (8 * j);
     }
-    vs[tl * vstride + c] = code;
+    *reinterpret_cast<uint32_t*>(vs + tl * vstride + c) = packed;
   }
   __syncthreads();
-  // each thread writes one vT row segment: (kv head, d) x 32 tokens.  tok0 % 32 == 0 and T % 32 == 0 is not required:
-  // segments that straddle a sequence boundary fall back to byte stores.
-  for (int c = threadIdx.x; c < vw; c += 256) {
+  // each thread writes one vT row segment: (kv head, d) x 16 tokens; segments that straddle a sequence boundary or are
+  // not 16-byte aligned fall back to byte stores.
+  const int b0 = tok0 / a.T, t0 = tok0 % a.T;
+  const bool fast = tok0 + kRopeTok <= M && t0 + kRopeTok <= a.T && (t0 & 15) == 0 && (a.T & 15) == 0;
+  for (int c = threadIdx.x; c < vw; c += blockDim.x) {
     const int kvh = c / a.hd, d = c % a.hd;
-    const int b0 = tok0 / a.T, t0 = tok0 % a.T;
-    if (tok0 + 32 <= M && t0 + 32 <= a.T && (t0 & 15) == 0 && (a.T & 15) == 0) {
-      uint32_t w[8];
+    if (fast) {
+      uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 4; ++j)
         w[j] = vs[(4 * j) * vstride + c] | (vs[(4 * j + 1) * vstride + c] << 8) | (vs[(4 * j + 2) * vstride + c] << 16) |
                (vs[(4 * j + 3) * vstride + c] << 24);
-      uint4* dst = reinterpret_cast<uint4*>(a.vt + ((int64_t(b0) * a.nkv + kvh) * a.hd + d) * a.T + t0);
-      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      *reinterpret_cast<uint4*>(a.vt + ((int64_t(b0) * a.nkv + kvh) * a.hd + d) * a.T + t0) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      for (int tl = 0; tl < 32; ++tl) {
+      for (int tl = 0; tl < kRopeTok; ++tl) {
         const int tok = tok0 + tl;
         if (tok >= M) break;
         const int b = tok / a.T, t = tok % a.T;
@@ -177,17 +240,24 @@ __global__ void __launch_bounds__(256) qrope_kernel(const RopeArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) qrope_kernel(const RopeArgs a, const int five) {
+  extern __shared__ __align__(16) uint8_t vs[];          // [16 tokens][nkv*hd + 4]
+  if (five) qrope_body<true>(a, vs); else qrope_body<false>(a, vs);
+}
+
 // =====================================================================================================================
 // K6: exact quantised causal attention == HFAttention.forward hm:510-534 with QMatMul qk_bmm / pv_bmm (qm:453-466):
 //   I_ij = sum_d (q-oq)(k-ok)                            int8 tensor-core MMA (mma.sync m16n8k32, s32 accumulate)
 //   c_ij = clamp(rne((float(I)*sq*sk)/s_s)+o_s, 0, qmax_s)        qk_bmm.output_quantizer (16 bit)
-//   E_ij = LUT[cmax_i - c_ij]                            LUT[k] = rne(2^31 * exp(-k*s_s/sqrt(hd))), host float64
+//   E_ij = (A[k>>8] * B[k&255]) >> 31,  k = cmax_i - c_ij          two-level exp table, A[i] = rne(2^31 exp(-256 i a)),
+//                                                                  B[j] = rne(2^31 exp(-j a)), a = s_s/sqrt(hd), float64 host
 //   p_ij = float(E_ij)/float(sum_j E_ij)                 fp32 softmax of (c-o_s)*s_s/sqrt(hd) + causal mask, exact sum (u64)
 //   cp_ij = clamp(rne(p/s_p)+o_p, 0, qmax_p)             pv_bmm.input_quantizer (16 bit, o_p == 0)
-//   A_id = sum_j cp_ij*(v_jd - ov)                       two u8 MMAs on the hi/lo bytes of cp, folded in s32 per key tile
+//   A_id = sum_j cp_ij*(v_jd - ov)                       two u8 MMAs on the hi/lo bytes of cp
 //   out  = clamp(rne((float(A)*s_p*s_v)/s_out)+o_out, 0, 255)     pv_bmm.output_quantizer, written token-major [M, nh*hd]
 // Three passes over the key tiles (row max, row sum, P.V): the [T,T] score matrix never touches HBM (the reference
-// materialises it ~9x per layer in fp32).  One CTA = 64 query rows of one head; each warp owns 16 rows.
+// materialises it ~9x per layer in fp32).  One CTA = 64 query rows of one head; each warp owns 16 rows.  K/V tiles are
+// double buffered with cp.async; every requantisation is the branch-free exact division of common.cuh.
 // =====================================================================================================================
 struct AttnArgs {
   const uint8_t *q, *k, *vt;
@@ -196,7 +266,7 @@ struct AttnArgs {
   float oq, ok, ov;            // integer zero points
   float sqk;                   // sq*sk
   float s_s, o_s, qmax_s;      // score quantizer
-  const uint32_t* lut;         // [qmax_s+1]
+  const uint32_t* lut;         // [512]: A[256] then B[256]
   float s_p, qmax_p;           // prob quantizer (offset 0)
   float spv;                   // s_p*s_v
   float s_out, o_out;          // output quantizer (8 bit)
@@ -209,17 +279,29 @@ __device__ __forceinline__ void mma_u8(int (&d)[4], const uint32_t (&a)[4], uint
                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int HD, int DV>
-__global__ void __launch_bounds__(128) qattn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const AttnArgs a) {
   constexpr int KT = 64;                      // keys per tile
   constexpr int QT = 64;                      // queries per CTA
   constexpr int KSTR = HD + 16;               // padded row strides (bank-conflict free fragment loads)
   constexpr int VSTR = KT + 16;
-  __shared__ __align__(16) uint8_t sq[QT * KSTR];
-  __shared__ __align__(16) uint8_t sk[KT * KSTR];
-  __shared__ __align__(16) uint8_t sv[DV * VSTR];
-  __shared__ int s_rsk[KT];
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  uint8_t* sk = smem_attn;                                   // [2][KT * KSTR]
+  uint8_t* sv = sk + 2 * KT * KSTR;                          // [2][DV * VSTR]
+  int* s_rsk = reinterpret_cast<int*>(sv + 2 * DV * VSTR);   // [2][KT]
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_rsk + 2 * KT);   // [512]
 
   // head dims above 128 are split into HD/DV output chunks (each CTA still contracts the full HD for the scores)
   constexpr int NCH = HD / DV;
@@ -233,175 +315,199 @@ __global__ void __launch_bounds__(128) qattn_kernel(const AttnArgs a) {
   const uint8_t* kbase = a.k + ((int64_t(b) * a.nkv + kvh) * a.T) * HD;
   const uint8_t* vbase = a.vt + ((int64_t(b) * a.nkv + kvh) * HD + d0) * a.T;
   const int32_t* rskb = a.rsk + (int64_t(b) * a.nkv + kvh) * a.T;
+  const bool v_aligned = (a.T & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.vt) & 15) == 0);
 
-  // ---- load the Q tile (zero rows beyond T)
-  for (int i = threadIdx.x; i < QT * (HD / 16); i += 128) {
-    const int r = i / (HD / 16), c = i % (HD / 16);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q0 + r < a.T) v = *reinterpret_cast<const uint4*>(qbase + int64_t(q0 + r) * HD + c * 16);
-    *reinterpret_cast<uint4*>(sq + r * KSTR + c * 16) = v;
-  }
-  __syncthreads();
-  // Q fragments of this warp's 16 rows stay in registers
+  for (int i = threadIdx.x; i < 512; i += 128) s_tab[i] = __ldg(a.lut + i);
+
+  // ---- Q fragments of this warp's 16 rows, straight from global (rows beyond T read as zero)
   uint32_t qa[HD / 32][4];
   const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+  const int qi_lo = q0 + r_lo, qi_hi = q0 + r_hi;      // absolute query positions of this thread's two rows
 #pragma unroll
   for (int ks = 0; ks < HD / 32; ++ks) {
-    qa[ks][0] = *reinterpret_cast<const uint32_t*>(sq + r_lo * KSTR + ks * 32 + 4 * t4);
-    qa[ks][1] = *reinterpret_cast<const uint32_t*>(sq + r_hi * KSTR + ks * 32 + 4 * t4);
-    qa[ks][2] = *reinterpret_cast<const uint32_t*>(sq + r_lo * KSTR + ks * 32 + 16 + 4 * t4);
-    qa[ks][3] = *reinterpret_cast<const uint32_t*>(sq + r_hi * KSTR + ks * 32 + 16 + 4 * t4);
+    qa[ks][0] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 4 * t4)) : 0u;
+    qa[ks][1] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 4 * t4)) : 0u;
+    qa[ks][2] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
+    qa[ks][3] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
   }
-  const int qi_lo = q0 + r_lo, qi_hi = q0 + r_hi;      // absolute query positions of this thread's two rows
   const int32_t* rsqb = a.rsq + (int64_t(b) * a.nh + h) * a.T;
-  const int rsq_lo = qi_lo < a.T ? rsqb[qi_lo] : 0, rsq_hi = qi_hi < a.T ? rsqb[qi_hi] : 0;
   const int ioq = (int)a.oq, iok = (int)a.ok, iov = (int)a.ov;
-  const int kconst = HD * ioq * iok;
+  // I = acc - iok*rsq - ioq*rsk + HD*ioq*iok : the row part is folded into one constant per row
+  const int rc_lo = HD * ioq * iok - iok * (qi_lo < a.T ? __ldg(rsqb + qi_lo) : 0);
+  const int rc_hi = HD * ioq * iok - iok * (qi_hi < a.T ? __ldg(rsqb + qi_hi) : 0);
   const int n_ktiles = (min(q0 + QT, a.T) + KT - 1) / KT;   // causal: keys <= last query of the tile
+  const int total_steps = 3 * n_ktiles;
 
-  auto load_k_tile = [&](int kt, bool with_v) {
-    __syncthreads();
+  auto issue_loads = [&](int step) {
+    const int buf = step & 1;
+    const int kt = step % n_ktiles;
+    const bool with_v = step >= 2 * n_ktiles;
     const int k0 = kt * KT;
+    uint8_t* skb = sk + buf * KT * KSTR;
     for (int i = threadIdx.x; i < KT * (HD / 16); i += 128) {
       const int r = i / (HD / 16), c = i % (HD / 16);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (k0 + r < a.T) v = *reinterpret_cast<const uint4*>(kbase + int64_t(k0 + r) * HD + c * 16);
-      *reinterpret_cast<uint4*>(sk + r * KSTR + c * 16) = v;
+      const bool ok = k0 + r < a.T;
+      cp_async16(skb + r * KSTR + c * 16, kbase + int64_t(ok ? k0 + r : 0) * HD + c * 16, ok);
     }
-    if (threadIdx.x < KT) s_rsk[threadIdx.x] = (k0 + threadIdx.x < a.T) ? rskb[k0 + threadIdx.x] : 0;
+    if (threadIdx.x < KT) {
+      const bool ok = k0 + threadIdx.x < a.T;
+      cp_async4(s_rsk + buf * KT + threadIdx.x, rskb + (ok ? k0 + threadIdx.x : 0), ok);
+    }
     if (with_v) {
+      uint8_t* svb = sv + buf * DV * VSTR;
       for (int i = threadIdx.x; i < DV * (KT / 16); i += 128) {
         const int d = i / (KT / 16), c = i % (KT / 16);
-        uint4 v = make_uint4(0, 0, 0, 0);
         const uint8_t* src = vbase + int64_t(d) * a.T + k0 + c * 16;
-        if (k0 + c * 16 + 16 <= a.T && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-          v = *reinterpret_cast<const uint4*>(src);
+        if (v_aligned) {
+          const bool ok = k0 + c * 16 + 16 <= a.T;
+          cp_async16(svb + d * VSTR + c * 16, ok ? src : vbase, ok);
         } else {
           uint8_t tmp[16];
           for (int j = 0; j < 16; ++j) tmp[j] = (k0 + c * 16 + j < a.T) ? src[j] : 0;
-          v = *reinterpret_cast<uint4*>(tmp);
+          *reinterpret_cast<uint4*>(svb + d * VSTR + c * 16) = *reinterpret_cast<uint4*>(tmp);
         }
-        *reinterpret_cast<uint4*>(sv + d * VSTR + c * 16) = v;
       }
     }
-    __syncthreads();
+    cp_async_commit();
   };
 
-  // scores of one key tile for this warp's 16 rows: I[nt][0..3] in the mma C layout (zero points removed)
-  auto score_tile = [&](int (&I)[KT / 8][4]) {
+  // per-thread state of its two rows
+  const QParam qs = make_qparam(a.s_s, a.o_s, a.qmax_s);
+  const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
+  const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
+  int mx_lo = INT_MIN, mx_hi = INT_MIN;
+  int cm_lo = 0, cm_hi = 0;                      // bits of (magic + clamped code - o_s) of the row maximum
+  unsigned long long sum_lo = 0, sum_hi = 0;
+  float den_lo = 1.f, den_hi = 1.f, rden_lo = 1.f, rden_hi = 1.f;
+  bool five3 = false;
+  int oacc[DV / 8][4];
+#pragma unroll
+  for (int i = 0; i < DV / 8; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0; }
+  int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
+
+  // raw accumulators of one key tile for this warp's 16 rows (MMA C layout), key zero-point term removed
+  auto score_tile = [&](const uint8_t* skb, const int* rk, int (&I)[KT / 8][4]) {
 #pragma unroll
     for (int nt = 0; nt < KT / 8; ++nt) {
       int acc[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int ks = 0; ks < HD / 32; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sk + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sk + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(skb + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(skb + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
         mma_u8(acc, qa[ks], b0, b1);
       }
-      const int c0 = nt * 8 + 2 * t4;
-      const int rk0 = s_rsk[c0], rk1 = s_rsk[c0 + 1];
-      I[nt][0] = acc[0] - iok * rsq_lo - ioq * rk0 + kconst;
-      I[nt][1] = acc[1] - iok * rsq_lo - ioq * rk1 + kconst;
-      I[nt][2] = acc[2] - iok * rsq_hi - ioq * rk0 + kconst;
-      I[nt][3] = acc[3] - iok * rsq_hi - ioq * rk1 + kconst;
+      const int2 rk2 = *reinterpret_cast<const int2*>(rk + nt * 8 + 2 * t4);
+      I[nt][0] = acc[0] - ioq * rk2.x; I[nt][1] = acc[1] - ioq * rk2.y;
+      I[nt][2] = acc[2] - ioq * rk2.x; I[nt][3] = acc[3] - ioq * rk2.y;
     }
   };
-  auto score_code = [&](int I) -> int {
-    return (int)quant_code(fmul(__int2float_rn(I), a.sqk), a.s_s, a.o_s, 0.f, a.qmax_s);
+  // bits of magic + (clamped code - o_s); differences of these bits are differences of codes
+  auto score_bits = [&](auto five_tag, int I) -> int {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    return __float_as_int(quant_magic<FIVE>(fmul(__int2float_rn(I), a.sqk), qs));
+  };
+  auto exp_tab = [&](int k) -> uint32_t {
+    const uint32_t ea = s_tab[__byte_perm((uint32_t)k, 0u, 0x4441)], eb = s_tab[256 + (k & 255)];   // (k >> 8) & 255: masked lanes stay in range
+    return (uint32_t)(((unsigned long long)ea * eb) >> 31);
   };
 
-  // ---- pass 1: row maxima of I (the code is monotone in I)
-  int mx_lo = INT_MIN, mx_hi = INT_MIN;
-  for (int kt = 0; kt < n_ktiles; ++kt) {
-    load_k_tile(kt, false);
+  issue_loads(0);
+  for (int step = 0; step < total_steps; ++step) {
+    const int buf = step & 1;
+    if (step + 1 < total_steps) { issue_loads(step + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int pass = step / n_ktiles, kt = step % n_ktiles;
+    const uint8_t* skb = sk + buf * KT * KSTR;
+    const uint8_t* svb = sv + buf * DV * VSTR;
+    const int* rk = s_rsk + buf * KT;
+    const bool diag = kt == n_ktiles - 1;       // the only tile that needs the causal / length mask
     int I[KT / 8][4];
-    score_tile(I);
+    score_tile(skb, rk, I);
+    if (pass == 0) {
+      // ---- pass 1: row maxima of I (the code is monotone in I)
 #pragma unroll
-    for (int nt = 0; nt < KT / 8; ++nt) {
-      const int key = kt * KT + nt * 8 + 2 * t4;
-      if (key <= qi_lo) mx_lo = max(mx_lo, I[nt][0]);
-      if (key + 1 <= qi_lo) mx_lo = max(mx_lo, I[nt][1]);
-      if (key <= qi_hi) mx_hi = max(mx_hi, I[nt][2]);
-      if (key + 1 <= qi_hi) mx_hi = max(mx_hi, I[nt][3]);
-    }
-  }
-  mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-  mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-  const int cmax_lo = score_code(mx_lo), cmax_hi = score_code(mx_hi);
-
-  // ---- pass 2: exact row sums of E
-  unsigned long long sum_lo = 0, sum_hi = 0;
-  for (int kt = 0; kt < n_ktiles; ++kt) {
-    load_k_tile(kt, false);
-    int I[KT / 8][4];
-    score_tile(I);
+      for (int nt = 0; nt < KT / 8; ++nt) {
+        const int key = kt * KT + nt * 8 + 2 * t4;
+        if (!diag || key <= qi_lo) mx_lo = max(mx_lo, I[nt][0]);
+        if (!diag || key + 1 <= qi_lo) mx_lo = max(mx_lo, I[nt][1]);
+        if (!diag || key <= qi_hi) mx_hi = max(mx_hi, I[nt][2]);
+        if (!diag || key + 1 <= qi_hi) mx_hi = max(mx_hi, I[nt][3]);
+      }
+      if (kt == n_ktiles - 1) {
+        mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        dispatch_five(qs.five, [&](auto ft) { cm_lo = score_bits(ft, mx_lo + rc_lo); cm_hi = score_bits(ft, mx_hi + rc_hi); });
+      }
+    } else if (pass == 1) {
+      // ---- pass 2: exact row sums of E
+      dispatch_five(qs.five, [&](auto ft) {
 #pragma unroll
-    for (int nt = 0; nt < KT / 8; ++nt) {
-      const int key = kt * KT + nt * 8 + 2 * t4;
-      if (key <= qi_lo) sum_lo += __ldg(a.lut + (cmax_lo - score_code(I[nt][0])));
-      if (key + 1 <= qi_lo) sum_lo += __ldg(a.lut + (cmax_lo - score_code(I[nt][1])));
-      if (key <= qi_hi) sum_hi += __ldg(a.lut + (cmax_hi - score_code(I[nt][2])));
-      if (key + 1 <= qi_hi) sum_hi += __ldg(a.lut + (cmax_hi - score_code(I[nt][3])));
-    }
-  }
-  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-  const float den_lo = __ull2float_rn(sum_lo), den_hi = __ull2float_rn(sum_hi);
-
-  // ---- pass 3: P codes and P.V
-  int oacc[DV / 8][4];
-#pragma unroll
-  for (int i = 0; i < DV / 8; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0; }
-  int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
-  auto prob_code = [&](int I, int cmax, float den, bool valid) -> int {
-    if (!valid) return 0;
-    const float e = __uint2float_rn(__ldg(a.lut + (cmax - score_code(I))));
-    return (int)quant_code(fdiv(e, den), a.s_p, 0.f, 0.f, a.qmax_p);
-  };
-  for (int kt = 0; kt < n_ktiles; ++kt) {
-    load_k_tile(kt, true);
-    int I[KT / 8][4];
-    score_tile(I);
-    // P codes in the C layout, then packed straight into A fragments (hi and lo bytes) with the key permutation
-    // slot(4t..4t+3) of k-step ks  <->  keys {8(4ks)+2t, +1, 8(4ks+1)+2t, +1};  slot(16+4t..) <-> n-tiles 4ks+2, 4ks+3
-    uint32_t ahi[KT / 32][4], alo[KT / 32][4];
-#pragma unroll
-    for (int ks = 0; ks < KT / 32; ++ks) {
-#pragma unroll
-      for (int hsel = 0; hsel < 2; ++hsel) {      // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
-        uint32_t hi_lo_row[2] = {0, 0}, lo_lo_row[2] = {0, 0};   // [row lo/hi]
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {             // two n-tiles feed the four bytes
-          const int nt = ks * 4 + hsel * 2 + w;
+        for (int nt = 0; nt < KT / 8; ++nt) {
           const int key = kt * KT + nt * 8 + 2 * t4;
-          const int c0 = prob_code(I[nt][0], cmax_lo, den_lo, key <= qi_lo);
-          const int c1 = prob_code(I[nt][1], cmax_lo, den_lo, key + 1 <= qi_lo);
-          const int c2 = prob_code(I[nt][2], cmax_hi, den_hi, key <= qi_hi);
-          const int c3 = prob_code(I[nt][3], cmax_hi, den_hi, key + 1 <= qi_hi);
-          psum_lo += c0 + c1; psum_hi += c2 + c3;
-          hi_lo_row[0] |= ((uint32_t)(c0 >> 8) | ((uint32_t)(c1 >> 8) << 8)) << (16 * w);
-          lo_lo_row[0] |= ((uint32_t)(c0 & 255) | ((uint32_t)(c1 & 255) << 8)) << (16 * w);
-          hi_lo_row[1] |= ((uint32_t)(c2 >> 8) | ((uint32_t)(c3 >> 8) << 8)) << (16 * w);
-          lo_lo_row[1] |= ((uint32_t)(c2 & 255) | ((uint32_t)(c3 & 255) << 8)) << (16 * w);
+          const uint32_t e0 = exp_tab(cm_lo - score_bits(ft, I[nt][0] + rc_lo)), e1 = exp_tab(cm_lo - score_bits(ft, I[nt][1] + rc_lo));
+          const uint32_t e2 = exp_tab(cm_hi - score_bits(ft, I[nt][2] + rc_hi)), e3 = exp_tab(cm_hi - score_bits(ft, I[nt][3] + rc_hi));
+          sum_lo += (!diag || key <= qi_lo) ? e0 : 0u; sum_lo += (!diag || key + 1 <= qi_lo) ? e1 : 0u;
+          sum_hi += (!diag || key <= qi_hi) ? e2 : 0u; sum_hi += (!diag || key + 1 <= qi_hi) ? e3 : 0u;
         }
-        ahi[ks][hsel * 2 + 0] = hi_lo_row[0]; ahi[ks][hsel * 2 + 1] = hi_lo_row[1];
-        alo[ks][hsel * 2 + 0] = lo_lo_row[0]; alo[ks][hsel * 2 + 1] = lo_lo_row[1];
+      });
+      if (kt == n_ktiles - 1) {
+        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+        den_lo = __ull2float_rn(sum_lo); den_hi = __ull2float_rn(sum_hi);
+        rden_lo = __frcp_rn(den_lo); rden_hi = __frcp_rn(den_hi);
+        five3 = __any_sync(0xffffffffu, mantissa_all_ones(den_lo) || mantissa_all_ones(den_hi)) || qs.five || qp.five;
+      }
+    } else {
+      // ---- pass 3: P codes and P.V.  (magic + code) keeps the 16-bit code in its low half-word (o_p == 0).
+      uint32_t ahi[KT / 32][4], alo[KT / 32][4];
+      dispatch_five(five3, [&](auto ft) {
+        constexpr bool FIVE = decltype(ft)::value;
+        auto prob_bits = [&](int Iv, int cm, float den, float rden, bool valid) -> uint32_t {
+          const uint32_t e = valid ? exp_tab(cm - score_bits(ft, Iv)) : 0u;
+          const float pr = div_rn<FIVE>(__uint2float_rn(e), den, rden);
+          return (uint32_t)__float_as_int(quant_magic<FIVE>(pr, qp));
+        };
+        // A fragments (hi and lo bytes) with the key permutation
+        // slot(4t..4t+3) of k-step ks  <->  keys {8(4ks)+2t, +1, 8(4ks+1)+2t, +1};  slot(16+4t..) <-> n-tiles 4ks+2, 4ks+3
+#pragma unroll
+        for (int ks = 0; ks < KT / 32; ++ks) {
+#pragma unroll
+          for (int hsel = 0; hsel < 2; ++hsel) {      // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
+            uint32_t pl[2], ph[2];                    // [n-tile w] packed code pairs of row lo / row hi
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const int nt = ks * 4 + hsel * 2 + w;
+              const int key = kt * KT + nt * 8 + 2 * t4;
+              const uint32_t c0 = prob_bits(I[nt][0] + rc_lo, cm_lo, den_lo, rden_lo, !diag || key <= qi_lo);
+              const uint32_t c1 = prob_bits(I[nt][1] + rc_lo, cm_lo, den_lo, rden_lo, !diag || key + 1 <= qi_lo);
+              const uint32_t c2 = prob_bits(I[nt][2] + rc_hi, cm_hi, den_hi, rden_hi, !diag || key <= qi_hi);
+              const uint32_t c3 = prob_bits(I[nt][3] + rc_hi, cm_hi, den_hi, rden_hi, !diag || key + 1 <= qi_hi);
+              pl[w] = __byte_perm(c0, c1, 0x5410);    // code0 | code1 << 16
+              ph[w] = __byte_perm(c2, c3, 0x5410);
+              psum_lo = (int)__dp2a_lo(pl[w], 0x0101u, (unsigned)psum_lo);
+              psum_hi = (int)__dp2a_lo(ph[w], 0x0101u, (unsigned)psum_hi);
+            }
+            alo[ks][hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x6420); ahi[ks][hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x7531);
+            alo[ks][hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x6420); ahi[ks][hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x7531);
+          }
+        }
+      });
+#pragma unroll
+      for (int dn = 0; dn < DV / 8; ++dn) {
+        int phi[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int ks = 0; ks < KT / 32; ++ks) {
+          const uint8_t* vrow = svb + (dn * 8 + g) * VSTR + ks * 32 + 2 * t4;
+          const uint32_t b0 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 8) << 16);
+          const uint32_t b1 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 24) << 16);
+          mma_u8(phi, ahi[ks], b0, b1);
+          mma_u8(oacc[dn], alo[ks], b0, b1);        // the lo-byte products accumulate straight into the output
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[dn][j] += phi[j] * 256;
       }
     }
-#pragma unroll
-    for (int dn = 0; dn < DV / 8; ++dn) {
-      int phi[4] = {0, 0, 0, 0}, plo[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int ks = 0; ks < KT / 32; ++ks) {
-        const uint8_t* vrow = sv + (dn * 8 + g) * VSTR + ks * 32 + 2 * t4;
-        const uint32_t b0 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 8) << 16);
-        const uint32_t b1 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 24) << 16);
-        mma_u8(phi, ahi[ks], b0, b1);
-        mma_u8(plo, alo[ks], b0, b1);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) oacc[dn][j] += phi[j] * 256 + plo[j];
-    }
+    __syncthreads();                              // everyone is done with `buf` before step+2's loads are issued into it
   }
   psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 1); psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 2);
   psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 1); psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 2);
@@ -409,30 +515,49 @@ __global__ void __launch_bounds__(128) qattn_kernel(const AttnArgs a) {
   // ---- epilogue: remove the V zero point, requantise, store token-major
   int csum_lo = 0, csum_hi = 0;
   const int ldo = a.nh * HD;
+  dispatch_five(qo.five, [&](auto ft) {
+    constexpr bool FIVE = decltype(ft)::value;
 #pragma unroll
-  for (int dn = 0; dn < DV / 8; ++dn) {
-    const int d = d0 + dn * 8 + 2 * t4;
-    int code[4];
+    for (int dn = 0; dn < DV / 8; ++dn) {
+      const int d = d0 + dn * 8 + 2 * t4;
+      int code[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int A = oacc[dn][j] - iov * (j < 2 ? psum_lo : psum_hi);
-      code[j] = (int)quant_code(fmul(__int2float_rn(A), a.spv), a.s_out, a.o_out, 0.f, 255.f);
+      for (int j = 0; j < 4; ++j) {
+        const int A = oacc[dn][j] - iov * (j < 2 ? psum_lo : psum_hi);
+        code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
+      }
+      if (qi_lo < a.T) {
+        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
+        csum_lo += code[0] + code[1];
+      }
+      if (qi_hi < a.T) {
+        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
+        csum_hi += code[2] + code[3];
+      }
     }
-    if (qi_lo < a.T) {
-      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
-      csum_lo += code[0] + code[1];
-    }
-    if (qi_hi < a.T) {
-      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
-      csum_hi += code[2] + code[3];
-    }
-  }
+  });
   csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 1); csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 2);
   csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 1); csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 2);
   if (t4 == 0 && a.rowsum_out) {
     if (qi_lo < a.T) atomicAdd(a.rowsum_out + int64_t(b) * a.T + qi_lo, csum_lo);
     if (qi_hi < a.T) atomicAdd(a.rowsum_out + int64_t(b) * a.T + qi_hi, csum_hi);
   }
+}
+
+template <int HD, int DV>
+static size_t attn_smem_bytes() { return size_t(2) * 64 * (HD + 16) + size_t(2) * DV * 80 + 2 * 64 * 4 + 512 * 4; }
+
+template <int HD, int DV>
+static int launch_qattn(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
+  const size_t smem = attn_smem_bytes<HD, DV>();
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(qattn_kernel<HD, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  qattn_kernel<HD, DV><<<grid, 128, smem, st>>>(a);
+  return check_launch(c, "mq_qattn");
 }
 
 }  // namespace mq
@@ -447,11 +572,21 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
   MQ_CTX(c, ctx);
   MQ_REQUIRE(c, x && w_fq && codes && rows > 0 && H > 0, "null pointer or empty input");
   MQ_REQUIRE(c, H % 4 == 0, "hidden size must be a multiple of 4");
-  MQ_REQUIRE(c, qmax_out <= 255.f, "norm output codes are 8 bit");
+  MQ_REQUIRE(c, qmax_out <= 255.f && qmax_in <= 65535.f, "norm output codes are 8 bit, input codes at most 16 bit");
+  MQ_REQUIRE(c, o_in == rintf(o_in) && o_out == rintf(o_out), "integer engine kernels need integral offsets (qm:60)");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_fq) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0,
+             "x / w_fq / bias must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
   unsigned grid = (unsigned)((rows + 3) / 4);
-  if (is_layernorm) qnorm_kernel<true><<<grid, 128, 0, st>>>(x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum);
-  else qnorm_kernel<false><<<grid, 128, 0, st>>>(x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum);
+#define MQ_NORM(LN, NV) qnorm_kernel<LN, NV><<<grid, 128, 0, st>>>(a)
+  if (is_layernorm) {
+    if (H == 2048) MQ_NORM(true, 16); else if (H == 1024) MQ_NORM(true, 8); else MQ_NORM(true, 0);
+  } else {
+    if (H == 2048) MQ_NORM(false, 16); else if (H == 1024) MQ_NORM(false, 8); else MQ_NORM(false, 0);
+  }
+#undef MQ_NORM
   return check_launch(c, "mq_qnorm");
 }
 
@@ -460,18 +595,24 @@ int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int n
              int32_t* rsk, void* stream) {
   MQ_CTX(c, ctx);
   MQ_REQUIRE(c, qkv && in_qparams && out_qparams && cos && sin && q && k && vt && rsq && rsk, "null pointer");
-  MQ_REQUIRE(c, B > 0 && T > 0 && nh > 0 && nkv > 0 && hd > 0 && rot >= 0 && rot <= hd && rot % 2 == 0, "bad shape");
+  MQ_REQUIRE(c, B > 0 && T > 0 && nh > 0 && nkv > 0 && hd > 0 && rot >= 0 && rot <= hd, "bad shape");
+  MQ_REQUIRE(c, (hd == 32 || hd == 64 || hd == 128 || hd == 256) && rot % 8 == 0, "head_dim must be 32/64/128/256 and the rotary width a multiple of 8");
+  MQ_REQUIRE(c, ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 3) == 0 && (reinterpret_cast<uintptr_t>(cos) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(sin) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(k) & 3) == 0, "qkv/q/k must be 4-byte aligned (ldq % 4 == 0), cos/sin 16-byte aligned");
   RopeArgs a;
   a.qkv = qkv; a.ldq = ldq; a.B = B; a.T = T; a.nh = nh; a.nkv = nkv; a.hd = hd; a.rot = rot;
   a.sq_in = in_qparams[0]; a.oq_in = in_qparams[1]; a.sk_in = in_qparams[2]; a.ok_in = in_qparams[3];
   a.sv_in = in_qparams[4]; a.ov_in = in_qparams[5];
   a.sq = out_qparams[0]; a.oq = out_qparams[1]; a.sk = out_qparams[2]; a.ok = out_qparams[3]; a.sv = out_qparams[4];
   a.ov = out_qparams[5];
+  MQ_REQUIRE(c, a.oq == rintf(a.oq) && a.ok == rintf(a.ok) && a.ov == rintf(a.ov), "integer engine kernels need integral offsets (qm:60)");
   a.cos = cos; a.sin = sin; a.q = q; a.k = k; a.vt = vt; a.rsq = rsq; a.rsk = rsk;
   const int M = B * T;
-  size_t smem = size_t(32) * (nkv * hd + 4);
+  size_t smem = size_t(kRopeTok) * (nkv * hd + 4);
   MQ_REQUIRE(c, smem <= 48 * 1024, "nkv*hd too large for the V transpose tile");
-  qrope_kernel<<<(M + 31) / 32, 256, smem, (cudaStream_t)stream>>>(a);
+  const int five = mantissa_all_ones(a.sq) || mantissa_all_ones(a.sk) || mantissa_all_ones(a.sv);
+  qrope_kernel<<<(M + kRopeTok - 1) / kRopeTok, 256, smem, (cudaStream_t)stream>>>(a, five);
   return check_launch(c, "mq_qrope");
 }
 
@@ -482,19 +623,21 @@ int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, c
   MQ_REQUIRE(c, q && k && vt && rsq && rsk && qparams && lut && out, "null pointer");
   MQ_REQUIRE(c, B > 0 && T > 0 && nh > 0 && nkv > 0 && nh % nkv == 0, "bad shape");
   MQ_REQUIRE(c, hd == 32 || hd == 64 || hd == 128 || hd == 256, "head_dim must be 32, 64, 128 or 256");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0, "q/k must be 16-byte aligned");
   AttnArgs a;
   a.q = q; a.k = k; a.vt = vt; a.rsq = rsq; a.rsk = rsk; a.B = B; a.T = T; a.nh = nh; a.nkv = nkv; a.hd = hd;
   a.oq = qparams[0]; a.ok = qparams[1]; a.ov = qparams[2]; a.sqk = qparams[3]; a.s_s = qparams[4]; a.o_s = qparams[5];
   a.qmax_s = qparams[6]; a.s_p = qparams[7]; a.qmax_p = qparams[8]; a.spv = qparams[9]; a.s_out = qparams[10];
   a.o_out = qparams[11];
+  MQ_REQUIRE(c, a.qmax_s <= 65535.f && a.qmax_p <= 65535.f, "score / probability codes are at most 16 bit");
+  MQ_REQUIRE(c, a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out), "integer engine kernels need integral offsets (qm:60)");
   a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
   dim3 grid((T + 63) / 64 * (hd == 256 ? 2 : 1), nh, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (hd == 32) qattn_kernel<32, 32><<<grid, 128, 0, st>>>(a);
-  else if (hd == 64) qattn_kernel<64, 64><<<grid, 128, 0, st>>>(a);
-  else if (hd == 128) qattn_kernel<128, 128><<<grid, 128, 0, st>>>(a);
-  else qattn_kernel<256, 128><<<grid, 128, 0, st>>>(a);
-  return check_launch(c, "mq_qattn");
+  if (hd == 32) return launch_qattn<32, 32>(c, a, grid, st);
+  if (hd == 64) return launch_qattn<64, 64>(c, a, grid, st);
+  if (hd == 128) return launch_qattn<128, 128>(c, a, grid, st);
+  return launch_qattn<256, 128>(c, a, grid, st);
 }
 
 }  // extern "C"

@@ -8,11 +8,14 @@
 // This is what QLinear.forward (qm:341-358) computes on de-quantised fp32 tensors, restated on the integer codes; the
 // CPU restatement the kernel is bit-exact against is oracle/int_ref.py:qlinear_int.
 //
-// Structure (one CTA per SM, persistent over 128 x BN output tiles):
+// Structure (one CTA per SM, persistent over 128 x 256 output tiles):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled A/B k-slices into a kStages-deep smem ring
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma.kind::i8 (M=128, N=BN, K=32) into TMEM; owns TMEM alloc
-//   warps 2..9  epilogue       : tcgen05.ld the s32 tile (2 warps per TMEM lane quarter), requantise, store
-//   TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma.kind::i8 (M=128, N=256, K=32) into TMEM; owns TMEM alloc
+//   warps 2..   epilogue       : tcgen05.ld the s32 tile (thread = output row, 32 columns at a time), requantise with the
+//                                branch-free exact division of common.cuh (no XU pipe, no slow path), store
+//   TMEM holds two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// The residual epilogue never loads the fp32 stream into the SM: each warp stages a 32x32 tile of de-quantised values in
+// 128B-swizzled smem and hands it to the TMA as an L2-side reduce-add (cp.reduce.async.bulk.tensor .add).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "ctx.h"
@@ -22,56 +25,64 @@ namespace mq {
 using namespace tc;
 
 constexpr int kBM = 128;          // UMMA M
+constexpr int kBN = 256;          // UMMA N
 constexpr int kBK = 128;          // bytes of K per stage == one 128B swizzle row
 constexpr int kUmmaK = 32;        // 8-bit operands: 32 elements per MMA
-constexpr int kNumEpiWarps = 8;
-constexpr int kThreads = 64 + kNumEpiWarps * 32;
+constexpr int kNE = 8;            // epilogue warps (multiple of 4: one TMEM lane quarter each)
+constexpr int kThreads = 64 + kNE * 32;
+constexpr int kParts = kNE / 4;   // column parts per lane quarter
 
 enum { EPI_QUANT = 0, EPI_ACTMUL = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_I32 = 4 };
-enum { CP_SXW = 0, CP_OW, CP_C0, CP_BIAS, CP_SO, CP_OO, CP_COUNT };
+enum { CP_NEGOW = 0, CP_C0, CP_SXW, CP_BIAS, CP_COUNT };
 
 struct QGemmArgs {
   int M, N, K;
-  int mode;
   const int32_t* rowsum;   // [M]
   const float* sxw;        // [N]
   const int32_t* ow;       // [N]
   const int32_t* c0;       // [N]
   const float* bias;       // [N] or null
-  const float* so;         // [N] output quantizer scale
-  const float* oo;         // [N] output quantizer offset
+  const float* so;         // [ceil(N/qgroup)] output quantizer scale per group of qgroup columns
+  const float* oo;         // [ceil(N/qgroup)] output quantizer offset (integral)
+  int qgroup;              // multiple of 32 (the epilogue's column chunk); ACTMUL: divides 128
   float qmax;              // output quantizer qmax (qmin = 0: activations are asymmetric)
   int out_bits;            // 8 or 16 (EPI_QUANT)
   void* out;               // codes / fp32 / int32
   int64_t ldo;
   int32_t* rowsum_out;     // [M] atomically accumulated sum of the emitted codes (or null)
   const float* lut;        // [256] EPI_ACTMUL: act(w1 code) as fp32 (QSiLU/QGELU folded, qm:739-753)
-  float s2, o2, qmax2;     // EPI_ACTMUL: w2.input_quantizer ; EPI_RESID unused
-  float* resid;            // EPI_RESID: [M, ldo] fp32 residual stream, updated in place
+  float s2, o2, qmax2;     // EPI_ACTMUL: w2.input_quantizer
 };
 
-template <int BN>
+template <int MODE>
 struct SmemLayout {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = MODE == EPI_RESID ? 3 : 4;
   static constexpr int kABytes = kBM * kBK;
-  static constexpr int kBBytes = BN * kBK;
+  static constexpr int kBBytes = kBN * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kColParamBytes = 2 * CP_COUNT * BN * 4;
-  static constexpr int kBarOffset = kStages * kStageBytes + kColParamBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int kColpOff = kStages * kStageBytes;                 // 2 x CP_COUNT x 256 x 4 B
+  static constexpr int kLutOff = kColpOff + 2 * CP_COUNT * kBN * 4;      // 256 floats
+  static constexpr int kOutOff = kLutOff + 1024;                         // RESID: per-warp 32x32 fp32 staging tiles
+  static constexpr int kOutBufs = 16 / kNE;                              // staging tiles per warp
+  static constexpr int kOutBytes = MODE == EPI_RESID ? kNE * kOutBufs * 4096 : 0;
+  static constexpr int kBarOff = kOutOff + kOutBytes;
+  static constexpr int kTotal = kBarOff + 256;
+  static_assert(kOutOff % 1024 == 0, "staging tiles must keep the 128B-swizzle phase");
+  static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
-template <int BN>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const QGemmArgs p,
-             const uint32_t idesc) {
-  using L = SmemLayout<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ CUtensorMap tmap_r, const QGemmArgs p, const uint32_t idesc) {
+  using L = SmemLayout<MODE>;
+  constexpr int BN = kBN;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + L::kStages * L::kABytes;
-  float* colp = reinterpret_cast<float*>(smem + L::kStages * L::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  float* colp = reinterpret_cast<float*>(smem + L::kColpOff);
+  float* lut_s = reinterpret_cast<float*>(smem + L::kLutOff);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tfull_bar = empty_bar + L::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -82,14 +93,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int num_tiles = m_tiles * n_tiles;
   const int k_iters = (p.K + kBK - 1) / kBK;
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();                 // the swizzle math below assumes a 1024B-aligned window
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (MODE == EPI_RESID) prefetch_tmap(&tmap_r);
     for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNumEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (MODE == EPI_ACTMUL && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < 256; i += kNE * 32) lut_s[i] = __ldg(p.lut + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,26 +156,28 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..kNE-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                // column half
-    const int etid = threadIdx.x - 64;       // 0..255
+    const int part = ew >> 2;                // column part
+    const int etid = threadIdx.x - 64;
+    const bool has_bias = p.bias != nullptr;
+    uint8_t* stage_out = smem + L::kOutOff + ew * L::kOutBufs * 4096;
+    int out_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
       // stage the per-column parameters of this tile (double buffered with the accumulator)
       float* cp = colp + acc * CP_COUNT * BN;
-      for (int c = etid; c < BN; c += kNumEpiWarps * 32) {
+      int* cpi = reinterpret_cast<int*>(cp);
+      for (int c = etid; c < BN; c += kNE * 32) {
         const int n = n0 + c;
         const bool ok = n < p.N;
+        cpi[CP_NEGOW * BN + c] = ok ? -__ldg(p.ow + n) : 0;
+        cpi[CP_C0 * BN + c] = ok ? __ldg(p.c0 + n) : 0;
         cp[CP_SXW * BN + c] = ok ? __ldg(p.sxw + n) : 0.f;
-        reinterpret_cast<int*>(cp)[CP_OW * BN + c] = ok ? __ldg(p.ow + n) : 0;
-        reinterpret_cast<int*>(cp)[CP_C0 * BN + c] = ok ? __ldg(p.c0 + n) : 0;
-        cp[CP_BIAS * BN + c] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-        cp[CP_SO * BN + c] = (ok && p.so) ? __ldg(p.so + n) : 1.f;
-        cp[CP_OO * BN + c] = (ok && p.oo) ? __ldg(p.oo + n) : 0.f;
+        cp[CP_BIAS * BN + c] = (ok && has_bias) ? __ldg(p.bias + n) : 0.f;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kNE * 32) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 
@@ -167,33 +185,61 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const bool row_ok = row < p.M;
       const int rs = row_ok ? __ldg(p.rowsum + row) : 0;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-      const int* cpi = reinterpret_cast<const int*>(cp);
+      const int4* v_negow = reinterpret_cast<const int4*>(cpi + CP_NEGOW * BN);
+      const int4* v_c0 = reinterpret_cast<const int4*>(cpi + CP_C0 * BN);
+      const float4* v_sxw = reinterpret_cast<const float4*>(cp + CP_SXW * BN);
+      const float4* v_bias = reinterpret_cast<const float4*>(cp + CP_BIAS * BN);
       int code_sum = 0;
 
-      if (p.mode == EPI_ACTMUL) {
-        // columns [0,BN/2) of the tile are w1 rows, [BN/2,BN) the matching w3 rows
+      // y[j] of 4 consecutive columns starting at tile column c (c % 4 == 0)
+      auto y4 = [&](const uint32_t* r, int c, float (&y)[4]) {
+        const int4 no = v_negow[c >> 2], cz = v_c0[c >> 2];
+        const float4 sx = v_sxw[c >> 2];
+        const int i0 = (int)r[0] + no.x * rs + cz.x, i1 = (int)r[1] + no.y * rs + cz.y;
+        const int i2 = (int)r[2] + no.z * rs + cz.z, i3 = (int)r[3] + no.w * rs + cz.w;
+        if (MODE == EPI_I32) {
+          y[0] = __int_as_float(i0); y[1] = __int_as_float(i1); y[2] = __int_as_float(i2); y[3] = __int_as_float(i3);
+          return;
+        }
+        y[0] = __fmul_rn(__int2float_rn(i0), sx.x); y[1] = __fmul_rn(__int2float_rn(i1), sx.y);
+        y[2] = __fmul_rn(__int2float_rn(i2), sx.z); y[3] = __fmul_rn(__int2float_rn(i3), sx.w);
+        if (has_bias) {
+          const float4 b = v_bias[c >> 2];
+          y[0] = __fadd_rn(y[0], b.x); y[1] = __fadd_rn(y[1], b.y); y[2] = __fadd_rn(y[2], b.z); y[3] = __fadd_rn(y[3], b.w);
+        }
+      };
+      auto group_q = [&](int col /* tile column */, float qmax) {
+        const int g = min((n0 + col) / p.qgroup, (p.N - 1) / p.qgroup);
+        return make_qparam(__ldg(p.so + g), __ldg(p.oo + g), qmax);
+      };
+
+      if (MODE == EPI_ACTMUL) {
+        // columns [0,128) of the tile are w1 rows, [128,256) the matching w3 rows
         constexpr int H = BN / 2;
-        for (int cc = half * (H / 2); cc < (half + 1) * (H / 2); cc += 32) {
+        const QParam q1 = group_q(0, p.qmax), q3 = group_q(H, p.qmax);
+        const QParam q2 = make_qparam(p.s2, p.o2, p.qmax2);
+        dispatch_five(q1.five | q2.five | q3.five, [&](auto five_tag) {
+        constexpr bool FIVE = decltype(five_tag)::value;
+        for (int cc = part * (H / kParts); cc < (part + 1) * (H / kParts); cc += 32) {
           uint32_t r1[32], r3[32];
           tmem_ld32(trow + cc, r1);
           tmem_ld32(trow + H + cc, r3);
           tc_wait_ld();
           uint32_t packed[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c1 = cc + j, c3 = H + cc + j;
-            const int i1 = (int)r1[j] - cpi[CP_OW * BN + c1] * rs + cpi[CP_C0 * BN + c1];
-            const int i3 = (int)r3[j] - cpi[CP_OW * BN + c3] * rs + cpi[CP_C0 * BN + c3];
-            const float y1 = fadd(fmul(__int2float_rn(i1), cp[CP_SXW * BN + c1]), cp[CP_BIAS * BN + c1]);
-            const float y3 = fadd(fmul(__int2float_rn(i3), cp[CP_SXW * BN + c3]), cp[CP_BIAS * BN + c3]);
-            const float q1 = quant_code(y1, cp[CP_SO * BN + c1], cp[CP_OO * BN + c1], 0.f, p.qmax);
-            const float q3 = quant_code(y3, cp[CP_SO * BN + c3], cp[CP_OO * BN + c3], 0.f, p.qmax);
-            const float a = __ldg(p.lut + (int)q1);                                   // fq_out(act(w1x))
-            const float u = dequant(q3, cp[CP_SO * BN + c3], cp[CP_OO * BN + c3]);  // fq(w3x)
-            const int code = (int)quant_code(fmul(a, u), p.s2, p.o2, 0.f, p.qmax2); // w2.input_quantizer
-            code_sum += code;
-            if ((j & 3) == 0) packed[j >> 2] = 0;
-            packed[j >> 2] |= (uint32_t)code << (8 * (j & 3));
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float y1[4], y3[4];
+            y4(r1 + 4 * j4, cc + 4 * j4, y1);
+            y4(r3 + 4 * j4, H + cc + 4 * j4, y3);
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = lut_s[quant_int<FIVE>(y1[e], q1)];                                      // fq_out(act(w1x))
+              const float u = __fmul_rn(__fsub_rn(quant_magic<FIVE>(y3[e], q3), kRoundMagic), q3.s);  // fq(w3x)
+              w |= (uint32_t)quant_int<FIVE>(__fmul_rn(a, u), q2) << (8 * e);                         // w2.input_quantizer
+            }
+            packed[j4] = w;
+            code_sum = (int)__dp4a(w, 0x01010101u, (unsigned)code_sum);
           }
           const int ncol = n0 / 2 + cc;       // output column (N/2 wide)
           if (row_ok) {
@@ -207,40 +253,43 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
           }
         }
+        });
       } else {
-        for (int cc = half * (BN / 2); cc < (half + 1) * (BN / 2); cc += 32) {
+        constexpr int W = BN / kParts;
+        for (int cc = part * W; cc < (part + 1) * W; cc += 32) {
           if (n0 + cc >= p.N) break;
           uint32_t r[32];
           tmem_ld32(trow + cc, r);
           tc_wait_ld();
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cc + j;
-            const int ii = (int)r[j] - cpi[CP_OW * BN + c] * rs + cpi[CP_C0 * BN + c];
-            y[j] = fadd(fmul(__int2float_rn(ii), cp[CP_SXW * BN + c]), cp[CP_BIAS * BN + c]);
-            if (p.mode == EPI_I32) y[j] = __int_as_float(ii);
-          }
           const int ncol = n0 + cc;
           const bool full = (ncol + 32 <= p.N);
-          if (p.mode == EPI_QUANT) {
-            uint32_t q[32];
+          if (MODE == EPI_QUANT) {
+            const QParam q = group_q(cc, p.qmax);
+            uint32_t code[32];
+            dispatch_five(q.five, [&](auto five_tag) {
+              constexpr bool FIVE = decltype(five_tag)::value;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              q[j] = (uint32_t)quant_code(y[j], cp[CP_SO * BN + cc + j], cp[CP_OO * BN + cc + j], 0.f, p.qmax);
-              if (ncol + j < p.N) code_sum += (int)q[j];
-            }
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float y[4];
+                y4(r + 4 * j4, cc + 4 * j4, y);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  code[4 * j4 + e] = (uint32_t)quant_int<FIVE>(y[e], q);
+                  if (full || ncol + 4 * j4 + e < p.N) code_sum += (int)code[4 * j4 + e];
+                }
+              }
+            });
             if (row_ok) {
               if (p.out_bits == 8) {
                 uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + int64_t(row) * p.ldo + ncol;
                 if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                   uint32_t w[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) w[j] = q[4 * j] | (q[4 * j + 1] << 8) | (q[4 * j + 2] << 16) | (q[4 * j + 3] << 24);
+                  for (int j = 0; j < 8; ++j) w[j] = code[4 * j] | (code[4 * j + 1] << 8) | (code[4 * j + 2] << 16) | (code[4 * j + 3] << 24);
                   reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                   reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 } else {
-                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint8_t)q[j];
+                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint8_t)code[j];
                 }
               } else {
                 uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + int64_t(row) * p.ldo + ncol;
@@ -249,39 +298,47 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                   for (int v = 0; v < 4; ++v) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) w[j] = q[8 * v + 2 * j] | (q[8 * v + 2 * j + 1] << 16);
+                    for (int j = 0; j < 4; ++j) w[j] = code[8 * v + 2 * j] | (code[8 * v + 2 * j + 1] << 16);
                     reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[0], w[1], w[2], w[3]);
                   }
                 } else {
-                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint16_t)q[j];
+                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint16_t)code[j];
                 }
               }
             }
-          } else if (p.mode == EPI_RESID) {
-            if (row_ok) {
-              float* dst = p.resid + int64_t(row) * p.ldo + ncol;
-              if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                float4 h4[8];
+          } else if (MODE == EPI_RESID) {
+            // de-quantised output-quantizer values (hm:1257,1270 add them to the fp32 stream) -> swizzled smem tile ->
+            // TMA reduce-add.  Row r of the tile is 128 B; its 16-byte chunk c lives at chunk (c ^ (r & 7)).
+            const QParam q = group_q(cc, p.qmax);
+            uint8_t* tile = stage_out + out_buf * 4096;
+            if (lane == 0) bulk_wait_read<L::kOutBufs - 1>();      // the tile's previous reduce has been read out
+            __syncwarp();
+            dispatch_five(q.five, [&](auto five_tag) {
+              constexpr bool FIVE = decltype(five_tag)::value;
 #pragma unroll
-                for (int v = 0; v < 8; ++v) h4[v] = reinterpret_cast<const float4*>(dst)[v];
-                float* hv = reinterpret_cast<float*>(h4);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float y[4], v[4];
+                y4(r + 4 * j4, cc + 4 * j4, y);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float so = cp[CP_SO * BN + cc + j], oo = cp[CP_OO * BN + cc + j];
-                  hv[j] = fadd(hv[j], dequant(quant_code(y[j], so, oo, 0.f, p.qmax), so, oo));   // hm:1257,1270
-                }
-#pragma unroll
-                for (int v = 0; v < 8; ++v) reinterpret_cast<float4*>(dst)[v] = h4[v];
-              } else {
-                for (int j = 0; j < 32; ++j) {
-                  if (ncol + j < p.N) {
-                    const float so = cp[CP_SO * BN + cc + j], oo = cp[CP_OO * BN + cc + j];
-                    dst[j] = fadd(dst[j], dequant(quant_code(y[j], so, oo, 0.f, p.qmax), so, oo));
-                  }
-                }
+                for (int e = 0; e < 4; ++e) v[e] = __fmul_rn(__fsub_rn(quant_magic<FIVE>(y[e], q), kRoundMagic), q.s);
+                *reinterpret_cast<float4*>(tile + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
               }
+            });
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmap_r, tile, ncol, m0 + quarter * 32);   // rows >= M / columns >= N are clipped by the TMA
+              bulk_commit();
             }
+            if (++out_buf == L::kOutBufs) out_buf = 0;
           } else {   // EPI_F32 / EPI_I32
+            float y[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float yy[4];
+              y4(r + 4 * j4, cc + 4 * j4, yy);
+              y[4 * j4] = yy[0]; y[4 * j4 + 1] = yy[1]; y[4 * j4 + 2] = yy[2]; y[4 * j4 + 3] = yy[3];
+            }
             if (row_ok) {
               float* dst = reinterpret_cast<float*>(p.out) + int64_t(row) * p.ldo + ncol;
               if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -295,13 +352,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           }
         }
       }
-      if (p.rowsum_out && row_ok && (p.mode == EPI_QUANT || p.mode == EPI_ACTMUL)) atomicAdd(p.rowsum_out + row, code_sum);
+      if (p.rowsum_out && row_ok && (MODE == EPI_QUANT || MODE == EPI_ACTMUL)) atomicAdd(p.rowsum_out + row, code_sum);
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (MODE == EPI_RESID && lane == 0) bulk_wait<0>();      // all reduce-adds have landed before the grid retires
   }
   tc_fence_before();
   __syncthreads();
@@ -325,34 +383,41 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D row-major byte matrix [rows, cols] (cols contiguous), box = 128 bytes x box_rows, 128B swizzle
-static bool make_tmap_u8(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+// 2D row-major matrix [rows, cols] of `esize`-byte elements (cols contiguous, row pitch `pitch_bytes`), box = 128 bytes x
+// box_rows, 128B swizzle
+static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
+                         int64_t pitch_bytes, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols};
-  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
-static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, int a_signed, int b_signed, cudaStream_t st) {
-  CUtensorMap ta, tb;
-  if (!make_tmap_u8(&ta, a, args.M, args.K, kBM) || !make_tmap_u8(&tb, b, args.N, args.K, BN))
+template <int MODE>
+static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
+                        cudaStream_t st) {
+  CUtensorMap ta, tb, tr;
+  if (!make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a, args.M, args.K, args.K, kBM) ||
+      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, kBN))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
+  tr = ta;
+  if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32))
+    return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the residual stream (16B-aligned pointer, ldo % 4 == 0)");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<MODE>::kTotal);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  const int m_tiles = (args.M + kBM - 1) / kBM, n_tiles = (args.N + BN - 1) / BN;
+  const int m_tiles = (args.M + kBM - 1) / kBM, n_tiles = (args.N + kBN - 1) / kBN;
   int grid = m_tiles * n_tiles;
   if (grid > c->sm_count) grid = c->sm_count;
-  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, kBM, BN);
-  qgemm_kernel<BN><<<grid, kThreads, SmemLayout<BN>::kTotal, st>>>(ta, tb, args, idesc);
+  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, kBM, kBN);
+  qgemm_kernel<MODE><<<grid, kThreads, SmemLayout<MODE>::kTotal, st>>>(ta, tb, tr, args, idesc);
   return check_launch(c, "mq_qgemm");
 }
 
@@ -363,7 +428,8 @@ using namespace mq;
 extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
                         const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
                         int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
-                        int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, void* stream) {
+                        int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                        void* stream) {
   MQ_CTX(c, ctx);
   MQ_REQUIRE(c, a_codes && b_codes && M > 0 && N > 0 && K > 0, "null operand or empty problem");
   MQ_REQUIRE(c, K % 16 == 0, "K must be a multiple of 16 bytes (TMA row pitch)");
@@ -373,11 +439,22 @@ extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void
   MQ_REQUIRE(c, mode >= EPI_QUANT && mode <= EPI_I32, "unknown epilogue mode");
   MQ_REQUIRE(c, mode != EPI_QUANT || (out && so && oo && (out_bits == 8 || out_bits == 16)), "EPI_QUANT needs out/so/oo, 8 or 16 bits");
   MQ_REQUIRE(c, mode != EPI_ACTMUL || (out && so && oo && lut && N % 256 == 0), "EPI_ACTMUL needs out/so/oo/lut and N % 256 == 0");
-  MQ_REQUIRE(c, mode != EPI_RESID || (resid && so && oo), "EPI_RESID needs resid/so/oo");
+  MQ_REQUIRE(c, mode != EPI_RESID || (resid && so && oo && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0),
+             "EPI_RESID needs so/oo and a 16-byte aligned resid with ldo % 4 == 0");
   MQ_REQUIRE(c, (mode != EPI_F32 && mode != EPI_I32) || out, "raw output needs out");
+  MQ_REQUIRE(c, qmax < 4194304.f && qmax2 < 4194304.f, "qmax must be below 2^22");
+  MQ_REQUIRE(c, (mode == EPI_F32 || mode == EPI_I32) || (qgroup > 0 && qgroup % 32 == 0), "qgroup must be a positive multiple of 32");
+  MQ_REQUIRE(c, mode != EPI_ACTMUL || 128 % qgroup == 0, "EPI_ACTMUL needs qgroup to divide 128");
   QGemmArgs args;
-  args.M = M; args.N = N; args.K = K; args.mode = mode; args.rowsum = rowsum; args.sxw = sxw; args.ow = ow; args.c0 = c0;
+  args.M = M; args.N = N; args.K = K; args.rowsum = rowsum; args.sxw = sxw; args.ow = ow; args.c0 = c0;
   args.bias = bias; args.so = so; args.oo = oo; args.qmax = qmax; args.out_bits = out_bits; args.out = out; args.ldo = ldo;
-  args.rowsum_out = rowsum_out; args.lut = lut; args.s2 = s2; args.o2 = o2; args.qmax2 = qmax2; args.resid = resid;
-  return launch_qgemm<256>(c, a_codes, b_codes, args, a_signed, b_signed, (cudaStream_t)stream);
+  args.qgroup = qgroup > 0 ? qgroup : 32; args.rowsum_out = rowsum_out; args.lut = lut; args.s2 = s2; args.o2 = o2; args.qmax2 = qmax2;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case EPI_QUANT: return launch_qgemm<EPI_QUANT>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
+    case EPI_ACTMUL: return launch_qgemm<EPI_ACTMUL>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
+    case EPI_RESID: return launch_qgemm<EPI_RESID>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
+    case EPI_F32: return launch_qgemm<EPI_F32>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
+    default: return launch_qgemm<EPI_I32>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
+  }
 }

@@ -465,6 +465,49 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int S, in
   out[c] = (float)s;
 }
 
+
+// ================================================================================================================
+// Self-test of the branch-free exact requantisation (common.cuh: div_rn / quant_int) against the IEEE reference
+// sequence rintf(__fdiv_rn(x, s)) on pseudo-random operands.  mode 0: random scales; 1: one fixed scale, integer-valued
+// numerators times a random factor (the GEMM / attention epilogue pattern); 2: scales with an all-ones significand.
+// ================================================================================================================
+__device__ __forceinline__ uint32_t xs32(uint64_t& st) {
+  st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+  return (uint32_t)(st >> 16);
+}
+__global__ void __launch_bounds__(256) selftest_div_kernel(int64_t n, uint64_t seed, int mode, float fixed_scale,
+                                                            unsigned long long* mism) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = int64_t(gridDim.x) * blockDim.x;
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + (uint64_t)tid * 0xD1342543DE82EF95ull + 1;
+  unsigned long long bad = 0;
+  for (int64_t i = tid; i < n; i += nthr) {
+    float a, b;
+    if (mode == 1) {
+      const int I = (int)(xs32(st) & 0xffffff) - 0x800000;
+      a = __fmul_rn(__int2float_rn(I), __uint_as_float(0x38000000u + (xs32(st) & 0x03ffffffu)));   // * [3e-5, 0.5)
+      b = fixed_scale;
+    } else {
+      a = __uint_as_float((xs32(st) & 0x807fffffu) | ((100u + (xs32(st) % 50u)) << 23));           // |a| in 2^[-27, 23)
+      b = __uint_as_float((xs32(st) & 0x007fffffu) | ((106u + (xs32(st) % 30u)) << 23));           // b in 2^[-21, 9)
+      if (mode == 2) b = __uint_as_float(__float_as_uint(b) | 0x007fffffu);
+    }
+    const float ref = __fdiv_rn(a, b);
+    const float rb = __frcp_rn(b);
+    const bool five = mantissa_all_ones(b);
+    const float got = five ? div_rn<true>(a, b, rb) : div_rn<false>(a, b, rb);
+    bad += (__float_as_uint(ref) != __float_as_uint(got)) && !(ref == 0.f && got == 0.f);
+    // code path: clamp(rne(a/b)+o, 0, qmax) for a 16-bit quantizer with an arbitrary integral offset
+    const float o = (float)(xs32(st) & 0xffff), qmax = 65535.f;
+    const float cref = fminf(fmaxf(__fadd_rn(rintf(ref), o), 0.f), qmax);
+    const QParam qp = make_qparam(b, o, qmax);
+    const int cgot = five ? quant_int<true>(a, qp) : quant_int<false>(a, qp);
+    bad += ((int)cref != cgot);
+  }
+  bad = warp_reduce(bad, OpSum());
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mism, bad);
+}
+
 }  // namespace mq
 
 using namespace mq;
@@ -618,6 +661,16 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
     colsum_final_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(partial, S, cols, g_col_fac);
   }
   return check_launch(c, "mq_wprep_bwd");
+}
+
+int mq_selftest_div(void* ctx, int64_t n, uint64_t seed, int mode, float fixed_scale, uint64_t* mismatches, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, n > 0 && mismatches && mode >= 0 && mode <= 2, "bad arguments");
+  MQ_REQUIRE(c, mode != 1 || fixed_scale > 0.f, "mode 1 needs a positive scale");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), st);
+  selftest_div_kernel<<<c->sm_count * 8, 256, 0, st>>>(n, seed, mode, fixed_scale, reinterpret_cast<unsigned long long*>(mismatches));
+  return check_launch(c, "mq_selftest_div");
 }
 
 }  // extern "C"

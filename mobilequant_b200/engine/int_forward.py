@@ -74,15 +74,22 @@ class IntEngine:
 
     def _percol(self, wq_list, sx, ox, Kdim, out_q, biases, pad_to=None):
         """Concatenate several quantised weight matrices along N and derive the per-column epilogue constants."""
-        codes, sw, ow, cs, so, oo, bias = [], [], [], [], [], [], []
+        codes, sw, ow, cs, bias = [], [], [], [], []
         signed = wq_list[0]["sym"]
+        # output quantizers are per tensor (qm:216-245): one (scale, offset) per fused segment, stored per group of
+        # `qgroup` columns (the gcd of the segment widths; a multiple of the kernel's 32-column chunk)
+        widths = [wq["rows"] for wq in wq_list]
+        qgroup = math.gcd(*widths) if len(widths) > 1 else (widths[0] + 31) // 32 * 32
+        if qgroup % 32:
+            raise NotImplementedError(f"fused projection segments {widths} must share a multiple-of-32 column group")
+        so = torch.tensor([oq[0] for oq, n in zip(out_q, widths) for _ in range(max(1, n // qgroup))], dtype=torch.float32, device=self.device)
+        oo = torch.tensor([oq[1] for oq, n in zip(out_q, widths) for _ in range(max(1, n // qgroup))], dtype=torch.float32, device=self.device)
         for wq, oq, b in zip(wq_list, out_q, biases):
             n = wq["rows"]
             codes.append(wq["codes"].view(torch.int8 if signed else torch.uint8))
             sw.append(wq["scale"].expand(n) if wq["scale"].numel() == 1 else wq["scale"])
             ow.append(wq["offset"].expand(n) if wq["offset"].numel() == 1 else wq["offset"])
             cs.append(wq["colsum"])
-            so.append(torch.full((n,), oq[0], device=self.device)); oo.append(torch.full((n,), oq[1], device=self.device))
             bias.append(torch.zeros(n, device=self.device) if b is None else b.detach().float().to(self.device))
         codes = torch.cat(codes); sw = torch.cat(sw).float(); ow = torch.cat(ow).to(torch.int64); cs = torch.cat(cs).to(torch.int64)
         sxw = (torch.tensor(sx, dtype=torch.float32, device=self.device) * sw).contiguous()
@@ -90,8 +97,8 @@ class IntEngine:
         assert c0.abs().max().item() < 2 ** 31
         bias = torch.cat(bias)
         return dict(codes=codes.contiguous(), sxw=sxw, ow=ow.to(torch.int32).contiguous(), c0=c0.to(torch.int32).contiguous(),
-                    bias=bias.contiguous() if bias.abs().max().item() > 0 else None, so=torch.cat(so).contiguous(),
-                    oo=torch.cat(oo).contiguous(), qmax=out_q[0][2], N=codes.shape[0], K=Kdim)
+                    bias=bias.contiguous() if bias.abs().max().item() > 0 else None, so=so, oo=oo, qgroup=qgroup,
+                    qmax=out_q[0][2], N=codes.shape[0], K=Kdim)
 
     def _build_layer(self, layer, p, qcfg, act):
         L = {}
@@ -116,8 +123,10 @@ class IntEngine:
         f = np.float32
         L["attn"] = [qk_in[1], qk_in2[1], pv_in2[1], float(f(qk_in[0]) * f(qk_in2[0])), qk_out[0], qk_out[1], qk_out[2], pv_in[0], pv_in[2],
                      float(f(pv_in[0]) * f(pv_in2[0])), pv_out[0], pv_out[1]]
-        k = np.arange(int(qk_out[2]) + 1, dtype=np.float64)
-        lut = np.rint(np.exp(-k * np.float64(f(qk_out[0])) / np.sqrt(np.float64(self.hd))) * 2.0 ** 31).astype(np.uint32)
+        # two-level exp table of the quantised softmax: E(k) = (A[k >> 8] * B[k & 255]) >> 31 (include/mqb200.h:mq_qattn)
+        al = np.float64(f(qk_out[0])) / np.sqrt(np.float64(self.hd))
+        i = np.arange(256, dtype=np.float64)
+        lut = np.concatenate([np.rint(np.exp(-256.0 * i * al) * 2.0 ** 31), np.rint(np.exp(-i * al) * 2.0 ** 31)]).astype(np.uint32)
         L["attn_lut"] = torch.from_numpy(lut.view(np.int32)).to(self.device)
         L["o"] = self._percol([self._wq(at.o_proj.weight, qcfg[pa + "o_proj"]["weight"])], pv_out[0], pv_out[1], self.nh * self.hd,
                               [_sq(act, qcfg, pa + "o_proj", "output")], [getattr(at.o_proj, "bias", None)])
@@ -176,10 +185,13 @@ class IntEngine:
         def il(x, y):
             return torch.stack([x.view(Ipad // 128, 128, *x.shape[1:]), y.view(Ipad // 128, 128, *y.shape[1:])], dim=1).reshape(2 * Ipad, *x.shape[1:]).contiguous()
 
-        out = dict(N=2 * Ipad, K=a["K"], qmax=a["qmax"])
+        out = dict(N=2 * Ipad, K=a["K"], qmax=a["qmax"], qgroup=128)
         out["codes"] = il(pad(a["codes"], 0), pad(b["codes"], 0))
-        for k, fill in (("sxw", 0.0), ("ow", 0), ("c0", 0), ("so", 1.0), ("oo", 0.0)):
+        for k, fill in (("sxw", 0.0), ("ow", 0), ("c0", 0)):
             out[k] = il(pad(a[k], fill), pad(b[k], fill))
+        # one (so, oo) entry per 128-column half tile: w1's output quantizer, then w3's
+        out["so"] = torch.stack([a["so"][:1].expand(Ipad // 128), b["so"][:1].expand(Ipad // 128)], dim=1).reshape(-1).contiguous()
+        out["oo"] = torch.stack([a["oo"][:1].expand(Ipad // 128), b["oo"][:1].expand(Ipad // 128)], dim=1).reshape(-1).contiguous()
         if a["bias"] is None and b["bias"] is None:
             out["bias"] = None
         else:
@@ -213,7 +225,8 @@ class IntEngine:
         return self._bufs[key]
 
     def _gemm(self, a, g, rowsum, mode, **kw):
-        return K.qgemm(a, g["codes"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"], **kw)
+        return K.qgemm(a, g["codes"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
+                       qgroup=g["qgroup"], **kw)
 
     @torch.no_grad()
     def block(self, h, L, B, T, bufs, trace=None):

@@ -23,11 +23,12 @@ def _protos():
     lib.mq_wprep_bwd.argtypes = [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
                                  _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qgemm.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
-                             c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, _P]
+                             c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P]
     lib.mq_qnorm.argtypes = [_P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float,
                              c_float, c_float, _P, _P, _P]
     lib.mq_qrope.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
+    lib.mq_selftest_div.argtypes = [_P, c_int64, ctypes.c_uint64, c_int, c_float, _P, _P]
     _protos_done = True
     return lib
 
@@ -191,8 +192,9 @@ EPI_QUANT, EPI_ACTMUL, EPI_RESID, EPI_F32, EPI_I32 = 0, 1, 2, 3, 4
 
 
 def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out_bits=8, out=None, ldo=None,
-          rowsum_out=None, lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None):
-    """a: [M,K] uint8/int8 codes, b: [N,K] uint8/int8 codes.  See include/mqb200.h:mq_qgemm."""
+          rowsum_out=None, lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None):
+    """a: [M,K] uint8/int8 codes, b: [N,K] uint8/int8 codes.  so/oo: one entry per `qgroup` columns (default: one
+    entry for the whole N when they have a single element).  See include/mqb200.h:mq_qgemm."""
     lib = _protos()
     M, K = a.shape
     N = b.shape[0]
@@ -209,12 +211,18 @@ def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255
             out = torch.empty(M, N, dtype=torch.int32, device=dev)
     if ldo is None:
         ldo = resid.shape[-1] if mode == EPI_RESID else out.shape[-1]
+    if qgroup is None:
+        qgroup = (N + 31) // 32 * 32 if (so is None or so.numel() == 1) else 0
+        if mode == EPI_ACTMUL and so is not None and so.numel() == N // 128:
+            qgroup = 128
+    if so is not None and mode in (EPI_QUANT, EPI_ACTMUL, EPI_RESID):
+        assert qgroup > 0 and so.numel() == (N + qgroup - 1) // qgroup == oo.numel(), "so/oo need one entry per qgroup columns"
     h = _h(a)
     with torch.cuda.device(dev):
         check(_launch("qgemm", lib.mq_qgemm, h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K,
                            ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias),
                            int(mode), ptr(so), ptr(oo), float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out),
-                           ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), stream_ptr()), h)
+                           ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup), stream_ptr()), h)
     return resid if mode == EPI_RESID else out
 
 
@@ -270,3 +278,14 @@ def qattn(bufs, B, T, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
         check(_launch("qattn", lib.mq_qattn, h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
                            ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
     return out
+
+
+def selftest_div(n, seed=1, mode=0, fixed_scale=1.0, device=None):
+    """Number of disagreements between the branch-free exact requantisation and IEEE division + rint (must be 0)."""
+    lib = _protos()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.zeros(1, dtype=torch.int64, device=dev)
+    h = _lib.ctx(dev.index)
+    with torch.cuda.device(dev):
+        check(_launch("selftest_div", lib.mq_selftest_div, h, int(n), int(seed), int(mode), float(fixed_scale), ptr(out), stream_ptr()), h)
+    return int(out.item())

@@ -140,10 +140,21 @@ def qrope_int(qkv_codes, B, T, nh, nkv, hd, rot, qin, qout, cos, sin):
     return outs
 
 
-def exp_lut(s_s, hd, qmax_s):
-    """LUT[k] = rne(2^31 * exp(-k * s_s / sqrt(hd))), float64 on the host, uint32."""
-    k = np.arange(int(qmax_s) + 1, dtype=np.float64)
-    return np.rint(np.exp(-k * np.float64(f32(s_s)) / np.sqrt(np.float64(hd))) * 2.0 ** 31).astype(np.uint32)
+def exp_tables(s_s, hd):
+    """Two-level exp table of the quantised softmax: A[i] = rne(2^31 exp(-256 i a)), B[j] = rne(2^31 exp(-j a)),
+    a = s_s / sqrt(hd) in float64; E(k) = (A[k >> 8] * B[k & 255]) >> 31 ~= 2^31 exp(-k a) for 16-bit k.
+    Returns one uint32[512] array (A then B) -- the `lut` argument of mq_qattn."""
+    a = np.float64(f32(s_s)) / np.sqrt(np.float64(hd))
+    i = np.arange(256, dtype=np.float64)
+    A = np.rint(np.exp(-256.0 * i * a) * 2.0 ** 31).astype(np.uint32)
+    B = np.rint(np.exp(-i * a) * 2.0 ** 31).astype(np.uint32)
+    return np.concatenate([A, B])
+
+
+def exp_eval(tab, k):
+    """E(k) for an int64 array k in [0, 65535] (uint64)."""
+    k = np.asarray(k, np.int64)
+    return (tab[k >> 8].astype(np.uint64) * tab[256 + (k & 255)].astype(np.uint64)) >> np.uint64(31)
 
 
 def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
@@ -152,7 +163,7 @@ def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
     B, _, T, hd = q.shape
     rep = nh // nkv
     if lut is None:
-        lut = exp_lut(qs[0], hd, qs[2])
+        lut = exp_tables(qs[0], hd)
     assert int(qp[1]) == 0
     sqk = f32(f32(qq[0]) * f32(qk[0])); spv = f32(f32(qp[0]) * f32(qv[0]))
     out = np.zeros((B, T, nh, hd), np.int64)
@@ -163,7 +174,7 @@ def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
             I = _mm_exact(q[b, h] - int(qq[1]), (k[b, kv] - int(qk[1])).T)
             c = quant_codes((I.astype(f32) * sqk).astype(f32), qs[0], qs[1], 0, qs[2]).astype(np.int64)
             cmax = np.where(causal, c, -1).max(axis=1, keepdims=True)
-            E = np.where(causal, lut[np.clip(cmax - c, 0, int(qs[2]))].astype(np.uint64), np.uint64(0))
+            E = np.where(causal, exp_eval(lut, np.clip(cmax - c, 0, int(qs[2]))), np.uint64(0))
             S = E.sum(axis=1, keepdims=True, dtype=np.uint64)
             p = (E.astype(f32) / S.astype(f32)).astype(f32)
             cp = np.where(causal, quant_codes(p, qp[0], 0, 0, qp[2]).astype(np.int64), 0)

@@ -7,9 +7,9 @@ def run(M, N, K, mode=Kn.EPI_QUANT, iters=20):
     b = torch.randint(0, 256, (N, K), dtype=torch.uint8, device=cuda)
     rowsum = a.to(torch.int32).sum(1).to(torch.int32); sxw = torch.full((N,), 1e-5, device=cuda)
     ow = torch.full((N,), 128, dtype=torch.int32, device=cuda); c0 = torch.zeros(N, dtype=torch.int32, device=cuda)
-    so = torch.full((N,), 0.05, device=cuda); oo = torch.full((N,), 128.0, device=cuda)
+    G = (N + 127) // 128; so = torch.full((G,), 0.05, device=cuda); oo = torch.full((G,), 128.0, device=cuda)
     lut = torch.randn(256, device=cuda)
-    kw = dict(so=so, oo=oo, qmax=255.0)
+    kw = dict(so=so, oo=oo, qmax=255.0, qgroup=128)
     if mode == Kn.EPI_ACTMUL: kw.update(lut=lut, s2=0.01, o2=128.0)
     if mode == Kn.EPI_RESID: kw.update(resid=torch.zeros(M, N, device=cuda), qmax=65535.0)
     out = None

@@ -61,7 +61,7 @@ def test_qattn(cuda, B, T, nh, nkv, hd):
     dev = lambda a: torch.from_numpy(a).to(cuda)
     bufs = dict(q=dev(q), k=dev(k), vt=dev(np.ascontiguousarray(v.transpose(0, 1, 3, 2))),
                 rsq=dev(q.astype(np.int32).sum(-1).astype(np.int32)), rsk=dev(k.astype(np.int32).sum(-1).astype(np.int32)))
-    lut = dev(ir.exp_lut(qs[0], hd, qs[2]).view(np.int32))
+    lut = dev(ir.exp_tables(qs[0], hd).view(np.int32))
     params = [qq[1], qk[1], qv[1], f32(qq[0]) * f32(qk[0]), qs[0], qs[1], qs[2], qp[0], qp[2], f32(qp[0]) * f32(qv[0]), qo[0], qo[1]]
     rs = torch.zeros(B * T, dtype=torch.int32, device=cuda)
     out = K.qattn(bufs, B, T, nh, nkv, hd, params, lut, rowsum_out=rs)

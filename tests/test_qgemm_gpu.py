@@ -53,7 +53,8 @@ def test_qgemm_quant_epilogue(cuda, bits):
     ref = ir.quant_codes(y, so.reshape(1, -1), oo.reshape(1, -1), 0, qmax).astype(np.int64)
     rs_out = torch.zeros(M, dtype=torch.int32, device=cuda)
     out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_QUANT, bias=torch.from_numpy(bias).to(cuda),
-                   so=torch.from_numpy(so).to(cuda), oo=torch.from_numpy(oo).to(cuda), qmax=qmax, out_bits=bits, rowsum_out=rs_out)
+                   so=torch.from_numpy(so[::N // 2].copy()).to(cuda), oo=torch.from_numpy(oo[::N // 2].copy()).to(cuda), qgroup=N // 2,
+                   qmax=qmax, out_bits=bits, rowsum_out=rs_out)
     got = out.cpu().numpy()
     got = got.astype(np.int64) if bits == 8 else got.view(np.uint16).astype(np.int64)
     assert np.array_equal(got, ref)
@@ -71,8 +72,8 @@ def test_qgemm_resid_epilogue(cuda):
     h = rng.normal(0, 1, size=(M, N)).astype(np.float32)
     ref = (h + ir.dequant(ir.quant_codes(y, so, oo, 0, 65535), so, oo)).astype(np.float32)
     th = torch.from_numpy(h.copy()).to(cuda)
-    Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_RESID, so=torch.full((N,), float(so), device=cuda),
-             oo=torch.full((N,), float(oo), device=cuda), qmax=65535, resid=th)
+    Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_RESID, so=torch.full((1,), float(so), device=cuda),
+             oo=torch.full((1,), float(oo), device=cuda), qmax=65535, resid=th)
     assert np.array_equal(th.cpu().numpy(), ref)
 
 
@@ -98,10 +99,10 @@ def test_qgemm_actmul_epilogue(cuda):
     il = lambda v1, v3: np.concatenate([np.concatenate([v1[i * 128:(i + 1) * 128], v3[i * 128:(i + 1) * 128]]) for i in range(nb)])
     ow = il(ow1, ow3); sw = il(sw1, sw3)
     ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
-    so = torch.from_numpy(il(np.full(I, so1, np.float32), np.full(I, so3, np.float32))).to(cuda)
-    oo = torch.from_numpy(il(np.full(I, oo1, np.float32), np.full(I, oo3, np.float32))).to(cuda)
+    so = torch.from_numpy(il(np.full(I, so1, np.float32), np.full(I, so3, np.float32))[::128].copy()).to(cuda)   # per 128-column half tile
+    oo = torch.from_numpy(il(np.full(I, oo1, np.float32), np.full(I, oo3, np.float32))[::128].copy()).to(cuda)
     rs_out = torch.zeros(M, dtype=torch.int32, device=cuda)
-    out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qmax=255, lut=torch.from_numpy(lut).to(cuda),
+    out = Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qgroup=128, qmax=255, lut=torch.from_numpy(lut).to(cuda),
                    s2=float(s2), o2=float(o2), qmax2=255, rowsum_out=rs_out)
     assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
     assert np.array_equal(rs_out.cpu().numpy().astype(np.int64), ref.sum(1))

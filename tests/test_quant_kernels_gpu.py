@@ -171,3 +171,11 @@ def test_wprep_pack4(cuda):
     sext = lambda v: torch.where(v >= 8, v - 16, v)
     un = torch.stack([sext(lo), sext(hi)], dim=-1).reshape(32, 64)
     assert torch.equal(un, codes)
+
+
+@pytest.mark.parametrize("mode,scale", [(0, 1.0), (2, 1.0), (1, 0.0123), (1, 9.1553e-4), (1, 1.0 / 65535), (1, 0.99999994), (1, 3.05e-5)])
+def test_div_rn_exact(cuda, mode, scale):
+    """The branch-free exact requantisation of the integer-engine kernels == IEEE division + rint (qm:286) on 2^28
+    pseudo-random operand pairs per case, including all-ones significands (the Markstein exception)."""
+    from mobilequant_b200 import kernels as K
+    assert K.selftest_div(1 << 28, seed=7 + mode, mode=mode, fixed_scale=scale) == 0
