@@ -142,78 +142,99 @@ __device__ __forceinline__ void unpack4(uint32_t w, float s, float o, float (&x)
   for (int j = 0; j < 4; ++j) x[j] = dequant(__uint2float_rn((w >> (8 * j)) & 255u), s, o);
 }
 
-template <bool FIVE>
+template <int HD, bool FIVE>
 __device__ __forceinline__ void qrope_body(const RopeArgs& a, uint8_t* vs) {
+  constexpr int WORDS = HD / 4;                          // 32-bit words per head
+  constexpr int WPT = WORDS > 32 ? WORDS / 32 : 1;       // words per thread (hd = 256 -> 2)
+  constexpr int LPI = WORDS / WPT;                       // lanes per (token, head): 8, 16 or 32
+  constexpr int HPW = 32 / LPI;                          // heads per warp iteration
   const int tok0 = blockIdx.x * kRopeTok;
   const int M = a.B * a.T;
   const int half = a.rot / 2;
-  const int words = a.hd / 4;                            // 32-bit words per head
-  const int wpt = words > 32 ? words / 32 : 1;           // words per thread (hd = 256 -> 2)
-  const int lpi = words / wpt;                           // lanes per (token, head): 8, 16 or 32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPI, grp = lane / LPI;
   const QParam qq = make_qparam(a.sq, a.oq, 255.f), qk = make_qparam(a.sk, a.ok, 255.f), qv = make_qparam(a.sv, a.ov, 255.f);
-  // ---- q and k
   const int heads_qk = a.nh + a.nkv;
-  const int items = kRopeTok * heads_qk * lpi;           // multiple of 8
-  for (int it = threadIdx.x; it < ((items + 31) & ~31); it += blockDim.x) {
-    const bool active = it < items;
-    const int sub = it % lpi, th = it / lpi;
-    const int tl = th / heads_qk, hh = th % heads_qk;
+  const int vw = a.nkv * HD;
+  const int vstride = vw + 4;
+  // ---- each warp owns tokens warp, warp + 8 of the CTA's 16
+  for (int tl = warp; tl < kRopeTok; tl += 8) {
     const int tok = tok0 + tl;
-    const bool ok = active && tok < M;
-    int csum = 0;
-    if (ok) {
-      const int b = tok / a.T, t = tok % a.T;
-      const bool is_q = hh < a.nh;
-      const int h = is_q ? hh : hh - a.nh;
-      const uint8_t* src = a.qkv + int64_t(tok) * a.ldq + hh * a.hd;      // q heads then k heads are contiguous in the row
-      const float s_in = is_q ? a.sq_in : a.sk_in, o_in = is_q ? a.oq_in : a.ok_in;
-      const QParam& qo = is_q ? qq : qk;
-      uint8_t* dst = is_q ? a.q + ((int64_t(b) * a.nh + h) * a.T + t) * a.hd : a.k + ((int64_t(b) * a.nkv + h) * a.T + t) * a.hd;
-      for (int wi = 0; wi < wpt; ++wi) {
-        const int d = (sub + wi * lpi) * 4;
-        float x[4], out[4];
-        unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + d)), s_in, o_in, x);
-        if (d < a.rot) {
-          // q_embed = (q * cos) + (rotate_half(q) * sin); rotate_half = cat(-x2, x1)
-          const int dp = d < half ? d + half : d - half;
-          float y[4];
-          unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + dp)), s_in, o_in, y);
-          const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
-          const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
+    if (tok >= M) {                                      // keep the V tile defined for the transpose below
+      for (int c = lane * 4; c < vw; c += 128) *reinterpret_cast<uint32_t*>(vs + tl * vstride + c) = 0u;
+      continue;
+    }
+    const int b = tok / a.T, t = tok % a.T;
+    const uint8_t* row = a.qkv + int64_t(tok) * a.ldq;
+    // cos/sin of this lane's head dims (shared by every head of the token)
+    float cv[WPT][4], sv[WPT][4];
+    int dpart[WPT];
+    bool rotd[WPT], neg[WPT];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) out[j] = fadd(fmul(x[j], cv[j]), fmul(d < half ? -y[j] : y[j], sv[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) out[j] = x[j];
-        }
-        uint32_t packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(out[j], qo) << (8 * j);
-        *reinterpret_cast<uint32_t*>(dst + d) = packed;
-        csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+    for (int wi = 0; wi < WPT; ++wi) {
+      const int d = (sub + wi * LPI) * 4;
+      rotd[wi] = d < a.rot;
+      neg[wi] = d < half;
+      dpart[wi] = d < half ? d + half : d - half;
+      if (rotd[wi]) {
+        const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
+        cv[wi][0] = c.x; cv[wi][1] = c.y; cv[wi][2] = c.z; cv[wi][3] = c.w;
+        sv[wi][0] = sn.x; sv[wi][1] = sn.y; sv[wi][2] = sn.z; sv[wi][3] = sn.w;
       }
     }
-    for (int dd = lpi >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
-    if (ok && sub == 0) {
-      const int b = tok / a.T, t = tok % a.T;
-      if (hh < a.nh) a.rsq[(int64_t(b) * a.nh + hh) * a.T + t] = csum;
-      else a.rsk[(int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t] = csum;
+    // ---- q and k heads: HPW heads per iteration, LPI adjacent lanes per head
+    for (int hh0 = 0; hh0 < heads_qk; hh0 += HPW) {
+      const int hh = hh0 + grp;
+      const bool ok = hh < heads_qk;
+      const bool is_q = hh < a.nh;
+      int csum = 0;
+      if (ok) {
+        const uint8_t* src = row + hh * HD;              // q heads then k heads are contiguous in the row
+        const float s_in = is_q ? a.sq_in : a.sk_in, o_in = is_q ? a.oq_in : a.ok_in;
+        QParam qo;
+        qo.s = is_q ? qq.s : qk.s; qo.rs = is_q ? qq.rs : qk.rs; qo.lo = is_q ? qq.lo : qk.lo; qo.hi = is_q ? qq.hi : qk.hi;
+        qo.ioff = is_q ? qq.ioff : qk.ioff; qo.five = false;
+        uint8_t* dst = is_q ? a.q + ((int64_t(b) * a.nh + hh) * a.T + t) * HD
+                            : a.k + ((int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t) * HD;
+#pragma unroll
+        for (int wi = 0; wi < WPT; ++wi) {
+          const int d = (sub + wi * LPI) * 4;
+          float x[4], out[4];
+          unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + d)), s_in, o_in, x);
+          if (rotd[wi]) {
+            // q_embed = (q * cos) + (rotate_half(q) * sin); rotate_half = cat(-x2, x1)
+            float y[4];
+            unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + dpart[wi])), s_in, o_in, y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = fadd(fmul(x[j], cv[wi][j]), fmul(neg[wi] ? -y[j] : y[j], sv[wi][j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = x[j];
+          }
+          uint32_t packed = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(out[j], qo) << (8 * j);
+          *reinterpret_cast<uint32_t*>(dst + d) = packed;
+          csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+        }
+      }
+#pragma unroll
+      for (int dd = LPI >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
+      if (ok && sub == 0) {
+        if (is_q) a.rsq[(int64_t(b) * a.nh + hh) * a.T + t] = csum;
+        else a.rsk[(int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t] = csum;
+      }
     }
-  }
-  // ---- v: requant into smem, then transposed store
-  const int vw = a.nkv * a.hd;
-  const int vstride = vw + 4;
-  for (int idx = threadIdx.x; idx < kRopeTok * (vw / 4); idx += blockDim.x) {
-    const int tl = idx / (vw / 4), c = (idx % (vw / 4)) * 4;
-    const int tok = tok0 + tl;
-    uint32_t packed = 0;
-    if (tok < M) {
+    // ---- v: requant into the smem tile
+    const uint8_t* vsrc = row + heads_qk * HD;
+    for (int c = lane * 4; c < vw; c += 128) {
       float x[4];
-      unpack4(__ldg(reinterpret_cast<const uint32_t*>(a.qkv + int64_t(tok) * a.ldq + (a.nh + a.nkv) * a.hd + c)), a.sv_in, a.ov_in, x);
+      unpack4(__ldg(reinterpret_cast<const uint32_t*>(vsrc + c)), a.sv_in, a.ov_in, x);
+      uint32_t packed = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(x[j], qv) << (8 * j);
+      *reinterpret_cast<uint32_t*>(vs + tl * vstride + c) = packed;
     }
-    *reinterpret_cast<uint32_t*>(vs + tl * vstride + c) = packed;
   }
   __syncthreads();
   // each thread writes one vT row segment: (kv head, d) x 16 tokens; segments that straddle a sequence boundary or are
@@ -221,28 +242,29 @@ __device__ __forceinline__ void qrope_body(const RopeArgs& a, uint8_t* vs) {
   const int b0 = tok0 / a.T, t0 = tok0 % a.T;
   const bool fast = tok0 + kRopeTok <= M && t0 + kRopeTok <= a.T && (t0 & 15) == 0 && (a.T & 15) == 0;
   for (int c = threadIdx.x; c < vw; c += blockDim.x) {
-    const int kvh = c / a.hd, d = c % a.hd;
+    const int kvh = c / HD, d = c % HD;
     if (fast) {
       uint32_t w[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         w[j] = vs[(4 * j) * vstride + c] | (vs[(4 * j + 1) * vstride + c] << 8) | (vs[(4 * j + 2) * vstride + c] << 16) |
                (vs[(4 * j + 3) * vstride + c] << 24);
-      *reinterpret_cast<uint4*>(a.vt + ((int64_t(b0) * a.nkv + kvh) * a.hd + d) * a.T + t0) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(a.vt + ((int64_t(b0) * a.nkv + kvh) * HD + d) * a.T + t0) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
       for (int tl = 0; tl < kRopeTok; ++tl) {
         const int tok = tok0 + tl;
         if (tok >= M) break;
         const int b = tok / a.T, t = tok % a.T;
-        a.vt[((int64_t(b) * a.nkv + kvh) * a.hd + d) * a.T + t] = vs[tl * vstride + c];
+        a.vt[((int64_t(b) * a.nkv + kvh) * HD + d) * a.T + t] = vs[tl * vstride + c];
       }
     }
   }
 }
 
+template <int HD>
 __global__ void __launch_bounds__(256) qrope_kernel(const RopeArgs a, const int five) {
   extern __shared__ __align__(16) uint8_t vs[];          // [16 tokens][nkv*hd + 4]
-  if (five) qrope_body<true>(a, vs); else qrope_body<false>(a, vs);
+  if (five) qrope_body<HD, true>(a, vs); else qrope_body<HD, false>(a, vs);
 }
 
 // =====================================================================================================================
@@ -291,9 +313,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int HD, int DV>
+template <int HD, int DV, bool FIVE>
 __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const AttnArgs a) {
-  constexpr int KT = 64;                      // keys per tile
+  constexpr int KT = 64;                      // keys per tile (two 32-key halves, processed by a rolled loop)
   constexpr int QT = 64;                      // queries per CTA
   constexpr int KSTR = HD + 16;               // padded row strides (bank-conflict free fragment loads)
   constexpr int VSTR = KT + 16;
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
   }
   const int32_t* rsqb = a.rsq + (int64_t(b) * a.nh + h) * a.T;
   const int ioq = (int)a.oq, iok = (int)a.ok, iov = (int)a.ov;
-  // I = acc - iok*rsq - ioq*rsk + HD*ioq*iok : the row part is folded into one constant per row
+  // I = acc - iok*rsq - ioq*rsk + HD*ioq*iok = acc + colc[key] + rc[row]
   const int rc_lo = HD * ioq * iok - iok * (qi_lo < a.T ? __ldg(rsqb + qi_lo) : 0);
   const int rc_hi = HD * ioq * iok - iok * (qi_hi < a.T ? __ldg(rsqb + qi_hi) : 0);
   const int n_ktiles = (min(q0 + QT, a.T) + KT - 1) / KT;   // causal: keys <= last query of the tile
@@ -375,40 +397,109 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
   const QParam qs = make_qparam(a.s_s, a.o_s, a.qmax_s);
   const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
   const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
-  int mx_lo = INT_MIN, mx_hi = INT_MIN;
+  int mx_lo = INT_MIN, mx_hi = INT_MIN;          // row maxima of acc + colc
   int cm_lo = 0, cm_hi = 0;                      // bits of (magic + clamped code - o_s) of the row maximum
   unsigned long long sum_lo = 0, sum_hi = 0;
   float den_lo = 1.f, den_hi = 1.f, rden_lo = 1.f, rden_hi = 1.f;
-  bool five3 = false;
   int oacc[DV / 8][4];
 #pragma unroll
   for (int i = 0; i < DV / 8; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0; }
   int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
 
-  // raw accumulators of one key tile for this warp's 16 rows (MMA C layout), key zero-point term removed
-  auto score_tile = [&](const uint8_t* skb, const int* rk, int (&I)[KT / 8][4]) {
+  // accumulators of 32 keys (4 n-tiles) for this warp's 16 rows in the MMA C layout, key zero-point term included
+  auto score_half = [&](const uint8_t* skh, const int* rkh, int (&I)[4][4]) {
 #pragma unroll
-    for (int nt = 0; nt < KT / 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
       int acc[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int ks = 0; ks < HD / 32; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(skb + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(skb + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
         mma_u8(acc, qa[ks], b0, b1);
       }
-      const int2 rk2 = *reinterpret_cast<const int2*>(rk + nt * 8 + 2 * t4);
-      I[nt][0] = acc[0] - ioq * rk2.x; I[nt][1] = acc[1] - ioq * rk2.y;
-      I[nt][2] = acc[2] - ioq * rk2.x; I[nt][3] = acc[3] - ioq * rk2.y;
+      const int2 rk2 = *reinterpret_cast<const int2*>(rkh + nt * 8 + 2 * t4);
+      const int c0 = -ioq * rk2.x, c1 = -ioq * rk2.y;
+      I[nt][0] = acc[0] + c0; I[nt][1] = acc[1] + c1; I[nt][2] = acc[2] + c0; I[nt][3] = acc[3] + c1;
     }
   };
   // bits of magic + (clamped code - o_s); differences of these bits are differences of codes
-  auto score_bits = [&](auto five_tag, int I) -> int {
-    constexpr bool FIVE = decltype(five_tag)::value;
-    return __float_as_int(quant_magic<FIVE>(fmul(__int2float_rn(I), a.sqk), qs));
-  };
+  auto score_bits = [&](int I) -> int { return __float_as_int(quant_magic<FIVE>(fmul(__int2float_rn(I), a.sqk), qs)); };
   auto exp_tab = [&](int k) -> uint32_t {
     const uint32_t ea = s_tab[__byte_perm((uint32_t)k, 0u, 0x4441)], eb = s_tab[256 + (k & 255)];   // (k >> 8) & 255: masked lanes stay in range
     return (uint32_t)(((unsigned long long)ea * eb) >> 31);
+  };
+
+  // one 64-key tile of one pass; DIAG = the tile holds keys beyond some query of the CTA (causal / length mask)
+  auto tile = [&](auto diag_tag, int pass, int kt, const uint8_t* skb, const uint8_t* svb, const int* rk) {
+    constexpr bool DIAG = decltype(diag_tag)::value;
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      int I[4][4];
+      score_half(skb + hf * 32 * KSTR, rk + hf * 32, I);
+      const int key0 = kt * KT + hf * 32 + 2 * t4;
+      if (pass == 0) {
+        // ---- pass 1: row maxima (the code is monotone in I)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int key = key0 + nt * 8;
+          if (!DIAG || key <= qi_lo) mx_lo = max(mx_lo, I[nt][0]);
+          if (!DIAG || key + 1 <= qi_lo) mx_lo = max(mx_lo, I[nt][1]);
+          if (!DIAG || key <= qi_hi) mx_hi = max(mx_hi, I[nt][2]);
+          if (!DIAG || key + 1 <= qi_hi) mx_hi = max(mx_hi, I[nt][3]);
+        }
+      } else if (pass == 1) {
+        // ---- pass 2: exact row sums of E
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int key = key0 + nt * 8;
+          const uint32_t e0 = exp_tab(cm_lo - score_bits(I[nt][0] + rc_lo)), e1 = exp_tab(cm_lo - score_bits(I[nt][1] + rc_lo));
+          const uint32_t e2 = exp_tab(cm_hi - score_bits(I[nt][2] + rc_hi)), e3 = exp_tab(cm_hi - score_bits(I[nt][3] + rc_hi));
+          sum_lo += (!DIAG || key <= qi_lo) ? e0 : 0u; sum_lo += (!DIAG || key + 1 <= qi_lo) ? e1 : 0u;
+          sum_hi += (!DIAG || key <= qi_hi) ? e2 : 0u; sum_hi += (!DIAG || key + 1 <= qi_hi) ? e3 : 0u;
+        }
+      } else {
+        // ---- pass 3: P codes and P.V.  (magic + code) keeps the 16-bit code in its low half-word (o_p == 0).
+        // The division by the row sum always takes the two-step form (the sum may have an all-ones significand).
+        auto prob_bits = [&](int Iv, int cm, float den, float rden, bool valid) -> uint32_t {
+          const uint32_t e = (!DIAG || valid) ? exp_tab(cm - score_bits(Iv)) : 0u;
+          const float pr = div_rn<true>(__uint2float_rn(e), den, rden);
+          return (uint32_t)__float_as_int(quant_magic<FIVE>(pr, qp));
+        };
+        // A fragments (hi and lo bytes) with the key permutation
+        // slot(4t..4t+3) of the k-step  <->  keys {8*0+2t, +1, 8*1+2t, +1};  slot(16+4t..) <-> n-tiles 2, 3
+        uint32_t ahi[4], alo[4];
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {      // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
+          uint32_t pl[2], ph[2];                    // [n-tile w] packed code pairs of row lo / row hi
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const int nt = hsel * 2 + w;
+            const int key = key0 + nt * 8;
+            const uint32_t c0 = prob_bits(I[nt][0] + rc_lo, cm_lo, den_lo, rden_lo, key <= qi_lo);
+            const uint32_t c1 = prob_bits(I[nt][1] + rc_lo, cm_lo, den_lo, rden_lo, key + 1 <= qi_lo);
+            const uint32_t c2 = prob_bits(I[nt][2] + rc_hi, cm_hi, den_hi, rden_hi, key <= qi_hi);
+            const uint32_t c3 = prob_bits(I[nt][3] + rc_hi, cm_hi, den_hi, rden_hi, key + 1 <= qi_hi);
+            pl[w] = __byte_perm(c0, c1, 0x5410);    // code0 | code1 << 16
+            ph[w] = __byte_perm(c2, c3, 0x5410);
+            psum_lo = (int)__dp2a_lo(pl[w], 0x0101u, (unsigned)psum_lo);
+            psum_hi = (int)__dp2a_lo(ph[w], 0x0101u, (unsigned)psum_hi);
+          }
+          alo[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x6420); ahi[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x7531);
+          alo[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x6420); ahi[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x7531);
+        }
+#pragma unroll
+        for (int dn = 0; dn < DV / 8; ++dn) {
+          int phi[4] = {0, 0, 0, 0};
+          const uint8_t* vrow = svb + (dn * 8 + g) * VSTR + hf * 32 + 2 * t4;
+          const uint32_t b0 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 8) << 16);
+          const uint32_t b1 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 24) << 16);
+          mma_u8(phi, ahi, b0, b1);
+          mma_u8(oacc[dn], alo, b0, b1);            // the lo-byte products accumulate straight into the output
+#pragma unroll
+          for (int j = 0; j < 4; ++j) oacc[dn][j] += phi[j] * 256;
+        }
+      }
+    }
   };
 
   issue_loads(0);
@@ -420,92 +511,20 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
     const uint8_t* skb = sk + buf * KT * KSTR;
     const uint8_t* svb = sv + buf * DV * VSTR;
     const int* rk = s_rsk + buf * KT;
-    const bool diag = kt == n_ktiles - 1;       // the only tile that needs the causal / length mask
-    int I[KT / 8][4];
-    score_tile(skb, rk, I);
-    if (pass == 0) {
-      // ---- pass 1: row maxima of I (the code is monotone in I)
-#pragma unroll
-      for (int nt = 0; nt < KT / 8; ++nt) {
-        const int key = kt * KT + nt * 8 + 2 * t4;
-        if (!diag || key <= qi_lo) mx_lo = max(mx_lo, I[nt][0]);
-        if (!diag || key + 1 <= qi_lo) mx_lo = max(mx_lo, I[nt][1]);
-        if (!diag || key <= qi_hi) mx_hi = max(mx_hi, I[nt][2]);
-        if (!diag || key + 1 <= qi_hi) mx_hi = max(mx_hi, I[nt][3]);
-      }
-      if (kt == n_ktiles - 1) {
+    if (kt == n_ktiles - 1) {                   // the only tile that needs the causal / length mask; ends the pass
+      tile(std::true_type{}, pass, kt, skb, svb, rk);
+      if (pass == 0) {
         mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
         mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-        dispatch_five(qs.five, [&](auto ft) { cm_lo = score_bits(ft, mx_lo + rc_lo); cm_hi = score_bits(ft, mx_hi + rc_hi); });
-      }
-    } else if (pass == 1) {
-      // ---- pass 2: exact row sums of E
-      dispatch_five(qs.five, [&](auto ft) {
-#pragma unroll
-        for (int nt = 0; nt < KT / 8; ++nt) {
-          const int key = kt * KT + nt * 8 + 2 * t4;
-          const uint32_t e0 = exp_tab(cm_lo - score_bits(ft, I[nt][0] + rc_lo)), e1 = exp_tab(cm_lo - score_bits(ft, I[nt][1] + rc_lo));
-          const uint32_t e2 = exp_tab(cm_hi - score_bits(ft, I[nt][2] + rc_hi)), e3 = exp_tab(cm_hi - score_bits(ft, I[nt][3] + rc_hi));
-          sum_lo += (!diag || key <= qi_lo) ? e0 : 0u; sum_lo += (!diag || key + 1 <= qi_lo) ? e1 : 0u;
-          sum_hi += (!diag || key <= qi_hi) ? e2 : 0u; sum_hi += (!diag || key + 1 <= qi_hi) ? e3 : 0u;
-        }
-      });
-      if (kt == n_ktiles - 1) {
+        cm_lo = score_bits(mx_lo + rc_lo); cm_hi = score_bits(mx_hi + rc_hi);
+      } else if (pass == 1) {
         sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
         sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
         den_lo = __ull2float_rn(sum_lo); den_hi = __ull2float_rn(sum_hi);
         rden_lo = __frcp_rn(den_lo); rden_hi = __frcp_rn(den_hi);
-        five3 = __any_sync(0xffffffffu, mantissa_all_ones(den_lo) || mantissa_all_ones(den_hi)) || qs.five || qp.five;
       }
     } else {
-      // ---- pass 3: P codes and P.V.  (magic + code) keeps the 16-bit code in its low half-word (o_p == 0).
-      uint32_t ahi[KT / 32][4], alo[KT / 32][4];
-      dispatch_five(five3, [&](auto ft) {
-        constexpr bool FIVE = decltype(ft)::value;
-        auto prob_bits = [&](int Iv, int cm, float den, float rden, bool valid) -> uint32_t {
-          const uint32_t e = valid ? exp_tab(cm - score_bits(ft, Iv)) : 0u;
-          const float pr = div_rn<FIVE>(__uint2float_rn(e), den, rden);
-          return (uint32_t)__float_as_int(quant_magic<FIVE>(pr, qp));
-        };
-        // A fragments (hi and lo bytes) with the key permutation
-        // slot(4t..4t+3) of k-step ks  <->  keys {8(4ks)+2t, +1, 8(4ks+1)+2t, +1};  slot(16+4t..) <-> n-tiles 4ks+2, 4ks+3
-#pragma unroll
-        for (int ks = 0; ks < KT / 32; ++ks) {
-#pragma unroll
-          for (int hsel = 0; hsel < 2; ++hsel) {      // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
-            uint32_t pl[2], ph[2];                    // [n-tile w] packed code pairs of row lo / row hi
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const int nt = ks * 4 + hsel * 2 + w;
-              const int key = kt * KT + nt * 8 + 2 * t4;
-              const uint32_t c0 = prob_bits(I[nt][0] + rc_lo, cm_lo, den_lo, rden_lo, !diag || key <= qi_lo);
-              const uint32_t c1 = prob_bits(I[nt][1] + rc_lo, cm_lo, den_lo, rden_lo, !diag || key + 1 <= qi_lo);
-              const uint32_t c2 = prob_bits(I[nt][2] + rc_hi, cm_hi, den_hi, rden_hi, !diag || key <= qi_hi);
-              const uint32_t c3 = prob_bits(I[nt][3] + rc_hi, cm_hi, den_hi, rden_hi, !diag || key + 1 <= qi_hi);
-              pl[w] = __byte_perm(c0, c1, 0x5410);    // code0 | code1 << 16
-              ph[w] = __byte_perm(c2, c3, 0x5410);
-              psum_lo = (int)__dp2a_lo(pl[w], 0x0101u, (unsigned)psum_lo);
-              psum_hi = (int)__dp2a_lo(ph[w], 0x0101u, (unsigned)psum_hi);
-            }
-            alo[ks][hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x6420); ahi[ks][hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x7531);
-            alo[ks][hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x6420); ahi[ks][hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x7531);
-          }
-        }
-      });
-#pragma unroll
-      for (int dn = 0; dn < DV / 8; ++dn) {
-        int phi[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int ks = 0; ks < KT / 32; ++ks) {
-          const uint8_t* vrow = svb + (dn * 8 + g) * VSTR + ks * 32 + 2 * t4;
-          const uint32_t b0 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 8) << 16);
-          const uint32_t b1 = (uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 16) | ((uint32_t)*reinterpret_cast<const uint16_t*>(vrow + 24) << 16);
-          mma_u8(phi, ahi[ks], b0, b1);
-          mma_u8(oacc[dn], alo[ks], b0, b1);        // the lo-byte products accumulate straight into the output
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) oacc[dn][j] += phi[j] * 256;
-      }
+      tile(std::false_type{}, pass, kt, skb, svb, rk);
     }
     __syncthreads();                              // everyone is done with `buf` before step+2's loads are issued into it
   }
@@ -515,27 +534,24 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
   // ---- epilogue: remove the V zero point, requantise, store token-major
   int csum_lo = 0, csum_hi = 0;
   const int ldo = a.nh * HD;
-  dispatch_five(qo.five, [&](auto ft) {
-    constexpr bool FIVE = decltype(ft)::value;
 #pragma unroll
-    for (int dn = 0; dn < DV / 8; ++dn) {
-      const int d = d0 + dn * 8 + 2 * t4;
-      int code[4];
+  for (int dn = 0; dn < DV / 8; ++dn) {
+    const int d = d0 + dn * 8 + 2 * t4;
+    int code[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int A = oacc[dn][j] - iov * (j < 2 ? psum_lo : psum_hi);
-        code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
-      }
-      if (qi_lo < a.T) {
-        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
-        csum_lo += code[0] + code[1];
-      }
-      if (qi_hi < a.T) {
-        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
-        csum_hi += code[2] + code[3];
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int A = oacc[dn][j] - iov * (j < 2 ? psum_lo : psum_hi);
+      code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
     }
-  });
+    if (qi_lo < a.T) {
+      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
+      csum_lo += code[0] + code[1];
+    }
+    if (qi_hi < a.T) {
+      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
+      csum_hi += code[2] + code[3];
+    }
+  }
   csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 1); csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 2);
   csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 1); csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 2);
   if (t4 == 0 && a.rowsum_out) {
@@ -547,17 +563,23 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
 template <int HD, int DV>
 static size_t attn_smem_bytes() { return size_t(2) * 64 * (HD + 16) + size_t(2) * DV * 80 + 2 * 64 * 4 + 512 * 4; }
 
-template <int HD, int DV>
-static int launch_qattn(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
+template <int HD, int DV, bool FIVE>
+static int launch_qattn2(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
   const size_t smem = attn_smem_bytes<HD, DV>();
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(qattn_kernel<HD, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qattn_kernel<HD, DV, FIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  qattn_kernel<HD, DV><<<grid, 128, smem, st>>>(a);
+  qattn_kernel<HD, DV, FIVE><<<grid, 128, smem, st>>>(a);
   return check_launch(c, "mq_qattn");
+}
+template <int HD, int DV>
+static int launch_qattn(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
+  // scales with an all-ones significand need the two-step exact division everywhere (common.cuh: div_rn)
+  const bool five = mantissa_all_ones(a.s_s) || mantissa_all_ones(a.s_p) || mantissa_all_ones(a.s_out);
+  return five ? launch_qattn2<HD, DV, true>(c, a, grid, st) : launch_qattn2<HD, DV, false>(c, a, grid, st);
 }
 
 }  // namespace mq
@@ -612,7 +634,12 @@ int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int n
   size_t smem = size_t(kRopeTok) * (nkv * hd + 4);
   MQ_REQUIRE(c, smem <= 48 * 1024, "nkv*hd too large for the V transpose tile");
   const int five = mantissa_all_ones(a.sq) || mantissa_all_ones(a.sk) || mantissa_all_ones(a.sv);
-  qrope_kernel<<<(M + kRopeTok - 1) / kRopeTok, 256, smem, (cudaStream_t)stream>>>(a, five);
+  const unsigned grid = (unsigned)((M + kRopeTok - 1) / kRopeTok);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hd == 32) qrope_kernel<32><<<grid, 256, smem, st>>>(a, five);
+  else if (hd == 64) qrope_kernel<64><<<grid, 256, smem, st>>>(a, five);
+  else if (hd == 128) qrope_kernel<128><<<grid, 256, smem, st>>>(a, five);
+  else qrope_kernel<256><<<grid, 256, smem, st>>>(a, five);
   return check_launch(c, "mq_qrope");
 }
 

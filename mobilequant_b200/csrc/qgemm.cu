@@ -20,6 +20,7 @@
 #include "tc_common.cuh"
 #include "ctx.h"
 #include <string>
+#include <cstdlib>
 
 namespace mq {
 using namespace tc;
@@ -54,11 +55,15 @@ struct QGemmArgs {
   float s2, o2, qmax2;     // EPI_ACTMUL: w2.input_quantizer
 };
 
-template <int MODE>
+// PAIR: two CTAs of a cluster (one TPC) share a 256 x 256 output tile: each loads its own 128 A rows and HALF of the B
+// rows, one tcgen05.mma.cta_group::2 (M = 256) issued by the leader consumes both halves -> B traffic from L2 and the B
+// shared-memory footprint per CTA are halved, which buys two more pipeline stages.
+template <int MODE, bool PAIR>
 struct SmemLayout {
-  static constexpr int kStages = MODE == EPI_RESID ? 3 : 4;
+  static constexpr int kStages = PAIR ? (MODE == EPI_RESID ? 4 : 6) : (MODE == EPI_RESID ? 3 : 4);
   static constexpr int kABytes = kBM * kBK;
-  static constexpr int kBBytes = kBN * kBK;
+  static constexpr int kBRows = PAIR ? kBN / 2 : kBN;
+  static constexpr int kBBytes = kBRows * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColpOff = kStages * kStageBytes;                 // 2 x CP_COUNT x 256 x 4 B
   static constexpr int kLutOff = kColpOff + 2 * CP_COUNT * kBN * 4;      // 256 floats
@@ -71,11 +76,15 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
-template <int MODE>
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_r, const QGemmArgs p, const uint32_t idesc) {
-  using L = SmemLayout<MODE>;
+  using L = SmemLayout<MODE, PAIR>;
+  constexpr int kCtas = PAIR ? 2 : 1;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
+  const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;         // persistent scheduling unit: a CTA or a CTA pair
+  const int num_units = PAIR ? gridDim.x >> 1 : gridDim.x;
   constexpr int BN = kBN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -89,7 +98,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + kCtas * kBM - 1) / (kCtas * kBM), n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_iters = (p.K + kBK - 1) / kBK;
 
@@ -99,15 +108,16 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     prefetch_tmap(&tmap_b);
     if (MODE == EPI_RESID) prefetch_tmap(&tmap_r);
     for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE * kCtas); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
   if (MODE == EPI_ACTMUL && threadIdx.x >= 64) {
     for (int i = threadIdx.x - 64; i < 256; i += kNE * 32) lut_s[i] = __ldg(p.lut + i);
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -115,22 +125,29 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
+      for (int t = unit; t < num_tiles; t += num_units) {
+        const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + cta_rank * L::kBRows;
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
-          tma_load_2d(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+          if (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            tma_load_2d_pair(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
+            tma_load_2d_pair(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
+            tma_load_2d(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+          }
           if (++stage == L::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = unit; t < num_tiles; t += num_units) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -143,18 +160,23 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
             // advance both descriptors by kk*32 bytes inside the 128B swizzle row (address field is in 16B units)
-            mma_i8(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc,
-                   (k | kk) != 0);
+            if (PAIR) mma_i8_pair(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc, (k | kk) != 0);
+            else mma_i8(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc, (k | kk) != 0);
           }
-          tc_commit(&empty_bar[stage]);                      // smem slot free once these MMAs retire
-          if (k == k_iters - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
+          if (PAIR) {
+            tc_commit_pair(&empty_bar[stage]);                      // smem slot free in both CTAs once these MMAs retire
+            if (k == k_iters - 1) tc_commit_pair(&tfull_bar[acc]);  // accumulator complete (both halves)
+          } else {
+            tc_commit(&empty_bar[stage]);
+            if (k == k_iters - 1) tc_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == L::kStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int ew = warp - 2;                 // 0..kNE-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
@@ -164,8 +186,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint8_t* stage_out = smem + L::kOutOff + ew * L::kOutBufs * 4096;
     int out_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
+    for (int t = unit; t < num_tiles; t += num_units) {
+      const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN;
       // stage the per-column parameters of this tile (double buffered with the accumulator)
       float* cp = colp + acc * CP_COUNT * BN;
       int* cpi = reinterpret_cast<int*>(cp);
@@ -356,14 +378,15 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if (PAIR && cta_rank != 0) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (MODE == EPI_RESID && lane == 0) bulk_wait<0>();      // all reduce-adds have landed before the grid retires
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (PAIR) cluster_sync_all();                 // the peer may still be reading this CTA's B half / signalling its barriers
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
@@ -397,28 +420,51 @@ static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, cons
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MODE>
-static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
-                        cudaStream_t st) {
+template <int MODE, bool PAIR>
+static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
+                         cudaStream_t st) {
+  using L = SmemLayout<MODE, PAIR>;
   CUtensorMap ta, tb, tr;
   if (!make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a, args.M, args.K, args.K, kBM) ||
-      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, kBN))
+      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBRows))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
   tr = ta;
   if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the residual stream (16B-aligned pointer, ldo % 4 == 0)");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<MODE>::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  const int m_tiles = (args.M + kBM - 1) / kBM, n_tiles = (args.N + kBN - 1) / kBN;
-  int grid = m_tiles * n_tiles;
-  if (grid > c->sm_count) grid = c->sm_count;
-  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, kBM, kBN);
-  qgemm_kernel<MODE><<<grid, kThreads, SmemLayout<MODE>::kTotal, st>>>(ta, tb, tr, args, idesc);
+  constexpr int kCtas = PAIR ? 2 : 1;
+  const int m_tiles = (args.M + kCtas * kBM - 1) / (kCtas * kBM), n_tiles = (args.N + kBN - 1) / kBN;
+  int units = m_tiles * n_tiles;
+  if (units > c->sm_count / kCtas) units = c->sm_count / kCtas;
+  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, kCtas * kBM, kBN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * kCtas); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = PAIR ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, PAIR>, ta, tb, tr, args, idesc);
+  if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemm launch: ") + cudaGetErrorString(e));
   return check_launch(c, "mq_qgemm");
+}
+
+// MQ_QGEMM_PAIR=0 selects the single-CTA kernel (A/B measurements); the CTA-pair kernel is the default.
+static bool use_pair() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MQ_QGEMM_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <int MODE>
+static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
+                        cudaStream_t st) {
+  return use_pair() ? launch_qgemm2<MODE, true>(c, a, b, args, resid, a_signed, b_signed, st)
+                    : launch_qgemm2<MODE, false>(c, a, b, args, resid, a_signed, b_signed, st);
 }
 
 }  // namespace mq

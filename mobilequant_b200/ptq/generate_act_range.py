@@ -62,10 +62,8 @@ def get_act_range(model, samples, per_channel=False):
     for h in hooks:
         h.remove()
     if world > 1 and not per_channel:
-        packed = torch.stack([stats[k] for k in order])                 # [n, 2]
-        packed[:, 0].neg_()
-        dist.all_reduce(packed, op=dist.ReduceOp.MAX)                   # one exchange: max(-min), max(max)
-        packed[:, 0].neg_()
+        from ..utils.dist import allreduce_ranges
+        packed = allreduce_ranges(torch.stack([stats[k] for k in order]))   # [n, 2]; one exchange: max(-min), max(max)
         for k, row in zip(order, packed):
             stats[k] = row
     act_dict = defaultdict(dict)

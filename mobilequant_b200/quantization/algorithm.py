@@ -25,10 +25,9 @@ CLIPMIN, CLIPMAX = 1e-5, 1e6
 class TruncateFunction(torch.autograd.Function):          # alg:27-42
     @staticmethod
     def forward(ctx, input, threshold):
-        t = input.clone()
-        small = t.abs() < threshold
-        t[small] = t[small].sign() * threshold
-        return t
+        # same values as the reference's boolean-mask assignment (exact zeros stay zero, alg:31) without the
+        # nonzero() host synchronisation, so that a whole training step can be captured in a CUDA graph
+        return torch.where(input.abs() < threshold, input.sign() * threshold, input)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -149,7 +148,7 @@ def _truncate_let(model, use_shift):
     with torch.no_grad():
         for name, p in model.named_parameters():
             if template in name:
-                p.data = truncate_number(p)               # alg:190-193
+                p.copy_(truncate_number(p))               # alg:190-193 (in place: graph replays keep the storage)
 
 
 def _let_plan(model, config, original_omniquant):
@@ -377,17 +376,8 @@ def _drop_learned(layer):
 
 def _allreduce_grads(params, world):
     """Data-parallel exchange: SUM of the learnable-scalar gradients over NCCL, then the batch mean (alg:459)."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+    from ..utils.dist import allreduce_grads
+    allreduce_grads(params, world)
 
 
 def _train_step(args, loss, optimizer, loss_scaler, params_fn, world):
@@ -397,6 +387,105 @@ def _train_step(args, loss, optimizer, loss_scaler, params_fn, world):
         _allreduce_grads(list(params_fn()), world)
         return loss_scaler.step_only(optimizer, parameters=params_fn())
     return loss_scaler(loss, optimizer, parameters=params_fn())
+
+
+def _use_graphs(device):
+    return device.type == "cuda" and os.environ.get("MQ_CUDA_GRAPH", "1") != "0"
+
+
+def _make_optimizer(groups, wd, device):
+    """AdamW of the reference (alg:513,716-722).  On the GPU the fused, capturable implementation is used so that the
+    learning rates live in device tensors and a non-finite gradient skips the update on the device (GradScaler
+    semantics, optim.py:37-38) -- both are needed to replay a step as a CUDA graph."""
+    if _use_graphs(device):
+        for g in groups:
+            g["lr"] = torch.tensor(float(g["lr"]), device=device, dtype=torch.float32)
+        opt = torch.optim.AdamW(groups, weight_decay=wd, fused=True, capturable=True)
+        opt.found_inf = torch.zeros((), device=device, dtype=torch.float32)
+        return opt
+    return torch.optim.AdamW(groups, weight_decay=wd)
+
+
+def _set_lr(optimizer, idx, value):
+    lr = optimizer.param_groups[idx]["lr"]
+    if isinstance(lr, torch.Tensor):
+        lr.fill_(value)
+    else:
+        optimizer.param_groups[idx]["lr"] = value
+
+
+class _Replay:
+    """fn(*static_inputs) -> tuple of tensors, executed eagerly the first time (warm-up: cuBLAS workspaces, autograd,
+    optimizer state) and captured into a CUDA graph on the second call; later calls copy the inputs into the static
+    buffers and replay.  The reference issues ~11 k kernel launches per e2e step from Python; a replay
+    is one launch, which is what makes the GPU -- not the interpreter -- the bound of the calibration loop."""
+
+    def __init__(self, fn, example_inputs, enabled, before_capture=None):
+        self.fn, self.enabled, self.before_capture = fn, enabled, before_capture
+        self.static_in = [torch.empty_like(t) for t in example_inputs] if enabled else None
+        self.graph, self.static_out, self.calls = None, None, 0
+        self.stream = torch.cuda.Stream() if enabled else None
+
+    def __call__(self, *inputs):
+        if not self.enabled:
+            return self.fn(*inputs)
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src)
+        self.calls += 1
+        if self.calls == 1:                         # eager warm-up on the side stream the capture will use
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                out = self.fn(*self.static_in)
+            torch.cuda.current_stream().wait_stream(self.stream)
+            return out
+        if self.graph is None:
+            if self.before_capture is not None:
+                self.before_capture()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.static_out = self.fn(*self.static_in)
+        self.graph.replay()
+        return self.static_out
+
+
+def _no_grad_replay(fn, example, device):
+    """Forward-only replay unit (FP-target and quant-input refresh passes, alg:471-479,567-573,674-688)."""
+    def body(x):
+        with torch.no_grad():
+            return fn(x)
+    return _Replay(body, [example], _use_graphs(device))
+
+
+def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, world, device, example_inputs):
+    """One optimiser step as a replayable unit: forward, MSE against the FP target(s), backward, (all-reduce,) global
+    grad norm, AdamW.  Returns step(x, y[, y2]) -> (loss, norm), both detached 0-d tensors."""
+    graphed = _use_graphs(device)
+
+    def body(x, *targets):
+        out = forward_fn(x)
+        loss = loss_func(targets[0], out)
+        for t in targets[1:]:
+            loss = loss + loss_func(t, out)
+        if not graphed:
+            return loss.detach(), _train_step(args, loss, optimizer, loss_scaler, params_fn, world).detach()
+        loss.backward()
+        params = list(params_fn())
+        if world > 1:
+            _allreduce_grads(params, world)
+        grads = [p.grad for p in params if p.grad is not None]
+        norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+        optimizer.found_inf.copy_((~torch.isfinite(norm)).float())     # skip-step-on-non-finite, on the device
+        optimizer.step()
+        return loss.detach(), norm
+
+    runner = _Replay(body, example_inputs, graphed, before_capture=lambda: optimizer.zero_grad(set_to_none=True))
+
+    def step(*inputs):
+        if graphed and runner.graph is None:
+            optimizer.zero_grad(set_to_none=True)    # eager warm-up step: fresh gradients, as in the captured graph
+        loss, norm = runner(*inputs)
+        return loss.clone(), norm.clone()
+    return step
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -440,11 +529,12 @@ def omniquant(args, model, dataloader, logger, device=None):
         qlayer = layers[i].to(device)
         disable_quant(qlayer)
         if args.epochs > 0:
-            with torch.no_grad():
-                for j in my_samples:
-                    fp_inps[j] = qlayer(fp_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
-                    if args.aug_loss:
-                        fp_inps_2[j] = qlayer(quant_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
+            fp_pass = _no_grad_replay(lambda x: qlayer(x, attention_mask=attention_mask, position_ids=position_ids)[0], fp_inps[:1], device)
+            for j in my_samples:
+                fp_inps[j] = fp_pass(fp_inps[j].unsqueeze(0))[0]
+                if args.aug_loss:
+                    fp_inps_2[j] = fp_pass(quant_inps[j].unsqueeze(0))[0]
+            del fp_pass
         enable_quant(args, qlayer)
         if args.let:
             _register_let(qlayer, pairs, device, dtype)
@@ -455,32 +545,38 @@ def omniquant(args, model, dataloader, logger, device=None):
                       {"params": lwc_parameters(qlayer), "lr": args.lwc_lr}]
             if args.lrl:
                 groups.append({"params": lrl_parameters(qlayer), "lr": args.lrl_lr})
-            optimizer = torch.optim.AdamW(groups, weight_decay=args.wd)
+            optimizer = _make_optimizer(groups, args.wd, device)
             loss_scaler = NativeScalerWithGradNormCount()
             max_iters = args.epochs * gsteps
             warmup_iters = args.warmup_epochs * gsteps
+
+            def forward_fn(x, qlayer=qlayer):
+                smooth_lm_temporary(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
+                return qlayer(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+
+            bs = args.batch_size
+            example = [quant_inps[:bs], fp_inps[:bs]] + ([fp_inps_2[:bs]] if args.aug_loss else [])
+            step = _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, lambda qlayer=qlayer: get_parameters(qlayer, args.use_shift),
+                              world, device, example)
             for epochs in range(args.epochs):
                 loss_list, norm_list = [], []
                 for g, j in enumerate(my_batches):
                     index = j * args.batch_size
                     it = epochs * gsteps + g
-                    optimizer.param_groups[0]["lr"] = get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters)
-                    optimizer.param_groups[1]["lr"] = get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters)
+                    _set_lr(optimizer, 0, get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters))
+                    _set_lr(optimizer, 1, get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters))
                     if args.lrl:
-                        optimizer.param_groups[2]["lr"] = get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters)
-                    smooth_lm_temporary(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
-                    quant_out = qlayer(quant_inps[index:index + args.batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
-                    loss = loss_func(fp_inps[index:index + args.batch_size], quant_out)
-                    if args.aug_loss:
-                        loss += loss_func(fp_inps_2[index:index + args.batch_size], quant_out)
-                    loss_list.append(loss.detach())
-                    norm = _train_step(args, loss, optimizer, loss_scaler, lambda: get_parameters(qlayer, args.use_shift), world)
-                    norm_list.append(norm.detach())
+                        _set_lr(optimizer, 2, get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters))
+                    batch = [quant_inps[index:index + bs], fp_inps[index:index + bs]] + ([fp_inps_2[index:index + bs]] if args.aug_loss else [])
+                    loss, norm = step(*batch)
+                    loss_list.append(loss)
+                    norm_list.append(norm)
                 loss_mean = torch.stack(loss_list).mean().item()
                 if not math.isfinite(loss_mean):
                     raise FloatingPointError(f"layer {i} epoch {epochs}: loss is not finite")   # reference: pdb (alg:536-538)
                 norm_mean = torch.stack(norm_list).mean().item()
                 logger.info(f"layer {i} iter {epochs} loss:{loss_mean} norm:{norm_mean} max memory_allocated {torch.cuda.max_memory_allocated(device) / 1024**2} ")
+            del step
             clear_temp_variable(qlayer)
             del optimizer
         if args.epochs > 0:
@@ -490,9 +586,10 @@ def omniquant(args, model, dataloader, logger, device=None):
         smooth_lm_inplace(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
         _drop_learned(qlayer)
         if args.epochs > 0:
-            with torch.no_grad():
-                for j in my_samples:
-                    quant_inps[j] = qlayer(quant_inps[j].unsqueeze(0), attention_mask=attention_mask, position_ids=position_ids)[0]
+            refresh = _no_grad_replay(lambda x: qlayer(x, attention_mask=attention_mask, position_ids=position_ids)[0], quant_inps[:1], device)
+            for j in my_samples:
+                quant_inps[j] = refresh(quant_inps[j].unsqueeze(0))[0]
+            del refresh
         layers[i] = qlayer
     del inps, quant_inps, fp_inps, fp_inps_2
     gc.collect()
@@ -534,12 +631,13 @@ def e2equant(args, model, dataloader, logger, device=None):
     backbone = LayerList(layers)
 
     if args.epochs > 0:
-        with torch.no_grad():
-            for j in my_batches:                            # FP targets of this rank's shard only
-                index = j * batch_size
-                fp_inps[index:index + batch_size] = backbone(fp_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
-                if args.aug_loss:
-                    fp_inps_2[index:index + batch_size] = backbone(quant_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+        fp_pass = _no_grad_replay(lambda x: backbone(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0], fp_inps[:batch_size], device)
+        for j in my_batches:                                # FP targets of this rank's shard only
+            index = j * batch_size
+            fp_inps[index:index + batch_size] = fp_pass(fp_inps[index:index + batch_size])
+            if args.aug_loss:
+                fp_inps_2[index:index + batch_size] = fp_pass(quant_inps[index:index + batch_size])
+        del fp_pass
     enable_quant(args, model)
     if args.let:
         for i in range(len(layers)):
@@ -549,29 +647,33 @@ def e2equant(args, model, dataloader, logger, device=None):
 
     optimizer = None
     if args.epochs > 0:
-        optimizer = torch.optim.AdamW([{"params": let_parameters(model, args.use_shift), "lr": args.let_lr},
-                                       {"params": lwc_parameters(model), "lr": args.lwc_lr},
-                                       {"params": lrl_parameters(model), "lr": args.lrl_lr}], weight_decay=args.wd)
+        optimizer = _make_optimizer([{"params": list(let_parameters(model, args.use_shift)), "lr": args.let_lr},
+                                     {"params": list(lwc_parameters(model)), "lr": args.lwc_lr},
+                                     {"params": list(lrl_parameters(model)), "lr": args.lrl_lr}], args.wd, device)
         loss_scaler = NativeScalerWithGradNormCount()
         max_iters = args.epochs * gsteps
         warmup_iters = args.warmup_epochs * gsteps
+
+        def forward_fn(x):
+            for k in range(len(layers)):
+                smooth_lm_temporary(layers[k], model.config, args.let, args.use_shift)
+            return backbone(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0]
+
+        example = [quant_inps[:batch_size], fp_inps[:batch_size]] + ([fp_inps_2[:batch_size]] if args.aug_loss else [])
+        step = _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, lambda: get_parameters(model, args.use_shift), world, device, example)
         for epochs in range(args.epochs):
             loss_list, norm_list = [], []
             for g, j in enumerate(my_batches):
                 index = j * batch_size
                 it = epochs * gsteps + g
-                optimizer.param_groups[0]["lr"] = get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters)
-                optimizer.param_groups[1]["lr"] = get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters)
-                optimizer.param_groups[2]["lr"] = get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters)
-                for k in range(len(layers)):
-                    smooth_lm_temporary(layers[k], model.config, args.let, args.use_shift)
-                quant_out = backbone(quant_inps[index:index + batch_size], attention_mask=attention_mask_batch, position_ids=position_ids)[0]
-                loss = loss_func(fp_inps[index:index + batch_size], quant_out)
-                if args.aug_loss:
-                    loss += loss_func(fp_inps_2[index:index + batch_size], quant_out)
-                loss_list.append(loss.detach())
-                norm = _train_step(args, loss, optimizer, loss_scaler, lambda: get_parameters(model, args.use_shift), world)
-                norm_list.append(norm.detach())
+                _set_lr(optimizer, 0, get_lr(args.let_lr, args.let_min_lr, it, warmup_iters, max_iters))
+                _set_lr(optimizer, 1, get_lr(args.lwc_lr, args.lwc_min_lr, it, warmup_iters, max_iters))
+                _set_lr(optimizer, 2, get_lr(args.lrl_lr, args.lrl_min_lr, it, warmup_iters, max_iters))
+                batch = [quant_inps[index:index + batch_size], fp_inps[index:index + batch_size]] + \
+                        ([fp_inps_2[index:index + batch_size]] if args.aug_loss else [])
+                loss, norm = step(*batch)
+                loss_list.append(loss)
+                norm_list.append(norm)
             loss_mean = torch.stack(loss_list).mean().item()
             if not math.isfinite(loss_mean):
                 raise FloatingPointError(f"epoch {epochs}: loss is not finite")
@@ -588,6 +690,7 @@ def e2equant(args, model, dataloader, logger, device=None):
         _drop_learned(layers[i])
     if rank == 0:
         torch.save(e2e_parameters, os.path.join(args.output_dir, "parameters.pth"))
+    step = None
     del optimizer, inps, quant_inps, fp_inps, fp_inps_2
     gc.collect()
     model.config.use_cache = use_cache
