@@ -453,17 +453,19 @@ static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& 
   return check_launch(c, "mq_qgemm");
 }
 
-// MQ_QGEMM_PAIR=0 selects the single-CTA kernel (A/B measurements); the CTA-pair kernel is the default.
-static bool use_pair() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MQ_QGEMM_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+// Kernel choice (measured on B200, profiles/r1_qgemm_variants.md): with K = 2048 the epilogue, not the operand traffic,
+// paces a tile and both variants tie; from K = 5632 the CTA-pair kernel is 8-15 % faster (2.8-3.0 POP/s at K = 8192,
+// above the cuBLASLt int8 proxy).  MQ_QGEMM_PAIR=0/1 forces one variant (A/B measurements).
+static bool use_pair(int K) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("MQ_QGEMM_PAIR"); v = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+  return v >= 0 ? v == 1 : K >= 4096;
 }
 
 template <int MODE>
 static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
                         cudaStream_t st) {
-  return use_pair() ? launch_qgemm2<MODE, true>(c, a, b, args, resid, a_signed, b_signed, st)
+  return use_pair(args.K) ? launch_qgemm2<MODE, true>(c, a, b, args, resid, a_signed, b_signed, st)
                     : launch_qgemm2<MODE, false>(c, a, b, args, resid, a_signed, b_signed, st);
 }
 
