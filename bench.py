@@ -30,7 +30,10 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=8, help="sequences per GPU per step")
     p.add_argument("--seqlen", type=int, default=SEQ)
-    p.add_argument("--model", default=MODEL)
+    p.add_argument("--model", default=MODEL, help="tinyllama-1.1b | stablelm-2-1.6b | gemma-2b (synthetic weights of that shape)")
+    p.add_argument("--wbits", type=int, default=8, choices=[4, 8],
+                   help="8: W8A8 per-tensor asymmetric weights (headline); 4: W4A8 per-channel symmetric (BASELINE config 3)")
+    p.add_argument("--calib-samples", type=int, default=96)
     p.add_argument("--layers", type=int, default=None, help="debug: override num_hidden_layers")
     p.add_argument("--no-calib", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -167,8 +170,10 @@ def run_ours(args):
     # several ranks the two samples are sharded and the packed ranges all-reduced, identical on every replica)
     act = get_act_range(model, [synth_ids(1, T, cfg.vocab_size, 7 + i) for i in range(2)])
     from mobilequant_b200.ptq.generate_qcfg import default_qcfg
-    qcfg = default_qcfg(cfg, Q.QuantConfig(bitwidth=8), Q.QuantConfig(bitwidth=8))
+    wq = Q.QuantConfig(bitwidth=8) if args.wbits == 8 else Q.QuantConfig(bitwidth=4, is_symmetric=True, is_per_channel=True)
+    qcfg = default_qcfg(cfg, wq, Q.QuantConfig(bitwidth=8))
     eng = IntEngine(model, qcfg, act, dev)
+    wtag = "W8A8" if args.wbits == 8 else "W4A8 per-channel symmetric"
     ids_host = synth_ids(B, T, cfg.vocab_size, 1000 + rank).pin_memory()
     ids_dev = ids_host.to(dev)
     out_host = torch.empty(B, dtype=torch.int64).pin_memory()
@@ -227,7 +232,7 @@ def run_ours(args):
     line = {"metric": "int8_tok_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{args.model} W8A8 static-quant integer forward, batch {B} x seq {T} per GPU, random-init weights",
+            "config": {"workload": f"{args.model} {wtag} static-quant integer forward, batch {B} x seq {T} per GPU, random-init weights",
                        "global_batch": B * world, "seq_len": T, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
                        "l2": "inputs larger than L2: 1.1 GB int8 weights + 1 GB logits streamed per step"},
             "clocks": clk.summary(), "gpu_launches": launches,
@@ -241,7 +246,7 @@ def run_ours(args):
         if not args.no_calib and world == 1:
             del eng
             torch.cuda.empty_cache()
-            line["calib"] = calib_throughput(model, qcfg, act, cfg, T, dev)
+            line["calib"] = calib_throughput(model, wq, act, cfg, T, dev, args.calib_samples)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -282,8 +287,12 @@ def roofline(eng, ids, B, T):
         torch._int_mm(a, b.t())
     e1.record(); torch.cuda.synchronize()
     lib = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
-    rl = {"kernel": "qgemm_kernel<256> (tcgen05 kind::i8)", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s",
-          "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1c_qgemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("avg_bytes_per_launch")      # ncu --set full capture of the same kernel, per launch
+    rl = {"kernel": "qgemm_kernel (tcgen05 kind::i8, TMA ring, TMEM double buffer)", "bound": "tensor", "achieved": achieved, "peak": peak,
+          "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic,
           "peak_source": ("2 x measured bf16 burst (MEASURED_PEAKS.json): int8 issues at twice the bf16 rate on sm_100"
                           if bf16 else "2 x fallback bf16 1.59 PF"),
           "avg_launch_ms": g["ms"] / g["n"], "launches_per_step": g["n"], "ops_per_step": ops,
@@ -291,16 +300,16 @@ def roofline(eng, ids, B, T):
     return rl, shares
 
 
-def calib_throughput(model, qcfg, act, cfg, T, dev, nsamples=4):
-    """MobileQuant e2e calibration (LET + LWC + LRL, experiments/w8a8/main/e2e_llama-s1024-ep60.sh learning rates) on the
-    module path: FP-target pass + one optimiser step per sample."""
+def calib_throughput(model, wq, act, cfg, T, dev, nsamples=96):
+    """MobileQuant e2e calibration (LET + LWC + LRL, experiments/w8a8/main/e2e_llama-s1024-ep60.sh learning rates):
+    FP-target pass + one optimiser step per sample (CUDA-graph replays after the first two), fuse, parameters.pth."""
     import types, tempfile, torch
     from mobilequant_b200.quantization import qmodule as Q, algorithm as A
 
     class _L:
         def info(self, *a, **k):
             pass
-    Q.create_sim_qmodel(model, Q.QuantConfig(bitwidth=8), Q.QuantConfig(bitwidth=8))
+    Q.create_sim_qmodel(model, wq, Q.QuantConfig(bitwidth=8))
     for p in model.parameters():
         p.requires_grad = False
     Q.update_quant_cfg(model)
@@ -318,7 +327,8 @@ def calib_throughput(model, qcfg, act, cfg, T, dev, nsamples=4):
     dt = time.perf_counter() - t0
     return {"value": nsamples / dt, "unit": "samples/s", "samples": nsamples, "seconds": dt,
             "what": "e2equant LET+LWC+LRL, bs 1, seq %d, 1 epoch, includes FP-target pass, fuse and parameters.pth save" % T,
-            "path": "module path (fused quantizer kernels + cuBLAS TF32 GEMMs); projected 512 samples: %.1f s" % (512 * dt / nsamples)}
+            "path": "fused quantizer / weight-prep kernels + cuBLAS TF32 GEMMs, whole step replayed as one CUDA graph; "
+                    "512 samples at this rate: %.1f s (fixed costs included pro rata)" % (512 * dt / nsamples)}
 
 
 def cpu_baseline(model, cfg, act, T, nseq):

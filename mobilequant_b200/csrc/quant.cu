@@ -434,6 +434,215 @@ __global__ void __launch_bounds__(256) wprep_bwd_apply_kernel(const float* __res
   }
 }
 
+// ---- vectorised variants (cols % 4 == 0, 16-byte aligned rows) -------------------------------------------------------
+// Same arithmetic, bit for bit, with 128-bit loads/stores and the branch-free exact division of common.cuh for every
+// division by the group scale / the row factor (the divisor is uniform over a CTA, so its reciprocal and the FIVE
+// variant are chosen once).  Divisions by a per-column LET factor (only norm weights, rows == 1) keep __fdiv_rn.
+struct RowDiv { float r, rr; bool five; };
+__device__ __forceinline__ RowDiv make_rowdiv(float r) { RowDiv d; d.r = r; d.rr = __frcp_rn(r); d.five = mantissa_all_ones(r); return d; }
+__device__ __forceinline__ float div_any(float a, const RowDiv& d) { return d.five ? div_rn<true>(a, d.r, d.rr) : div_rn<false>(a, d.r, d.rr); }
+
+__device__ __forceinline__ float let_apply_v(float w, float c, const RowDiv& rd, int col_mode, int row_mode) {
+  float t = w;
+  if (col_mode == 2) t = fmul(t, c); else if (col_mode == 1) t = fdiv(t, c);
+  if (row_mode == 1) t = div_any(t, rd); else if (row_mode == 2) t = fmul(t, rd.r);
+  return t;
+}
+__device__ __forceinline__ float4 let_apply4(float4 w, const float* col_fac, int64_t k, const RowDiv& rd, const LetArgs& la) {
+  float4 c = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (la.col_mode) c = ldg4(col_fac + k);
+  return make_float4(let_apply_v(w.x, c.x, rd, la.col_mode, la.row_mode), let_apply_v(w.y, c.y, rd, la.col_mode, la.row_mode),
+                     let_apply_v(w.z, c.z, rd, la.col_mode, la.row_mode), let_apply_v(w.w, c.w, rd, la.col_mode, la.row_mode));
+}
+// rintf(u) for the purposes of a quantizer whose code range lies inside +-2^22: |u| is clamped first, which cannot change
+// clamp(rne(u) + o, qmin, qmax) nor the in-range test
+__device__ __forceinline__ float rne_magic(float u) {
+  const float uc = fminf(fmaxf(u, -4194303.f), 4194303.f);
+  return __fsub_rn(__fadd_rn(uc, kRoundMagic), kRoundMagic);
+}
+template <bool FIVE>
+__device__ __forceinline__ float quant_code_v(float x, float s, float rs, float o, float qmin, float qmax) {
+  return fminf(fmaxf(fadd(rne_magic(div_rn<FIVE>(x, s, rs)), o), qmin), qmax);
+}
+template <bool FIVE>
+__device__ __forceinline__ FqGrad fq_bwd_elem_v(float x, float g, float s, float rs, float o, float qmin, float qmax) {
+  const float u = div_rn<FIVE>(x, s, rs);
+  const float t3 = fadd(rne_magic(u), o);
+  const bool m = (t3 >= qmin) && (t3 <= qmax);
+  const float t5 = fsub(fminf(fmaxf(t3, qmin), qmax), o);
+  const float gs5 = fmul(g, s);
+  const float gt1 = m ? gs5 : 0.f;
+  FqGrad r;
+  r.gx = div_rn<FIVE>(gt1, s, rs);
+  r.gs = fsub(fmul(g, t5), fmul(gt1, div_rn<FIVE>(u, s, rs)));
+  r.go = fsub(gt1, gs5);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) wprep_rowminmax_v_kernel(const float* __restrict__ w, int64_t cols, LetArgs la,
+                                                                 float* __restrict__ row_mn, float* __restrict__ row_mx) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* wr = w + row * cols;
+  const RowDiv rd = make_rowdiv(la.row_mode ? __ldg(la.row_fac + row) : 1.f);
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (int64_t k = 4 * threadIdx.x; k < cols; k += 4 * blockDim.x) {
+    const float4 t = let_apply4(ldg4_stream(wr + k), la.col_fac, k, rd, la);
+    mn = fminf(fminf(mn, t.x), fminf(t.y, fminf(t.z, t.w)));
+    mx = fmaxf(fmaxf(mx, t.x), fmaxf(t.y, fmaxf(t.z, t.w)));
+  }
+  mn = block_reduce(mn, OpFMin(), red);
+  mx = block_reduce(mx, OpFMax(), red);
+  if (threadIdx.x == 0) { row_mn[row] = mn; row_mx[row] = mx; }
+}
+
+template <bool FIVE>
+__device__ __forceinline__ void wprep_quant_v_body(const float* __restrict__ w, int64_t cols, const LetArgs& la, const GroupQ& q,
+                                                    int64_t row, float* __restrict__ w_fq, uint8_t* __restrict__ codes, int pack4,
+                                                    int32_t* __restrict__ colsum, float* __restrict__ wt_out, int* redi) {
+  const float* wr = w + row * cols;
+  const RowDiv rd = make_rowdiv(la.row_mode ? __ldg(la.row_fac + row) : 1.f);
+  const float rs = __frcp_rn(q.s);
+  int csum = 0;
+  for (int64_t k = 4 * threadIdx.x; k < cols; k += 4 * blockDim.x) {
+    const float4 t = let_apply4(ldg4_stream(wr + k), la.col_fac, k, rd, la);
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    float qc[4]; int code[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { qc[j] = quant_code_v<FIVE>(tv[j], q.s, rs, q.o, q.qmin, q.qmax); code[j] = (int)qc[j]; csum += code[j]; }
+    if (w_fq) *reinterpret_cast<float4*>(w_fq + row * cols + k) =
+        make_float4(dequant(qc[0], q.s, q.o), dequant(qc[1], q.s, q.o), dequant(qc[2], q.s, q.o), dequant(qc[3], q.s, q.o));
+    if (wt_out) *reinterpret_cast<float4*>(wt_out + row * cols + k) = t;
+    if (codes) {
+      if (pack4) {
+        *reinterpret_cast<uint16_t*>(codes + ((row * cols + k) >> 1)) =
+            (uint16_t)((code[0] & 0xF) | ((code[1] & 0xF) << 4) | ((code[2] & 0xF) << 8) | ((code[3] & 0xF) << 12));
+      } else {
+        *reinterpret_cast<uint32_t*>(codes + row * cols + k) =
+            (uint32_t)(code[0] & 0xFF) | ((uint32_t)(code[1] & 0xFF) << 8) | ((uint32_t)(code[2] & 0xFF) << 16) | ((uint32_t)(code[3] & 0xFF) << 24);
+      }
+    }
+  }
+  if (colsum) {
+    int tot = block_reduce(csum, OpSum(), redi);
+    if (threadIdx.x == 0) colsum[row] = tot;
+  }
+}
+__global__ void __launch_bounds__(256) wprep_quant_v_kernel(const float* __restrict__ w, int64_t cols, LetArgs la,
+                                                             const float* __restrict__ row_mn, const float* __restrict__ row_mx,
+                                                             const float* __restrict__ sig_up, const float* __restrict__ sig_low,
+                                                             int per_channel, int bits, int sym, float* __restrict__ w_fq,
+                                                             uint8_t* __restrict__ codes, int pack4, float* __restrict__ scale_out,
+                                                             float* __restrict__ offset_out, int32_t* __restrict__ colsum,
+                                                             float* __restrict__ wt_out) {
+  __shared__ int redi[32];
+  const int64_t row = blockIdx.x;
+  const int64_t g = per_channel ? row : 0;
+  const GroupQ q = group_quant(row_mn[g], row_mx[g], sig_up, sig_low, g, bits, sym != 0);
+  if (mantissa_all_ones(q.s)) wprep_quant_v_body<true>(w, cols, la, q, row, w_fq, codes, pack4, colsum, wt_out, redi);
+  else wprep_quant_v_body<false>(w, cols, la, q, row, w_fq, codes, pack4, colsum, wt_out, redi);
+  if (threadIdx.x == 0 && (per_channel || row == 0)) {
+    if (scale_out) scale_out[g] = q.s;
+    if (offset_out) offset_out[g] = q.o;
+  }
+}
+
+template <bool FIVE>
+__device__ __forceinline__ void wprep_bwd_stats_v_body(const float* __restrict__ wr, const float* __restrict__ gr, int64_t cols,
+                                                        const LetArgs& la, const RowDiv& rd, const GroupQ& q, float gmn, float gmx,
+                                                        float& acc, int& cmn, int& cmx) {
+  const float rs = __frcp_rn(q.s);
+  for (int64_t k = 4 * threadIdx.x; k < cols; k += 4 * blockDim.x) {
+    const float4 t = let_apply4(ldg4_stream(wr + k), la.col_fac, k, rd, la);
+    const float4 gv = ldg4_stream(gr + k);
+    const float tv[4] = {t.x, t.y, t.z, t.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const FqGrad e = fq_bwd_elem_v<FIVE>(tv[j], gg[j], q.s, rs, q.o, q.qmin, q.qmax);
+      acc += e.gs;
+      cmn += (tv[j] == gmn); cmx += (tv[j] == gmx);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) wprep_bwd_stats_v_kernel(const float* __restrict__ w, const float* __restrict__ g,
+                                                                 int64_t cols, LetArgs la, const float* __restrict__ row_mn,
+                                                                 const float* __restrict__ row_mx, const float* __restrict__ sig_up,
+                                                                 const float* __restrict__ sig_low, int per_channel, int bits, int sym,
+                                                                 double* __restrict__ row_gs, int* __restrict__ row_cmn,
+                                                                 int* __restrict__ row_cmx) {
+  __shared__ float redf[32];
+  __shared__ int redi[32];
+  const int64_t row = blockIdx.x;
+  const int64_t gi = per_channel ? row : 0;
+  const float gmn = row_mn[gi], gmx = row_mx[gi];
+  const GroupQ q = group_quant(gmn, gmx, sig_up, sig_low, gi, bits, sym != 0);
+  const RowDiv rd = make_rowdiv(la.row_mode ? __ldg(la.row_fac + row) : 1.f);
+  float acc = 0.f; int cmn = 0, cmx = 0;
+  if (mantissa_all_ones(q.s)) wprep_bwd_stats_v_body<true>(w + row * cols, g + row * cols, cols, la, rd, q, gmn, gmx, acc, cmn, cmx);
+  else wprep_bwd_stats_v_body<false>(w + row * cols, g + row * cols, cols, la, rd, q, gmn, gmx, acc, cmn, cmx);
+  float tot = block_reduce(acc, OpSum(), redf);
+  int tmn = block_reduce(cmn, OpSum(), redi);
+  int tmx = block_reduce(cmx, OpSum(), redi);
+  if (threadIdx.x == 0) { row_gs[row] = tot; row_cmn[row] = tmn; row_cmx[row] = tmx; }
+}
+
+template <bool FIVE>
+__device__ __forceinline__ float wprep_bwd_apply_v_body(const float* __restrict__ wr, const float* __restrict__ gr, int64_t cols,
+                                                         const LetArgs& la, const RowDiv& rd, const GroupQ& q, float gmn, float gmx,
+                                                         const GroupGrad& sh, float* __restrict__ col_contrib, float* __restrict__ g_wt) {
+  const float rs = __frcp_rn(q.s);
+  float acc_r = 0.f;
+  for (int64_t k = 4 * threadIdx.x; k < cols; k += 4 * blockDim.x) {
+    const float4 w4 = ldg4_stream(wr + k), g4 = ldg4_stream(gr + k);
+    float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (la.col_mode) c4 = ldg4(la.col_fac + k);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+    float dw[4], cc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = wv[j];                                   // after the column op
+      if (la.col_mode == 2) t = fmul(wv[j], cv[j]); else if (la.col_mode == 1) t = fdiv(wv[j], cv[j]);
+      float wp = t;                                      // after the row op == W'
+      if (la.row_mode == 1) wp = div_any(t, rd); else if (la.row_mode == 2) wp = fmul(t, rd.r);
+      const FqGrad e = fq_bwd_elem_v<FIVE>(wp, gv[j], q.s, rs, q.o, q.qmin, q.qmax);
+      float dwp = e.gx;
+      if (wp == gmx) dwp += sh.share_mx;
+      if (wp == gmn) dwp += sh.share_mn;
+      dw[j] = dwp;
+      float gt = dwp;                                    // dL/dt
+      if (la.row_mode == 1) { gt = div_any(dwp, rd); acc_r -= fmul(dwp, div_any(wp, rd)); }
+      else if (la.row_mode == 2) { gt = fmul(dwp, rd.r); acc_r += fmul(dwp, t); }
+      cc[j] = 0.f;
+      if (la.col_mode == 2) cc[j] = fmul(gt, wv[j]); else if (la.col_mode == 1) cc[j] = -fmul(gt, fdiv(t, cv[j]));
+    }
+    if (g_wt) *reinterpret_cast<float4*>(g_wt + k) = make_float4(dw[0], dw[1], dw[2], dw[3]);
+    if (col_contrib) *reinterpret_cast<float4*>(col_contrib + k) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+  }
+  return acc_r;
+}
+__global__ void __launch_bounds__(256) wprep_bwd_apply_v_kernel(const float* __restrict__ w, const float* __restrict__ g,
+                                                                 int64_t cols, LetArgs la, const float* __restrict__ row_mn,
+                                                                 const float* __restrict__ row_mx, const float* __restrict__ sig_up,
+                                                                 const float* __restrict__ sig_low, int per_channel, int bits, int sym,
+                                                                 const GroupGrad* __restrict__ gg, float* __restrict__ col_contrib,
+                                                                 float* __restrict__ g_row_fac, float* __restrict__ g_wt) {
+  __shared__ float redf[32];
+  const int64_t row = blockIdx.x;
+  const int64_t gi = per_channel ? row : 0;
+  const float gmn = row_mn[gi], gmx = row_mx[gi];
+  const GroupQ q = group_quant(gmn, gmx, sig_up, sig_low, gi, bits, sym != 0);
+  const GroupGrad sh = gg[gi];
+  const RowDiv rd = make_rowdiv(la.row_mode ? __ldg(la.row_fac + row) : 1.f);
+  float* cc = col_contrib ? col_contrib + row * cols : nullptr;
+  float* gw = g_wt ? g_wt + row * cols : nullptr;
+  float acc_r = mantissa_all_ones(q.s) ? wprep_bwd_apply_v_body<true>(w + row * cols, g + row * cols, cols, la, rd, q, gmn, gmx, sh, cc, gw)
+                                       : wprep_bwd_apply_v_body<false>(w + row * cols, g + row * cols, cols, la, rd, q, gmn, gmx, sh, cc, gw);
+  if (g_row_fac) {
+    float tot = block_reduce(acc_r, OpSum(), redf);
+    if (threadIdx.x == 0) g_row_fac[row] = tot;
+  }
+}
+
 // deterministic column sums of a [rows, cols] matrix: grid (col tiles of 128, S row segments) -> partial[S, cols]
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ a, int64_t rows, int64_t cols,
                                                               float* __restrict__ partial) {
@@ -582,6 +791,12 @@ int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_
   return check_launch(c, "mq_minmax_2d");
 }
 
+// the vectorised kernels need 16-byte aligned rows of every fp32 operand (and whole words of packed codes)
+static bool wprep_vec_ok(int64_t cols, const void* a, const void* b, const void* c, const void* d, const void* codes, int /*pack4*/) {
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
+  return cols % 4 == 0 && al(a, 15) && al(b, 15) && al(c, 15) && al(d, 15) && al(codes, 3);
+}
+
 static int wprep_check(Ctx* c, const float* w, int64_t rows, int64_t cols, const float* col_fac, int col_mode,
                        const float* row_fac, int row_mode, mq_qcfg cfg) {
   MQ_REQUIRE(c, w && rows > 0 && cols > 0, "null pointer or empty weight");
@@ -605,11 +820,18 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
   LetArgs la{col_fac, row_fac, col_mode, row_mode};
   float* row_mn = reinterpret_cast<float*>(c->ws);
   float* row_mx = row_mn + rows;
-  wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+  const bool vec = wprep_vec_ok(cols, w, col_fac, w_fq, wt_out, codes, pack4);
+  if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+  else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
   if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
-  wprep_quant_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
-                                                     cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
-                                                     scale_out, offset_out, colsum, wt_out);
+  if (vec)
+    wprep_quant_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+                                                         cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
+                                                         scale_out, offset_out, colsum, wt_out);
+  else
+    wprep_quant_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+                                                       cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
+                                                       scale_out, offset_out, colsum, wt_out);
   return check_launch(c, "mq_wprep_fwd");
 }
 
@@ -637,18 +859,29 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   float* partial = reinterpret_cast<float*>(p);
   size_t partial_cap = (c->ws_bytes - size_t(p - reinterpret_cast<char*>(c->ws))) / sizeof(float);
 
-  wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+  const bool vec = wprep_vec_ok(cols, w, col_fac, g, g_wt, scratch, 0);
+  if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+  else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
   if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
-  wprep_bwd_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
-                                                         cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);
+  if (vec)
+    wprep_bwd_stats_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+                                                             cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);
+  else
+    wprep_bwd_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+                                                           cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);
   unsigned ggrid = per_channel ? (unsigned)((rows + 255) / 256) : 1u;
   wprep_bwd_group_kernel<<<ggrid, 256, 0, st>>>(row_mn, row_mx, sig_up, sig_low, per_channel, cfg.bitwidth,
                                                 cfg.is_symmetric, rows, row_gs, row_cmn, row_cmx, gg, g_sig_up,
                                                 g_sig_low);
   if (g_col_fac || g_row_fac || g_wt) {
-    wprep_bwd_apply_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
-                                                           per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
-                                                           g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
+    if (vec)
+      wprep_bwd_apply_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
+                                                               per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
+                                                               g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
+    else
+      wprep_bwd_apply_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
+                                                             per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
+                                                             g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
   }
   if (g_col_fac) {
     unsigned gx = (unsigned)((cols + 127) / 128);

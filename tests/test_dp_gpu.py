@@ -1,0 +1,98 @@
+"""Two-GPU NCCL checks of the sample-sharded calibration (skipped with fewer than two devices):
+  * act-range mode: ranges from 2 ranks x half the samples + one MAX all-reduce == single-GPU ranges, bit for bit
+  * LET/LWC/LRL mode: e2equant on 2 ranks (micro-batch 1 each, SUM all-reduce of the gradients) == single-GPU e2equant with
+    batch_size 2 (the MSE loss is a batch mean, alg:459,532-533), up to fp32 summation order."""
+import os, socket
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _model_and_samples(dev, n):
+    from mobilequant_b200.model import HFConfig, HFForCausalLM
+    torch.manual_seed(1337)
+    cfg = HFConfig(vocab_size=512, hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=4,
+                   num_key_value_heads=2, hidden_act="silu", use_cache=False, use_matmul_as_module=True, l2norm_as_rmsnorm=True)
+    model = HFForCausalLM(cfg).float().to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    samples = [torch.randint(3, 512, (1, 32), generator=g) for _ in range(n)]
+    return cfg, model, samples
+
+
+def _calibrate(model, act, samples, dev, out_dir, batch_size):
+    import types
+    from mobilequant_b200.quantization import qmodule as Q, algorithm as A
+
+    class _L:
+        def info(self, *a, **k):
+            pass
+    Q.create_sim_qmodel(model, Q.QuantConfig(bitwidth=8), Q.QuantConfig(bitwidth=8))
+    for p in model.parameters():
+        p.requires_grad = False
+    Q.update_quant_cfg(model)
+    Q.set_scale_and_offset(model, act, "parameter")
+    args = types.SimpleNamespace(nsamples=len(samples), seqlen=32, batch_size=batch_size, epochs=2, warmup_epochs=0, deactive_amp=True,
+                                 let=True, lwc=True, lrl=True, use_shift=False, aug_loss=False, let_lr=1e-3, lwc_lr=1e-2, lrl_lr=1e-6,
+                                 let_min_lr=1e-4, lwc_min_lr=1e-3, lrl_min_lr=1e-7, wd=0.0, resume=None, cache_in_gpu=True,
+                                 original_omniquant=False, dtype=torch.float32, output_dir=out_dir)
+    A.e2equant(args, model, [(s, None) for s in samples], _L(), device=dev)
+    return torch.load(os.path.join(out_dir, "parameters.pth"), weights_only=False)
+
+
+def _worker(rank, world, port, tmp, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from mobilequant_b200.ptq.generate_act_range import get_act_range
+        cfg, model, samples = _model_and_samples(dev, 8)
+        act = get_act_range(model, samples)                       # sharded: 4 samples per rank + MAX all-reduce
+        out = os.path.join(tmp, f"dp_rank{rank}")
+        os.makedirs(out, exist_ok=True)
+        learned = _calibrate(model, act, samples, dev, out, batch_size=1)   # data parallel, micro-batch 1 per rank
+        if rank == 0:
+            q.put((act, {i: {k: v.cpu() for k, v in d.items()} for i, d in learned.items()}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_calibration_matches_single_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    act_dp, learned_dp = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # single-GPU reference: all samples on one device, batch_size 2
+    from mobilequant_b200.ptq.generate_act_range import get_act_range
+    dev = torch.device("cuda:0")
+    cfg, model, samples = _model_and_samples(dev, 8)
+    act = get_act_range(model, samples)
+    assert act == act_dp                                           # bit-identical ranges
+    out = os.path.join(str(tmp_path), "single")
+    os.makedirs(out, exist_ok=True)
+    learned = _calibrate(model, act, samples, dev, out, batch_size=2)
+    assert learned.keys() == learned_dp.keys()
+    worst = 0.0
+    for i in learned:
+        assert learned[i].keys() == learned_dp[i].keys()
+        for k, ref in learned[i].items():
+            d = (learned_dp[i][k].float() - ref.cpu().float()).abs().max().item()
+            worst = max(worst, d / max(1.0, ref.abs().max().item()))
+    assert worst < 1e-4, worst
