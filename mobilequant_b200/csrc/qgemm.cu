@@ -29,9 +29,8 @@ constexpr int kBM = 128;          // UMMA M
 constexpr int kBN = 256;          // UMMA N
 constexpr int kBK = 128;          // bytes of K per stage == one 128B swizzle row
 constexpr int kUmmaK = 32;        // 8-bit operands: 32 elements per MMA
-constexpr int kNE = 8;            // epilogue warps (multiple of 4: one TMEM lane quarter each)
-constexpr int kThreads = 64 + kNE * 32;
-constexpr int kParts = kNE / 4;   // column parts per lane quarter
+// NE = epilogue warps (multiple of 4: one TMEM lane quarter each): 8 (32-column chunks) or 16 (16-column chunks so
+// that 576 threads fit the register file).
 
 enum { EPI_QUANT = 0, EPI_ACTMUL = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_I32 = 4 };
 enum { CP_NEGOW = 0, CP_C0, CP_SXW, CP_BIAS, CP_COUNT };
@@ -53,38 +52,52 @@ struct QGemmArgs {
   int32_t* rowsum_out;     // [M] atomically accumulated sum of the emitted codes (or null)
   const float* lut;        // [256] EPI_ACTMUL: act(w1 code) as fp32 (QSiLU/QGELU folded, qm:739-753)
   float s2, o2, qmax2;     // EPI_ACTMUL: w2.input_quantizer
+  int dbg;                 // measurement only (MQ_QGEMM_DBG): 1 = epilogue releases the accumulator without reading it
 };
 
-// PAIR: two CTAs of a cluster (one TPC) share a 256 x 256 output tile: each loads its own 128 A rows and HALF of the B
-// rows, one tcgen05.mma.cta_group::2 (M = 256) issued by the leader consumes both halves -> B traffic from L2 and the B
-// shared-memory footprint per CTA are halved, which buys two more pipeline stages.
-template <int MODE, bool PAIR>
+// CL = CTAs per cluster.
+// CL 2 (PAIR): two CTAs of a cluster (one TPC) share a 256 x 256 output tile: each loads its own 128 A rows and HALF of
+// the B rows, one tcgen05.mma.cta_group::2 (M = 256) issued by the leader consumes both halves -> B traffic from L2 and
+// the B shared-memory footprint per CTA are halved, which buys two more pipeline stages.
+// CL 4 (QUAD): two such pairs stacked along M (a 512 x 256 super-tile) read the SAME B tile: each CTA fetches only a
+// quarter of it (64 rows) and the TMA multicasts the box to the CTA of the other pair that needs the same half -> per
+// CTA and k-slice 16 KB of A + 8 KB of B leave the L2 instead of 16 + 32 (single) / 16 + 16 (pair).  At 128 MMA cycles
+// per 32 bytes of K the single-CTA kernel asks the L2 for 96 B/clk/SM, more than twice what it sustains chip-wide
+// (~43-50 B/clk/SM): the operand traffic, not the tensor pipe, was the ceiling of the first two variants.
+template <int MODE, int CL, int NE>
 struct SmemLayout {
+  static constexpr bool PAIR = CL >= 2;
+  static constexpr int kCW = NE == 16 ? 16 : 32;             // accumulator columns per tcgen05.ld / per staging tile
+  static constexpr int kOutTile = 32 * kCW * 4;              // RESID: one fp32 staging tile (32 rows x kCW columns)
   static constexpr int kStages = PAIR ? (MODE == EPI_RESID ? 4 : 6) : (MODE == EPI_RESID ? 3 : 4);
   static constexpr int kABytes = kBM * kBK;
-  static constexpr int kBRows = PAIR ? kBN / 2 : kBN;
+  static constexpr int kBRows = PAIR ? kBN / 2 : kBN;       // B rows resident per CTA
+  static constexpr int kBBoxRows = CL == 4 ? kBRows / 2 : kBRows;   // B rows per TMA box
   static constexpr int kBBytes = kBRows * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColpOff = kStages * kStageBytes;                 // 2 x CP_COUNT x 256 x 4 B
   static constexpr int kLutOff = kColpOff + 2 * CP_COUNT * kBN * 4;      // 256 floats
   static constexpr int kOutOff = kLutOff + 1024;                         // RESID: per-warp 32x32 fp32 staging tiles
-  static constexpr int kOutBufs = 16 / kNE;                              // staging tiles per warp
-  static constexpr int kOutBytes = MODE == EPI_RESID ? kNE * kOutBufs * 4096 : 0;
+  static constexpr int kOutBufs = 2;                                     // staging tiles per warp
+  static constexpr int kOutBytes = MODE == EPI_RESID ? NE * kOutBufs * kOutTile : 0;
   static constexpr int kBarOff = kOutOff + kOutBytes;
   static constexpr int kTotal = kBarOff + 256;
   static_assert(kOutOff % 1024 == 0, "staging tiles must keep the 128B-swizzle phase");
   static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
-template <int MODE, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int MODE, int CL, int NE>
+__global__ void __launch_bounds__(64 + NE * 32, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_r, const QGemmArgs p, const uint32_t idesc) {
-  using L = SmemLayout<MODE, PAIR>;
-  constexpr int kCtas = PAIR ? 2 : 1;
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs of the pair)
-  const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;         // persistent scheduling unit: a CTA or a CTA pair
-  const int num_units = PAIR ? gridDim.x >> 1 : gridDim.x;
+  using L = SmemLayout<MODE, CL, NE>;
+  constexpr bool PAIR = CL >= 2, QUAD = CL == 4;
+  constexpr int kNE = NE, kParts = NE / 4, CW = L::kCW;        // kParts = column parts per TMEM lane quarter
+  constexpr int kCtas = CL;                                     // CTAs (128-row blocks) per scheduling unit
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // rank in the cluster; even ranks lead their pair
+  const uint32_t pair_rank = cta_rank & 1u, pair_id = cta_rank >> 1;
+  const int unit = blockIdx.x / CL;                             // persistent scheduling unit: a CTA, a pair or two pairs
+  const int num_units = gridDim.x / CL;
   constexpr int BN = kBN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -107,8 +120,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (MODE == EPI_RESID) prefetch_tmap(&tmap_r);
-    for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE * kCtas); }
+    // QUAD: a stage is free once BOTH pairs have retired the MMAs that read it (the B quarters are written across pairs)
+    for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], QUAD ? 2 : 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE * (PAIR ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
@@ -126,14 +140,18 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = unit; t < num_tiles; t += num_units) {
-        const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + cta_rank * L::kBRows;
+        const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + pair_rank * L::kBRows;
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
-            // the leader's barrier collects the bytes of both CTAs
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            // the pair leader's barrier collects the bytes of both CTAs
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
             tma_load_2d_pair(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
-            tma_load_2d_pair(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+            if (QUAD)   // this CTA's quarter of the B tile, delivered to the same half of both pairs
+              tma_load_2d_pair_mc(smem_b + stage * L::kBBytes + pair_id * (L::kBBoxRows * kBK), &tmap_b, &full_bar[stage], k * kBK,
+                                  n0 + pair_id * L::kBBoxRows, (uint16_t)(0x5u << pair_rank));
+            else
+              tma_load_2d_pair(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
           } else {
             mbar_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
@@ -143,8 +161,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && cta_rank == 0) {
+  } else if (warp == 1 && pair_rank == 0) {
     // ===================== MMA issuer (the leader CTA of a pair) =====================
+    const uint16_t pair_mask = (uint16_t)(0x3u << (2 * pair_id)), all_mask = (uint16_t)((1u << CL) - 1u);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
@@ -164,8 +183,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             else mma_i8(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc, (k | kk) != 0);
           }
           if (PAIR) {
-            tc_commit_pair(&empty_bar[stage]);                      // smem slot free in both CTAs once these MMAs retire
-            if (k == k_iters - 1) tc_commit_pair(&tfull_bar[acc]);  // accumulator complete (both halves)
+            tc_commit_pair(&empty_bar[stage], all_mask);                       // smem slot free once these MMAs retire
+            if (k == k_iters - 1) tc_commit_pair(&tfull_bar[acc], pair_mask);  // accumulator complete (both halves)
           } else {
             tc_commit(&empty_bar[stage]);
             if (k == k_iters - 1) tc_commit(&tfull_bar[acc]);
@@ -183,7 +202,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int part = ew >> 2;                // column part
     const int etid = threadIdx.x - 64;
     const bool has_bias = p.bias != nullptr;
-    uint8_t* stage_out = smem + L::kOutOff + ew * L::kOutBufs * 4096;
+    uint8_t* stage_out = smem + L::kOutOff + ew * L::kOutBufs * L::kOutTile;
     int out_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = unit; t < num_tiles; t += num_units) {
@@ -204,7 +223,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       tc_fence_after();
 
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < p.M && p.dbg != 1;
+      if (p.dbg == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR && pair_rank != 0) mbar_arrive_remote(&tempty_bar[acc], cta_rank & ~1u); else mbar_arrive(&tempty_bar[acc]); }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int rs = row_ok ? __ldg(p.rowsum + row) : 0;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int4* v_negow = reinterpret_cast<const int4*>(cpi + CP_NEGOW * BN);
@@ -242,14 +268,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const QParam q2 = make_qparam(p.s2, p.o2, p.qmax2);
         dispatch_five(q1.five | q2.five | q3.five, [&](auto five_tag) {
         constexpr bool FIVE = decltype(five_tag)::value;
-        for (int cc = part * (H / kParts); cc < (part + 1) * (H / kParts); cc += 32) {
-          uint32_t r1[32], r3[32];
-          tmem_ld32(trow + cc, r1);
-          tmem_ld32(trow + H + cc, r3);
+        for (int cc = part * (H / kParts); cc < (part + 1) * (H / kParts); cc += CW) {
+          uint32_t r1[CW], r3[CW];
+          tmem_ld(trow + cc, r1);
+          tmem_ld(trow + H + cc, r3);
           tc_wait_ld();
-          uint32_t packed[8];
+          uint32_t packed[CW / 4];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < CW / 4; ++j4) {
             float y1[4], y3[4];
             y4(r1 + 4 * j4, cc + 4 * j4, y1);
             y4(r3 + 4 * j4, H + cc + 4 * j4, y3);
@@ -266,11 +292,12 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const int ncol = n0 / 2 + cc;       // output column (N/2 wide)
           if (row_ok) {
             uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + int64_t(row) * p.ldo + ncol;
-            if (ncol + 32 <= p.N / 2 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-              reinterpret_cast<uint4*>(dst)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              reinterpret_cast<uint4*>(dst)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            if (ncol + CW <= p.N / 2 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int v = 0; v < CW / 16; ++v)
+                reinterpret_cast<uint4*>(dst)[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
             } else {
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < CW; ++j)
                 if (ncol + j < p.N / 2) dst[j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
             }
           }
@@ -278,72 +305,77 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         });
       } else {
         constexpr int W = BN / kParts;
-        for (int cc = part * W; cc < (part + 1) * W; cc += 32) {
+        for (int cc = part * W; cc < (part + 1) * W; cc += CW) {
           if (n0 + cc >= p.N) break;
-          uint32_t r[32];
-          tmem_ld32(trow + cc, r);
+          uint32_t r[CW];
+          tmem_ld(trow + cc, r);
           tc_wait_ld();
           const int ncol = n0 + cc;
-          const bool full = (ncol + 32 <= p.N);
+          const bool full = (ncol + CW <= p.N);
           if (MODE == EPI_QUANT) {
             const QParam q = group_q(cc, p.qmax);
-            uint32_t code[32];
+            uint32_t code[CW];
             dispatch_five(q.five, [&](auto five_tag) {
               constexpr bool FIVE = decltype(five_tag)::value;
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
+              for (int j4 = 0; j4 < CW / 4; ++j4) {
                 float y[4];
                 y4(r + 4 * j4, cc + 4 * j4, y);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  code[4 * j4 + e] = (uint32_t)quant_int<FIVE>(y[e], q);
-                  if (full || ncol + 4 * j4 + e < p.N) code_sum += (int)code[4 * j4 + e];
-                }
+                for (int e = 0; e < 4; ++e) code[4 * j4 + e] = (uint32_t)quant_int<FIVE>(y[e], q);
               }
             });
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) code_sum += (int)code[j];
+            } else {
+              for (int j = 0; j < CW; ++j) if (ncol + j < p.N) code_sum += (int)code[j];
+            }
             if (row_ok) {
               if (p.out_bits == 8) {
                 uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + int64_t(row) * p.ldo + ncol;
                 if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                  uint32_t w[8];
+                  uint32_t w[CW / 4];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) w[j] = code[4 * j] | (code[4 * j + 1] << 8) | (code[4 * j + 2] << 16) | (code[4 * j + 3] << 24);
-                  reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                  reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                  for (int j = 0; j < CW / 4; ++j) w[j] = code[4 * j] | (code[4 * j + 1] << 8) | (code[4 * j + 2] << 16) | (code[4 * j + 3] << 24);
+#pragma unroll
+                  for (int v = 0; v < CW / 16; ++v) reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
                 } else {
-                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint8_t)code[j];
+                  for (int j = 0; j < CW; ++j) if (ncol + j < p.N) dst[j] = (uint8_t)code[j];
                 }
               } else {
                 uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + int64_t(row) * p.ldo + ncol;
                 if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                  for (int v = 0; v < 4; ++v) {
+                  for (int v = 0; v < CW / 8; ++v) {
                     uint32_t w[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) w[j] = code[8 * v + 2 * j] | (code[8 * v + 2 * j + 1] << 16);
                     reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[0], w[1], w[2], w[3]);
                   }
                 } else {
-                  for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = (uint16_t)code[j];
+                  for (int j = 0; j < CW; ++j) if (ncol + j < p.N) dst[j] = (uint16_t)code[j];
                 }
               }
             }
           } else if (MODE == EPI_RESID) {
             // de-quantised output-quantizer values (hm:1257,1270 add them to the fp32 stream) -> swizzled smem tile ->
-            // TMA reduce-add.  Row r of the tile is 128 B; its 16-byte chunk c lives at chunk (c ^ (r & 7)).
+            // TMA reduce-add.  CW 32: row r of the tile is 128 B, its 16-byte chunk c lives at chunk (c ^ (r & 7))
+            // (SWIZZLE_128B); CW 16: rows of 64 B, chunk (c ^ ((r >> 1) & 3)) (SWIZZLE_64B).
             const QParam q = group_q(cc, p.qmax);
-            uint8_t* tile = stage_out + out_buf * 4096;
+            uint8_t* tile = stage_out + out_buf * L::kOutTile;
             if (lane == 0) bulk_wait_read<L::kOutBufs - 1>();      // the tile's previous reduce has been read out
             __syncwarp();
             dispatch_five(q.five, [&](auto five_tag) {
               constexpr bool FIVE = decltype(five_tag)::value;
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
+              for (int j4 = 0; j4 < CW / 4; ++j4) {
                 float y[4], v[4];
                 y4(r + 4 * j4, cc + 4 * j4, y);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v[e] = __fmul_rn(__fsub_rn(quant_magic<FIVE>(y[e], q), kRoundMagic), q.s);
-                *reinterpret_cast<float4*>(tile + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                const int sw = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+                *reinterpret_cast<float4*>(tile + lane * (CW * 4) + ((j4 ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
               }
             });
             fence_proxy_async();
@@ -354,9 +386,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
             if (++out_buf == L::kOutBufs) out_buf = 0;
           } else {   // EPI_F32 / EPI_I32
-            float y[32];
+            float y[CW];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < CW / 4; ++j4) {
               float yy[4];
               y4(r + 4 * j4, cc + 4 * j4, yy);
               y[4 * j4] = yy[0]; y[4 * j4 + 1] = yy[1]; y[4 * j4 + 2] = yy[2]; y[4 * j4 + 3] = yy[3];
@@ -365,10 +397,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               float* dst = reinterpret_cast<float*>(p.out) + int64_t(row) * p.ldo + ncol;
               if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
+                for (int v = 0; v < CW / 4; ++v)
                   reinterpret_cast<float4*>(dst)[v] = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
               } else {
-                for (int j = 0; j < 32; ++j) if (ncol + j < p.N) dst[j] = y[j];
+                for (int j = 0; j < CW; ++j) if (ncol + j < p.N) dst[j] = y[j];
               }
             }
           }
@@ -378,7 +410,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       // release the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (PAIR && cta_rank != 0) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+      if (lane == 0) { if (PAIR && pair_rank != 0) mbar_arrive_remote(&tempty_bar[acc], cta_rank & ~1u); else mbar_arrive(&tempty_bar[acc]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (MODE == EPI_RESID && lane == 0) bulk_wait<0>();      // all reduce-adds have landed before the grid retires
@@ -406,67 +438,102 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D row-major matrix [rows, cols] of `esize`-byte elements (cols contiguous, row pitch `pitch_bytes`), box = 128 bytes x
-// box_rows, 128B swizzle
+// 2D row-major matrix [rows, cols] of `esize`-byte elements (cols contiguous, row pitch `pitch_bytes`), box = box_bytes
+// (128 or 64) x box_rows, swizzle span == box width
 static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
-                         int64_t pitch_bytes, int box_rows) {
+                         int64_t pitch_bytes, int box_rows, int box_bytes = 128) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)pitch_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   return enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, int CL, int NE>
 static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
                          cudaStream_t st) {
-  using L = SmemLayout<MODE, PAIR>;
+  using L = SmemLayout<MODE, CL, NE>;
+  constexpr bool PAIR = CL >= 2;
+  constexpr int kThreads = 64 + NE * 32;
   CUtensorMap ta, tb, tr;
   if (!make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a, args.M, args.K, args.K, kBM) ||
-      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBRows))
+      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBBoxRows))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
   tr = ta;
-  if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32))
+  if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32, L::kCW * 4))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the residual stream (16B-aligned pointer, ldo % 4 == 0)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+  static int max_units = -1;                    // co-resident clusters of this variant (GPC boundaries can cost a few)
+  if (max_units < 0) {
+    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
+    if (CL > 2 && (e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess)
+      return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute(cluster): ") + cudaGetErrorString(e));
+    max_units = c->sm_count / CL;
+    if (PAIR) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(c->sm_count / CL * CL); q.blockDim = dim3(kThreads); q.dynamicSmemBytes = L::kTotal;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, qgemm_kernel<MODE, CL, NE>, &q) == cudaSuccess && n > 0 && n < max_units) max_units = n;
+      cudaGetLastError();
+    }
   }
-  constexpr int kCtas = PAIR ? 2 : 1;
-  const int m_tiles = (args.M + kCtas * kBM - 1) / (kCtas * kBM), n_tiles = (args.N + kBN - 1) / kBN;
+  const int m_tiles = (args.M + CL * kBM - 1) / (CL * kBM), n_tiles = (args.N + kBN - 1) / kBN;
   int units = m_tiles * n_tiles;
-  if (units > c->sm_count / kCtas) units = c->sm_count / kCtas;
-  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, kCtas * kBM, kBN);
+  if (units > max_units) units = max_units;
+  const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, (PAIR ? 2 : 1) * kBM, kBN);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(units * kCtas); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
+  cfg.gridDim = dim3(units * CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = PAIR ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, PAIR>, ta, tb, tr, args, idesc);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, CL, NE>, ta, tb, tr, args, idesc);
   if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemm launch: ") + cudaGetErrorString(e));
   return check_launch(c, "mq_qgemm");
 }
 
-// Kernel choice (measured on B200, profiles/r1_qgemm_variants.md): with K = 2048 the epilogue, not the operand traffic,
-// paces a tile and both variants tie; from K = 5632 the CTA-pair kernel is 8-15 % faster (2.8-3.0 POP/s at K = 8192,
-// above the cuBLASLt int8 proxy).  MQ_QGEMM_PAIR=0/1 forces one variant (A/B measurements).
-static bool use_pair(int K) {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("MQ_QGEMM_PAIR"); v = !e ? -1 : (e[0] == '0' ? 0 : 1); }
-  return v >= 0 ? v == 1 : K >= 4096;
+// Kernel choice (measured on B200, profiles/r1_qgemm_variants.md): the operand traffic from L2 is the ceiling of the
+// single-CTA kernel; the CTA-pair kernel halves the B traffic, the two-pair cluster with B multicast halves it again.
+// MQ_QGEMM_CL=1/2/4 forces one variant (A/B measurements; read per call); MQ_QGEMM_PAIR=0/1 is the older spelling.
+static int pick_cluster(int M, int K) {
+  const char* e = getenv("MQ_QGEMM_CL");
+  if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) return e[0] - '0';
+  e = getenv("MQ_QGEMM_PAIR");
+  if (e) return e[0] == '0' ? 1 : 2;
+  (void)M;
+  return K >= 4096 ? 2 : 1;
 }
 
+// MQ_QGEMM_NE=8/16 picks the number of epilogue warps (A/B measurements; read per call).  Measured on B200
+// (profiles/r1d_qgemm_variants.md): 16 warps do not shorten the tile -- under a sustained load the GEMM runs into the
+// 1000 W power cap (SM clock 1.1-1.6 GHz), not into epilogue latency -- so 8 stays the default.
+static int pick_epi_warps() {
+  const char* e = getenv("MQ_QGEMM_NE");
+  return (e && e[0] == '1') ? 16 : 8;
+}
+
+template <int MODE, int NE>
+static int launch_qgemm1(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
+                         cudaStream_t st) {
+  switch (pick_cluster(args.M, args.K)) {
+    case 4: return launch_qgemm2<MODE, 4, NE>(c, a, b, args, resid, a_signed, b_signed, st);
+    case 2: return launch_qgemm2<MODE, 2, NE>(c, a, b, args, resid, a_signed, b_signed, st);
+    default: return launch_qgemm2<MODE, 1, NE>(c, a, b, args, resid, a_signed, b_signed, st);
+  }
+}
 template <int MODE>
 static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
                         cudaStream_t st) {
-  return use_pair(args.K) ? launch_qgemm2<MODE, true>(c, a, b, args, resid, a_signed, b_signed, st)
-                    : launch_qgemm2<MODE, false>(c, a, b, args, resid, a_signed, b_signed, st);
+  return pick_epi_warps() == 8 ? launch_qgemm1<MODE, 8>(c, a, b, args, resid, a_signed, b_signed, st)
+                               : launch_qgemm1<MODE, 16>(c, a, b, args, resid, a_signed, b_signed, st);
 }
 
 }  // namespace mq
@@ -496,6 +563,7 @@ extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void
   QGemmArgs args;
   args.M = M; args.N = N; args.K = K; args.rowsum = rowsum; args.sxw = sxw; args.ow = ow; args.c0 = c0;
   args.bias = bias; args.so = so; args.oo = oo; args.qmax = qmax; args.out_bits = out_bits; args.out = out; args.ldo = ldo;
+  { const char* e = getenv("MQ_QGEMM_DBG"); args.dbg = e ? atoi(e) : 0; }
   args.qgroup = qgroup > 0 ? qgroup : 32; args.rowsum_out = rowsum_out; args.lut = lut; args.s2 = s2; args.o2 = o2; args.qmax2 = qmax2;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {

@@ -1,4 +1,4 @@
-import sys, torch, time
+import os, sys, torch, time
 sys.path.insert(0, "/root/repo")
 from mobilequant_b200 import kernels as Kn
 cuda = torch.device("cuda:0")
@@ -21,9 +21,13 @@ def run(M, N, K, mode=Kn.EPI_QUANT, iters=20):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f"M={M} N={N} K={K} mode={mode}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TOP/s")
-for M in (8192, 32768):
-    run(M, 2560, 2048); run(M, 2048, 2048, Kn.EPI_RESID); run(M, 11264, 2048, Kn.EPI_ACTMUL); run(M, 2048, 5632, Kn.EPI_RESID)
-    run(M, 8192, 8192, Kn.EPI_I32)
+for spec in (sys.argv[1:] or ["1/8", "1/16", "2/8", "2/16", "4/16"]):
+    cl, ne = spec.split("/")
+    os.environ["MQ_QGEMM_CL"] = cl; os.environ["MQ_QGEMM_NE"] = ne
+    print("== cluster", cl, "epilogue warps", ne, flush=True)
+    for M in (8192,):
+        run(M, 2560, 2048); run(M, 2048, 2048, Kn.EPI_RESID); run(M, 11264, 2048, Kn.EPI_ACTMUL); run(M, 2048, 5632, Kn.EPI_RESID)
+        run(M, 8192, 8192, Kn.EPI_I32)
 # library proxy for the INT8 peak
 a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=cuda); b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=cuda)
 for _ in range(3): torch._int_mm(a, b.t())

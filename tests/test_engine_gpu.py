@@ -45,9 +45,17 @@ def test_qrope(cuda, B, T, nh, nkv, hd, rot):
     assert np.array_equal(out["rsk"].cpu().numpy().astype(np.int64), k.sum(-1))
 
 
-@pytest.mark.parametrize("B,T,nh,nkv,hd", [(1, 64, 2, 1, 64), (2, 100, 4, 2, 32), (1, 200, 4, 4, 64), (1, 130, 2, 1, 128), (1, 96, 2, 1, 256)])
-def test_qattn(cuda, B, T, nh, nkv, hd):
+@pytest.mark.parametrize("impl", ["codes-in-smem", "3pass"])
+@pytest.mark.parametrize("B,T,nh,nkv,hd", [(1, 64, 2, 1, 64), (2, 100, 4, 2, 32), (1, 200, 4, 4, 64), (1, 130, 2, 1, 128), (1, 96, 2, 1, 256),
+                                           (1, 1, 2, 2, 64), (1, 33, 2, 1, 64), (1, 520, 2, 1, 64), (1, 391, 1, 1, 256)])
+def test_qattn(cuda, B, T, nh, nkv, hd, impl, monkeypatch):
+    """Both attention kernels (single-QK-pass with the score codes parked in shared memory; streaming three-pass
+    fallback for long sequences) against the integer oracle: ragged T, T = 1, multi-stage T, GQA, every head dim."""
     from mobilequant_b200 import kernels as K
+    if impl == "3pass":
+        monkeypatch.setenv("MQB200_QATTN", "3pass")
+    else:
+        monkeypatch.delenv("MQB200_QATTN", raising=False)
     rng = np.random.default_rng(T * hd)
     q = rng.integers(0, 256, size=(B, nh, T, hd)).astype(np.uint8)
     k = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)

@@ -106,3 +106,43 @@ def test_qgemm_actmul_epilogue(cuda):
                    s2=float(s2), o2=float(o2), qmax2=255, rowsum_out=rs_out)
     assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
     assert np.array_equal(rs_out.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+@pytest.mark.parametrize("ne", [8, 16])
+@pytest.mark.parametrize("cl", [1, 2, 4])
+@pytest.mark.parametrize("M,N,K", [(100, 96, 352), (1300, 1280, 2048), (2048, 512, 5632)])
+def test_qgemm_cluster_variants(cuda, cl, ne, M, N, K, monkeypatch):
+    """Every shape of the kernel (single CTA, CTA pair, two pairs with multicast B; 8 or 16 epilogue warps) gives the
+    same exact integers, raw and through each fused epilogue; the small shape is checked against the oracle directly."""
+    from mobilequant_b200 import kernels as Kn
+    a, b, ox, ow, sx, sw = _prep(M, N, K, M + N + K + 5, per_channel=True)
+    ta, tb, rowsum, sxw, tow, c0 = _dev(a, b, ox, ow, sx, sw, K, cuda)
+    G = (N + 127) // 128
+    so = torch.full((G,), 0.02, device=cuda); oo = torch.full((G,), 128.0, device=cuda)
+    lut = torch.randn(256, generator=torch.Generator().manual_seed(1)).to(cuda)
+    h0 = torch.randn(M, N, generator=torch.Generator().manual_seed(2)).to(cuda)
+
+    def run_all():
+        outs = [Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_I32)]
+        rs = torch.zeros(M, dtype=torch.int32, device=cuda)
+        outs.append(Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_QUANT, so=so, oo=oo, qgroup=128, qmax=255, out_bits=8, rowsum_out=rs))
+        outs.append(rs)
+        h = h0.clone()
+        Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_RESID, so=so[:1], oo=oo[:1], qgroup=128 * G, qmax=65535, resid=h)
+        outs.append(h)
+        if N % 256 == 0:
+            outs.append(Kn.qgemm(ta, tb, rowsum, sxw, tow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qgroup=128, qmax=255, lut=lut,
+                                 s2=0.01, o2=128.0, qmax2=255))
+        torch.cuda.synchronize()
+        return outs
+
+    monkeypatch.delenv("MQ_QGEMM_CL", raising=False)
+    monkeypatch.delenv("MQ_QGEMM_NE", raising=False)
+    base = run_all()
+    if M <= 128:
+        assert np.array_equal(base[0].cpu().numpy().astype(np.int64), ir.int_acc(a, b, ox, ow))
+    monkeypatch.setenv("MQ_QGEMM_CL", str(cl))
+    monkeypatch.setenv("MQ_QGEMM_NE", str(ne))
+    got = run_all()
+    for x, y in zip(base, got):
+        assert torch.equal(x, y)
