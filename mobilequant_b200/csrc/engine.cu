@@ -5,6 +5,7 @@
 #include <string>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 namespace mq {
 
@@ -573,11 +574,15 @@ __global__ void __launch_bounds__(128, (HD <= 64 ? 4 : 2)) qattn_kernel(const At
 // slab, and the four key-split warps of a row group combine max / sum / P.V partials through shared memory.
 // K rows are written to shared memory in the order that makes the QK^T accumulator fragment of a thread hold keys
 // 4t..4t+3 (the A-fragment slots of the P.V MMA), so V fragments are plain 32-bit loads of the natural vT layout.
-// The two exp tables are replicated 8x across banks (lane & 7 picks the copy): random-index LUT reads were the LSU
-// hot spot of the three-pass kernel.
+// The two exp tables are replicated 4x / 8x across banks (lane & 3 / lane & 7 picks the copy): random-index LUT reads
+// were the LSU hot spot of the three-pass kernel.  CTAs are persistent (tables filled once) and walk the work items
+// round-robin, heaviest query tiles first; K/V stages go through a three-buffer cp.async ring with one barrier each.
 // =====================================================================================================================
 constexpr int kA4Stage = 128;     // keys per staged tile
-constexpr int kA4Rep = 8;         // bank replication of the exp tables
+constexpr int kA4RepA = 4;        // bank replication of the exp tables: A (index k >> 8), 16 B per entry
+constexpr int kA4RepB = 8;        //                                     B (index k & 255), 32 B per entry
+constexpr int kA4TabBytes = 256 * (kA4RepA + kA4RepB) * 4;
+constexpr int kA4Bufs = 3;        // staged-tile ring depth (one barrier per stage)
 
 template <int HD, int DV>
 __host__ __device__ constexpr int a4_stage_bytes() {
@@ -588,64 +593,48 @@ __host__ __device__ constexpr int a4_red_bytes() { return 8 * 32 * (DV / 2) * 4;
 template <int HD, int DV>
 static size_t a4_smem_bytes(int cpw) {
   const size_t region0 = std::max<size_t>(size_t(8) * cpw * 1024, a4_red_bytes<DV>());
-  return region0 + 2 * size_t(a4_stage_bytes<HD, DV>()) + 2 * kA4Stage * 4 + 512 * kA4Rep * 4 + 128 * 4 + 128 * 8 + 32 * 4;
+  return region0 + kA4Bufs * size_t(a4_stage_bytes<HD, DV>()) + kA4Bufs * kA4Stage * 4 + kA4TabBytes + 128 * 4 + 128 * 8 + 32 * 4;
 }
 
 template <int HD, int DV, bool FIVE>
-__global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const AttnArgs a, const int cpw) {
+__global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const AttnArgs a, const int cpw, const int n_items) {
   constexpr int ST = kA4Stage;
   constexpr int KSTR = HD + 16;               // padded row strides (bank-conflict free fragment loads)
   constexpr int VSTR = ST + 16;
   constexpr int STAGE = a4_stage_bytes<HD, DV>();
   constexpr int NCH = HD / DV;
   constexpr int NDN = DV / 8;                 // output n-tiles per warp
+  constexpr int CPR = HD / 16;                // 16-byte chunks per K row
+  constexpr int NKL = ST * CPR / 256;         // K cp.async per thread and stage
+  constexpr int NVL = DV * (ST / 16) / 256;   // V cp.async per thread and stage
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int code_bytes = 8 * cpw * 1024;
   const int region0 = code_bytes > a4_red_bytes<DV>() ? code_bytes : a4_red_bytes<DV>();
   uint4* s_codes = reinterpret_cast<uint4*>(smem_attn);                    // [8 warps][cpw][2 rows][32 lanes] uint4
   int* s_red = reinterpret_cast<int*>(smem_attn);                          // aliases the codes after pass C
-  uint8_t* s_stage = smem_attn + region0;                                  // [2][STAGE]
-  int* s_rsk = reinterpret_cast<int*>(s_stage + 2 * STAGE);                // [2][ST]
-  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_rsk + 2 * ST);           // [512][kA4Rep]
-  int* s_xi = reinterpret_cast<int*>(s_tab + 512 * kA4Rep);                // [2 rg][4 w][16 rows]
+  uint8_t* s_stage = smem_attn + region0;                                  // [kA4Bufs][STAGE]
+  int* s_rsk = reinterpret_cast<int*>(s_stage + kA4Bufs * STAGE);          // [kA4Bufs][ST]
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_rsk + kA4Bufs * ST);     // A [256][kA4RepA] then B [256][kA4RepB]
+  int* s_xi = reinterpret_cast<int*>(s_tab + kA4TabBytes / 4);             // [2 rg][4 w][16 rows]
   unsigned long long* s_xs = reinterpret_cast<unsigned long long*>(s_xi + 128);   // [2][4][16]
   int* s_cs = reinterpret_cast<int*>(s_xs + 128);                          // [2][16]
 
-  const int d0 = (blockIdx.x % NCH) * DV;
-  const int qt = (gridDim.x / NCH) - 1 - (blockIdx.x / NCH);   // heavy (late) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int kvh = h / (a.nh / a.nkv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const int rg = warp >> 2, w = warp & 3;
-  const int q0 = qt * 32;
-  const uint8_t* qbase = a.q + ((int64_t(b) * a.nh + h) * a.T) * HD;
-  const uint8_t* kbase = a.k + ((int64_t(b) * a.nkv + kvh) * a.T) * HD;
-  const uint8_t* vbase = a.vt + ((int64_t(b) * a.nkv + kvh) * HD + d0) * a.T;
-  const int32_t* rskb = a.rsk + (int64_t(b) * a.nkv + kvh) * a.T;
   const bool v_aligned = (a.T & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.vt) & 15) == 0);
-  const int key_end = min(a.T, q0 + 32);                       // keys this CTA ever needs
-  const int n_st = (qt + 1 + 3) >> 2;                          // stages of 4 chunks; chunk qt is the diagonal one
+  const int nqt = (a.T + 31) >> 5;
+  const int per_qt = a.B * a.nh * NCH;        // work items of one query-tile row, heavy (late) tiles first
 
-  for (int i = threadIdx.x; i < 512 * kA4Rep; i += 256) s_tab[i] = __ldg(a.lut + i / kA4Rep);
-  if (threadIdx.x < 32) s_cs[threadIdx.x] = 0;
-  const uint8_t* tabA = reinterpret_cast<const uint8_t*>(s_tab) + (lane & (kA4Rep - 1)) * 4;
-  const uint8_t* tabB = tabA + 256 * kA4Rep * 4;
-
-  // ---- Q fragments of this row group's 16 rows, straight from global (rows beyond T read as zero)
-  uint32_t qa[HD / 32][4];
-  const int qi_lo = q0 + rg * 16 + g, qi_hi = qi_lo + 8;       // absolute query positions of this thread's two rows
-#pragma unroll
-  for (int ks = 0; ks < HD / 32; ++ks) {
-    qa[ks][0] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 4 * t4)) : 0u;
-    qa[ks][1] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 4 * t4)) : 0u;
-    qa[ks][2] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
-    qa[ks][3] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
+  // ---- once per CTA: the two exp tables, entries replicated across banks (lane & 3 / lane & 7 picks the copy)
+  static_assert(kA4RepA == 4 && kA4RepB == 8, "table fill writes one / two uint4 per entry");
+  {
+    const uint32_t va = __ldg(a.lut + threadIdx.x), vb = __ldg(a.lut + 256 + threadIdx.x);
+    reinterpret_cast<uint4*>(s_tab)[threadIdx.x] = make_uint4(va, va, va, va);
+    reinterpret_cast<uint4*>(s_tab)[256 + 2 * threadIdx.x] = make_uint4(vb, vb, vb, vb);
+    reinterpret_cast<uint4*>(s_tab)[256 + 2 * threadIdx.x + 1] = make_uint4(vb, vb, vb, vb);
   }
-  const int32_t* rsqb = a.rsq + (int64_t(b) * a.nh + h) * a.T;
-  const int ioq = (int)a.oq, iok = (int)a.ok, iov = (int)a.ov;
-  // I = acc - iok*rsq - ioq*rsk + HD*ioq*iok = acc + colc[key] + rc[row]
-  const int rc_lo = HD * ioq * iok - iok * (qi_lo < a.T ? __ldg(rsqb + qi_lo) : 0);
-  const int rc_hi = HD * ioq * iok - iok * (qi_hi < a.T ? __ldg(rsqb + qi_hi) : 0);
+  const uint8_t* tabA = reinterpret_cast<const uint8_t*>(s_tab) + (lane & (kA4RepA - 1)) * 4;
+  const uint8_t* tabB = reinterpret_cast<const uint8_t*>(s_tab) + 256 * kA4RepA * 4 + (lane & (kA4RepB - 1)) * 4;
 
   // shared-memory row of key kk (0..127 within a stage): accumulator column (nt, j) of a 32-key chunk holds key
   // 16*(nt>>1) + 4*(j>>1) + 2*(nt&1) + (j&1), i.e. thread t4 (columns 2t4, 2t4+1) owns keys 4t4..4t4+3 of each half
@@ -654,55 +643,34 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
     const int nt = 2 * ((kk >> 4) & 1) + ((r >> 1) & 1), j = 2 * (r >> 2) + (r & 1);
     return (kk & ~31) + nt * 8 + j;
   };
-  auto issue_k = [&](int s, int buf) {
-    uint8_t* skb = s_stage + buf * STAGE;
-    for (int i = threadIdx.x; i < ST * (HD / 16); i += 256) {
-      const int kk = i / (HD / 16), c = i % (HD / 16);
-      const int key = s * ST + kk;
-      const bool ok = key < key_end;
-      cp_async16(skb + krow(kk) * KSTR + c * 16, kbase + int64_t(ok ? key : 0) * HD + c * 16, ok);
-    }
-    if (threadIdx.x < ST) {
-      const int key = s * ST + threadIdx.x;
-      const bool ok = key < key_end;
-      cp_async4(s_rsk + buf * ST + krow(threadIdx.x), rskb + (ok ? key : 0), ok);
-    }
-    cp_async_commit();
-  };
-  auto issue_v = [&](int s, int buf) {
-    uint8_t* svb = s_stage + buf * STAGE;
-    const int k0 = s * ST;
-    for (int i = threadIdx.x; i < DV * (ST / 16); i += 256) {
-      const int d = i / (ST / 16), c = i % (ST / 16);
-      const uint8_t* src = vbase + int64_t(d) * a.T + k0 + c * 16;
-      if (v_aligned) {
-        const bool ok = k0 + c * 16 + 16 <= a.T;
-        cp_async16(svb + d * VSTR + c * 16, ok ? src : vbase, ok);
-      } else {
-        uint8_t tmp[16];
-        for (int j = 0; j < 16; ++j) tmp[j] = (k0 + c * 16 + j < a.T) ? src[j] : 0;
-        *reinterpret_cast<uint4*>(svb + d * VSTR + c * 16) = *reinterpret_cast<uint4*>(tmp);
-      }
-    }
-    cp_async_commit();
-  };
+  // per-thread copy descriptors (stage independent): K chunk l moves key kk_l, 16-byte column kc; V chunk l row vd_l
+  const int kc = threadIdx.x % CPR;
+  int k_kk[NKL], k_dst[NKL];
+#pragma unroll
+  for (int l = 0; l < NKL; ++l) {
+    k_kk[l] = threadIdx.x / CPR + l * (256 / CPR);
+    k_dst[l] = krow(k_kk[l]) * KSTR + kc * 16;
+  }
+  const int rsk_dst = krow(threadIdx.x & (ST - 1));
+  const int vc = threadIdx.x & 7, vd0 = threadIdx.x >> 3;
 
   const QParam qs = make_qparam(a.s_s, a.o_s, a.qmax_s);
   const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
   const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
+  const int ioq = (int)a.oq, iok = (int)a.ok, iov = (int)a.ov;
   // E(k) = (A[k >> 8] * B[k & 255]) >> 31; indices are masked so that discarded (masked) lanes stay in range
   auto exp_tab = [&](int k) -> uint32_t {
-    const uint32_t ea = *reinterpret_cast<const uint32_t*>(tabA + (((uint32_t)k >> 8 & 255u) * (kA4Rep * 4)));
-    const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + (((uint32_t)k & 255u) * (kA4Rep * 4)));
+    const uint32_t ea = *reinterpret_cast<const uint32_t*>(tabA + (((uint32_t)k >> 8 & 255u) * (kA4RepA * 4)));
+    const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + (((uint32_t)k & 255u) * (kA4RepB * 4)));
     return (uint32_t)(((unsigned long long)ea * eb) >> 31);
   };
   // both codes of a packed word at once: kk = (cm | cm << 16) - word holds the two 16-bit differences (no borrow: every
-  // code of a fully visible chunk is <= its row maximum); each table index is one shift + one mask (32 B per entry)
-  static_assert(kA4Rep * 4 == 32, "exp_pair assumes 32-byte table entries");
+  // code of a fully visible chunk is <= its row maximum); each table index is one shift + one mask (16 / 32 B entries)
+  static_assert(kA4RepA * 4 == 16 && kA4RepB * 4 == 32, "exp_pair hard-codes the table entry sizes");
   auto exp_pair = [&](uint32_t kk, uint32_t& e0, uint32_t& e1) {
-    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(tabA + ((kk >> 3) & 0x1FE0u));
+    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(tabA + ((kk >> 4) & 0xFF0u));
     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(tabB + ((kk << 5) & 0x1FE0u));
-    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(tabA + ((kk >> 19) & 0x1FE0u));
+    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(tabA + ((kk >> 20) & 0xFF0u));
     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(tabB + ((kk >> 11) & 0x1FE0u));
     e0 = (uint32_t)(((unsigned long long)a0 * b0) >> 31);
     e1 = (uint32_t)(((unsigned long long)a1 * b1) >> 31);
@@ -711,210 +679,283 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
   auto koff = [&](int nt, int e) -> int { return 16 * (nt >> 1) + 4 * t4 + 2 * (nt & 1) + e; };
   uint4* my_codes = s_codes + (size_t(warp) * cpw) * 64 + lane;
 
-  // ================================================ pass A: codes + row max ============================================
-  int mx_lo = -1, mx_hi = -1;
-  issue_k(0, 0);
-  for (int s = 0; s < n_st; ++s) {
-    const int buf = s & 1;
-    if (s + 1 < n_st) { issue_k(s + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const int c = 4 * s + w;
-    if (c <= qt) {
-      const uint8_t* skh = s_stage + buf * STAGE + w * 32 * KSTR;
-      const int* rkh = s_rsk + buf * ST + w * 32;
-      const bool diag = c == qt;
-      uint32_t wl[4], wh[4];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        int acc[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int ks = 0; ks < HD / 32; ++ks) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
-          mma_u8(acc, qa[ks], b0, b1);
-        }
-        const int2 rk2 = *reinterpret_cast<const int2*>(rkh + nt * 8 + 2 * t4);
-        const int c0 = -ioq * rk2.x, c1 = -ioq * rk2.y;
-        int code[4];
-        code[0] = quant_int<FIVE>(fmul(__int2float_rn(acc[0] + c0 + rc_lo), a.sqk), qs);
-        code[1] = quant_int<FIVE>(fmul(__int2float_rn(acc[1] + c1 + rc_lo), a.sqk), qs);
-        code[2] = quant_int<FIVE>(fmul(__int2float_rn(acc[2] + c0 + rc_hi), a.sqk), qs);
-        code[3] = quant_int<FIVE>(fmul(__int2float_rn(acc[3] + c1 + rc_hi), a.sqk), qs);
-        wl[nt] = (uint32_t)code[0] | ((uint32_t)code[1] << 16);
-        wh[nt] = (uint32_t)code[2] | ((uint32_t)code[3] << 16);
-        if (diag) {
-          const int key = c * 32 + koff(nt, 0);
-          if (key > qi_lo) code[0] = -1;
-          if (key + 1 > qi_lo) code[1] = -1;
-          if (key > qi_hi) code[2] = -1;
-          if (key + 1 > qi_hi) code[3] = -1;
-        }
-        mx_lo = max(mx_lo, max(code[0], code[1]));
-        mx_hi = max(mx_hi, max(code[2], code[3]));
-      }
-      my_codes[(s * 2 + 0) * 32] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-      my_codes[(s * 2 + 1) * 32] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-    }
-    __syncthreads();                              // everyone is done with `buf` before stage s+2 is loaded into it
-  }
-  issue_v(0, 0);                                  // V stage 0 streams in underneath pass B
-  mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-  mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-  if (t4 == 0) { s_xi[(rg * 4 + w) * 16 + g] = mx_lo; s_xi[(rg * 4 + w) * 16 + g + 8] = mx_hi; }
-  __syncthreads();
-  int cm_lo = -1, cm_hi = -1;                     // row maxima of the score codes
-#pragma unroll
-  for (int ww = 0; ww < 4; ++ww) { cm_lo = max(cm_lo, s_xi[(rg * 4 + ww) * 16 + g]); cm_hi = max(cm_hi, s_xi[(rg * 4 + ww) * 16 + g + 8]); }
+  // ======================= persistent loop over (query tile, batch, head[, d chunk]) work items =======================
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int qt = nqt - 1 - item / per_qt;
+    int rem = item % per_qt;
+    const int d0 = (rem % NCH) * DV; rem /= NCH;
+    const int h = rem % a.nh, b = rem / a.nh;
+    const int kvh = h / (a.nh / a.nkv);
+    const int q0 = qt * 32;
+    const uint8_t* qbase = a.q + ((int64_t(b) * a.nh + h) * a.T) * HD;
+    const uint8_t* kbase = a.k + ((int64_t(b) * a.nkv + kvh) * a.T) * HD;
+    const uint8_t* vbase = a.vt + ((int64_t(b) * a.nkv + kvh) * HD + d0) * a.T;
+    const int32_t* rskb = a.rsk + (int64_t(b) * a.nkv + kvh) * a.T;
+    const int key_end = min(a.T, q0 + 32);                       // keys this item ever needs
+    const int n_st = (qt + 1 + 3) >> 2;                          // stages of 4 chunks; chunk qt is the diagonal one
 
-  const uint32_t cmcm_lo = (uint32_t)cm_lo | ((uint32_t)cm_lo << 16), cmcm_hi = (uint32_t)cm_hi | ((uint32_t)cm_hi << 16);
-
-  // ================================================ pass B: exact row sums of E ========================================
-  unsigned long long sum_lo = 0, sum_hi = 0;
-  for (int s = 0; 4 * s + w <= qt; ++s) {
-    const int c = 4 * s + w;
-    const uint4 vl = my_codes[(s * 2 + 0) * 32], vh = my_codes[(s * 2 + 1) * 32];
-    const uint32_t wl[4] = {vl.x, vl.y, vl.z, vl.w}, wh[4] = {vh.x, vh.y, vh.z, vh.w};
-    if (c < qt) {
+    auto issue_k = [&](int s, int buf) {
+      uint8_t* skb = s_stage + buf * STAGE;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t e0, e1, e2, e3;                  // E <= 2^31 - 1 + rounding slack: summed in 64 bits below
-        exp_pair(cmcm_lo - wl[nt], e0, e1); exp_pair(cmcm_hi - wh[nt], e2, e3);
-        sum_lo += (unsigned long long)e0 + e1; sum_hi += (unsigned long long)e2 + e3;
+      for (int l = 0; l < NKL; ++l) {
+        const int key = s * ST + k_kk[l];
+        const bool ok = key < key_end;
+        cp_async16(skb + k_dst[l], kbase + int64_t(ok ? key : 0) * HD + kc * 16, ok);
       }
-    } else {
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int key = c * 32 + koff(nt, 0);
-        const uint32_t e0 = exp_tab(cm_lo - (int)(wl[nt] & 0xffffu)), e1 = exp_tab(cm_lo - (int)(wl[nt] >> 16));
-        const uint32_t e2 = exp_tab(cm_hi - (int)(wh[nt] & 0xffffu)), e3 = exp_tab(cm_hi - (int)(wh[nt] >> 16));
-        sum_lo += key <= qi_lo ? e0 : 0u; sum_lo += key + 1 <= qi_lo ? e1 : 0u;
-        sum_hi += key <= qi_hi ? e2 : 0u; sum_hi += key + 1 <= qi_hi ? e3 : 0u;
+      if (threadIdx.x < ST) {
+        const int key = s * ST + threadIdx.x;
+        const bool ok = key < key_end;
+        cp_async4(s_rsk + buf * ST + rsk_dst, rskb + (ok ? key : 0), ok);
       }
-    }
-  }
-  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
-  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-  if (t4 == 0) { s_xs[(rg * 4 + w) * 16 + g] = sum_lo; s_xs[(rg * 4 + w) * 16 + g + 8] = sum_hi; }
-  __syncthreads();
-  sum_lo = 0; sum_hi = 0;
-#pragma unroll
-  for (int ww = 0; ww < 4; ++ww) { sum_lo += s_xs[(rg * 4 + ww) * 16 + g]; sum_hi += s_xs[(rg * 4 + ww) * 16 + g + 8]; }
-  // rows beyond T (and nothing else) have an empty sum; keep their arithmetic finite, they are never stored
-  const float den_lo = sum_lo ? __ull2float_rn(sum_lo) : 1.f, den_hi = sum_hi ? __ull2float_rn(sum_hi) : 1.f;
-  const float rden_lo = __frcp_rn(den_lo), rden_hi = __frcp_rn(den_hi);
-  // the Markstein division needs its second step only for an all-ones significand of the divisor (common.cuh)
-  const bool den_five = __any_sync(0xffffffffu, mantissa_all_ones(den_lo) || mantissa_all_ones(den_hi));
-
-  // ================================================ pass C: P codes and P.V ============================================
-  int olo[NDN][4], ohi[NDN][4];
-#pragma unroll
-  for (int i = 0; i < NDN; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
-  int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
-  auto chunk_pv = [&](auto five_tag, auto diag_tag, int s, int c, const uint8_t* svb) {
-    constexpr bool DF = decltype(five_tag)::value;
-    constexpr bool DIAG = decltype(diag_tag)::value;
-    const uint4 vl = my_codes[(s * 2 + 0) * 32], vh = my_codes[(s * 2 + 1) * 32];
-    const uint32_t wl[4] = {vl.x, vl.y, vl.z, vl.w}, wh[4] = {vh.x, vh.y, vh.z, vh.w};
-    // (magic + code) keeps the 16-bit prob code in its low half-word (o_p == 0)
-    // p >= 0 and o_p == 0: the lower clamp of the quantizer can never bind
-    auto prob_of = [&](uint32_t e, float den, float rden) -> uint32_t {
-      const float pr = div_rn<DF>(__uint2float_rn(e), den, rden);
-      return (uint32_t)__float_as_int(__fadd_rn(fminf(div_rn<FIVE>(pr, qp.s, qp.rs), qp.hi), kRoundMagic));
+      cp_async_commit();
     };
-    uint32_t ahi[4], alo[4];
+    auto issue_v = [&](int s, int buf) {
+      uint8_t* svb = s_stage + buf * STAGE;
+      const int k0 = s * ST + vc * 16;
 #pragma unroll
-    for (int hsel = 0; hsel < 2; ++hsel) {        // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
-      uint32_t pl[2], ph[2];
-#pragma unroll
-      for (int ww = 0; ww < 2; ++ww) {
-        const int nt = hsel * 2 + ww;
-        const int key = c * 32 + koff(nt, 0);
-        uint32_t e0, e1, e2, e3;
-        if (DIAG) {
-          e0 = key <= qi_lo ? exp_tab(cm_lo - (int)(wl[nt] & 0xffffu)) : 0u;
-          e1 = key + 1 <= qi_lo ? exp_tab(cm_lo - (int)(wl[nt] >> 16)) : 0u;
-          e2 = key <= qi_hi ? exp_tab(cm_hi - (int)(wh[nt] & 0xffffu)) : 0u;
-          e3 = key + 1 <= qi_hi ? exp_tab(cm_hi - (int)(wh[nt] >> 16)) : 0u;
+      for (int l = 0; l < NVL; ++l) {
+        const int d = vd0 + l * 32;
+        const uint8_t* src = vbase + int64_t(d) * a.T + k0;
+        if (v_aligned) {
+          const bool ok = k0 + 16 <= a.T;
+          cp_async16(svb + d * VSTR + vc * 16, ok ? src : vbase, ok);
         } else {
-          exp_pair(cmcm_lo - wl[nt], e0, e1); exp_pair(cmcm_hi - wh[nt], e2, e3);
+          uint8_t tmp[16];
+          for (int j = 0; j < 16; ++j) tmp[j] = (k0 + j < a.T) ? src[j] : 0;
+          *reinterpret_cast<uint4*>(svb + d * VSTR + vc * 16) = *reinterpret_cast<uint4*>(tmp);
         }
-        const uint32_t c0 = prob_of(e0, den_lo, rden_lo), c1 = prob_of(e1, den_lo, rden_lo);
-        const uint32_t c2 = prob_of(e2, den_hi, rden_hi), c3 = prob_of(e3, den_hi, rden_hi);
-        pl[ww] = __byte_perm(c0, c1, 0x5410);     // code0 | code1 << 16
-        ph[ww] = __byte_perm(c2, c3, 0x5410);
-        psum_lo = (int)__dp2a_lo(pl[ww], 0x0101u, (unsigned)psum_lo);
-        psum_hi = (int)__dp2a_lo(ph[ww], 0x0101u, (unsigned)psum_hi);
       }
-      alo[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x6420); ahi[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x7531);
-      alo[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x6420); ahi[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x7531);
-    }
-#pragma unroll
-    for (int dn = 0; dn < NDN; ++dn) {
-      const uint8_t* vrow = svb + (dn * 8 + g) * VSTR + w * 32 + 4 * t4;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow), b1 = *reinterpret_cast<const uint32_t*>(vrow + 16);
-      mma_u8(ohi[dn], ahi, b0, b1);
-      mma_u8(olo[dn], alo, b0, b1);
-    }
-  };
-  for (int s = 0; s < n_st; ++s) {
-    const int buf = s & 1;
-    if (s + 1 < n_st) { issue_v(s + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const int c = 4 * s + w;
-    const uint8_t* svb = s_stage + buf * STAGE;
-    if (c < qt) {
-      if (den_five) chunk_pv(std::true_type{}, std::false_type{}, s, c, svb);
-      else chunk_pv(std::false_type{}, std::false_type{}, s, c, svb);
-    } else if (c == qt) {
-      chunk_pv(std::true_type{}, std::true_type{}, s, c, svb);
-    }
-    __syncthreads();
-  }
-  psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 1); psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 2);
-  psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 1); psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 2);
-  if (t4 == 0) { s_xi[(rg * 4 + w) * 16 + g] = psum_lo; s_xi[(rg * 4 + w) * 16 + g + 8] = psum_hi; }
-  // ---- combine the four key-split partials of each row group (the codes are dead: the loop ended with a barrier)
-  int* my_red = s_red + (size_t(rg * 4 + w) * (DV / 2)) * 32 + lane;
-#pragma unroll
-  for (int dn = 0; dn < NDN; ++dn)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) my_red[(dn * 4 + j) * 32] = olo[dn][j] + ohi[dn][j] * 256;
-  __syncthreads();
-  psum_lo = 0; psum_hi = 0;
-#pragma unroll
-  for (int ww = 0; ww < 4; ++ww) { psum_lo += s_xi[(rg * 4 + ww) * 16 + g]; psum_hi += s_xi[(rg * 4 + ww) * 16 + g + 8]; }
+      cp_async_commit();
+    };
 
-  // ---- epilogue: warp w finalises output n-tiles [w*NDN/4, (w+1)*NDN/4): remove the V zero point, requantise, store
-  int csum_lo = 0, csum_hi = 0;
-  const int ldo = a.nh * HD;
+    issue_k(0, 0);
+    if (n_st > 1) issue_k(1, 1);
+
+    // ---- Q fragments of this row group's 16 rows, straight from global (rows beyond T read as zero)
+    uint32_t qa[HD / 32][4];
+    const int qi_lo = q0 + rg * 16 + g, qi_hi = qi_lo + 8;       // absolute query positions of this thread's two rows
 #pragma unroll
-  for (int i = 0; i < NDN / 4; ++i) {
-    const int dn = w * (NDN / 4) + i;
-    const int d = d0 + dn * 8 + 2 * t4;
-    int code[4];
+    for (int ks = 0; ks < HD / 32; ++ks) {
+      qa[ks][0] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 4 * t4)) : 0u;
+      qa[ks][1] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 4 * t4)) : 0u;
+      qa[ks][2] = qi_lo < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_lo) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
+      qa[ks][3] = qi_hi < a.T ? __ldg(reinterpret_cast<const uint32_t*>(qbase + int64_t(qi_hi) * HD + ks * 32 + 16 + 4 * t4)) : 0u;
+    }
+    const int32_t* rsqb = a.rsq + (int64_t(b) * a.nh + h) * a.T;
+    // I = acc - iok*rsq - ioq*rsk + HD*ioq*iok = acc + colc[key] + rc[row]
+    const int rc_lo = HD * ioq * iok - iok * (qi_lo < a.T ? __ldg(rsqb + qi_lo) : 0);
+    const int rc_hi = HD * ioq * iok - iok * (qi_hi < a.T ? __ldg(rsqb + qi_hi) : 0);
+    if (threadIdx.x < 32) s_cs[threadIdx.x] = 0;
+
+    // ================================================ pass A: codes + row max ==========================================
+    // three-buffer ring, one barrier per stage: the barrier of stage s also proves stage s-1 has been consumed, so its
+    // buffer (== buffer of stage s+2) can be refilled right away
+    int mx_lo = -1, mx_hi = -1;
+    for (int s = 0; s < n_st; ++s) {
+      const int buf = s % kA4Bufs;
+      if (s + 1 < n_st) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+      if (s + 2 < n_st) issue_k(s + 2, (s + 2) % kA4Bufs);
+      const int c = 4 * s + w;
+      if (c <= qt) {
+        const uint8_t* skh = s_stage + buf * STAGE + w * 32 * KSTR;
+        const int* rkh = s_rsk + buf * ST + w * 32;
+        const bool diag = c == qt;
+        uint32_t wl[4], wh[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int A = 0;
+        for (int nt = 0; nt < 4; ++nt) {
+          int acc[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int ww = 0; ww < 4; ++ww) A += s_red[(size_t(rg * 4 + ww) * (DV / 2) + dn * 4 + j) * 32 + lane];
-      A -= iov * (j < 2 ? psum_lo : psum_hi);
-      code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
+          for (int ks = 0; ks < HD / 32; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 4 * t4);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(skh + (nt * 8 + g) * KSTR + ks * 32 + 16 + 4 * t4);
+            mma_u8(acc, qa[ks], b0, b1);
+          }
+          const int2 rk2 = *reinterpret_cast<const int2*>(rkh + nt * 8 + 2 * t4);
+          const int c0 = -ioq * rk2.x, c1 = -ioq * rk2.y;
+          int code[4];
+          code[0] = quant_int<FIVE>(fmul(__int2float_rn(acc[0] + c0 + rc_lo), a.sqk), qs);
+          code[1] = quant_int<FIVE>(fmul(__int2float_rn(acc[1] + c1 + rc_lo), a.sqk), qs);
+          code[2] = quant_int<FIVE>(fmul(__int2float_rn(acc[2] + c0 + rc_hi), a.sqk), qs);
+          code[3] = quant_int<FIVE>(fmul(__int2float_rn(acc[3] + c1 + rc_hi), a.sqk), qs);
+          wl[nt] = (uint32_t)code[0] | ((uint32_t)code[1] << 16);
+          wh[nt] = (uint32_t)code[2] | ((uint32_t)code[3] << 16);
+          if (diag) {
+            const int key = c * 32 + koff(nt, 0);
+            if (key > qi_lo) code[0] = -1;
+            if (key + 1 > qi_lo) code[1] = -1;
+            if (key > qi_hi) code[2] = -1;
+            if (key + 1 > qi_hi) code[3] = -1;
+          }
+          mx_lo = max(mx_lo, max(code[0], code[1]));
+          mx_hi = max(mx_hi, max(code[2], code[3]));
+        }
+        my_codes[(s * 2 + 0) * 32] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        my_codes[(s * 2 + 1) * 32] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      }
     }
-    if (qi_lo < a.T) {
-      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
-      csum_lo += code[0] + code[1];
+    mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    if (t4 == 0) { s_xi[(rg * 4 + w) * 16 + g] = mx_lo; s_xi[(rg * 4 + w) * 16 + g + 8] = mx_hi; }
+    __syncthreads();                                // row maxima published; every K buffer has been consumed
+    issue_v(0, 0);                                  // V streams in underneath pass B
+    if (n_st > 1) issue_v(1, 1);
+    int cm_lo = -1, cm_hi = -1;                     // row maxima of the score codes
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) { cm_lo = max(cm_lo, s_xi[(rg * 4 + ww) * 16 + g]); cm_hi = max(cm_hi, s_xi[(rg * 4 + ww) * 16 + g + 8]); }
+    const uint32_t cmcm_lo = (uint32_t)cm_lo | ((uint32_t)cm_lo << 16), cmcm_hi = (uint32_t)cm_hi | ((uint32_t)cm_hi << 16);
+
+    // ================================================ pass B: exact row sums of E ======================================
+    unsigned long long sum_lo = 0, sum_hi = 0;
+    for (int s = 0; 4 * s + w <= qt; ++s) {
+      const int c = 4 * s + w;
+      const uint4 vl = my_codes[(s * 2 + 0) * 32], vh = my_codes[(s * 2 + 1) * 32];
+      const uint32_t wl[4] = {vl.x, vl.y, vl.z, vl.w}, wh[4] = {vh.x, vh.y, vh.z, vh.w};
+      if (c < qt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t e0, e1, e2, e3;                  // E <= 2^31: pairs are summed in 64 bits
+          exp_pair(cmcm_lo - wl[nt], e0, e1); exp_pair(cmcm_hi - wh[nt], e2, e3);
+          sum_lo += (unsigned long long)e0 + e1; sum_hi += (unsigned long long)e2 + e3;
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int key = c * 32 + koff(nt, 0);
+          const uint32_t e0 = exp_tab(cm_lo - (int)(wl[nt] & 0xffffu)), e1 = exp_tab(cm_lo - (int)(wl[nt] >> 16));
+          const uint32_t e2 = exp_tab(cm_hi - (int)(wh[nt] & 0xffffu)), e3 = exp_tab(cm_hi - (int)(wh[nt] >> 16));
+          sum_lo += key <= qi_lo ? e0 : 0u; sum_lo += key + 1 <= qi_lo ? e1 : 0u;
+          sum_hi += key <= qi_hi ? e2 : 0u; sum_hi += key + 1 <= qi_hi ? e3 : 0u;
+        }
+      }
     }
-    if (qi_hi < a.T) {
-      *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
-      csum_hi += code[2] + code[3];
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    if (t4 == 0) { s_xs[(rg * 4 + w) * 16 + g] = sum_lo; s_xs[(rg * 4 + w) * 16 + g + 8] = sum_hi; }
+
+    // ================================================ pass C: P codes and P.V ==========================================
+    // (the first barrier of the loop below also publishes the row sums)
+    float den_lo = 1.f, den_hi = 1.f, rden_lo = 1.f, rden_hi = 1.f;
+    bool den_five = true;
+    int olo[NDN][4], ohi[NDN][4];
+#pragma unroll
+    for (int i = 0; i < NDN; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
+    int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
+    auto chunk_pv = [&](auto five_tag, auto diag_tag, int s, int c, const uint8_t* svb) {
+      constexpr bool DF = decltype(five_tag)::value;
+      constexpr bool DIAG = decltype(diag_tag)::value;
+      const uint4 vl = my_codes[(s * 2 + 0) * 32], vh = my_codes[(s * 2 + 1) * 32];
+      const uint32_t wl[4] = {vl.x, vl.y, vl.z, vl.w}, wh[4] = {vh.x, vh.y, vh.z, vh.w};
+      // (magic + code) keeps the 16-bit prob code in its low half-word (o_p == 0); p >= 0: the lower clamp never binds
+      auto prob_of = [&](uint32_t e, float den, float rden) -> uint32_t {
+        const float pr = div_rn<DF>(__uint2float_rn(e), den, rden);
+        return (uint32_t)__float_as_int(__fadd_rn(fminf(div_rn<FIVE>(pr, qp.s, qp.rs), qp.hi), kRoundMagic));
+      };
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for (int hsel = 0; hsel < 2; ++hsel) {        // hsel 0 -> a0/a1 (slots 4t..), 1 -> a2/a3 (slots 16+4t..)
+        uint32_t pl[2], ph[2];
+#pragma unroll
+        for (int ww = 0; ww < 2; ++ww) {
+          const int nt = hsel * 2 + ww;
+          const int key = c * 32 + koff(nt, 0);
+          uint32_t e0, e1, e2, e3;
+          if (DIAG) {
+            e0 = key <= qi_lo ? exp_tab(cm_lo - (int)(wl[nt] & 0xffffu)) : 0u;
+            e1 = key + 1 <= qi_lo ? exp_tab(cm_lo - (int)(wl[nt] >> 16)) : 0u;
+            e2 = key <= qi_hi ? exp_tab(cm_hi - (int)(wh[nt] & 0xffffu)) : 0u;
+            e3 = key + 1 <= qi_hi ? exp_tab(cm_hi - (int)(wh[nt] >> 16)) : 0u;
+          } else {
+            exp_pair(cmcm_lo - wl[nt], e0, e1); exp_pair(cmcm_hi - wh[nt], e2, e3);
+          }
+          const uint32_t c0 = prob_of(e0, den_lo, rden_lo), c1 = prob_of(e1, den_lo, rden_lo);
+          const uint32_t c2 = prob_of(e2, den_hi, rden_hi), c3 = prob_of(e3, den_hi, rden_hi);
+          pl[ww] = __byte_perm(c0, c1, 0x5410);     // code0 | code1 << 16
+          ph[ww] = __byte_perm(c2, c3, 0x5410);
+          psum_lo = (int)__dp2a_lo(pl[ww], 0x0101u, (unsigned)psum_lo);
+          psum_hi = (int)__dp2a_lo(ph[ww], 0x0101u, (unsigned)psum_hi);
+        }
+        alo[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x6420); ahi[hsel * 2 + 0] = __byte_perm(pl[0], pl[1], 0x7531);
+        alo[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x6420); ahi[hsel * 2 + 1] = __byte_perm(ph[0], ph[1], 0x7531);
+      }
+#pragma unroll
+      for (int dn = 0; dn < NDN; ++dn) {
+        const uint8_t* vrow = svb + (dn * 8 + g) * VSTR + w * 32 + 4 * t4;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow), b1 = *reinterpret_cast<const uint32_t*>(vrow + 16);
+        mma_u8(ohi[dn], ahi, b0, b1);
+        mma_u8(olo[dn], alo, b0, b1);
+      }
+    };
+    for (int s = 0; s < n_st; ++s) {
+      const int buf = s % kA4Bufs;
+      if (s + 1 < n_st) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+      if (s + 2 < n_st) issue_v(s + 2, (s + 2) % kA4Bufs);
+      if (s == 0) {
+        unsigned long long t_lo = 0, t_hi = 0;
+#pragma unroll
+        for (int ww = 0; ww < 4; ++ww) { t_lo += s_xs[(rg * 4 + ww) * 16 + g]; t_hi += s_xs[(rg * 4 + ww) * 16 + g + 8]; }
+        den_lo = __ull2float_rn(t_lo); den_hi = __ull2float_rn(t_hi);      // >= 1: the row maximum contributes E(0) = 2^31
+        rden_lo = __frcp_rn(den_lo); rden_hi = __frcp_rn(den_hi);
+        // the Markstein division needs its second step only for an all-ones significand of the divisor (common.cuh)
+        den_five = __any_sync(0xffffffffu, mantissa_all_ones(den_lo) || mantissa_all_ones(den_hi));
+      }
+      const int c = 4 * s + w;
+      const uint8_t* svb = s_stage + buf * STAGE;
+      if (c < qt) {
+        if (den_five) chunk_pv(std::true_type{}, std::false_type{}, s, c, svb);
+        else chunk_pv(std::false_type{}, std::false_type{}, s, c, svb);
+      } else if (c == qt) {
+        chunk_pv(std::true_type{}, std::true_type{}, s, c, svb);
+      }
     }
-  }
-  if (a.rowsum_out) {
-    csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 1); csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 2);
-    csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 1); csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 2);
-    if (t4 == 0) { atomicAdd(s_cs + rg * 16 + g, csum_lo); atomicAdd(s_cs + rg * 16 + g + 8, csum_hi); }
+    psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 1); psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 2);
+    psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 1); psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 2);
+    __syncthreads();                               // every warp is done with its codes and with the row maxima in s_xi
+    if (t4 == 0) { s_xi[(rg * 4 + w) * 16 + g] = psum_lo; s_xi[(rg * 4 + w) * 16 + g + 8] = psum_hi; }
+    // ---- combine the four key-split partials of each row group (the partials overwrite the dead codes)
+    int* my_red = s_red + (size_t(rg * 4 + w) * (DV / 2)) * 32 + lane;
+#pragma unroll
+    for (int dn = 0; dn < NDN; ++dn)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) my_red[(dn * 4 + j) * 32] = olo[dn][j] + ohi[dn][j] * 256;
     __syncthreads();
-    if (threadIdx.x < 32) {
+    psum_lo = 0; psum_hi = 0;
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) { psum_lo += s_xi[(rg * 4 + ww) * 16 + g]; psum_hi += s_xi[(rg * 4 + ww) * 16 + g + 8]; }
+
+    // ---- epilogue: warp w finalises output n-tiles [w*NDN/4, (w+1)*NDN/4): remove the V zero point, requantise, store
+    int csum_lo = 0, csum_hi = 0;
+    const int ldo = a.nh * HD;
+#pragma unroll
+    for (int i = 0; i < NDN / 4; ++i) {
+      const int dn = w * (NDN / 4) + i;
+      const int d = d0 + dn * 8 + 2 * t4;
+      int code[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int A = 0;
+#pragma unroll
+        for (int ww = 0; ww < 4; ++ww) A += s_red[(size_t(rg * 4 + ww) * (DV / 2) + dn * 4 + j) * 32 + lane];
+        A -= iov * (j < 2 ? psum_lo : psum_hi);
+        code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
+      }
+      if (qi_lo < a.T) {
+        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_lo) * ldo + h * HD + d) = (uint16_t)(code[0] | (code[1] << 8));
+        csum_lo += code[0] + code[1];
+      }
+      if (qi_hi < a.T) {
+        *reinterpret_cast<uint16_t*>(a.out + (int64_t(b) * a.T + qi_hi) * ldo + h * HD + d) = (uint16_t)(code[2] | (code[3] << 8));
+        csum_hi += code[2] + code[3];
+      }
+    }
+    if (a.rowsum_out) {
+      csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 1); csum_lo += __shfl_xor_sync(0xffffffffu, csum_lo, 2);
+      csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 1); csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 2);
+      if (t4 == 0) { atomicAdd(s_cs + rg * 16 + g, csum_lo); atomicAdd(s_cs + rg * 16 + g + 8, csum_hi); }
+    }
+    __syncthreads();                               // partials consumed: the next item may overwrite codes / s_xi / s_cs
+    if (a.rowsum_out && threadIdx.x < 32) {
       const int qi = q0 + threadIdx.x;
       if (qi < a.T) atomicAdd(a.rowsum_out + int64_t(b) * a.T + qi, s_cs[threadIdx.x]);
     }
@@ -939,13 +980,25 @@ static int launch_qattn2(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) 
 template <int HD, int DV, bool FIVE>
 static int launch_qattn4(Ctx* c, const AttnArgs& a, int cpw, size_t smem, cudaStream_t st) {
   static size_t attr_smem = 0;                   // opt-in grows monotonically with the longest sequence seen
+  static int ctas_per_sm = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(qattn4_kernel<HD, DV, FIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_smem = smem;
+    ctas_per_sm = 0;
   }
-  dim3 grid((a.T + 31) / 32 * (HD / DV), a.nh, a.B);
-  qattn4_kernel<HD, DV, FIVE><<<grid, 256, smem, st>>>(a, cpw);
+  if (ctas_per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, qattn4_kernel<HD, DV, FIVE>, 256, attr_smem) != cudaSuccess || ctas_per_sm < 1) {
+      cudaGetLastError();
+      ctas_per_sm = 1;
+    }
+    if (getenv("MQB200_DEBUG")) fprintf(stderr, "[mqb200] qattn<%d,%d>: %zu B smem, %d CTAs/SM\n", HD, DV, attr_smem, ctas_per_sm);
+  }
+  // persistent CTAs walk the (query tile, batch, head) items round-robin, heaviest query tiles first
+  const long long n_items = (long long)((a.T + 31) / 32) * a.B * a.nh * (HD / DV);
+  if (n_items > 0x7fffffffLL) return fail(c, MQ_INVALID_ARGUMENT, "mq_qattn: too many work items");
+  const int grid = (int)std::min<long long>(n_items, (long long)c->sm_count * ctas_per_sm);
+  qattn4_kernel<HD, DV, FIVE><<<grid, 256, attr_smem, st>>>(a, cpw, (int)n_items);
   return check_launch(c, "mq_qattn");
 }
 // MQB200_QATTN=3pass forces the streaming three-pass kernel (the fallback for sequences whose score codes do not fit
