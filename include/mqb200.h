@@ -141,6 +141,35 @@ int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, c
              int T, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out, int32_t* rowsum_out,
              void* stream);
 
+/* ---- decode step: one new token per sequence against an int8 KV cache ---------------------------------------------
+ * Reference: SimModel.generate / SimModel.forward with k_cache, v_cache (mobilellm/model/sim_model.py:105-132,181-235) and
+ * the on-device loop capp/src/llm.cpp:545-653 (uint8 caches [L, n_heads, T-1, head_dim]).  The static quantizers are the
+ * prefill's, so every integer tensor of a decode step equals row `pos` of the full-sequence forward (mq_qgemm / mq_qattn).
+ *
+ * mq_qgemv: acc[b, n] += sum_k x[b, k] * w[n, k] for B <= 128 rows (u8/s8 codes, s32 accumulate on tcgen05 with the
+ * weights as the 128-row operand); the K loop is split over `ksplit` CTAs per 128-row weight tile (<= 0: chosen so that
+ * every SM streams) and the partial sums are combined with integer red.add, so acc must be zero on entry (exact,
+ * order-independent).  mq_qgemv_epilogue applies mq_qgemm's zero-point removal and epilogue `mode` (0 QUANT 8-bit,
+ * 1 ACTMUL, 2 RESID; same arguments, same arithmetic) to acc[B, N] and leaves acc zeroed for the next call.        */
+int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
+             int ldacc, int ksplit, void* stream);
+int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
+                      const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
+                      int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                      void* stream);
+
+/* mq_qattn_decode: qkv u8 codes [B, ldq] of the new token's fused q|k|v projection -> RoPE at position pos between the
+ * projection output quantizers and the bmm input quantizers (rope_in/out_qparams as in mq_qrope, HOST arrays; cos/sin
+ * device [> pos, rot]) -> k / v codes and the k code sum appended at row pos of the caches
+ *   k_cache, v_cache u8 [B, nkv, Tmax, hd],  rsk_cache s32 [B, nkv, Tmax]
+ * -> exact quantised softmax attention of the new row over keys 0..pos (qparams / lut as in mq_qattn) -> out u8 [B, nh*hd]
+ * and rowsum_out[B] += sum of the emitted codes.  pos is read from *pos_dev when pos_dev != NULL (CUDA-graph replay of
+ * the step; pos_bound is then the largest position the launch must accommodate), else from `pos`.                   */
+int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int nkv, int hd, int rot, int Tmax, int pos,
+                    const int* pos_dev, int pos_bound, const float* rope_in_qparams, const float* rope_out_qparams, const float* cos,
+                    const float* sin, uint8_t* k_cache, uint8_t* v_cache, int32_t* rsk_cache, const float* qparams,
+                    const uint32_t* lut, uint8_t* out, int32_t* rowsum_out, void* stream);
+
 /* ---- test hook ---------------------------------------------------------------------------------------------------
  * The integer-engine kernels requantise with a branch-free exact division (RN(a/b) from RN(1/b) and two FMAs, a
  * third/fourth for scales whose significand is all ones) instead of the IEEE division + rint of qm:286.  This entry

@@ -1,0 +1,587 @@
+// Decode step of the statically-quantised integer forward: one new token per sequence against an int8 KV cache.
+//
+// The reference decodes with SimModel.generate (mobilellm/model/sim_model.py:181-235: context encoding, then one-token
+// steps that append to k_cache / v_cache [L, n_heads, T-1, head_dim]) and, on the phone, with the capp loop
+// (capp/src/llm.cpp:545-653, uint8 caches); both run the same static quantizers as the prefill, so the integer tensors
+// of a decode step equal row `pos` of a full-sequence forward.  Two kernels + one epilogue cover it here:
+//
+//   mq_qgemv          skinny GEMM  acc[b, n] += sum_k X[b, k] W[n, k]  for B <= 128 rows: the WEIGHTS are the 128-row
+//                     UMMA operand (tcgen05.mma kind::i8, M = 128, N = padded batch), every weight byte leaves HBM exactly
+//                     once, the K loop is split across CTAs so that all SMs stream, partial sums meet in an s32
+//                     accumulator with red.global.add (integer adds commute: the result is exact and deterministic)
+//   mq_qgemv_epilogue the requantisation epilogues of mq_qgemm (QUANT / ACTMUL / RESID) on that accumulator, same
+//                     arithmetic, and the accumulator is handed back zeroed
+//   mq_qattn_decode   RoPE + requant of the new token's q / k / v codes, append to the cache, exact quantised softmax
+//                     attention of the new row over keys 0..pos (same integer arithmetic as mq_qattn)
+// All three are HBM-bound (weights / cache streamed once); oracle: oracle/int_ref.py (full forward, row pos).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "ctx.h"
+#include <string>
+#include <algorithm>
+
+namespace mq {
+using namespace tc;
+
+// =====================================================================================================================
+// qgemv
+// =====================================================================================================================
+constexpr int kGvBM = 128;        // weight rows per tile == UMMA M
+constexpr int kGvBK = 128;        // bytes of K per stage == one 128B swizzle row
+constexpr int kGvStages = 4;      // 4 x (16 KB + BP x 128 B): two CTAs per SM stay resident up to BP = 64
+
+struct QGemvArgs {
+  int B, N, K;
+  int32_t* acc;       // [B, ldacc] s32, accumulated with red.add
+  int ldacc;
+  int ksplit;
+};
+
+template <int BP>
+struct GvSmem {
+  static constexpr int kWBytes = kGvBM * kGvBK;
+  static constexpr int kXBytes = BP * kGvBK;
+  static constexpr int kXOff = kGvStages * kWBytes;
+  static constexpr int kBarOff = kXOff + kGvStages * kXBytes;
+  static constexpr int kTotal = kBarOff + 128;
+  static constexpr int kTmemCols = BP < 32 ? 32 : BP;
+};
+
+template <int BP>
+__global__ void __launch_bounds__(192, 1)
+qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const QGemvArgs p, const uint32_t idesc) {
+  using L = GvSmem<BP>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + L::kXOff;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kGvStages;
+  uint64_t* tfull_bar = empty_bar + kGvStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.ksplit, ks = blockIdx.x % p.ksplit;
+  const int k_iters = (p.K + kGvBK - 1) / kGvBK;
+  const int k0 = (int)((long long)ks * k_iters / p.ksplit), k1 = (int)((long long)(ks + 1) * k_iters / p.ksplit);
+  if (k0 >= k1) return;                         // uniform per CTA: nothing allocated yet
+  const int n0 = tile * kGvBM;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_x);
+    for (int i = 0; i < kGvStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, L::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int k = k0; k < k1; ++k) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], L::kWBytes + L::kXBytes);
+        tma_load_2d(smem_w + stage * L::kWBytes, &tmap_w, &full_bar[stage], k * kGvBK, n0);
+        tma_load_2d(smem_x + stage * L::kXBytes, &tmap_x, &full_bar[stage], k * kGvBK, 0);   // rows >= B are zero-filled
+        if (++stage == kGvStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0; uint32_t phase = 0;
+    for (int k = k0; k < k1; ++k) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = smem_desc_k128(smem_u32(smem_w + stage * L::kWBytes));
+        const uint64_t bdesc = smem_desc_k128(smem_u32(smem_x + stage * L::kXBytes));
+#pragma unroll
+        for (int kk = 0; kk < kGvBK / 32; ++kk)
+          mma_i8(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k > k0) | (kk != 0));
+        tc_commit(&empty_bar[stage]);
+        if (k == k1 - 1) tc_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++stage == kGvStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // warps 2..5: TMEM lane quarter (warp & 3) == 32 weight rows; thread = weight row n, registers = batch columns
+    const int quarter = warp & 3;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int n = n0 + quarter * 32 + lane;
+    const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < BP; c += 16) {
+      if (c >= p.B) break;
+      uint32_t r[16];
+      tmem_ld16(trow + c, r);
+      tc_wait_ld();
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c + j < p.B) atomicAdd(p.acc + int64_t(c + j) * p.ldacc + n, (int)r[j]);   // result unused -> RED.ADD
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
+}
+
+// =====================================================================================================================
+// epilogue of the skinny GEMM: same arithmetic as qgemm_kernel's epilogue (qgemm.cu), one thread = one row m and four
+// consecutive output columns; blockIdx.y = m so that the emitted-code sum of a block belongs to one row.
+// =====================================================================================================================
+enum { GV_QUANT = 0, GV_ACTMUL = 1, GV_RESID = 2 };
+
+struct GvEpiArgs {
+  int B, N;
+  int32_t* acc; int ldacc;
+  const int32_t* rowsum; const float* sxw; const int32_t* ow; const int32_t* c0; const float* bias;
+  const float* so; const float* oo; int qgroup; float qmax;
+  uint8_t* out; int64_t ldo; int32_t* rowsum_out;
+  const float* lut; float s2, o2, qmax2;
+  float* resid;
+};
+
+__device__ __forceinline__ float gv_y(const GvEpiArgs& a, int acc, int rs, int n) {
+  const int I = acc - __ldg(a.ow + n) * rs + __ldg(a.c0 + n);
+  float y = __fmul_rn(__int2float_rn(I), __ldg(a.sxw + n));
+  if (a.bias) y = __fadd_rn(y, __ldg(a.bias + n));
+  return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) qgemv_epi_kernel(const GvEpiArgs a) {
+  __shared__ int s_sum[4];
+  const int m = blockIdx.y;
+  const int NO = MODE == GV_ACTMUL ? a.N / 2 : a.N;                 // output columns
+  const int j0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int rs = __ldg(a.rowsum + m);
+  int32_t* accm = a.acc + int64_t(m) * a.ldacc;
+  int csum = 0;
+  if (j0 < NO) {
+    const int gmax = (a.N - 1) / a.qgroup;
+    if (MODE == GV_ACTMUL) {
+      // output column j <-> w1 accumulator column (j / 128) * 256 + j % 128, w3 column 128 further
+      const int n1 = (j0 >> 7) * 256 + (j0 & 127), n3 = n1 + 128;
+      const int4 a1 = *reinterpret_cast<const int4*>(accm + n1), a3 = *reinterpret_cast<const int4*>(accm + n3);
+      *reinterpret_cast<int4*>(accm + n1) = make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4*>(accm + n3) = make_int4(0, 0, 0, 0);
+      const int g1 = min(n1 / a.qgroup, gmax), g3 = min(n3 / a.qgroup, gmax);
+      const QParam q1 = make_qparam(__ldg(a.so + g1), __ldg(a.oo + g1), a.qmax), q3 = make_qparam(__ldg(a.so + g3), __ldg(a.oo + g3), a.qmax);
+      const QParam q2 = make_qparam(a.s2, a.o2, a.qmax2);
+      const int v1[4] = {a1.x, a1.y, a1.z, a1.w}, v3[4] = {a3.x, a3.y, a3.z, a3.w};
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float y1 = gv_y(a, v1[e], rs, n1 + e), y3 = gv_y(a, v3[e], rs, n3 + e);
+        const float act = __ldg(a.lut + quant_int<true>(y1, q1));
+        const float u = __fmul_rn(__fsub_rn(quant_magic<true>(y3, q3), kRoundMagic), q3.s);
+        w |= (uint32_t)quant_int<true>(__fmul_rn(act, u), q2) << (8 * e);
+      }
+      csum = (int)__dp4a(w, 0x01010101u, 0u);
+      *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
+    } else {
+      const int4 av = *reinterpret_cast<const int4*>(accm + j0);
+      *reinterpret_cast<int4*>(accm + j0) = make_int4(0, 0, 0, 0);
+      const int g = min(j0 / a.qgroup, gmax);
+      const QParam q = make_qparam(__ldg(a.so + g), __ldg(a.oo + g), a.qmax);
+      const int v[4] = {av.x, av.y, av.z, av.w};
+      if (MODE == GV_QUANT) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w |= (uint32_t)quant_int<true>(gv_y(a, v[e], rs, j0 + e), q) << (8 * e);
+        csum = (int)__dp4a(w, 0x01010101u, 0u);
+        *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
+      } else {
+        float4* dst = reinterpret_cast<float4*>(a.resid + int64_t(m) * a.ldo + j0);
+        float4 h = *dst;
+        float d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = __fmul_rn(__fsub_rn(quant_magic<true>(gv_y(a, v[e], rs, j0 + e), q), kRoundMagic), q.s);
+        h.x = __fadd_rn(h.x, d[0]); h.y = __fadd_rn(h.y, d[1]); h.z = __fadd_rn(h.z, d[2]); h.w = __fadd_rn(h.w, d[3]);
+        *dst = h;
+      }
+    }
+  }
+  if (MODE != GV_RESID && a.rowsum_out) {
+    csum = warp_reduce(csum, OpSum());
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = csum;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(a.rowsum_out + m, s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3]);
+  }
+}
+
+// =====================================================================================================================
+// mq_qattn_decode: one CTA per (sequence, kv head); the R = nh / nkv query heads that share the kv head ride together.
+//   1. new token: de-quantise q/k/v projection codes, RoPE at position pos, re-quantise (== qrope_kernel, engine.cu);
+//      k / v codes and the k code sum are appended to the cache at row pos
+//   2. scores of the R query rows against keys 0..pos (dp4a on the u8 codes, exact zero-point removal), 16-bit codes
+//   3. row max -> E = tab(cmax - c) -> exact u64 row sum -> p = E / sum -> 16-bit prob codes   (== qattn kernels)
+//   4. A = P.V on the codes, zero-point removal, 8-bit output quantizer, token-major store, code sum for o_proj
+// Cache layouts: K, V  u8 [B, nkv, Tmax, hd];  rsk  s32 [B, nkv, Tmax].
+// =====================================================================================================================
+struct AttnDecArgs {
+  const uint8_t* qkv; int ldq;
+  int B, nh, nkv, hd, rot, Tmax, pos;
+  const int* pos_dev;
+  float sq_in, oq_in, sk_in, ok_in, sv_in, ov_in;     // projection output quantizers
+  float sq, oq, sk, ok, sv, ov;                       // qk_bmm.input / input2, pv_bmm.input2
+  const float* cos; const float* sin;                 // [>= pos + 1, rot]
+  uint8_t* kc; uint8_t* vc; int32_t* rskc;
+  float sqk, s_s, o_s, qmax_s, s_p, qmax_p, spv, s_out, o_out;
+  const uint32_t* lut;
+  uint8_t* out; int32_t* rowsum_out;
+  int Tpad;                                           // score slab stride (multiple of 8 >= pos + 1)
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce256(T v, Op op, T* scratch /* 8 entries */) {
+  v = warp_reduce(v, op);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = scratch[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = op(r, scratch[i]);
+  return r;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) {
+  constexpr int WPR = HD / 4;                 // 32-bit words per head row
+  constexpr int KS = 256 / WPR;               // key slices of the P.V pass
+  constexpr int RMAX = 8;
+  extern __shared__ __align__(16) uint8_t smem_dec[];
+  const int R = a.nh / a.nkv;
+  uint32_t* s_q = reinterpret_cast<uint32_t*>(smem_dec);                 // [R][WPR] q codes of the new token
+  uint32_t* s_tab = s_q + RMAX * WPR;                                     // [512]
+  int* s_red = reinterpret_cast<int*>(s_tab + 512);                       // [KS][R][HD] P.V partials
+  unsigned long long* s_scr = reinterpret_cast<unsigned long long*>(s_red + KS * RMAX * HD);   // [8] reduction scratch
+  int* s_rsq = reinterpret_cast<int*>(s_scr + 8);                         // [RMAX]
+  int* s_cm = s_rsq + RMAX;                                               // [RMAX]
+  int* s_ps = s_cm + RMAX;                                                // [RMAX]
+  float* s_den = reinterpret_cast<float*>(s_ps + RMAX);                   // [RMAX]
+  uint16_t* s_c = reinterpret_cast<uint16_t*>(s_den + RMAX);              // [R][Tpad] score codes, then prob codes
+
+  const int b = blockIdx.x / a.nkv, kvh = blockIdx.x % a.nkv;
+  const int pos = a.pos_dev ? *a.pos_dev : a.pos;
+  const int Tk = pos + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* row = a.qkv + int64_t(b) * a.ldq;
+  uint8_t* kcache = a.kc + (int64_t(b) * a.nkv + kvh) * a.Tmax * HD;
+  uint8_t* vcache = a.vc + (int64_t(b) * a.nkv + kvh) * a.Tmax * HD;
+  int32_t* rsk = a.rskc + (int64_t(b) * a.nkv + kvh) * a.Tmax;
+  const int half = a.rot / 2;
+
+  for (int i = tid; i < 512; i += 256) s_tab[i] = __ldg(a.lut + i);
+
+  // ---- 1. RoPE + requant of the new token: heads 0..R-1 = q, R = k, R+1 = v; one thread = 4 head dims
+  const QParam qq = make_qparam(a.sq, a.oq, 255.f), qk = make_qparam(a.sk, a.ok, 255.f), qv = make_qparam(a.sv, a.ov, 255.f);
+  for (int i = tid; i < (R + 2) * WPR; i += 256) {
+    const int hh = i / WPR, d = (i % WPR) * 4;
+    const bool is_q = hh < R, is_k = hh == R;
+    const uint8_t* src = is_q ? row + (kvh * R + hh) * HD : (is_k ? row + (a.nh + kvh) * HD : row + (a.nh + a.nkv + kvh) * HD);
+    const float s_in = is_q ? a.sq_in : (is_k ? a.sk_in : a.sv_in), o_in = is_q ? a.oq_in : (is_k ? a.ok_in : a.ov_in);
+    const QParam& qo = is_q ? qq : (is_k ? qk : qv);
+    const uint32_t wx = *reinterpret_cast<const uint32_t*>(src + d);
+    float x[4], o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = dequant(__uint2float_rn((wx >> (8 * j)) & 255u), s_in, o_in);
+    if (hh <= R && d < a.rot) {
+      const int dp = d < half ? d + half : d - half;
+      const bool neg = d < half;
+      const uint32_t wy = *reinterpret_cast<const uint32_t*>(src + dp);
+      const float4 c = ldg4(a.cos + int64_t(pos) * a.rot + d), sn = ldg4(a.sin + int64_t(pos) * a.rot + d);
+      const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = dequant(__uint2float_rn((wy >> (8 * j)) & 255u), s_in, o_in);
+        o[j] = fadd(fmul(x[j], cv[j]), fmul(neg ? -y : y, sv[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = x[j];
+    }
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<true>(o[j], qo) << (8 * j);
+    if (is_q) s_q[hh * WPR + (d >> 2)] = packed;
+    else if (is_k) *reinterpret_cast<uint32_t*>(kcache + int64_t(pos) * HD + d) = packed;
+    else *reinterpret_cast<uint32_t*>(vcache + int64_t(pos) * HD + d) = packed;
+  }
+  __syncthreads();                            // s_q, s_tab and the appended cache rows are visible to the block
+  // code sums: warp r sums q head r; warp R sums the new k row
+  for (int hh = warp; hh <= R; hh += 8) {
+    int sum = 0;
+    for (int wd = lane; wd < WPR; wd += 32) {
+      const uint32_t wv = hh < R ? s_q[hh * WPR + wd] : *reinterpret_cast<const uint32_t*>(kcache + int64_t(pos) * HD + wd * 4);
+      sum = (int)__dp4a(wv, 0x01010101u, (unsigned)sum);
+    }
+    sum = warp_reduce(sum, OpSum());
+    if (lane == 0) { if (hh < R) s_rsq[hh] = sum; else rsk[pos] = sum; }
+  }
+  __syncthreads();
+
+  // ---- 2. scores: thread = key, all R query rows at once
+  const QParam qs = make_qparam(a.s_s, a.o_s, a.qmax_s);
+  const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
+  const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
+  const int ioq = (int)a.oq, iok = (int)a.ok, iov = (int)a.ov;
+  int mx[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) mx[r] = -1;
+  for (int j = tid; j < Tk; j += 256) {
+    const uint4* krow = reinterpret_cast<const uint4*>(kcache + int64_t(j) * HD);
+    int acc[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[r] = 0;
+#pragma unroll 2
+    for (int w4 = 0; w4 < WPR / 4; ++w4) {
+      const uint4 kv = krow[w4];
+      const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < R) acc[r] = (int)__dp4a(kw[e], s_q[r * WPR + w4 * 4 + e], (unsigned)acc[r]);
+    }
+    const int colc = -ioq * rsk[j] + HD * ioq * iok;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < R) {
+        const int I = acc[r] + colc - iok * s_rsq[r];
+        const int code = quant_int<true>(fmul(__int2float_rn(I), a.sqk), qs);
+        s_c[r * a.Tpad + j] = (uint16_t)code;
+        mx[r] = max(mx[r], code);
+      }
+    }
+  }
+  for (int r = 0; r < R; ++r) {
+    const int m = block_reduce256(mx[r], OpMax(), reinterpret_cast<int*>(s_scr));
+    if (tid == 0) s_cm[r] = m;
+  }
+  __syncthreads();
+
+  // ---- 3. exact softmax on the codes
+  auto exp_tab = [&](int k) -> uint32_t {
+    const uint32_t ea = s_tab[(k >> 8) & 255], eb = s_tab[256 + (k & 255)];
+    return (uint32_t)(((unsigned long long)ea * eb) >> 31);
+  };
+  for (int r = 0; r < R; ++r) {
+    const int cm = s_cm[r];
+    unsigned long long sum = 0;
+    for (int j = tid; j < Tk; j += 256) sum += exp_tab(cm - (int)s_c[r * a.Tpad + j]);
+    sum = block_reduce256(sum, OpSum(), s_scr);
+    if (tid == 0) s_den[r] = __ull2float_rn(sum);
+  }
+  __syncthreads();
+  for (int r = 0; r < R; ++r) {
+    const int cm = s_cm[r];
+    const float den = s_den[r], rden = __frcp_rn(den);
+    int ps = 0;
+    for (int j = tid; j < Tk; j += 256) {
+      const uint32_t e = exp_tab(cm - (int)s_c[r * a.Tpad + j]);
+      const float pr = div_rn<true>(__uint2float_rn(e), den, rden);
+      const int cp = quant_int<true>(pr, qp);
+      s_c[r * a.Tpad + j] = (uint16_t)cp;
+      ps += cp;
+    }
+    ps = block_reduce256(ps, OpSum(), reinterpret_cast<int*>(s_scr));
+    if (tid == 0) s_ps[r] = ps;
+  }
+  __syncthreads();
+
+  // ---- 4. P.V: thread = (key slice, 4 head dims)
+  {
+    const int slice = tid / WPR, dq = tid % WPR;
+    int pv[RMAX][4];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) { pv[r][0] = pv[r][1] = pv[r][2] = pv[r][3] = 0; }
+    for (int j = slice; j < Tk; j += KS) {
+      const uint32_t vw = *reinterpret_cast<const uint32_t*>(vcache + int64_t(j) * HD + dq * 4);
+      const int v0 = vw & 255u, v1 = (vw >> 8) & 255u, v2 = (vw >> 16) & 255u, v3 = vw >> 24;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R) {
+          const int c = s_c[r * a.Tpad + j];
+          pv[r][0] += c * v0; pv[r][1] += c * v1; pv[r][2] += c * v2; pv[r][3] += c * v3;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) *reinterpret_cast<int4*>(s_red + (slice * RMAX + r) * HD + dq * 4) = make_int4(pv[r][0], pv[r][1], pv[r][2], pv[r][3]);
+  }
+  __syncthreads();
+  int csum = 0;
+  const int ldo = a.nh * HD;
+  for (int i = tid; i < R * HD; i += 256) {
+    const int r = i / HD, d = i % HD;
+    int A = 0;
+    for (int s = 0; s < KS; ++s) A += s_red[(s * RMAX + r) * HD + d];
+    A -= iov * s_ps[r];
+    const int code = quant_int<true>(fmul(__int2float_rn(A), a.spv), qo);
+    a.out[int64_t(b) * ldo + (kvh * R + r) * HD + d] = (uint8_t)code;
+    csum += code;
+  }
+  if (a.rowsum_out) {
+    csum = block_reduce256(csum, OpSum(), reinterpret_cast<int*>(s_scr));
+    if (tid == 0) atomicAdd(a.rowsum_out + b, csum);
+  }
+}
+
+static size_t attn_dec_smem(int hd, int R, int Tpad) {
+  const int WPR = hd / 4, KS = 256 / WPR;
+  return size_t(8) * WPR * 4 + 512 * 4 + size_t(KS) * 8 * hd * 4 + 8 * 8 + 4 * 8 * 4 + size_t(R) * Tpad * 2 + 16;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (same helper as qgemm.cu, local copy of the lookup)
+typedef CUresult (*PFN_encodeTiledGv)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiledGv gv_encode() {
+  static PFN_encodeTiledGv fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiledGv>(p);
+  }
+  return fn;
+}
+static bool gv_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  PFN_encodeTiledGv enc = gv_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BP>
+static int launch_qgemv(Ctx* c, const void* x, int x_signed, const void* w, int w_signed, const QGemvArgs& args, cudaStream_t st) {
+  using L = GvSmem<BP>;
+  CUtensorMap tw, tx;
+  if (!gv_tmap(&tw, w, args.N, args.K, kGvBM) || !gv_tmap(&tx, x, args.B, args.K, BP))
+    return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const uint32_t idesc = make_idesc(2u, w_signed ? 1u : 0u, x_signed ? 1u : 0u, 0u, 0u, kGvBM, BP);
+  const int n_tiles = (args.N + kGvBM - 1) / kGvBM;
+  qgemv_kernel<BP><<<n_tiles * args.ksplit, 192, L::kTotal, st>>>(tw, tx, args, idesc);
+  return check_launch(c, "mq_qgemv");
+}
+
+}  // namespace mq
+
+using namespace mq;
+
+extern "C" {
+
+int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
+             int ldacc, int ksplit, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, x_codes && w_codes && acc && B > 0 && N > 0 && K > 0, "null operand or empty problem");
+  MQ_REQUIRE(c, B <= 128, "the skinny GEMM covers up to 128 rows; use mq_qgemm above");
+  MQ_REQUIRE(c, K % 16 == 0 && ldacc >= N, "K must be a multiple of 16 and ldacc >= N");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x_codes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_codes) & 15) == 0, "operands must be 16-byte aligned");
+  const int k_iters = (K + kGvBK - 1) / kGvBK;
+  const int n_tiles = (N + kGvBM - 1) / kGvBM;
+  if (ksplit <= 0) {
+    // fill the machine (two CTAs per SM) but keep at least two 128-byte K slices per CTA
+    ksplit = std::max(1, std::min(2 * c->sm_count / n_tiles, std::max(1, k_iters / 2)));
+  }
+  ksplit = std::min(ksplit, k_iters);
+  QGemvArgs args{B, N, K, acc, ldacc, ksplit};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 16) return launch_qgemv<16>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  if (B <= 32) return launch_qgemv<32>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  if (B <= 64) return launch_qgemv<64>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  return launch_qgemv<128>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+}
+
+int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
+                      const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
+                      int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                      void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, acc && rowsum && sxw && ow && c0 && so && oo && B > 0 && N > 0, "null pointer or empty problem");
+  MQ_REQUIRE(c, mode >= GV_QUANT && mode <= GV_RESID, "mode must be 0 (QUANT), 1 (ACTMUL) or 2 (RESID)");
+  MQ_REQUIRE(c, N % 4 == 0 && ldacc % 4 == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0, "N, ldacc must be multiples of 4, acc 16-byte aligned");
+  MQ_REQUIRE(c, qgroup > 0 && qgroup % 4 == 0, "qgroup must be a positive multiple of 4");
+  MQ_REQUIRE(c, mode != GV_QUANT || (out && ldo % 4 == 0 && qmax <= 255.f), "QUANT needs out, ldo % 4 == 0, 8-bit codes");
+  MQ_REQUIRE(c, mode != GV_ACTMUL || (out && lut && N % 256 == 0 && 128 % qgroup == 0 && ldo % 4 == 0), "ACTMUL needs out/lut, N % 256 == 0, qgroup | 128");
+  MQ_REQUIRE(c, mode != GV_RESID || (resid && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0), "RESID needs a 16-byte aligned resid, ldo % 4 == 0");
+  MQ_REQUIRE(c, qmax < 4194304.f && qmax2 < 4194304.f, "qmax must be below 2^22");
+  GvEpiArgs a{B, N, acc, ldacc, rowsum, sxw, ow, c0, bias, so, oo, qgroup, qmax, out, ldo, rowsum_out, lut, s2, o2, qmax2, resid};
+  const int NO = mode == GV_ACTMUL ? N / 2 : N;
+  dim3 grid((NO / 4 + 127) / 128, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == GV_QUANT) qgemv_epi_kernel<GV_QUANT><<<grid, 128, 0, st>>>(a);
+  else if (mode == GV_ACTMUL) qgemv_epi_kernel<GV_ACTMUL><<<grid, 128, 0, st>>>(a);
+  else qgemv_epi_kernel<GV_RESID><<<grid, 128, 0, st>>>(a);
+  return check_launch(c, "mq_qgemv_epilogue");
+}
+
+int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int nkv, int hd, int rot, int Tmax, int pos,
+                    const int* pos_dev, int pos_bound, const float* rope_in_qparams, const float* rope_out_qparams, const float* cos,
+                    const float* sin, uint8_t* k_cache, uint8_t* v_cache, int32_t* rsk_cache, const float* qparams,
+                    const uint32_t* lut, uint8_t* out, int32_t* rowsum_out, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, qkv && rope_in_qparams && rope_out_qparams && cos && sin && k_cache && v_cache && rsk_cache && qparams && lut && out, "null pointer");
+  MQ_REQUIRE(c, B > 0 && nh > 0 && nkv > 0 && nh % nkv == 0 && nh / nkv <= 8, "bad head counts (at most 8 query heads per kv head)");
+  MQ_REQUIRE(c, hd == 32 || hd == 64 || hd == 128 || hd == 256, "head_dim must be 32, 64, 128 or 256");
+  MQ_REQUIRE(c, rot >= 0 && rot <= hd && rot % 8 == 0 && ldq % 4 == 0, "rotary width must be a multiple of 8, ldq of 4");
+  if (!pos_dev) pos_bound = pos;
+  MQ_REQUIRE(c, pos_bound >= 0 && pos_bound < Tmax && (pos_dev || (pos >= 0 && pos < Tmax)), "position outside the cache");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(qkv) & 3) == 0 && (reinterpret_cast<uintptr_t>(k_cache) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(cos) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(sin) & 15) == 0, "qkv must be 4-byte, caches and cos/sin 16-byte aligned");
+  AttnDecArgs a;
+  a.qkv = qkv; a.ldq = ldq; a.B = B; a.nh = nh; a.nkv = nkv; a.hd = hd; a.rot = rot; a.Tmax = Tmax; a.pos = pos; a.pos_dev = pos_dev;
+  a.sq_in = rope_in_qparams[0]; a.oq_in = rope_in_qparams[1]; a.sk_in = rope_in_qparams[2]; a.ok_in = rope_in_qparams[3];
+  a.sv_in = rope_in_qparams[4]; a.ov_in = rope_in_qparams[5];
+  a.sq = rope_out_qparams[0]; a.oq = rope_out_qparams[1]; a.sk = rope_out_qparams[2]; a.ok = rope_out_qparams[3];
+  a.sv = rope_out_qparams[4]; a.ov = rope_out_qparams[5];
+  MQ_REQUIRE(c, a.oq == qparams[0] && a.ok == qparams[1] && a.ov == qparams[2], "rope output offsets must match the attention zero points");
+  a.cos = cos; a.sin = sin; a.kc = k_cache; a.vc = v_cache; a.rskc = rsk_cache;
+  a.sqk = qparams[3]; a.s_s = qparams[4]; a.o_s = qparams[5]; a.qmax_s = qparams[6]; a.s_p = qparams[7]; a.qmax_p = qparams[8];
+  a.spv = qparams[9]; a.s_out = qparams[10]; a.o_out = qparams[11];
+  MQ_REQUIRE(c, a.qmax_s <= 65535.f && a.qmax_p <= 65535.f, "score / probability codes are at most 16 bit");
+  MQ_REQUIRE(c, a.oq == rintf(a.oq) && a.ok == rintf(a.ok) && a.ov == rintf(a.ov) && a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out),
+             "integer engine kernels need integral offsets (qm:60)");
+  a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
+  a.Tpad = (pos_bound + 1 + 7) / 8 * 8;
+  const size_t smem = attn_dec_smem(hd, nh / nkv, a.Tpad);
+  MQ_REQUIRE(c, smem <= 227 * 1024, "sequence too long for the decode attention score slab");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = B * nkv;
+#define MQ_DEC(HDV)                                                                                                         \
+  {                                                                                                                         \
+    static size_t attr = 48 * 1024;                                                                                         \
+    if (smem > attr) {                                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));  \
+      attr = smem;                                                                                                          \
+    }                                                                                                                       \
+    qattn_decode_kernel<HDV><<<grid, 256, smem, st>>>(a);                                                                   \
+  }
+  if (hd == 32) MQ_DEC(32) else if (hd == 64) MQ_DEC(64) else if (hd == 128) MQ_DEC(128) else MQ_DEC(256)
+#undef MQ_DEC
+  return check_launch(c, "mq_qattn_decode");
+}
+
+}  // extern "C"

@@ -229,12 +229,18 @@ class IntEngine:
                        qgroup=g["qgroup"], **kw)
 
     @torch.no_grad()
-    def block(self, h, L, B, T, bufs, trace=None):
-        """One decoder block on the fp32 residual stream h [B*T, H] (updated in place)."""
+    def block(self, h, L, B, T, bufs, trace=None, cache=None):
+        """One decoder block on the fp32 residual stream h [B*T, H] (updated in place).  cache = (KVCache, layer index):
+        the rotated k / v codes of the T tokens are also written to the decode cache."""
         cos, sin = self._rope(T)
         K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
         self._gemm(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, out=bufs["qkv"], out_bits=8)
         K.qrope(bufs["qkv"], B, T, self.nh, self.nkv, self.hd, self.rot, L["rope_in"], L["rope_out"], cos, sin, bufs["rope"])
+        if cache is not None:
+            kv, li = cache
+            kv.k[li][:, :, :T].copy_(bufs["rope"]["k"])
+            kv.v[li][:, :, :T].copy_(bufs["rope"]["vt"].transpose(2, 3))
+            kv.rsk[li][:, :, :T].copy_(bufs["rope"]["rsk"])
         bufs["rs_attn"].zero_()
         K.qattn(bufs["rope"], B, T, self.nh, self.nkv, self.hd, L["attn"], L["attn_lut"], bufs["attn"], bufs["rs_attn"])
         if trace is not None:
@@ -254,12 +260,12 @@ class IntEngine:
         return h
 
     @torch.no_grad()
-    def backbone(self, h, B, T, trace_layer=None):
+    def backbone(self, h, B, T, trace_layer=None, cache=None):
         bufs = self._buffers(B, T)
         trace = None
         for i, L in enumerate(self.layers):
             tr = {} if trace_layer == i else None
-            self.block(h, L, B, T, bufs, tr)
+            self.block(h, L, B, T, bufs, tr, None if cache is None else (cache, i))
             if tr is not None:
                 trace = tr
         return (h, trace) if trace_layer is not None else h
@@ -281,3 +287,151 @@ class IntEngine:
         return torch.nn.functional.linear(hn, self.lm_head)
 
     __call__ = forward
+
+    # ---- decode against an int8 KV cache (reference: SimModel.generate, sim_model.py:181-235; capp/src/llm.cpp:545-653) --
+    def new_cache(self, B, Tmax):
+        return KVCache(len(self.layers), B, self.nkv, Tmax, self.hd, self.device)
+
+    def _embed(self, ids):
+        h = torch.nn.functional.embedding(ids, self.embed)
+        if self.cfg.normalize_embed:
+            h = h * (self.H ** 0.5)
+        return h
+
+    def _head(self, h):
+        return torch.nn.functional.linear(self.final_norm(h), self.lm_head)
+
+    @torch.no_grad()
+    def prefill(self, input_ids, cache):
+        """Context encoding: full integer forward over input_ids [B, T] that also fills the cache; returns the logits of
+        the last position [B, V] (sim_model.py:195-212)."""
+        B, T = input_ids.shape
+        assert B == cache.B and T <= cache.Tmax
+        h = self._embed(input_ids).reshape(B * T, self.H).contiguous()
+        h = self.backbone(h, B, T, cache=cache).view(B, T, self.H)
+        cache.length = T
+        cache.pos_dev.fill_(T)
+        return self._head(h[:, -1, :])
+
+    def _decode_bufs(self, B):
+        key = ("dec", B)
+        if key not in self._bufs:
+            dev = self.device
+            u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+            nmax = max(L[k]["N"] for L in self.layers for k in ("qkv", "o", "w13", "w2"))
+            self._bufs[key] = dict(x=u8(B, self.H), rs=torch.empty(B, dtype=torch.int32, device=dev), qkv=u8(B, (self.nh + 2 * self.nkv) * self.hd),
+                                   attn=u8(B, self.nh * self.hd), rs_attn=torch.zeros(B, dtype=torch.int32, device=dev), act=u8(B, self.Ipad),
+                                   rs_act=torch.zeros(B, dtype=torch.int32, device=dev), acc=torch.zeros(B, nmax, dtype=torch.int32, device=dev))
+        return self._bufs[key]
+
+    def _gemv(self, a, g, rowsum, mode, acc, **kw):
+        K.qgemv(a, g["codes"], acc)
+        return K.qgemv_epilogue(acc, a.shape[0], g["N"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"],
+                                qmax=g["qmax"], qgroup=g["qgroup"], **kw)
+
+    @torch.no_grad()
+    def decode_hidden(self, h, cache, use_pos_dev=False):
+        """One decode step on the fp32 residual rows h [B, H] of the new tokens (position cache.length); updated in place."""
+        B = h.shape[0]
+        bufs = self._decode_bufs(B)
+        cos, sin = self._rope(cache.Tmax)
+        pos = cache.length
+        pkw = dict(pos_dev=cache.pos_dev, pos_bound=cache.Tmax - 1) if use_pos_dev else {}
+        for i, L in enumerate(self.layers):
+            K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
+            self._gemv(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, bufs["acc"], out=bufs["qkv"])
+            bufs["rs_attn"].zero_()
+            K.qattn_decode(bufs["qkv"], B, self.nh, self.nkv, self.hd, self.rot, pos, L["rope_in"], L["rope_out"], cos, sin, cache.k[i], cache.v[i],
+                           cache.rsk[i], L["attn"], L["attn_lut"], out=bufs["attn"], rowsum_out=bufs["rs_attn"], **pkw)
+            self._gemv(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, bufs["acc"], resid=h)
+            K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
+            bufs["rs_act"].zero_()
+            w2in = L["w2_in"]
+            self._gemv(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, bufs["acc"], out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1],
+                       qmax2=w2in[2], rowsum_out=bufs["rs_act"])
+            self._gemv(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, bufs["acc"], resid=h)
+        return h
+
+    @torch.no_grad()
+    def decode_step(self, tokens, cache):
+        """tokens: LongTensor [B] (the tokens at position cache.length).  Returns next-token logits [B, V]."""
+        assert cache.length < cache.Tmax, "KV cache is full"
+        h = self._embed(tokens.view(-1)).contiguous()
+        self.decode_hidden(h, cache)
+        cache.length += 1
+        cache.pos_dev.fill_(cache.length)
+        return self._head(h)
+
+    @torch.no_grad()
+    def capture_decode(self, cache):
+        """CUDA graph of one greedy decode step: token buffer -> logits -> argmax -> token buffer, position += 1 on the
+        device.  Returns (graph, tokens, logits); each replay advances every sequence of the cache by one token."""
+        B = cache.B
+        tokens = torch.zeros(B, dtype=torch.long, device=self.device)
+        state = dict(logits=None)
+
+        def step():
+            h = self._embed(tokens).contiguous()
+            self.decode_hidden(h, cache, use_pos_dev=True)
+            state["logits"] = self._head(h)
+            tokens.copy_(state["logits"].argmax(-1))
+            cache.pos_dev.add_(1)
+
+        # warm-up outside the capture (function attributes, workspaces), then restore the position and the scratch state
+        keep = cache.length
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        cache.pos_dev.fill_(keep)
+        tokens.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        cache.pos_dev.fill_(keep)
+        return g, tokens, state["logits"]
+
+    @torch.no_grad()
+    def generate(self, context_ids, max_new_tokens, eos_token_id=None, pad_token_id=0, do_sample=False, temperature=0.5, Tmax=None):
+        """Greedy / sampled generation with the int8 KV cache; same contract as SimModel.generate (sim_model.py:181-235):
+        context_ids LongTensor [B, context_len] -> LongTensor [B, context_len + generated] (stops once every sequence has
+        emitted an eos token; finished sequences are padded with pad_token_id)."""
+        context_ids = context_ids.to(self.device)
+        B, T0 = context_ids.shape
+        Tmax = Tmax or (T0 + max_new_tokens)
+        assert T0 < Tmax and T0 + max_new_tokens <= Tmax
+        eos = [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id or [])
+        cache = self.new_cache(B, Tmax)
+        logits = self.prefill(context_ids, cache)
+        out = [context_ids]
+        done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        for i in range(max_new_tokens):
+            if do_sample:
+                nxt = torch.multinomial(torch.softmax(logits / temperature, dim=-1), num_samples=1).view(-1)
+            else:
+                nxt = logits.argmax(-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+            out.append(nxt.view(B, 1))
+            for e in eos:
+                done |= nxt == e
+            if bool(done.all()) or i + 1 == max_new_tokens or cache.length >= cache.Tmax:
+                break
+            logits = self.decode_step(nxt, cache)
+        return torch.cat(out, dim=1)
+
+
+class KVCache:
+    """uint8 key / value codes of every layer, k and v [B, nkv, Tmax, hd] (the reference keeps [L, n_heads, T-1, head_dim],
+    sim_model.py:118-119), plus the per-key code sums the zero-point correction of the scores needs."""
+
+    def __init__(self, n_layers, B, nkv, Tmax, hd, device):
+        self.B, self.Tmax, self.length = B, Tmax, 0
+        u8 = lambda: torch.zeros(B, nkv, Tmax, hd, dtype=torch.uint8, device=device)
+        self.k = [u8() for _ in range(n_layers)]
+        self.v = [u8() for _ in range(n_layers)]
+        self.rsk = [torch.zeros(B, nkv, Tmax, dtype=torch.int32, device=device) for _ in range(n_layers)]
+        self.pos_dev = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.k + self.v + self.rsk)

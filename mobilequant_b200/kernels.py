@@ -28,6 +28,11 @@ def _protos():
                              c_float, c_float, _P, _P, _P]
     lib.mq_qrope.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
+    lib.mq_qgemv.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]
+    lib.mq_qgemv_epilogue.argtypes = [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float, _P, c_int64, _P, _P,
+                                      c_float, c_float, c_float, _P, c_int, _P]
+    lib.mq_qattn_decode.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P]
     lib.mq_selftest_div.argtypes = [_P, c_int64, ctypes.c_uint64, c_int, c_float, _P, _P]
     _protos_done = True
     return lib
@@ -277,6 +282,60 @@ def qattn(bufs, B, T, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
     with torch.cuda.device(dev):
         check(_launch("qattn", lib.mq_qattn, h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
                            ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
+    return out
+
+
+# ---- decode step (skinny GEMM + epilogue, RoPE/append/attention against the int8 KV cache) ---------------------------
+def qgemv(x, w, acc, ksplit=0):
+    """acc[B, ldacc] (int32, zero on entry) += x[B, K] codes @ w[N, K]^T codes, B <= 128."""
+    lib = _protos()
+    B, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and acc.dtype == torch.int32 and acc.shape[0] >= B and acc.stride(0) >= N
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(_launch("qgemv", lib.mq_qgemv, h, ptr(x), int(x.dtype == torch.int8), ptr(w), int(w.dtype == torch.int8), B, N, K,
+                           ptr(acc, torch.int32), int(acc.stride(0)), int(ksplit), stream_ptr()), h)
+    return acc
+
+
+def qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out=None, ldo=None, rowsum_out=None,
+                   lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None):
+    """mq_qgemm's epilogue `mode` (EPI_QUANT 8-bit / EPI_ACTMUL / EPI_RESID) on the accumulator of qgemv; zeroes acc."""
+    lib = _protos()
+    dev = acc.device
+    if out is None and mode != EPI_RESID:
+        out = torch.empty(B, N // 2 if mode == EPI_ACTMUL else N, dtype=torch.uint8, device=dev)
+    if ldo is None:
+        ldo = resid.stride(0) if mode == EPI_RESID else out.stride(0)
+    if qgroup is None:
+        qgroup = 128 if (mode == EPI_ACTMUL and so.numel() == N // 128) else (N + 31) // 32 * 32
+    assert so.numel() == (N + qgroup - 1) // qgroup == oo.numel(), "so/oo need one entry per qgroup columns"
+    h = _h(acc)
+    with torch.cuda.device(dev):
+        check(_launch("qgemv_epi", lib.mq_qgemv_epilogue, h, ptr(acc, torch.int32), int(acc.stride(0)), B, N, ptr(rowsum, torch.int32),
+                           ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias), int(mode), ptr(so), ptr(oo), float(qmax),
+                           ptr(out), int(ldo), ptr(rowsum_out), ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup),
+                           stream_ptr()), h)
+    return resid if mode == EPI_RESID else out
+
+
+def qattn_decode(qkv, B, nh, nkv, hd, rot, pos, qin, qout, cos, sin, k_cache, v_cache, rsk_cache, qparams, lut, out=None,
+                 rowsum_out=None, pos_dev=None, pos_bound=None):
+    """qkv u8 [B, ldq]; caches u8 [B, nkv, Tmax, hd] / int32 [B, nkv, Tmax] (row `pos` is written)."""
+    lib = _protos()
+    dev = qkv.device
+    if out is None:
+        out = torch.empty(B, nh * hd, dtype=torch.uint8, device=dev)
+    Tmax = k_cache.shape[2]
+    h = _h(qkv)
+    pin = _host_floats([v for so in qin for v in so]); pout = _host_floats([v for so in qout for v in so])
+    pq = _host_floats(qparams)
+    with torch.cuda.device(dev):
+        check(_launch("qattn_decode", lib.mq_qattn_decode, h, ptr(qkv), int(qkv.stride(0)), B, nh, nkv, hd, rot, Tmax, int(pos),
+                           ptr(pos_dev), int(pos if pos_bound is None else pos_bound), ctypes.cast(pin, _P), ctypes.cast(pout, _P),
+                           ptr(cos, F32), ptr(sin, F32), ptr(k_cache), ptr(v_cache), ptr(rsk_cache, torch.int32), ctypes.cast(pq, _P),
+                           ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
     return out
 
 
