@@ -156,7 +156,13 @@ int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, 
 int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
                       const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
                       int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
-                      void* stream);
+                      int32_t* zero_out, void* stream);
+/* zero_out (optional, [B]): a code-sum buffer some LATER kernel of the step accumulates into; cleared here so that the
+ * step needs no separate memset launches (it must not alias rowsum / rowsum_out of this call).
+ *
+ * mq_fgemv: out[b, v] = sum_k x[b, k] * w[v, k] in fp32 for B <= 16 rows -- the unquantised lm_head (qm:843-845) of the
+ * decode step, one pass over w at HBM speed (fixed summation order, run-to-run deterministic).                      */
+int mq_fgemv(void* ctx, const float* x, const float* w, float* out, int B, int V, int K, void* stream);
 
 /* mq_qattn_decode: qkv u8 codes [B, ldq] of the new token's fused q|k|v projection -> RoPE at position pos between the
  * projection output quantizers and the bmm input quantizers (rope_in/out_qparams as in mq_qrope, HOST arrays; cos/sin

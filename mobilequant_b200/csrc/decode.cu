@@ -147,6 +147,7 @@ struct GvEpiArgs {
   uint8_t* out; int64_t ldo; int32_t* rowsum_out;
   const float* lut; float s2, o2, qmax2;
   float* resid;
+  int32_t* zero_out;       // [B] or null: cleared here so that the NEXT accumulation into it starts from zero
 };
 
 __device__ __forceinline__ float gv_y(const GvEpiArgs& a, int acc, int rs, int n) {
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(128) qgemv_epi_kernel(const GvEpiArgs a) {
   const int rs = __ldg(a.rowsum + m);
   int32_t* accm = a.acc + int64_t(m) * a.ldacc;
   int csum = 0;
+  if (a.zero_out && blockIdx.x == 0 && threadIdx.x == 0) a.zero_out[m] = 0;
   if (j0 < NO) {
     const int gmax = (a.N - 1) / a.qgroup;
     if (MODE == GV_ACTMUL) {
@@ -238,41 +240,82 @@ struct AttnDecArgs {
   float sqk, s_s, o_s, qmax_s, s_p, qmax_p, spv, s_out, o_out;
   const uint32_t* lut;
   uint8_t* out; int32_t* rowsum_out;
-  int Tpad;                                           // score slab stride (multiple of 8 >= pos + 1)
+  int CS;                                             // CTAs per cluster == key slices per (sequence, kv head)
+  int Tslice;                                         // score slab stride (multiple of 8 >= ceil((pos + 1) / CS))
 };
 
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce256(T v, Op op, T* scratch /* 8 entries */) {
-  v = warp_reduce(v, op);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  T r = scratch[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) r = op(r, scratch[i]);
+// cross-CTA exchange block (one per CTA, read by the cluster peers through distributed shared memory)
+struct DecXchg {
+  unsigned long long sum[8];
+  int mx[8];
+  int ps[8];
+};
+
+__device__ __forceinline__ uint32_t map_peer(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
+}
+__device__ __forceinline__ int ld_peer_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_peer_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// reduce R (<= 8) per-thread values over the 256 threads of the block at once; result in every thread
+template <typename T, typename Op>
+__device__ __forceinline__ void block_reduce256_n(T (&v)[8], int R, Op op, T* scratch /* [8 warps][8] */) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) if (r < R) v[r] = warp_reduce(v[r], op);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < R) scratch[(threadIdx.x >> 5) * 8 + r] = v[r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (r < R) {
+      T t = scratch[r];
+#pragma unroll
+      for (int wi = 1; wi < 8; ++wi) t = op(t, scratch[wi * 8 + r]);
+      v[r] = t;
+    }
+  }
 }
 
 template <int HD>
 __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) {
   constexpr int WPR = HD / 4;                 // 32-bit words per head row
-  constexpr int KS = 256 / WPR;               // key slices of the P.V pass
+  constexpr int KS = 256 / WPR;               // key sub-slices of the P.V pass inside a CTA
   constexpr int RMAX = 8;
   extern __shared__ __align__(16) uint8_t smem_dec[];
   const int R = a.nh / a.nkv;
-  uint32_t* s_q = reinterpret_cast<uint32_t*>(smem_dec);                 // [R][WPR] q codes of the new token
-  uint32_t* s_tab = s_q + RMAX * WPR;                                     // [512]
-  int* s_red = reinterpret_cast<int*>(s_tab + 512);                       // [KS][R][HD] P.V partials
-  unsigned long long* s_scr = reinterpret_cast<unsigned long long*>(s_red + KS * RMAX * HD);   // [8] reduction scratch
-  int* s_rsq = reinterpret_cast<int*>(s_scr + 8);                         // [RMAX]
-  int* s_cm = s_rsq + RMAX;                                               // [RMAX]
-  int* s_ps = s_cm + RMAX;                                                // [RMAX]
-  float* s_den = reinterpret_cast<float*>(s_ps + RMAX);                   // [RMAX]
-  uint16_t* s_c = reinterpret_cast<uint16_t*>(s_den + RMAX);              // [R][Tpad] score codes, then prob codes
+  DecXchg* s_x = reinterpret_cast<DecXchg*>(smem_dec);                    // first: same offset in every CTA of the cluster
+  unsigned long long* s_scr = reinterpret_cast<unsigned long long*>(s_x + 1);   // [8][8] reduction scratch
+  uint32_t* s_q = reinterpret_cast<uint32_t*>(s_scr + 64);                // [RMAX][WPR] q codes of the new token
+  uint32_t* s_knew = s_q + RMAX * WPR;                                    // [WPR] new k codes
+  uint32_t* s_vnew = s_knew + WPR;                                        // [WPR] new v codes
+  uint32_t* s_tab = s_vnew + WPR;                                         // [512]
+  int* s_red = reinterpret_cast<int*>(s_tab + 512);                       // [KS][RMAX][HD] P.V partials
+  int* s_rsq = s_red + KS * RMAX * HD;                                    // [RMAX] (+ [RMAX] = code sum of the new k row)
+  int* s_cm = s_rsq + 2 * RMAX;                                           // [RMAX]
+  float* s_den = reinterpret_cast<float*>(s_cm + RMAX);                   // [RMAX]
+  uint16_t* s_c = reinterpret_cast<uint16_t*>(s_den + RMAX);              // [R][Tslice] score codes, then prob codes
 
-  const int b = blockIdx.x / a.nkv, kvh = blockIdx.x % a.nkv;
+  const int CS = a.CS;
+  const int cr = (int)cluster_ctarank();
+  const int grp = blockIdx.x / CS;
+  const int b = grp / a.nkv, kvh = grp % a.nkv;
   const int pos = a.pos_dev ? *a.pos_dev : a.pos;
   const int Tk = pos + 1;
+  const int per = (Tk + CS - 1) / CS;
+  const int j_lo = min(Tk, cr * per), j_hi = min(Tk, j_lo + per);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t* row = a.qkv + int64_t(b) * a.ldq;
   uint8_t* kcache = a.kc + (int64_t(b) * a.nkv + kvh) * a.Tmax * HD;
@@ -282,7 +325,8 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
 
   for (int i = tid; i < 512; i += 256) s_tab[i] = __ldg(a.lut + i);
 
-  // ---- 1. RoPE + requant of the new token: heads 0..R-1 = q, R = k, R+1 = v; one thread = 4 head dims
+  // ---- 1. RoPE + requant of the new token (every CTA of the cluster, redundantly: it is a few hundred elements);
+  //         heads 0..R-1 = q, R = k, R+1 = v; one thread = 4 head dims; rank 0 appends k / v to the cache
   const QParam qq = make_qparam(a.sq, a.oq, 255.f), qk = make_qparam(a.sk, a.ok, 255.f), qv = make_qparam(a.sv, a.ov, 255.f);
   for (int i = tid; i < (R + 2) * WPR; i += 256) {
     const int hh = i / WPR, d = (i % WPR) * 4;
@@ -313,23 +357,20 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<true>(o[j], qo) << (8 * j);
     if (is_q) s_q[hh * WPR + (d >> 2)] = packed;
-    else if (is_k) *reinterpret_cast<uint32_t*>(kcache + int64_t(pos) * HD + d) = packed;
-    else *reinterpret_cast<uint32_t*>(vcache + int64_t(pos) * HD + d) = packed;
+    else if (is_k) { s_knew[d >> 2] = packed; if (cr == 0) *reinterpret_cast<uint32_t*>(kcache + int64_t(pos) * HD + d) = packed; }
+    else { s_vnew[d >> 2] = packed; if (cr == 0) *reinterpret_cast<uint32_t*>(vcache + int64_t(pos) * HD + d) = packed; }
   }
-  __syncthreads();                            // s_q, s_tab and the appended cache rows are visible to the block
-  // code sums: warp r sums q head r; warp R sums the new k row
+  __syncthreads();
+  // code sums: q head r -> s_rsq[r], new k row -> s_rsq[RMAX] (and the cache, rank 0)
   for (int hh = warp; hh <= R; hh += 8) {
     int sum = 0;
-    for (int wd = lane; wd < WPR; wd += 32) {
-      const uint32_t wv = hh < R ? s_q[hh * WPR + wd] : *reinterpret_cast<const uint32_t*>(kcache + int64_t(pos) * HD + wd * 4);
-      sum = (int)__dp4a(wv, 0x01010101u, (unsigned)sum);
-    }
+    for (int wd = lane; wd < WPR; wd += 32) sum = (int)__dp4a(hh < R ? s_q[hh * WPR + wd] : s_knew[wd], 0x01010101u, (unsigned)sum);
     sum = warp_reduce(sum, OpSum());
-    if (lane == 0) { if (hh < R) s_rsq[hh] = sum; else rsk[pos] = sum; }
+    if (lane == 0) { if (hh < R) s_rsq[hh] = sum; else { s_rsq[RMAX] = sum; if (cr == 0) rsk[pos] = sum; } }
   }
   __syncthreads();
 
-  // ---- 2. scores: thread = key, all R query rows at once
+  // ---- 2. scores of this CTA's key slice: thread = key, all R query rows at once
   const QParam qs = make_qparam(a.s_s, a.o_s, a.qmax_s);
   const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
   const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
@@ -337,12 +378,12 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   int mx[RMAX];
 #pragma unroll
   for (int r = 0; r < RMAX; ++r) mx[r] = -1;
-  for (int j = tid; j < Tk; j += 256) {
-    const uint4* krow = reinterpret_cast<const uint4*>(kcache + int64_t(j) * HD);
+  for (int j = j_lo + tid; j < j_hi; j += 256) {
+    const uint4* krow = j == pos ? reinterpret_cast<const uint4*>(s_knew) : reinterpret_cast<const uint4*>(kcache + int64_t(j) * HD);
     int acc[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) acc[r] = 0;
-#pragma unroll 2
+#pragma unroll 4
     for (int w4 = 0; w4 < WPR / 4; ++w4) {
       const uint4 kv = krow[w4];
       const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
@@ -352,20 +393,24 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
         for (int r = 0; r < RMAX; ++r)
           if (r < R) acc[r] = (int)__dp4a(kw[e], s_q[r * WPR + w4 * 4 + e], (unsigned)acc[r]);
     }
-    const int colc = -ioq * rsk[j] + HD * ioq * iok;
+    const int colc = -ioq * (j == pos ? s_rsq[RMAX] : rsk[j]) + HD * ioq * iok;
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
       if (r < R) {
         const int I = acc[r] + colc - iok * s_rsq[r];
         const int code = quant_int<true>(fmul(__int2float_rn(I), a.sqk), qs);
-        s_c[r * a.Tpad + j] = (uint16_t)code;
+        s_c[r * a.Tslice + (j - j_lo)] = (uint16_t)code;
         mx[r] = max(mx[r], code);
       }
     }
   }
-  for (int r = 0; r < R; ++r) {
-    const int m = block_reduce256(mx[r], OpMax(), reinterpret_cast<int*>(s_scr));
-    if (tid == 0) s_cm[r] = m;
+  block_reduce256_n(mx, R, OpMax(), reinterpret_cast<int*>(s_scr));
+  if (tid < R) s_x->mx[tid] = mx[tid];
+  cluster_sync_all();                                   // #1: slice maxima visible across the cluster
+  if (tid < R) {
+    int m = -1;
+    for (int p = 0; p < CS; ++p) m = max(m, ld_peer_s32(map_peer(&s_x->mx[tid], p)));
+    s_cm[tid] = m;
   }
   __syncthreads();
 
@@ -374,72 +419,150 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
     const uint32_t ea = s_tab[(k >> 8) & 255], eb = s_tab[256 + (k & 255)];
     return (uint32_t)(((unsigned long long)ea * eb) >> 31);
   };
-  for (int r = 0; r < R; ++r) {
-    const int cm = s_cm[r];
-    unsigned long long sum = 0;
-    for (int j = tid; j < Tk; j += 256) sum += exp_tab(cm - (int)s_c[r * a.Tpad + j]);
-    sum = block_reduce256(sum, OpSum(), s_scr);
-    if (tid == 0) s_den[r] = __ull2float_rn(sum);
-  }
-  __syncthreads();
-  for (int r = 0; r < R; ++r) {
-    const int cm = s_cm[r];
-    const float den = s_den[r], rden = __frcp_rn(den);
-    int ps = 0;
-    for (int j = tid; j < Tk; j += 256) {
-      const uint32_t e = exp_tab(cm - (int)s_c[r * a.Tpad + j]);
-      const float pr = div_rn<true>(__uint2float_rn(e), den, rden);
-      const int cp = quant_int<true>(pr, qp);
-      s_c[r * a.Tpad + j] = (uint16_t)cp;
-      ps += cp;
+  const int nloc = j_hi - j_lo;
+  {
+    unsigned long long sum[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) sum[r] = 0;
+    for (int jj = tid; jj < nloc; jj += 256) {
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) if (r < R) sum[r] += exp_tab(s_cm[r] - (int)s_c[r * a.Tslice + jj]);
     }
-    ps = block_reduce256(ps, OpSum(), reinterpret_cast<int*>(s_scr));
-    if (tid == 0) s_ps[r] = ps;
+    block_reduce256_n(sum, R, OpSum(), s_scr);
+    if (tid < R) s_x->sum[tid] = sum[tid];
+  }
+  cluster_sync_all();                                   // #2: slice sums visible
+  if (tid < R) {
+    unsigned long long t = 0;
+    for (int p = 0; p < CS; ++p) t += ld_peer_u64(map_peer(&s_x->sum[tid], p));
+    s_den[tid] = __ull2float_rn(t);
   }
   __syncthreads();
+  {
+    int ps[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) ps[r] = 0;
+    for (int jj = tid; jj < nloc; jj += 256) {
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R) {
+          const float den = s_den[r];
+          const uint32_t e = exp_tab(s_cm[r] - (int)s_c[r * a.Tslice + jj]);
+          const float pr = div_rn<true>(__uint2float_rn(e), den, __frcp_rn(den));
+          const int cp = quant_int<true>(pr, qp);
+          s_c[r * a.Tslice + jj] = (uint16_t)cp;
+          ps[r] += cp;
+        }
+      }
+    }
+    block_reduce256_n(ps, R, OpSum(), reinterpret_cast<int*>(s_scr));   // its barriers also publish the prob codes
+    if (tid < R) s_x->ps[tid] = ps[tid];
+  }
 
-  // ---- 4. P.V: thread = (key slice, 4 head dims)
+  // ---- 4. P.V over the slice: thread = (key sub-slice, 4 head dims); four keys in flight per thread
   {
     const int slice = tid / WPR, dq = tid % WPR;
     int pv[RMAX][4];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) { pv[r][0] = pv[r][1] = pv[r][2] = pv[r][3] = 0; }
-    for (int j = slice; j < Tk; j += KS) {
-      const uint32_t vw = *reinterpret_cast<const uint32_t*>(vcache + int64_t(j) * HD + dq * 4);
+    auto vword = [&](int jj) -> uint32_t {
+      const int j = j_lo + jj;
+      return j == pos ? s_vnew[dq] : *reinterpret_cast<const uint32_t*>(vcache + int64_t(j) * HD + dq * 4);
+    };
+    auto fma_key = [&](int jj, uint32_t vw) {
       const int v0 = vw & 255u, v1 = (vw >> 8) & 255u, v2 = (vw >> 16) & 255u, v3 = vw >> 24;
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) {
         if (r < R) {
-          const int c = s_c[r * a.Tpad + j];
+          const int c = s_c[r * a.Tslice + jj];
           pv[r][0] += c * v0; pv[r][1] += c * v1; pv[r][2] += c * v2; pv[r][3] += c * v3;
         }
       }
+    };
+    int jj = slice;
+    for (; jj + 3 * KS < nloc; jj += 4 * KS) {
+      const uint32_t w0 = vword(jj), w1 = vword(jj + KS), w2 = vword(jj + 2 * KS), w3 = vword(jj + 3 * KS);
+      fma_key(jj, w0); fma_key(jj + KS, w1); fma_key(jj + 2 * KS, w2); fma_key(jj + 3 * KS, w3);
     }
+    for (; jj < nloc; jj += KS) fma_key(jj, vword(jj));
 #pragma unroll
     for (int r = 0; r < RMAX; ++r)
       if (r < R) *reinterpret_cast<int4*>(s_red + (slice * RMAX + r) * HD + dq * 4) = make_int4(pv[r][0], pv[r][1], pv[r][2], pv[r][3]);
   }
   __syncthreads();
-  int csum = 0;
-  const int ldo = a.nh * HD;
+  // fold the KS sub-slices into sub-slice 0 (what the cluster leader reads)
   for (int i = tid; i < R * HD; i += 256) {
     const int r = i / HD, d = i % HD;
     int A = 0;
-    for (int s = 0; s < KS; ++s) A += s_red[(s * RMAX + r) * HD + d];
-    A -= iov * s_ps[r];
-    const int code = quant_int<true>(fmul(__int2float_rn(A), a.spv), qo);
-    a.out[int64_t(b) * ldo + (kvh * R + r) * HD + d] = (uint8_t)code;
-    csum += code;
+    for (int sl = 0; sl < KS; ++sl) A += s_red[(sl * RMAX + r) * HD + d];
+    s_red[r * HD + d] = A;                               // (sub-slice 0, row r) is only read by this thread
   }
-  if (a.rowsum_out) {
-    csum = block_reduce256(csum, OpSum(), reinterpret_cast<int*>(s_scr));
-    if (tid == 0) atomicAdd(a.rowsum_out + b, csum);
+  cluster_sync_all();                                   // #3: slice partials and prob-code sums visible
+  if (cr == 0) {
+    int csum = 0;
+    const int ldo = a.nh * HD;
+    for (int i = tid; i < R * HD; i += 256) {
+      const int r = i / HD, d = i % HD;
+      int A = 0, psum = 0;
+      for (int p = 0; p < CS; ++p) {
+        A += ld_peer_s32(map_peer(s_red + r * HD + d, p));
+        psum += ld_peer_s32(map_peer(&s_x->ps[r], p));
+      }
+      A -= iov * psum;
+      const int code = quant_int<true>(fmul(__int2float_rn(A), a.spv), qo);
+      a.out[int64_t(b) * ldo + (kvh * R + r) * HD + d] = (uint8_t)code;
+      csum += code;
+    }
+    if (a.rowsum_out) {
+      int one[8] = {csum, 0, 0, 0, 0, 0, 0, 0};
+      block_reduce256_n(one, 1, OpSum(), reinterpret_cast<int*>(s_scr));
+      if (tid == 0) atomicAdd(a.rowsum_out + b, one[0]);
+    }
   }
+  cluster_sync_all();                                   // #4: peers keep their shared memory alive until the leader has read it
 }
 
-static size_t attn_dec_smem(int hd, int R, int Tpad) {
+static size_t attn_dec_smem(int hd, int R, int Tslice) {
   const int WPR = hd / 4, KS = 256 / WPR;
-  return size_t(8) * WPR * 4 + 512 * 4 + size_t(KS) * 8 * hd * 4 + 8 * 8 + 4 * 8 * 4 + size_t(R) * Tpad * 2 + 16;
+  return sizeof(DecXchg) + 64 * 8 + size_t(8 + 2) * WPR * 4 + 512 * 4 + size_t(KS) * 8 * hd * 4 + 4 * 8 * 4 + size_t(R) * Tslice * 2 + 16;
+}
+
+// =====================================================================================================================
+// fp32 lm_head for the decode step: logits[b, v] = sum_k x[b, k] * W[v, k] for B <= 16 rows.  The reference keeps lm_head
+// unquantised (qm:843-845); a library SGEMM moves its 0.26-2.1 GB of weights at 2.4-2.6 TB/s for these shapes, this kernel
+// streams every weight row once with 16-byte loads (one warp per vocabulary row, x rows via L1) and is HBM-bound.
+// Summation order is fixed (lane-strided partials, then a shuffle tree): run-to-run deterministic.
+// =====================================================================================================================
+template <int BMAX>
+__global__ void __launch_bounds__(256) fgemv_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
+                                                    int B, int V, int K) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (v >= V) return;
+  const float* wr = w + int64_t(v) * K;
+  float acc[BMAX];
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wv = ldg4_stream(wr + k);
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) {
+      if (b < B) {
+        const float4 xv = ldg4(x + int64_t(b) * K + k);
+        acc[b] = __fmaf_rn(wv.x, xv.x, acc[b]); acc[b] = __fmaf_rn(wv.y, xv.y, acc[b]);
+        acc[b] = __fmaf_rn(wv.z, xv.z, acc[b]); acc[b] = __fmaf_rn(wv.w, xv.w, acc[b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < BMAX; ++b) {
+    if (b < B) {
+      float t = acc[b];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+      if (lane == 0) out[int64_t(b) * V + v] = t;
+    }
+  }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (same helper as qgemm.cu, local copy of the lookup)
@@ -516,8 +639,9 @@ int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, 
 int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
                       const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
                       int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
-                      void* stream) {
+                      int32_t* zero_out, void* stream) {
   MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, zero_out != rowsum && (zero_out == nullptr || zero_out != rowsum_out), "zero_out must not alias rowsum / rowsum_out");
   MQ_REQUIRE(c, acc && rowsum && sxw && ow && c0 && so && oo && B > 0 && N > 0, "null pointer or empty problem");
   MQ_REQUIRE(c, mode >= GV_QUANT && mode <= GV_RESID, "mode must be 0 (QUANT), 1 (ACTMUL) or 2 (RESID)");
   MQ_REQUIRE(c, N % 4 == 0 && ldacc % 4 == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0, "N, ldacc must be multiples of 4, acc 16-byte aligned");
@@ -526,7 +650,7 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
   MQ_REQUIRE(c, mode != GV_ACTMUL || (out && lut && N % 256 == 0 && 128 % qgroup == 0 && ldo % 4 == 0), "ACTMUL needs out/lut, N % 256 == 0, qgroup | 128");
   MQ_REQUIRE(c, mode != GV_RESID || (resid && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0), "RESID needs a 16-byte aligned resid, ldo % 4 == 0");
   MQ_REQUIRE(c, qmax < 4194304.f && qmax2 < 4194304.f, "qmax must be below 2^22");
-  GvEpiArgs a{B, N, acc, ldacc, rowsum, sxw, ow, c0, bias, so, oo, qgroup, qmax, out, ldo, rowsum_out, lut, s2, o2, qmax2, resid};
+  GvEpiArgs a{B, N, acc, ldacc, rowsum, sxw, ow, c0, bias, so, oo, qgroup, qmax, out, ldo, rowsum_out, lut, s2, o2, qmax2, resid, zero_out};
   const int NO = mode == GV_ACTMUL ? N / 2 : N;
   dim3 grid((NO / 4 + 127) / 128, B);
   cudaStream_t st = (cudaStream_t)stream;
@@ -534,6 +658,18 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
   else if (mode == GV_ACTMUL) qgemv_epi_kernel<GV_ACTMUL><<<grid, 128, 0, st>>>(a);
   else qgemv_epi_kernel<GV_RESID><<<grid, 128, 0, st>>>(a);
   return check_launch(c, "mq_qgemv_epilogue");
+}
+
+int mq_fgemv(void* ctx, const float* x, const float* w, float* out, int B, int V, int K, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, x && w && out && B > 0 && V > 0 && K > 0, "null pointer or empty problem");
+  MQ_REQUIRE(c, B <= 16 && K % 4 == 0, "the decode lm_head kernel covers up to 16 rows, K a multiple of 4");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "x and w must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((V + 7) / 8);
+  if (B <= 8) fgemv_kernel<8><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
+  else fgemv_kernel<16><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
+  return check_launch(c, "mq_fgemv");
 }
 
 int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int nkv, int hd, int rot, int Tmax, int pos,
@@ -564,23 +700,40 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
   MQ_REQUIRE(c, a.oq == rintf(a.oq) && a.ok == rintf(a.ok) && a.ov == rintf(a.ov) && a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out),
              "integer engine kernels need integral offsets (qm:60)");
   a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
-  a.Tpad = (pos_bound + 1 + 7) / 8 * 8;
-  const size_t smem = attn_dec_smem(hd, nh / nkv, a.Tpad);
+  // key slices: one cluster per (sequence, kv head); enough CTAs to fill the machine, at least 64 keys per slice
+  int CS = 1;
+  while (CS < 8 && B * nkv * CS * 2 <= 2 * c->sm_count && (pos_bound + 1) / (CS * 2) >= 64) CS *= 2;
+  a.CS = CS;
+  a.Tslice = (((pos_bound + 1) + CS - 1) / CS + 7) / 8 * 8;
+  const size_t smem = attn_dec_smem(hd, nh / nkv, a.Tslice);
   MQ_REQUIRE(c, smem <= 227 * 1024, "sequence too long for the decode attention score slab");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = B * nkv;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * nkv * CS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaSuccess;
 #define MQ_DEC(HDV)                                                                                                         \
   {                                                                                                                         \
-    static size_t attr = 48 * 1024;                                                                                         \
-    if (smem > attr) {                                                                                                      \
+    static size_t attr_smem = 48 * 1024;                                                                                    \
+    static bool np_set = false;                                                                                             \
+    if (smem > attr_smem) {                                                                                                 \
       cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));  \
-      attr = smem;                                                                                                          \
+      attr_smem = smem;                                                                                                     \
     }                                                                                                                       \
-    qattn_decode_kernel<HDV><<<grid, 256, smem, st>>>(a);                                                                   \
+    if (CS > 8 && !np_set) {                                                                                                \
+      cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);    \
+      if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));  \
+      np_set = true;                                                                                                        \
+    }                                                                                                                       \
+    le = cudaLaunchKernelEx(&cfg, qattn_decode_kernel<HDV>, a);                                                             \
   }
   if (hd == 32) MQ_DEC(32) else if (hd == 64) MQ_DEC(64) else if (hd == 128) MQ_DEC(128) else MQ_DEC(256)
 #undef MQ_DEC
+  if (le != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qattn_decode launch: ") + cudaGetErrorString(le));
   return check_launch(c, "mq_qattn_decode");
 }
 

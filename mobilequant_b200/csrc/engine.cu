@@ -118,6 +118,92 @@ __global__ void __launch_bounds__(128) qnorm_kernel(const NormArgs a) {
   if (lane == 0 && a.rowsum) a.rowsum[row] = csum;
 }
 
+// Few-row variant (decode step: rows == batch): one warp per row leaves a ~3 k-instruction dependent chain on a single
+// warp (17 us per launch for 8 rows); here one 256-thread CTA owns a row, statistics meet through shared memory.  Same
+// arithmetic: the integer sums are exact, so the reduction order does not matter.
+template <bool kLayerNorm>
+__global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a) {
+  __shared__ unsigned long long s_s2[8];
+  __shared__ long long s_s1[8];
+  __shared__ int s_cs[8];
+  const int64_t row = blockIdx.x;
+  const int H = a.H, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = a.x + row * H;
+  const QParam qi = make_qparam(a.s_in, a.o_in, a.qmax_in);
+  const QParam qo = make_qparam(a.s_out, a.o_out, a.qmax_out);
+  constexpr int NR = 8;                           // float4 per thread: H <= 8192
+  float rr[NR][4];
+  unsigned long long s2 = 0; long long s1 = 0;
+#pragma unroll
+  for (int it = 0; it < NR; ++it) {
+    const int k = (it * 256 + tid) * 4;
+    if (k < H) {
+      const float4 v = ldg4_stream(xr + k);
+      rr[it][0] = __fsub_rn(quant_magic<true>(v.x, qi), kRoundMagic); rr[it][1] = __fsub_rn(quant_magic<true>(v.y, qi), kRoundMagic);
+      rr[it][2] = __fsub_rn(quant_magic<true>(v.z, qi), kRoundMagic); rr[it][3] = __fsub_rn(quant_magic<true>(v.w, qi), kRoundMagic);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = __float2int_rn(rr[it][j]);
+        s2 += (unsigned long long)((long long)i * i);
+        if (kLayerNorm) s1 += i;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    if (kLayerNorm) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+  }
+  if (lane == 0) { s_s2[warp] = s2; s_s1[warp] = s1; }
+  __syncthreads();
+  s2 = 0; s1 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s2 += s_s2[i]; s1 += s_s1[i]; }
+  float denom = 1.f, rdenom = 1.f, mean = 0.f, rstd = 1.f;
+  if (kLayerNorm) {
+    const double m = (double)s1 / (double)H;
+    const double var = (double)s2 / (double)H - m * m;
+    mean = (float)(m * (double)a.s_in);
+    rstd = (float)(1.0 / sqrt(var * (double)a.s_in * (double)a.s_in + (double)a.eps));
+  } else {
+    denom = fmaxf(fmul(__fsqrt_rn(__ull2float_rn(s2)), a.s_in), 1e-12f);
+    rdenom = __frcp_rn(denom);
+  }
+  int csum = 0;
+#pragma unroll
+  for (int it = 0; it < NR; ++it) {
+    const int k = (it * 256 + tid) * 4;
+    if (k < H) {
+      const float4 w = ldg4(a.w_fq + k);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.bias) { const float4 b = ldg4(a.bias + k); bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w; }
+      uint32_t packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmul(rr[it][j], a.s_in);
+        float t;
+        if (kLayerNorm) t = fmul(fmul(fsub(xh, mean), rstd), wv[j]);
+        else t = fmul(wv[j], fmul(a.alpha, div_rn<true>(xh, denom, rdenom)));
+        if (a.bias) t = fadd(t, bv[j]);
+        packed |= (uint32_t)quant_int<true>(t, qo) << (8 * j);
+      }
+      csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+      *reinterpret_cast<uint32_t*>(a.codes + row * H + k) = packed;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
+  if (lane == 0) s_cs[warp] = csum;
+  __syncthreads();
+  if (tid == 0 && a.rowsum) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_cs[i];
+    a.rowsum[row] = t;
+  }
+}
+
 // =====================================================================================================================
 // K5: de-quantise q/k/v projection codes, RoPE (hm:338-367, partial rotary hm:489-501), re-quantise with the qk_bmm /
 // pv_bmm input quantizers (qm:455-459) and write the attention layouts:
@@ -1037,6 +1123,11 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
              "x / w_fq / bias must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
+  if (rows <= 256 && H <= 8192) {                 // decode-sized inputs: one CTA per row
+    if (is_layernorm) qnorm_row_kernel<true><<<(unsigned)rows, 256, 0, st>>>(a);
+    else qnorm_row_kernel<false><<<(unsigned)rows, 256, 0, st>>>(a);
+    return check_launch(c, "mq_qnorm");
+  }
   unsigned grid = (unsigned)((rows + 3) / 4);
 #define MQ_NORM(LN, NV) qnorm_kernel<LN, NV><<<grid, 128, 0, st>>>(a)
   if (is_layernorm) {

@@ -299,7 +299,10 @@ class IntEngine:
         return h
 
     def _head(self, h):
-        return torch.nn.functional.linear(self.final_norm(h), self.lm_head)
+        hn = self.final_norm(h)
+        if hn.dim() == 2 and hn.shape[0] <= 16:        # decode step: HBM-bound fp32 GEMV instead of a library SGEMM
+            return K.fgemv(hn.contiguous(), self.lm_head)
+        return torch.nn.functional.linear(hn, self.lm_head)
 
     @torch.no_grad()
     def prefill(self, input_ids, cache):
@@ -339,16 +342,15 @@ class IntEngine:
         pkw = dict(pos_dev=cache.pos_dev, pos_bound=cache.Tmax - 1) if use_pos_dev else {}
         for i, L in enumerate(self.layers):
             K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
-            self._gemv(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, bufs["acc"], out=bufs["qkv"])
-            bufs["rs_attn"].zero_()
+            # code-sum buffers are cleared by an epilogue that runs between their consumer and their next producer
+            self._gemv(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, bufs["acc"], out=bufs["qkv"], zero_out=bufs["rs_act"])
             K.qattn_decode(bufs["qkv"], B, self.nh, self.nkv, self.hd, self.rot, pos, L["rope_in"], L["rope_out"], cos, sin, cache.k[i], cache.v[i],
                            cache.rsk[i], L["attn"], L["attn_lut"], out=bufs["attn"], rowsum_out=bufs["rs_attn"], **pkw)
             self._gemv(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, bufs["acc"], resid=h)
             K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
-            bufs["rs_act"].zero_()
             w2in = L["w2_in"]
             self._gemv(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, bufs["acc"], out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1],
-                       qmax2=w2in[2], rowsum_out=bufs["rs_act"])
+                       qmax2=w2in[2], rowsum_out=bufs["rs_act"], zero_out=bufs["rs_attn"])
             self._gemv(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, bufs["acc"], resid=h)
         return h
 

@@ -30,7 +30,8 @@ def _protos():
     lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
     lib.mq_qgemv.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]
     lib.mq_qgemv_epilogue.argtypes = [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float, _P, c_int64, _P, _P,
-                                      c_float, c_float, c_float, _P, c_int, _P]
+                                      c_float, c_float, c_float, _P, c_int, _P, _P]
+    lib.mq_fgemv.argtypes = [_P, _P, _P, _P, c_int, c_int, c_int, _P]
     lib.mq_qattn_decode.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P]
     lib.mq_selftest_div.argtypes = [_P, c_int64, ctypes.c_uint64, c_int, c_float, _P, _P]
@@ -299,8 +300,21 @@ def qgemv(x, w, acc, ksplit=0):
     return acc
 
 
+def fgemv(x, w, out=None):
+    """fp32 out[B, V] = x[B, K] @ w[V, K]^T for B <= 16 (decode-step lm_head)."""
+    lib = _protos()
+    B, Kd = x.shape
+    V = w.shape[0]
+    if out is None:
+        out = torch.empty(B, V, dtype=F32, device=x.device)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(_launch("fgemv", lib.mq_fgemv, h, ptr(x, F32), ptr(w, F32), ptr(out, F32), B, V, Kd, stream_ptr()), h)
+    return out
+
+
 def qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out=None, ldo=None, rowsum_out=None,
-                   lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None):
+                   lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None, zero_out=None):
     """mq_qgemm's epilogue `mode` (EPI_QUANT 8-bit / EPI_ACTMUL / EPI_RESID) on the accumulator of qgemv; zeroes acc."""
     lib = _protos()
     dev = acc.device
@@ -316,7 +330,7 @@ def qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=
         check(_launch("qgemv_epi", lib.mq_qgemv_epilogue, h, ptr(acc, torch.int32), int(acc.stride(0)), B, N, ptr(rowsum, torch.int32),
                            ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias), int(mode), ptr(so), ptr(oo), float(qmax),
                            ptr(out), int(ldo), ptr(rowsum_out), ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup),
-                           stream_ptr()), h)
+                           ptr(zero_out), stream_ptr()), h)
     return resid if mode == EPI_RESID else out
 
 

@@ -68,7 +68,7 @@ def test_qgemv_epilogues_match_qgemm(cuda, B):
 
 
 @pytest.mark.parametrize("B,T,nh,nkv,hd,rot", [(2, 40, 4, 2, 32, 32), (1, 70, 8, 8, 64, 16), (2, 33, 8, 1, 64, 64), (1, 50, 2, 1, 128, 128),
-                                               (1, 37, 8, 1, 256, 256)])
+                                               (1, 37, 8, 1, 256, 256), (1, 300, 8, 2, 64, 64)])
 def test_qattn_decode_matches_oracle_rows(cuda, B, T, nh, nkv, hd, rot):
     """Token by token: RoPE + append + attention of the new row == row t of the oracle's qrope + causal attention."""
     from mobilequant_b200 import kernels as K
@@ -158,3 +158,14 @@ def test_engine_generate_and_graph_replay(cuda):
         graph.replay()
         got.append(tokens.clone())
     assert torch.equal(torch.stack(got, dim=1), ids[:, 12:])
+
+
+def test_fgemv_lm_head(cuda):
+    from mobilequant_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    for B, V, Kd in ((1, 1000, 256), (8, 32000, 2048), (13, 777, 512)):
+        x = torch.randn(B, Kd, generator=g).to(cuda); w = (torch.randn(V, Kd, generator=g) * 0.02).to(cuda)
+        ref = (x.double() @ w.double().t()).float()
+        got = K.fgemv(x, w)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+        assert torch.equal(got, K.fgemv(x, w))          # deterministic

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 f32 = np.float32
 
 
-@pytest.mark.parametrize("layernorm,H,rows", [(False, 128, 37), (False, 2048, 64), (True, 256, 50)])
+@pytest.mark.parametrize("layernorm,H,rows", [(False, 128, 37), (False, 2048, 64), (True, 256, 50),      # one CTA per row
+                                              (False, 128, 257), (False, 2048, 300), (True, 256, 260), (False, 1024, 290)])  # one warp per row
 def test_qnorm(cuda, layernorm, H, rows):
     from mobilequant_b200 import kernels as K
     rng = np.random.default_rng(H + rows)
