@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--no-calib", action="store_true")
     p.add_argument("--no-decode", action="store_true")
     p.add_argument("--decode-steps", type=int, default=64, help="decode tokens per sequence in the decode leg")
+    p.add_argument("--decode-batch", type=int, default=None, help="sequences in the decode leg (default: --batch)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seq", type=int, default=1, help="sequences in the bounded CPU sample")
     p.add_argument("--profile-step", action="store_true",
@@ -246,7 +247,9 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(model, cfg, act, T, args.cpu_seq)
         if not args.no_decode and world == 1:
-            line["decode"] = decode_throughput(eng, ids_dev, B, T, args.decode_steps)
+            Bd = args.decode_batch or B
+            ids_dec = ids_dev if Bd == B else synth_ids(Bd, T, cfg.vocab_size, 2000 + rank).to(dev)
+            line["decode"] = decode_throughput(eng, ids_dec, Bd, T, args.decode_steps)
         if not args.no_calib and world == 1:
             del eng
             torch.cuda.empty_cache()

@@ -157,6 +157,12 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
                       const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
                       int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
                       int32_t* zero_out, void* stream);
+/* mq_qgemv_fused = mq_qgemv + mq_qgemv_epilogue in one launch: the last CTA to arrive at a group of 128 output columns
+ * (arrival counters inside the context, so one stream per context) finds all partial sums in L2 and runs the epilogue. */
+int mq_qgemv_fused(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
+                   int ldacc, int ksplit, const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                   int mode, const float* so, const float* oo, float qmax, uint8_t* out, int64_t ldo, int32_t* rowsum_out, const float* lut,
+                   float s2, float o2, float qmax2, float* resid, int qgroup, int32_t* zero_out, void* stream);
 /* zero_out (optional, [B]): a code-sum buffer some LATER kernel of the step accumulates into; cleared here so that the
  * step needs no separate memset launches (it must not alias rowsum / rowsum_out of this call).
  *

@@ -72,8 +72,18 @@ int mq_setup(void** ctx, int device) {
   e = cudaMalloc(&c->ws, c->ws_bytes);
   cudaSetDevice(cur);
   if (e != cudaSuccess) {
+    cudaSetDevice(cur);
     c->ws = nullptr;
     return mq::fail(c, MQ_FAILED_ALLOCATION, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  cudaSetDevice(device);
+  c->n_counters = 8192;
+  e = cudaMalloc(reinterpret_cast<void**>(&c->counters), c->n_counters * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, c->n_counters * sizeof(int));
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) {
+    c->counters = nullptr;
+    return mq::fail(c, MQ_FAILED_ALLOCATION, std::string("counter cudaMalloc: ") + cudaGetErrorString(e));
   }
   return MQ_NO_ERROR;
 }
@@ -88,6 +98,7 @@ int mq_release(void* ctx) {
   MQ_CTX(c, ctx);
   if (c->refs.fetch_sub(1) == 1) {
     if (c->ws) cudaFree(c->ws);
+    if (c->counters) cudaFree(c->counters);
     c->magic = 0;
     delete c;
   }

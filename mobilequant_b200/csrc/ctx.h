@@ -18,6 +18,8 @@ struct Ctx {
   int sm_count = 148;
   void* ws = nullptr;      // device scratch (deterministic two-stage reductions, split-K partials)
   size_t ws_bytes = 0;
+  int* counters = nullptr; // zero-initialised arrival counters of the fused skinny-GEMM epilogue (self-resetting)
+  int n_counters = 0;
   std::string last_error[6];
 };
 

@@ -24,6 +24,101 @@ namespace mq {
 using namespace tc;
 
 // =====================================================================================================================
+// epilogue of the skinny GEMM: same arithmetic as qgemm_kernel's epilogue (qgemm.cu); the unit of work is one row m and
+// four consecutive output columns.  Used by the standalone epilogue kernel and by the last CTA of a column group inside
+// qgemv_kernel (fused path).
+// =====================================================================================================================
+enum { GV_NONE = -1, GV_QUANT = 0, GV_ACTMUL = 1, GV_RESID = 2 };
+
+struct GvEpiArgs {
+  int B, N;
+  int32_t* acc; int ldacc;
+  const int32_t* rowsum; const float* sxw; const int32_t* ow; const int32_t* c0; const float* bias;
+  const float* so; const float* oo; int qgroup; float qmax;
+  uint8_t* out; int64_t ldo; int32_t* rowsum_out;
+  const float* lut; float s2, o2, qmax2;
+  float* resid;
+  int32_t* zero_out;       // [B] or null: cleared here so that the NEXT accumulation into it starts from zero
+};
+
+__device__ __forceinline__ float gv_y(const GvEpiArgs& a, int acc, int rs, int n) {
+  const int I = acc - __ldg(a.ow + n) * rs + __ldg(a.c0 + n);
+  float y = __fmul_rn(__int2float_rn(I), __ldg(a.sxw + n));
+  if (a.bias) y = __fadd_rn(y, __ldg(a.bias + n));
+  return y;
+}
+
+// row m, output columns j0..j0+3 (j0 % 4 == 0, j0 < number of output columns); returns the sum of the emitted codes.
+// The accumulator words are read from L2 (they were produced by red.add of other CTAs) and handed back zeroed.
+template <int MODE>
+__device__ __forceinline__ int gv_epi_quad(const GvEpiArgs& a, int m, int j0) {
+  const int rs = __ldg(a.rowsum + m);
+  int32_t* accm = a.acc + int64_t(m) * a.ldacc;
+  const int gmax = (a.N - 1) / a.qgroup;
+  int csum = 0;
+  if (MODE == GV_ACTMUL) {
+    // output column j <-> w1 accumulator column (j / 128) * 256 + j % 128, w3 column 128 further
+    const int n1 = (j0 >> 7) * 256 + (j0 & 127), n3 = n1 + 128;
+    const int4 a1 = __ldcg(reinterpret_cast<const int4*>(accm + n1)), a3 = __ldcg(reinterpret_cast<const int4*>(accm + n3));
+    *reinterpret_cast<int4*>(accm + n1) = make_int4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(accm + n3) = make_int4(0, 0, 0, 0);
+    const int g1 = min(n1 / a.qgroup, gmax), g3 = min(n3 / a.qgroup, gmax);
+    const QParam q1 = make_qparam(__ldg(a.so + g1), __ldg(a.oo + g1), a.qmax), q3 = make_qparam(__ldg(a.so + g3), __ldg(a.oo + g3), a.qmax);
+    const QParam q2 = make_qparam(a.s2, a.o2, a.qmax2);
+    const int v1[4] = {a1.x, a1.y, a1.z, a1.w}, v3[4] = {a3.x, a3.y, a3.z, a3.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float y1 = gv_y(a, v1[e], rs, n1 + e), y3 = gv_y(a, v3[e], rs, n3 + e);
+      const float act = __ldg(a.lut + quant_int<true>(y1, q1));
+      const float u = __fmul_rn(__fsub_rn(quant_magic<true>(y3, q3), kRoundMagic), q3.s);
+      w |= (uint32_t)quant_int<true>(__fmul_rn(act, u), q2) << (8 * e);
+    }
+    csum = (int)__dp4a(w, 0x01010101u, 0u);
+    *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
+  } else {
+    const int4 av = __ldcg(reinterpret_cast<const int4*>(accm + j0));
+    *reinterpret_cast<int4*>(accm + j0) = make_int4(0, 0, 0, 0);
+    const int g = min(j0 / a.qgroup, gmax);
+    const QParam q = make_qparam(__ldg(a.so + g), __ldg(a.oo + g), a.qmax);
+    const int v[4] = {av.x, av.y, av.z, av.w};
+    if (MODE == GV_QUANT) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w |= (uint32_t)quant_int<true>(gv_y(a, v[e], rs, j0 + e), q) << (8 * e);
+      csum = (int)__dp4a(w, 0x01010101u, 0u);
+      *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
+    } else {
+      float4* dst = reinterpret_cast<float4*>(a.resid + int64_t(m) * a.ldo + j0);
+      float4 h = *dst;
+      float d[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[e] = __fmul_rn(__fsub_rn(quant_magic<true>(gv_y(a, v[e], rs, j0 + e), q), kRoundMagic), q.s);
+      h.x = __fadd_rn(h.x, d[0]); h.y = __fadd_rn(h.y, d[1]); h.z = __fadd_rn(h.z, d[2]); h.w = __fadd_rn(h.w, d[3]);
+      *dst = h;
+    }
+  }
+  return csum;
+}
+
+// standalone epilogue: blockIdx.y = m so that the emitted-code sum of a block belongs to one row
+template <int MODE>
+__global__ void __launch_bounds__(128) qgemv_epi_kernel(const GvEpiArgs a) {
+  __shared__ int s_sum[4];
+  const int m = blockIdx.y;
+  const int NO = MODE == GV_ACTMUL ? a.N / 2 : a.N;                 // output columns
+  const int j0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (a.zero_out && blockIdx.x == 0 && threadIdx.x == 0) a.zero_out[m] = 0;
+  int csum = j0 < NO ? gv_epi_quad<MODE>(a, m, j0) : 0;
+  if (MODE != GV_RESID && a.rowsum_out) {
+    csum = warp_reduce(csum, OpSum());
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = csum;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(a.rowsum_out + m, s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3]);
+  }
+}
+
+// =====================================================================================================================
 // qgemv
 // =====================================================================================================================
 constexpr int kGvBM = 128;        // weight rows per tile == UMMA M
@@ -35,6 +130,9 @@ struct QGemvArgs {
   int32_t* acc;       // [B, ldacc] s32, accumulated with red.add
   int ldacc;
   int ksplit;
+  int mode;           // GV_NONE: raw accumulator only; else the last CTA of each column group runs that epilogue
+  int* counters;      // [column groups] arrival counters (zero on entry, reset by the last CTA)
+  GvEpiArgs epi;
 };
 
 template <int BP>
@@ -58,6 +156,7 @@ qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
   uint64_t* empty_bar = full_bar + kGvStages;
   uint64_t* tfull_bar = empty_bar + kGvStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  volatile int* epi_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.ksplit, ks = blockIdx.x % p.ksplit;
@@ -127,97 +226,45 @@ qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
           if (c + j < p.B) atomicAdd(p.acc + int64_t(c + j) * p.ldacc + n, (int)r[j]);   // result unused -> RED.ADD
       }
     }
+    if (p.mode != GV_NONE) {
+      // ---- fused epilogue: the last CTA to arrive at a column group (one 128-row weight tile; a w1|w3 tile pair for
+      // ACTMUL) finds every partial sum in L2 and requantises the group for all B rows
+      const int et = threadIdx.x - 64;                       // 0..127
+      const int gr = p.mode == GV_ACTMUL ? 2 : 1;
+      const int group = tile / gr;
+      __threadfence();                                        // this thread's red.adds before the arrival
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const int total = gr * p.ksplit;
+        const int old = atomicAdd(p.counters + group, 1);
+        *epi_flag = (old == total - 1);
+        if (old == total - 1) p.counters[group] = 0;          // self-cleaning for the next GEMV on this stream
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*epi_flag) {
+        __threadfence();
+        const int NO = p.mode == GV_ACTMUL ? p.N / 2 : p.N;
+        const int jbase = group * 128;                        // 128 output columns per group in every mode
+        if (group == 0 && p.epi.zero_out) for (int m = et; m < p.B; m += 128) p.epi.zero_out[m] = 0;
+        for (int item = et; item < p.B * 32; item += 128) {   // a warp's 32 items share the row m
+          const int m = item >> 5, j0 = jbase + (item & 31) * 4;
+          int csum = 0;
+          if (j0 < NO) {
+            if (p.mode == GV_QUANT) csum = gv_epi_quad<GV_QUANT>(p.epi, m, j0);
+            else if (p.mode == GV_ACTMUL) csum = gv_epi_quad<GV_ACTMUL>(p.epi, m, j0);
+            else csum = gv_epi_quad<GV_RESID>(p.epi, m, j0);
+          }
+          if (p.mode != GV_RESID && p.epi.rowsum_out) {
+            csum = warp_reduce(csum, OpSum());
+            if (lane == 0) atomicAdd(p.epi.rowsum_out + m, csum);
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
-}
-
-// =====================================================================================================================
-// epilogue of the skinny GEMM: same arithmetic as qgemm_kernel's epilogue (qgemm.cu), one thread = one row m and four
-// consecutive output columns; blockIdx.y = m so that the emitted-code sum of a block belongs to one row.
-// =====================================================================================================================
-enum { GV_QUANT = 0, GV_ACTMUL = 1, GV_RESID = 2 };
-
-struct GvEpiArgs {
-  int B, N;
-  int32_t* acc; int ldacc;
-  const int32_t* rowsum; const float* sxw; const int32_t* ow; const int32_t* c0; const float* bias;
-  const float* so; const float* oo; int qgroup; float qmax;
-  uint8_t* out; int64_t ldo; int32_t* rowsum_out;
-  const float* lut; float s2, o2, qmax2;
-  float* resid;
-  int32_t* zero_out;       // [B] or null: cleared here so that the NEXT accumulation into it starts from zero
-};
-
-__device__ __forceinline__ float gv_y(const GvEpiArgs& a, int acc, int rs, int n) {
-  const int I = acc - __ldg(a.ow + n) * rs + __ldg(a.c0 + n);
-  float y = __fmul_rn(__int2float_rn(I), __ldg(a.sxw + n));
-  if (a.bias) y = __fadd_rn(y, __ldg(a.bias + n));
-  return y;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(128) qgemv_epi_kernel(const GvEpiArgs a) {
-  __shared__ int s_sum[4];
-  const int m = blockIdx.y;
-  const int NO = MODE == GV_ACTMUL ? a.N / 2 : a.N;                 // output columns
-  const int j0 = (blockIdx.x * 128 + threadIdx.x) * 4;
-  const int rs = __ldg(a.rowsum + m);
-  int32_t* accm = a.acc + int64_t(m) * a.ldacc;
-  int csum = 0;
-  if (a.zero_out && blockIdx.x == 0 && threadIdx.x == 0) a.zero_out[m] = 0;
-  if (j0 < NO) {
-    const int gmax = (a.N - 1) / a.qgroup;
-    if (MODE == GV_ACTMUL) {
-      // output column j <-> w1 accumulator column (j / 128) * 256 + j % 128, w3 column 128 further
-      const int n1 = (j0 >> 7) * 256 + (j0 & 127), n3 = n1 + 128;
-      const int4 a1 = *reinterpret_cast<const int4*>(accm + n1), a3 = *reinterpret_cast<const int4*>(accm + n3);
-      *reinterpret_cast<int4*>(accm + n1) = make_int4(0, 0, 0, 0);
-      *reinterpret_cast<int4*>(accm + n3) = make_int4(0, 0, 0, 0);
-      const int g1 = min(n1 / a.qgroup, gmax), g3 = min(n3 / a.qgroup, gmax);
-      const QParam q1 = make_qparam(__ldg(a.so + g1), __ldg(a.oo + g1), a.qmax), q3 = make_qparam(__ldg(a.so + g3), __ldg(a.oo + g3), a.qmax);
-      const QParam q2 = make_qparam(a.s2, a.o2, a.qmax2);
-      const int v1[4] = {a1.x, a1.y, a1.z, a1.w}, v3[4] = {a3.x, a3.y, a3.z, a3.w};
-      uint32_t w = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float y1 = gv_y(a, v1[e], rs, n1 + e), y3 = gv_y(a, v3[e], rs, n3 + e);
-        const float act = __ldg(a.lut + quant_int<true>(y1, q1));
-        const float u = __fmul_rn(__fsub_rn(quant_magic<true>(y3, q3), kRoundMagic), q3.s);
-        w |= (uint32_t)quant_int<true>(__fmul_rn(act, u), q2) << (8 * e);
-      }
-      csum = (int)__dp4a(w, 0x01010101u, 0u);
-      *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
-    } else {
-      const int4 av = *reinterpret_cast<const int4*>(accm + j0);
-      *reinterpret_cast<int4*>(accm + j0) = make_int4(0, 0, 0, 0);
-      const int g = min(j0 / a.qgroup, gmax);
-      const QParam q = make_qparam(__ldg(a.so + g), __ldg(a.oo + g), a.qmax);
-      const int v[4] = {av.x, av.y, av.z, av.w};
-      if (MODE == GV_QUANT) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) w |= (uint32_t)quant_int<true>(gv_y(a, v[e], rs, j0 + e), q) << (8 * e);
-        csum = (int)__dp4a(w, 0x01010101u, 0u);
-        *reinterpret_cast<uint32_t*>(a.out + int64_t(m) * a.ldo + j0) = w;
-      } else {
-        float4* dst = reinterpret_cast<float4*>(a.resid + int64_t(m) * a.ldo + j0);
-        float4 h = *dst;
-        float d[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = __fmul_rn(__fsub_rn(quant_magic<true>(gv_y(a, v[e], rs, j0 + e), q), kRoundMagic), q.s);
-        h.x = __fadd_rn(h.x, d[0]); h.y = __fadd_rn(h.y, d[1]); h.z = __fadd_rn(h.z, d[2]); h.w = __fadd_rn(h.w, d[3]);
-        *dst = h;
-      }
-    }
-  }
-  if (MODE != GV_RESID && a.rowsum_out) {
-    csum = warp_reduce(csum, OpSum());
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = csum;
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(a.rowsum_out + m, s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3]);
-  }
 }
 
 // =====================================================================================================================
@@ -533,34 +580,49 @@ static size_t attn_dec_smem(int hd, int R, int Tslice) {
 // streams every weight row once with 16-byte loads (one warp per vocabulary row, x rows via L1) and is HBM-bound.
 // Summation order is fixed (lane-strided partials, then a shuffle tree): run-to-run deterministic.
 // =====================================================================================================================
+// One warp owns kFgRows consecutive vocabulary rows so that every x vector fetched from L1 feeds kFgRows x 4 FMAs
+// (a single row per warp re-reads x once per weight vector and is L1-bandwidth bound at 3.0-3.5 TB/s).
+constexpr int kFgRows = 4;
 template <int BMAX>
 __global__ void __launch_bounds__(256) fgemv_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
                                                     int B, int V, int K) {
   const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (v >= V) return;
-  const float* wr = w + int64_t(v) * K;
-  float acc[BMAX];
+  const int v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kFgRows;
+  if (v0 >= V) return;
+  float acc[kFgRows][BMAX];
 #pragma unroll
-  for (int b = 0; b < BMAX; ++b) acc[b] = 0.f;
+  for (int r = 0; r < kFgRows; ++r)
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) acc[r][b] = 0.f;
+  const float* wr[kFgRows];
+#pragma unroll
+  for (int r = 0; r < kFgRows; ++r) wr[r] = w + int64_t(min(v0 + r, V - 1)) * K;      // tail rows alias the last row (not stored)
   for (int k = lane * 4; k < K; k += 128) {
-    const float4 wv = ldg4_stream(wr + k);
+    float4 wv[kFgRows];
+#pragma unroll
+    for (int r = 0; r < kFgRows; ++r) wv[r] = ldg4_stream(wr[r] + k);
 #pragma unroll
     for (int b = 0; b < BMAX; ++b) {
       if (b < B) {
         const float4 xv = ldg4(x + int64_t(b) * K + k);
-        acc[b] = __fmaf_rn(wv.x, xv.x, acc[b]); acc[b] = __fmaf_rn(wv.y, xv.y, acc[b]);
-        acc[b] = __fmaf_rn(wv.z, xv.z, acc[b]); acc[b] = __fmaf_rn(wv.w, xv.w, acc[b]);
+#pragma unroll
+        for (int r = 0; r < kFgRows; ++r) {
+          acc[r][b] = __fmaf_rn(wv[r].x, xv.x, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].y, xv.y, acc[r][b]);
+          acc[r][b] = __fmaf_rn(wv[r].z, xv.z, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].w, xv.w, acc[r][b]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int b = 0; b < BMAX; ++b) {
-    if (b < B) {
-      float t = acc[b];
+  for (int r = 0; r < kFgRows; ++r) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-      if (lane == 0) out[int64_t(b) * V + v] = t;
+    for (int b = 0; b < BMAX; ++b) {
+      if (b < B) {
+        float t = acc[r][b];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0 && v0 + r < V) out[int64_t(b) * V + v0 + r] = t;
+      }
     }
   }
 }
@@ -614,33 +676,31 @@ using namespace mq;
 
 extern "C" {
 
-int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
-             int ldacc, int ksplit, void* stream) {
-  MQ_CTX(c, ctx);
+static int qgemv_dispatch(Ctx* c, const void* x_codes, int x_signed, const void* w_codes, int w_signed, QGemvArgs& args, cudaStream_t st) {
+  const int k_iters = (args.K + kGvBK - 1) / kGvBK;
+  const int n_tiles = (args.N + kGvBM - 1) / kGvBM;
+  if (args.ksplit <= 0) {
+    // fill the machine (two CTAs per SM) but keep at least two 128-byte K slices per CTA
+    args.ksplit = std::max(1, std::min(2 * c->sm_count / n_tiles, std::max(1, k_iters / 2)));
+  }
+  args.ksplit = std::min(args.ksplit, k_iters);
+  if (args.B <= 16) return launch_qgemv<16>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  if (args.B <= 32) return launch_qgemv<32>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  if (args.B <= 64) return launch_qgemv<64>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  return launch_qgemv<128>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+}
+
+static int qgemv_check(Ctx* c, const void* x_codes, const void* w_codes, const int32_t* acc, int B, int N, int K, int ldacc) {
   MQ_REQUIRE(c, x_codes && w_codes && acc && B > 0 && N > 0 && K > 0, "null operand or empty problem");
   MQ_REQUIRE(c, B <= 128, "the skinny GEMM covers up to 128 rows; use mq_qgemm above");
   MQ_REQUIRE(c, K % 16 == 0 && ldacc >= N, "K must be a multiple of 16 and ldacc >= N");
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x_codes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_codes) & 15) == 0, "operands must be 16-byte aligned");
-  const int k_iters = (K + kGvBK - 1) / kGvBK;
-  const int n_tiles = (N + kGvBM - 1) / kGvBM;
-  if (ksplit <= 0) {
-    // fill the machine (two CTAs per SM) but keep at least two 128-byte K slices per CTA
-    ksplit = std::max(1, std::min(2 * c->sm_count / n_tiles, std::max(1, k_iters / 2)));
-  }
-  ksplit = std::min(ksplit, k_iters);
-  QGemvArgs args{B, N, K, acc, ldacc, ksplit};
-  cudaStream_t st = (cudaStream_t)stream;
-  if (B <= 16) return launch_qgemv<16>(c, x_codes, x_signed, w_codes, w_signed, args, st);
-  if (B <= 32) return launch_qgemv<32>(c, x_codes, x_signed, w_codes, w_signed, args, st);
-  if (B <= 64) return launch_qgemv<64>(c, x_codes, x_signed, w_codes, w_signed, args, st);
-  return launch_qgemv<128>(c, x_codes, x_signed, w_codes, w_signed, args, st);
+  return MQ_NO_ERROR;
 }
 
-int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
-                      const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
-                      int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
-                      int32_t* zero_out, void* stream) {
-  MQ_CTX(c, ctx);
+static int qgemv_epi_check(Ctx* c, const int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
+                           const int32_t* c0, int mode, const float* so, const float* oo, float qmax, const uint8_t* out, int64_t ldo,
+                           const int32_t* rowsum_out, const float* lut, float qmax2, const float* resid, int qgroup, const int32_t* zero_out) {
   MQ_REQUIRE(c, zero_out != rowsum && (zero_out == nullptr || zero_out != rowsum_out), "zero_out must not alias rowsum / rowsum_out");
   MQ_REQUIRE(c, acc && rowsum && sxw && ow && c0 && so && oo && B > 0 && N > 0, "null pointer or empty problem");
   MQ_REQUIRE(c, mode >= GV_QUANT && mode <= GV_RESID, "mode must be 0 (QUANT), 1 (ACTMUL) or 2 (RESID)");
@@ -650,6 +710,38 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
   MQ_REQUIRE(c, mode != GV_ACTMUL || (out && lut && N % 256 == 0 && 128 % qgroup == 0 && ldo % 4 == 0), "ACTMUL needs out/lut, N % 256 == 0, qgroup | 128");
   MQ_REQUIRE(c, mode != GV_RESID || (resid && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0), "RESID needs a 16-byte aligned resid, ldo % 4 == 0");
   MQ_REQUIRE(c, qmax < 4194304.f && qmax2 < 4194304.f, "qmax must be below 2^22");
+  return MQ_NO_ERROR;
+}
+
+int mq_qgemv(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
+             int ldacc, int ksplit, void* stream) {
+  MQ_CTX(c, ctx);
+  if (int rc = qgemv_check(c, x_codes, w_codes, acc, B, N, K, ldacc)) return rc;
+  QGemvArgs args{};
+  args.B = B; args.N = N; args.K = K; args.acc = acc; args.ldacc = ldacc; args.ksplit = ksplit; args.mode = GV_NONE; args.counters = nullptr;
+  return qgemv_dispatch(c, x_codes, x_signed, w_codes, w_signed, args, (cudaStream_t)stream);
+}
+
+int mq_qgemv_fused(void* ctx, const void* x_codes, int x_signed, const void* w_codes, int w_signed, int B, int N, int K, int32_t* acc,
+                   int ldacc, int ksplit, const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                   int mode, const float* so, const float* oo, float qmax, uint8_t* out, int64_t ldo, int32_t* rowsum_out, const float* lut,
+                   float s2, float o2, float qmax2, float* resid, int qgroup, int32_t* zero_out, void* stream) {
+  MQ_CTX(c, ctx);
+  if (int rc = qgemv_check(c, x_codes, w_codes, acc, B, N, K, ldacc)) return rc;
+  if (int rc = qgemv_epi_check(c, acc, ldacc, B, N, rowsum, sxw, ow, c0, mode, so, oo, qmax, out, ldo, rowsum_out, lut, qmax2, resid, qgroup, zero_out)) return rc;
+  MQ_REQUIRE(c, c->counters && (N + 127) / 128 <= c->n_counters, "too many column groups for the arrival counters");
+  QGemvArgs args{};
+  args.B = B; args.N = N; args.K = K; args.acc = acc; args.ldacc = ldacc; args.ksplit = ksplit; args.mode = mode; args.counters = c->counters;
+  args.epi = GvEpiArgs{B, N, acc, ldacc, rowsum, sxw, ow, c0, bias, so, oo, qgroup, qmax, out, ldo, rowsum_out, lut, s2, o2, qmax2, resid, zero_out};
+  return qgemv_dispatch(c, x_codes, x_signed, w_codes, w_signed, args, (cudaStream_t)stream);
+}
+
+int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const int32_t* rowsum, const float* sxw, const int32_t* ow,
+                      const int32_t* c0, const float* bias, int mode, const float* so, const float* oo, float qmax, uint8_t* out,
+                      int64_t ldo, int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                      int32_t* zero_out, void* stream) {
+  MQ_CTX(c, ctx);
+  if (int rc = qgemv_epi_check(c, acc, ldacc, B, N, rowsum, sxw, ow, c0, mode, so, oo, qmax, out, ldo, rowsum_out, lut, qmax2, resid, qgroup, zero_out)) return rc;
   GvEpiArgs a{B, N, acc, ldacc, rowsum, sxw, ow, c0, bias, so, oo, qgroup, qmax, out, ldo, rowsum_out, lut, s2, o2, qmax2, resid, zero_out};
   const int NO = mode == GV_ACTMUL ? N / 2 : N;
   dim3 grid((NO / 4 + 127) / 128, B);
@@ -666,7 +758,7 @@ int mq_fgemv(void* ctx, const float* x, const float* w, float* out, int B, int V
   MQ_REQUIRE(c, B <= 16 && K % 4 == 0, "the decode lm_head kernel covers up to 16 rows, K a multiple of 4");
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "x and w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)((V + 7) / 8);
+  const unsigned grid = (unsigned)((V + 8 * kFgRows - 1) / (8 * kFgRows));
   if (B <= 8) fgemv_kernel<8><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
   else fgemv_kernel<16><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
   return check_launch(c, "mq_fgemv");

@@ -31,6 +31,8 @@ def _protos():
     lib.mq_qgemv.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]
     lib.mq_qgemv_epilogue.argtypes = [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float, _P, c_int64, _P, _P,
                                       c_float, c_float, c_float, _P, c_int, _P, _P]
+    lib.mq_qgemv_fused.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
+                                   _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P, _P]
     lib.mq_fgemv.argtypes = [_P, _P, _P, _P, c_int, c_int, c_int, _P]
     lib.mq_qattn_decode.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P]
@@ -331,6 +333,29 @@ def qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=
                            ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias), int(mode), ptr(so), ptr(oo), float(qmax),
                            ptr(out), int(ldo), ptr(rowsum_out), ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup),
                            ptr(zero_out), stream_ptr()), h)
+    return resid if mode == EPI_RESID else out
+
+
+def qgemv_fused(x, w, acc, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out=None, ldo=None, rowsum_out=None,
+                lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None, zero_out=None, ksplit=0):
+    """qgemv + qgemv_epilogue in one launch (the last CTA of each 128-column group runs the epilogue)."""
+    lib = _protos()
+    B, Kd = x.shape
+    N = w.shape[0]
+    dev = x.device
+    if out is None and mode != EPI_RESID:
+        out = torch.empty(B, N // 2 if mode == EPI_ACTMUL else N, dtype=torch.uint8, device=dev)
+    if ldo is None:
+        ldo = resid.stride(0) if mode == EPI_RESID else out.stride(0)
+    if qgroup is None:
+        qgroup = 128 if (mode == EPI_ACTMUL and so.numel() == N // 128) else (N + 31) // 32 * 32
+    assert so.numel() == (N + qgroup - 1) // qgroup == oo.numel(), "so/oo need one entry per qgroup columns"
+    h = _h(x)
+    with torch.cuda.device(dev):
+        check(_launch("qgemv_fused", lib.mq_qgemv_fused, h, ptr(x), int(x.dtype == torch.int8), ptr(w), int(w.dtype == torch.int8), B, N, Kd,
+                           ptr(acc, torch.int32), int(acc.stride(0)), int(ksplit), ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32),
+                           ptr(c0, torch.int32), ptr(bias), int(mode), ptr(so), ptr(oo), float(qmax), ptr(out), int(ldo), ptr(rowsum_out),
+                           ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup), ptr(zero_out), stream_ptr()), h)
     return resid if mode == EPI_RESID else out
 
 

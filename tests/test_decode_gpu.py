@@ -52,6 +52,9 @@ def test_qgemv_epilogues_match_qgemm(cuda, B):
     Kn.qgemv(a, b, acc)
     got = Kn.qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, Kn.EPI_QUANT, bias=bias, so=so, oo=oo, qgroup=128, qmax=255, rowsum_out=rs2)
     assert torch.equal(ref, got) and torch.equal(rs1, rs2) and int(acc.abs().max()) == 0
+    rs2.zero_(); z = torch.full((B,), 7, dtype=torch.int32, device=cuda)
+    got = Kn.qgemv_fused(a, b, acc, rowsum, sxw, ow, c0, Kn.EPI_QUANT, bias=bias, so=so, oo=oo, qgroup=128, qmax=255, rowsum_out=rs2, zero_out=z)
+    assert torch.equal(ref, got) and torch.equal(rs1, rs2) and int(acc.abs().max()) == 0 and int(z.abs().max()) == 0
     # ACTMUL
     rs1.zero_(); rs2.zero_()
     ref = Kn.qgemm(a, b, rowsum, sxw, ow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qgroup=128, qmax=255, lut=lut, s2=0.01, o2=128.0, qmax2=255, rowsum_out=rs1)
@@ -59,12 +62,21 @@ def test_qgemv_epilogues_match_qgemm(cuda, B):
     got = Kn.qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qgroup=128, qmax=255, lut=lut, s2=0.01, o2=128.0, qmax2=255,
                             rowsum_out=rs2)
     assert torch.equal(ref, got) and torch.equal(rs1, rs2) and int(acc.abs().max()) == 0
+    rs2.zero_()
+    got = Kn.qgemv_fused(a, b, acc, rowsum, sxw, ow, c0, Kn.EPI_ACTMUL, so=so, oo=oo, qgroup=128, qmax=255, lut=lut, s2=0.01, o2=128.0, qmax2=255,
+                         rowsum_out=rs2)
+    assert torch.equal(ref, got) and torch.equal(rs1, rs2) and int(acc.abs().max()) == 0
     # RESID
     h1, h2 = h0.clone(), h0.clone()
     Kn.qgemm(a, b, rowsum, sxw, ow, c0, Kn.EPI_RESID, so=so[:1], oo=oo[:1], qgroup=N, qmax=65535, resid=h1)
     Kn.qgemv(a, b, acc)
     Kn.qgemv_epilogue(acc, B, N, rowsum, sxw, ow, c0, Kn.EPI_RESID, so=so[:1], oo=oo[:1], qgroup=N, qmax=65535, resid=h2)
     assert torch.equal(h1, h2) and int(acc.abs().max()) == 0
+    h3 = h0.clone()
+    for _ in range(3):                                   # repeated launches: the arrival counters reset themselves
+        h3.copy_(h0)
+        Kn.qgemv_fused(a, b, acc, rowsum, sxw, ow, c0, Kn.EPI_RESID, so=so[:1], oo=oo[:1], qgroup=N, qmax=65535, resid=h3)
+        assert torch.equal(h1, h3) and int(acc.abs().max()) == 0
 
 
 @pytest.mark.parametrize("B,T,nh,nkv,hd,rot", [(2, 40, 4, 2, 32, 32), (1, 70, 8, 8, 64, 16), (2, 33, 8, 1, 64, 64), (1, 50, 2, 1, 128, 128),
