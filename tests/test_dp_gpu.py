@@ -60,9 +60,17 @@ def _worker(rank, world, port, tmp, q):
         learned = _calibrate(model, act, samples, dev, out, batch_size=1)   # data parallel, micro-batch 1 per rank
         if rank == 0:
             q.put((act, {i: {k: v.cpu() for k, v in d.items()} for i, d in learned.items()}))
+            q.close(); q.join_thread()                            # results are in the pipe before this process may exit
+        torch.cuda.synchronize()
         dist.barrier()
-    finally:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    # The captured training-step graphs hold NCCL kernels; tearing the communicator down under them can block for
+    # minutes (observed on the 2 x B200 box).  Both ranks are past the barrier: leave without the NCCL teardown.
+    os._exit(0)
 
 
 def test_two_gpu_calibration_matches_single_gpu(tmp_path):
