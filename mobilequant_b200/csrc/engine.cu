@@ -668,7 +668,10 @@ constexpr int kA4Stage = 128;     // keys per staged tile
 constexpr int kA4RepA = 4;        // bank replication of the exp tables: A (index k >> 8), 16 B per entry
 constexpr int kA4RepB = 8;        //                                     B (index k & 255), 32 B per entry
 constexpr int kA4TabBytes = 256 * (kA4RepA + kA4RepB) * 4;
-constexpr int kA4Bufs = 3;        // staged-tile ring depth (one barrier per stage)
+// staged-tile ring depth: 3 (one barrier per stage) where it fits next to the score codes, 2 (two barriers per stage) for
+// head dims above 128, whose 128-key K stage is 34 KB
+template <int HD>
+__host__ __device__ constexpr int a4_bufs() { return HD > 128 ? 2 : 3; }
 
 template <int HD, int DV>
 __host__ __device__ constexpr int a4_stage_bytes() {
@@ -679,7 +682,7 @@ __host__ __device__ constexpr int a4_red_bytes() { return 8 * 32 * (DV / 2) * 4;
 template <int HD, int DV>
 static size_t a4_smem_bytes(int cpw) {
   const size_t region0 = std::max<size_t>(size_t(8) * cpw * 1024, a4_red_bytes<DV>());
-  return region0 + kA4Bufs * size_t(a4_stage_bytes<HD, DV>()) + kA4Bufs * kA4Stage * 4 + kA4TabBytes + 128 * 4 + 128 * 8 + 32 * 4;
+  return region0 + a4_bufs<HD>() * size_t(a4_stage_bytes<HD, DV>()) + a4_bufs<HD>() * kA4Stage * 4 + kA4TabBytes + 128 * 4 + 128 * 8 + 32 * 4;
 }
 
 template <int HD, int DV, bool FIVE>
@@ -698,9 +701,14 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
   const int region0 = code_bytes > a4_red_bytes<DV>() ? code_bytes : a4_red_bytes<DV>();
   uint4* s_codes = reinterpret_cast<uint4*>(smem_attn);                    // [8 warps][cpw][2 rows][32 lanes] uint4
   int* s_red = reinterpret_cast<int*>(smem_attn);                          // aliases the codes after pass C
-  uint8_t* s_stage = smem_attn + region0;                                  // [kA4Bufs][STAGE]
-  int* s_rsk = reinterpret_cast<int*>(s_stage + kA4Bufs * STAGE);          // [kA4Bufs][ST]
-  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_rsk + kA4Bufs * ST);     // A [256][kA4RepA] then B [256][kA4RepB]
+  constexpr int BUFS = a4_bufs<HD>();
+  uint8_t* s_stage = smem_attn + region0;                                  // [BUFS][STAGE]
+  int* s_rsk = reinterpret_cast<int*>(s_stage + BUFS * STAGE);             // [BUFS][ST]
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_rsk + BUFS * ST);        // A [256][kA4RepA] then B [256][kA4RepB]
+  // head dims above DV: the output chunks of DV dims are produced one after the other from the parked codes (pass C runs
+  // HD / DV times, passes A and B once); their cross-warp partials go through the then idle stage buffers
+  static_assert(NCH == 1 || BUFS * STAGE >= a4_red_bytes<DV>(), "stage ring too small for the P.V partials");
+  int* s_redp = NCH == 1 ? s_red : reinterpret_cast<int*>(s_stage);
   int* s_xi = reinterpret_cast<int*>(s_tab + kA4TabBytes / 4);             // [2 rg][4 w][16 rows]
   unsigned long long* s_xs = reinterpret_cast<unsigned long long*>(s_xi + 128);   // [2][4][16]
   int* s_cs = reinterpret_cast<int*>(s_xs + 128);                          // [2][16]
@@ -709,7 +717,7 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
   const int rg = warp >> 2, w = warp & 3;
   const bool v_aligned = (a.T & 15) == 0 && ((reinterpret_cast<uintptr_t>(a.vt) & 15) == 0);
   const int nqt = (a.T + 31) >> 5;
-  const int per_qt = a.B * a.nh * NCH;        // work items of one query-tile row, heavy (late) tiles first
+  const int per_qt = a.B * a.nh;              // work items of one query-tile row, heavy (late) tiles first
 
   // ---- once per CTA: the two exp tables, entries replicated across banks (lane & 3 / lane & 7 picks the copy)
   static_assert(kA4RepA == 4 && kA4RepB == 8, "table fill writes one / two uint4 per entry");
@@ -768,14 +776,13 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
   // ======================= persistent loop over (query tile, batch, head[, d chunk]) work items =======================
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int qt = nqt - 1 - item / per_qt;
-    int rem = item % per_qt;
-    const int d0 = (rem % NCH) * DV; rem /= NCH;
+    const int rem = item % per_qt;
     const int h = rem % a.nh, b = rem / a.nh;
     const int kvh = h / (a.nh / a.nkv);
     const int q0 = qt * 32;
     const uint8_t* qbase = a.q + ((int64_t(b) * a.nh + h) * a.T) * HD;
     const uint8_t* kbase = a.k + ((int64_t(b) * a.nkv + kvh) * a.T) * HD;
-    const uint8_t* vbase = a.vt + ((int64_t(b) * a.nkv + kvh) * HD + d0) * a.T;
+    const uint8_t* vbase = a.vt + ((int64_t(b) * a.nkv + kvh) * HD) * a.T;       // advanced by DV rows per output chunk
     const int32_t* rskb = a.rsk + (int64_t(b) * a.nkv + kvh) * a.T;
     const int key_end = min(a.T, q0 + 32);                       // keys this item ever needs
     const int n_st = (qt + 1 + 3) >> 2;                          // stages of 4 chunks; chunk qt is the diagonal one
@@ -838,10 +845,10 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
     // buffer (== buffer of stage s+2) can be refilled right away
     int mx_lo = -1, mx_hi = -1;
     for (int s = 0; s < n_st; ++s) {
-      const int buf = s % kA4Bufs;
+      const int buf = s % BUFS;
       if (s + 1 < n_st) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncthreads();
-      if (s + 2 < n_st) issue_k(s + 2, (s + 2) % kA4Bufs);
+      if (BUFS == 3 && s + 2 < n_st) issue_k(s + 2, (s + 2) % BUFS);
       const int c = 4 * s + w;
       if (c <= qt) {
         const uint8_t* skh = s_stage + buf * STAGE + w * 32 * KSTR;
@@ -879,6 +886,7 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
         my_codes[(s * 2 + 0) * 32] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         my_codes[(s * 2 + 1) * 32] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
       }
+      if (BUFS == 2 && s + 2 < n_st) { __syncthreads(); issue_k(s + 2, buf); }   // two-buffer ring: refill after everyone is done
     }
     mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = max(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
     mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = max(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
@@ -924,8 +932,6 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
     float den_lo = 1.f, den_hi = 1.f, rden_lo = 1.f, rden_hi = 1.f;
     bool den_five = true;
     int olo[NDN][4], ohi[NDN][4];
-#pragma unroll
-    for (int i = 0; i < NDN; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
     int psum_lo = 0, psum_hi = 0;                 // sum_j cp_ij (zero-point correction of V)
     auto chunk_pv = [&](auto five_tag, auto diag_tag, int s, int c, const uint8_t* svb) {
       constexpr bool DF = decltype(five_tag)::value;
@@ -972,12 +978,23 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
         mma_u8(olo[dn], alo, b0, b1);
       }
     };
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+    const int d0 = ch * DV;
+    if (ch > 0) {                                   // (the first chunk's V stages were issued before pass B)
+      vbase += int64_t(DV) * a.T;
+      issue_v(0, 0);
+      if (n_st > 1) issue_v(1, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < NDN; ++i) { olo[i][0] = olo[i][1] = olo[i][2] = olo[i][3] = 0; ohi[i][0] = ohi[i][1] = ohi[i][2] = ohi[i][3] = 0; }
+    psum_lo = 0; psum_hi = 0;
     for (int s = 0; s < n_st; ++s) {
-      const int buf = s % kA4Bufs;
+      const int buf = s % BUFS;
       if (s + 1 < n_st) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncthreads();
-      if (s + 2 < n_st) issue_v(s + 2, (s + 2) % kA4Bufs);
-      if (s == 0) {
+      if (BUFS == 3 && s + 2 < n_st) issue_v(s + 2, (s + 2) % BUFS);
+      if (s == 0 && ch == 0) {
         unsigned long long t_lo = 0, t_hi = 0;
 #pragma unroll
         for (int ww = 0; ww < 4; ++ww) { t_lo += s_xs[(rg * 4 + ww) * 16 + g]; t_hi += s_xs[(rg * 4 + ww) * 16 + g + 8]; }
@@ -994,13 +1011,14 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
       } else if (c == qt) {
         chunk_pv(std::true_type{}, std::true_type{}, s, c, svb);
       }
+      if (BUFS == 2 && s + 2 < n_st) { __syncthreads(); issue_v(s + 2, buf); }
     }
     psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 1); psum_lo += __shfl_xor_sync(0xffffffffu, psum_lo, 2);
     psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 1); psum_hi += __shfl_xor_sync(0xffffffffu, psum_hi, 2);
-    __syncthreads();                               // every warp is done with its codes and with the row maxima in s_xi
+    __syncthreads();                               // every warp is done with this chunk's V stages (and, NCH == 1, its codes)
     if (t4 == 0) { s_xi[(rg * 4 + w) * 16 + g] = psum_lo; s_xi[(rg * 4 + w) * 16 + g + 8] = psum_hi; }
-    // ---- combine the four key-split partials of each row group (the partials overwrite the dead codes)
-    int* my_red = s_red + (size_t(rg * 4 + w) * (DV / 2)) * 32 + lane;
+    // ---- combine the four key-split partials of each row group (over the dead codes, or the idle stage ring)
+    int* my_red = s_redp + (size_t(rg * 4 + w) * (DV / 2)) * 32 + lane;
 #pragma unroll
     for (int dn = 0; dn < NDN; ++dn)
 #pragma unroll
@@ -1022,7 +1040,7 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
       for (int j = 0; j < 4; ++j) {
         int A = 0;
 #pragma unroll
-        for (int ww = 0; ww < 4; ++ww) A += s_red[(size_t(rg * 4 + ww) * (DV / 2) + dn * 4 + j) * 32 + lane];
+        for (int ww = 0; ww < 4; ++ww) A += s_redp[(size_t(rg * 4 + ww) * (DV / 2) + dn * 4 + j) * 32 + lane];
         A -= iov * (j < 2 ? psum_lo : psum_hi);
         code[j] = quant_int<FIVE>(fmul(__int2float_rn(A), a.spv), qo);
       }
@@ -1040,7 +1058,8 @@ __global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1)) qattn4_kernel(const A
       csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 1); csum_hi += __shfl_xor_sync(0xffffffffu, csum_hi, 2);
       if (t4 == 0) { atomicAdd(s_cs + rg * 16 + g, csum_lo); atomicAdd(s_cs + rg * 16 + g + 8, csum_hi); }
     }
-    __syncthreads();                               // partials consumed: the next item may overwrite codes / s_xi / s_cs
+    __syncthreads();                               // partials consumed: the next chunk / item may overwrite them, s_xi, s_cs
+    }                                              // output chunks
     if (a.rowsum_out && threadIdx.x < 32) {
       const int qi = q0 + threadIdx.x;
       if (qi < a.T) atomicAdd(a.rowsum_out + int64_t(b) * a.T + qi, s_cs[threadIdx.x]);
@@ -1081,7 +1100,7 @@ static int launch_qattn4(Ctx* c, const AttnArgs& a, int cpw, size_t smem, cudaSt
     if (getenv("MQB200_DEBUG")) fprintf(stderr, "[mqb200] qattn<%d,%d>: %zu B smem, %d CTAs/SM\n", HD, DV, attr_smem, ctas_per_sm);
   }
   // persistent CTAs walk the (query tile, batch, head) items round-robin, heaviest query tiles first
-  const long long n_items = (long long)((a.T + 31) / 32) * a.B * a.nh * (HD / DV);
+  const long long n_items = (long long)((a.T + 31) / 32) * a.B * a.nh;
   if (n_items > 0x7fffffffLL) return fail(c, MQ_INVALID_ARGUMENT, "mq_qattn: too many work items");
   const int grid = (int)std::min<long long>(n_items, (long long)c->sm_count * ctas_per_sm);
   qattn4_kernel<HD, DV, FIVE><<<grid, 256, attr_smem, st>>>(a, cpw, (int)n_items);
