@@ -298,7 +298,7 @@ def roofline(eng, ids, B, T):
     e1.record(); torch.cuda.synchronize()
     lib = 10 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1c_qgemm_traffic.json")                # ncu --set full, dram read + write per launch
+    tpath = os.path.join(ROOT, "profiles", "r1d_qgemm_traffic.json")                # ncu --set full, dram read + write per launch
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("avg_bytes_per_launch")      # ncu --set full capture of the same kernel, per launch
     rl = {"kernel": "qgemm_kernel (tcgen05 kind::i8, TMA ring, TMEM double buffer)", "bound": "tensor", "achieved": achieved, "peak": peak,

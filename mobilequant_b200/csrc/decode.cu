@@ -19,6 +19,7 @@
 #include "ctx.h"
 #include <string>
 #include <algorithm>
+#include <cstdlib>
 
 namespace mq {
 using namespace tc;
@@ -597,21 +598,33 @@ __global__ void __launch_bounds__(256) fgemv_kernel(const float* __restrict__ x,
   const float* wr[kFgRows];
 #pragma unroll
   for (int r = 0; r < kFgRows; ++r) wr[r] = w + int64_t(min(v0 + r, V - 1)) * K;      // tail rows alias the last row (not stored)
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 wv[kFgRows];
+  // two k-steps (2 x kFgRows 16-byte weight loads per lane) in flight: ~65 KB outstanding per SM, what 6.5 TB/s needs
+  auto fma_step = [&](const float4 (&wv)[kFgRows], int k) {
+    float4 xv[BMAX];                             // all x vectors of the step first: one L1 round trip, not BMAX in a chain
 #pragma unroll
-    for (int r = 0; r < kFgRows; ++r) wv[r] = ldg4_stream(wr[r] + k);
+    for (int b = 0; b < BMAX; ++b) xv[b] = ldg4(x + int64_t(min(b, B - 1)) * K + k);
 #pragma unroll
     for (int b = 0; b < BMAX; ++b) {
-      if (b < B) {
-        const float4 xv = ldg4(x + int64_t(b) * K + k);
 #pragma unroll
-        for (int r = 0; r < kFgRows; ++r) {
-          acc[r][b] = __fmaf_rn(wv[r].x, xv.x, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].y, xv.y, acc[r][b]);
-          acc[r][b] = __fmaf_rn(wv[r].z, xv.z, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].w, xv.w, acc[r][b]);
-        }
+      for (int r = 0; r < kFgRows; ++r) {
+        acc[r][b] = __fmaf_rn(wv[r].x, xv[b].x, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].y, xv[b].y, acc[r][b]);
+        acc[r][b] = __fmaf_rn(wv[r].z, xv[b].z, acc[r][b]); acc[r][b] = __fmaf_rn(wv[r].w, xv[b].w, acc[r][b]);
       }
     }
+  };
+  int k = lane * 4;
+  for (; k + 128 < K; k += 256) {
+    float4 w0[kFgRows], w1[kFgRows];
+#pragma unroll
+    for (int r = 0; r < kFgRows; ++r) { w0[r] = ldg4_stream(wr[r] + k); w1[r] = ldg4_stream(wr[r] + k + 128); }
+    fma_step(w0, k);
+    fma_step(w1, k + 128);
+  }
+  for (; k < K; k += 128) {
+    float4 w0[kFgRows];
+#pragma unroll
+    for (int r = 0; r < kFgRows; ++r) w0[r] = ldg4_stream(wr[r] + k);
+    fma_step(w0, k);
   }
 #pragma unroll
   for (int r = 0; r < kFgRows; ++r) {
@@ -794,7 +807,10 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
   a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
   // key slices: one cluster per (sequence, kv head); enough CTAs to fill the machine, at least 64 keys per slice
   int CS = 1;
-  while (CS < 8 && B * nkv * CS * 2 <= 2 * c->sm_count && (pos_bound + 1) / (CS * 2) >= 64) CS *= 2;
+  int cs_max = 8;
+  { const char* e = getenv("MQB200_DEC_CS"); if (e && atoi(e) >= 1 && atoi(e) <= 8) cs_max = atoi(e); }   // A/B measurements
+  // measured (profiles/r1d_decode_kernels.md): slices of >= 256 keys; 1024 keys -> 4 CTAs (22.8 us), 2048 keys -> 8 (50.3 us)
+  while (CS < cs_max && B * nkv * CS * 2 <= 2 * c->sm_count && (pos_bound + 1) / (CS * 2) >= 256) CS *= 2;
   a.CS = CS;
   a.Tslice = (((pos_bound + 1) + CS - 1) / CS + 7) / 8 * 8;
   const size_t smem = attn_dec_smem(hd, nh / nkv, a.Tslice);

@@ -4,14 +4,24 @@ sys.path.insert(0, "/root/repo")
 from mobilequant_b200 import kernels as K
 from oracle import int_ref as ir
 cuda = torch.device("cuda:0"); f32 = np.float32
-def timeit(name, fn, bytes_=None, iters=50):
-    for _ in range(5): fn()
+def timeit(name, fn, bytes_=None, iters=20):
+    """GPU time per launch: `iters` launches captured in one CUDA graph (no host launch overhead), 5 replays."""
+    for _ in range(3): fn()
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters): fn()
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): fn()
+    for _ in range(5): g.replay()
     e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / iters * 1e3
+    us = e0.elapsed_time(e1) / (5 * iters) * 1e3
     extra = f"  {bytes_/us/1e3:.0f} GB/s" if bytes_ else ""
     print(f"{name:44s} {us:8.2f} us{extra}", flush=True)
 def gemv_suite(tag, B, H, I, nh, nkv, hd, V, T):
@@ -61,6 +71,12 @@ def gemv_suite(tag, B, H, I, nh, nkv, hd, V, T):
     cos, sin = ir.rope_tables(T, hd)
     dcos, dsin = torch.from_numpy(cos).to(cuda), torch.from_numpy(sin).to(cuda)
     out = torch.empty(B, nh * hd, dtype=torch.uint8, device=cuda); rso = torch.zeros(B, dtype=torch.int32, device=cuda)
+    import os
+    for cs in ("2", "4", "8"):
+        os.environ["MQB200_DEC_CS"] = cs
+        timeit(f"qattn_decode pos={T-1} max cluster {cs}", lambda: K.qattn_decode(qkv, B, nh, nkv, hd, hd, T - 1, qi, qo, dcos, dsin, kc, vc, rsk, params, lut, out=out, rowsum_out=rso),
+               2 * B * nkv * T * hd)
+    os.environ.pop("MQB200_DEC_CS", None)
     timeit(f"qattn_decode pos={T-1}", lambda: K.qattn_decode(qkv, B, nh, nkv, hd, hd, T - 1, qi, qo, dcos, dsin, kc, vc, rsk, params, lut, out=out, rowsum_out=rso),
            2 * B * nkv * T * hd)
     # lm_head
