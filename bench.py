@@ -176,7 +176,7 @@ def run_ours(args):
     wq = Q.QuantConfig(bitwidth=8) if args.wbits == 8 else Q.QuantConfig(bitwidth=4, is_symmetric=True, is_per_channel=True)
     qcfg = default_qcfg(cfg, wq, Q.QuantConfig(bitwidth=8))
     eng = IntEngine(model, qcfg, act, dev)
-    wtag = "W8A8" if args.wbits == 8 else "W4A8 per-channel symmetric"
+    wtag = "W8A8" if args.wbits == 8 else "W4A8 per-channel symmetric (weights packed 2/byte in HBM, %.2f GB, expanded per layer into L2)" % (eng.weight_bytes() / 1e9)
     ids_host = synth_ids(B, T, cfg.vocab_size, 1000 + rank).pin_memory()
     ids_dev = ids_host.to(dev)
     out_host = torch.empty(B, dtype=torch.int64).pin_memory()
@@ -336,7 +336,7 @@ def decode_throughput(eng, ids, B, T, nsteps):
         graph.replay()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / nsteps
-    wbytes = sum(L[k]["codes"].numel() for L in eng.layers for k in ("qkv", "o", "w13", "w2"))
+    wbytes = sum(L[k]["N"] * L[k]["K"] for L in eng.layers for k in ("qkv", "o", "w13", "w2"))   # one byte per code reaches the GEMV
     head = eng.lm_head.numel() * 4
     avg_keys = T0 + (nsteps + 1) / 2.0
     kv = 2.0 * len(eng.layers) * B * eng.nkv * avg_keys * eng.hd

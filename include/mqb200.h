@@ -182,6 +182,11 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
                     const float* sin, uint8_t* k_cache, uint8_t* v_cache, int32_t* rsk_cache, const float* qparams,
                     const uint32_t* lut, uint8_t* out, int32_t* rowsum_out, void* stream);
 
+/* mq_unpack4: n_codes packed 4-bit weight codes (two per byte, low nibble first, as written by mq_wprep_fwd with pack4)
+ * -> one code per byte (int8 when is_signed, i.e. symmetric weights, else uint8): W4A8 weights stay packed in HBM and a
+ * layer is expanded into an L2-sized scratch buffer right before its mq_qgemm / mq_qgemv.  n_codes % 32 == 0.        */
+int mq_unpack4(void* ctx, const uint8_t* packed, int64_t n_codes, int is_signed, void* out, void* stream);
+
 /* ---- test hook ---------------------------------------------------------------------------------------------------
  * The integer-engine kernels requantise with a branch-free exact division (RN(a/b) from RN(1/b) and two FMAs, a
  * third/fourth for scales whose significand is all ones) instead of the IEEE division + rint of qm:286.  This entry

@@ -640,6 +640,32 @@ __global__ void __launch_bounds__(256) fgemv_kernel(const float* __restrict__ x,
   }
 }
 
+// =====================================================================================================================
+// mq_unpack4: packed 4-bit weight codes (two per byte, low nibble = even column; mq_wprep_fwd pack4) -> one int8 / uint8
+// code per byte, the operand format of the tcgen05 kind::i8 GEMMs.  W4A8 weights stay packed in HBM (0.48 GB for
+// TinyLlama-1.1B); a layer's matrices are expanded right before their GEMM into a scratch buffer that fits the 126 MB L2,
+// so the GEMM's operand traffic is served from L2 and the expansion costs one pass over the packed bytes.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) unpack4_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16, int is_signed) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 p = __ldg(src + i);
+  const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t lo = pw[j] & 0x0F0F0F0Fu, hi = (pw[j] >> 4) & 0x0F0F0F0Fu;
+    uint32_t a = __byte_perm(lo, hi, 0x5140), b = __byte_perm(lo, hi, 0x7362);     // l0 h0 l1 h1 | l2 h2 l3 h3
+    if (is_signed) {                                                              // 4-bit two's complement -> int8
+      a |= (a & 0x08080808u) * 0x1Eu;
+      b |= (b & 0x08080808u) * 0x1Eu;
+    }
+    o[2 * j] = a; o[2 * j + 1] = b;
+  }
+  dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (same helper as qgemm.cu, local copy of the lookup)
 typedef CUresult (*PFN_encodeTiledGv)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -763,6 +789,17 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
   else if (mode == GV_ACTMUL) qgemv_epi_kernel<GV_ACTMUL><<<grid, 128, 0, st>>>(a);
   else qgemv_epi_kernel<GV_RESID><<<grid, 128, 0, st>>>(a);
   return check_launch(c, "mq_qgemv_epilogue");
+}
+
+int mq_unpack4(void* ctx, const uint8_t* packed, int64_t n_codes, int is_signed, void* out, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, packed && out && n_codes > 0, "null pointer or empty input");
+  MQ_REQUIRE(c, n_codes % 32 == 0, "the number of codes must be a multiple of 32");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "buffers must be 16-byte aligned");
+  const int64_t n16 = n_codes / 32;
+  unpack4_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(packed),
+                                                                                 reinterpret_cast<uint4*>(out), n16, is_signed);
+  return check_launch(c, "mq_unpack4");
 }
 
 int mq_fgemv(void* ctx, const float* x, const float* w, float* out, int B, int V, int K, void* stream) {

@@ -41,9 +41,13 @@ def _f64_sigmoid(x):
 
 
 class IntEngine:
-    def __init__(self, model, qcfg, act_dict, device=None):
+    def __init__(self, model, qcfg, act_dict, device=None, pack4=True):
         """model: float HFForCausalLM holding the *fused* weights (LET folded, LWC-clamped) -- e.g. the output of
-        ptq.mobilequant.quantize / create_fp_model, or any float checkpoint for plain static PTQ."""
+        ptq.mobilequant.quantize / create_fp_model, or any float checkpoint for plain static PTQ.
+        pack4: 4-bit weight matrices are kept packed (two codes per byte) in HBM and expanded into an L2-sized scratch
+        buffer right before their GEMM (mq_unpack4); False keeps one code per byte."""
+        self.pack4 = bool(pack4)
+        self._scratch = {}
         self.cfg = cfg = model.config
         self.device = dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if dev.type != "cuda":
@@ -75,6 +79,7 @@ class IntEngine:
         out = K.wprep_fwd(w2, bits, sym, pc, want_fq=want_fq, want_codes=bits <= 8)
         out["sym"] = sym
         out["rows"] = w2.shape[0]
+        out["bits"] = bits
         return out
 
     def _percol(self, wq_list, sx, ox, Kdim, out_q, biases, pad_to=None):
@@ -101,7 +106,7 @@ class IntEngine:
         c0 = (Kdim * int(ox) * ow - int(ox) * cs)
         assert c0.abs().max().item() < 2 ** 31
         bias = torch.cat(bias)
-        return dict(codes=codes.contiguous(), sxw=sxw, ow=ow.to(torch.int32).contiguous(), c0=c0.to(torch.int32).contiguous(),
+        return dict(wbits=max(wq["bits"] for wq in wq_list), codes=codes.contiguous(), sxw=sxw, ow=ow.to(torch.int32).contiguous(), c0=c0.to(torch.int32).contiguous(),
                     bias=bias.contiguous() if bias.abs().max().item() > 0 else None, so=so, oo=oo, qgroup=qgroup,
                     qmax=out_q[0][2], N=codes.shape[0], K=Kdim)
 
@@ -162,7 +167,38 @@ class IntEngine:
         L["w2_in"] = w2_in
         w2 = self._wq(mlp.w2.weight, qcfg[pm + "w2"]["weight"])
         L["w2"] = self._percol([self._pad_cols(w2)], w2_in[0], w2_in[1], self.Ipad, [_sq(act, qcfg, pm + "w2", "output")], [getattr(mlp.w2, "bias", None)])
+        if self.pack4:
+            for k in ("qkv", "o", "w13", "w2"):
+                self._pack(L[k])
         return L
+
+    def _pack(self, g):
+        """4-bit matrix (already arranged: fused / interleaved / K-padded) -> two codes per byte; the int8 copy is dropped."""
+        c = g["codes"]
+        if g["wbits"] > 4 or (c.shape[0] * c.shape[1]) % 32 or c.shape[1] % 2:
+            return
+        u = c.view(torch.uint8)
+        g["packed"] = ((u[:, 0::2] & 0xF) | ((u[:, 1::2] & 0xF) << 4)).contiguous()
+        g["shape"], g["dtype"] = tuple(c.shape), c.dtype
+        g["codes"] = None
+
+    def _codes(self, g):
+        """The [N, K] one-code-per-byte operand of a GEMM: the resident tensor, or the packed one expanded into scratch."""
+        if g["codes"] is not None:
+            return g["codes"]
+        n = g["shape"][0] * g["shape"][1]
+        buf = self._scratch.get(g["dtype"])
+        if buf is None or buf.numel() < n:
+            nmax = max(L[k]["shape"][0] * L[k]["shape"][1] for L in self.layers for k in ("qkv", "o", "w13", "w2") if L[k]["codes"] is None) \
+                if getattr(self, "layers", None) else n
+            buf = self._scratch[g["dtype"]] = torch.empty(max(n, nmax), dtype=g["dtype"], device=self.device)
+        out = buf[:n].view(g["shape"])
+        K.unpack4(g["packed"], out)
+        return out
+
+    def weight_bytes(self):
+        """Bytes of quantised weight codes resident in HBM."""
+        return sum((g["codes"] if g["codes"] is not None else g["packed"]).numel() for L in self.layers for g in (L[k] for k in ("qkv", "o", "w13", "w2")))
 
     def _pad_cols(self, wq):
         """Pad K (=intermediate) to Ipad with the row's zero point so that padded columns contribute exactly 0."""
@@ -190,7 +226,7 @@ class IntEngine:
         def il(x, y):
             return torch.stack([x.view(Ipad // 128, 128, *x.shape[1:]), y.view(Ipad // 128, 128, *y.shape[1:])], dim=1).reshape(2 * Ipad, *x.shape[1:]).contiguous()
 
-        out = dict(N=2 * Ipad, K=a["K"], qmax=a["qmax"], qgroup=128)
+        out = dict(N=2 * Ipad, K=a["K"], qmax=a["qmax"], qgroup=128, wbits=max(a["wbits"], b["wbits"]))
         out["codes"] = il(pad(a["codes"], 0), pad(b["codes"], 0))
         for k, fill in (("sxw", 0.0), ("ow", 0), ("c0", 0)):
             out[k] = il(pad(a[k], fill), pad(b[k], fill))
@@ -230,7 +266,7 @@ class IntEngine:
         return self._bufs[key]
 
     def _gemm(self, a, g, rowsum, mode, **kw):
-        return K.qgemm(a, g["codes"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
+        return K.qgemm(a, self._codes(g), rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
                        qgroup=g["qgroup"], **kw)
 
     @torch.no_grad()
@@ -334,9 +370,9 @@ class IntEngine:
 
     def _gemv(self, a, g, rowsum, mode, acc, **kw):
         if self.fused_gemv:
-            return K.qgemv_fused(a, g["codes"], acc, rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"],
+            return K.qgemv_fused(a, self._codes(g), acc, rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"],
                                  qmax=g["qmax"], qgroup=g["qgroup"], **kw)
-        K.qgemv(a, g["codes"], acc)
+        K.qgemv(a, self._codes(g), acc)
         return K.qgemv_epilogue(acc, a.shape[0], g["N"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"],
                                 qmax=g["qmax"], qgroup=g["qgroup"], **kw)
 

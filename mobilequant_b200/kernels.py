@@ -33,6 +33,7 @@ def _protos():
                                       c_float, c_float, c_float, _P, c_int, _P, _P]
     lib.mq_qgemv_fused.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
                                    _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P, _P]
+    lib.mq_unpack4.argtypes = [_P, _P, c_int64, c_int, _P, _P]
     lib.mq_fgemv.argtypes = [_P, _P, _P, _P, c_int, c_int, c_int, _P]
     lib.mq_qattn_decode.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P]
@@ -300,6 +301,17 @@ def qgemv(x, w, acc, ksplit=0):
         check(_launch("qgemv", lib.mq_qgemv, h, ptr(x), int(x.dtype == torch.int8), ptr(w), int(w.dtype == torch.int8), B, N, K,
                            ptr(acc, torch.int32), int(acc.stride(0)), int(ksplit), stream_ptr()), h)
     return acc
+
+
+def unpack4(packed, out):
+    """packed uint8 [N, K/2] (two 4-bit codes per byte) -> out int8/uint8 [N, K]; out.dtype decides sign extension."""
+    lib = _protos()
+    n = packed.numel() * 2
+    assert out.numel() == n
+    h = _h(packed)
+    with torch.cuda.device(packed.device):
+        check(_launch("unpack4", lib.mq_unpack4, h, ptr(packed), n, int(out.dtype == torch.int8), ptr(out), stream_ptr()), h)
+    return out
 
 
 def fgemv(x, w, out=None):

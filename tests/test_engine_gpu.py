@@ -121,3 +121,35 @@ def test_engine_vs_reference_fake_quant(cuda, tag):
     scale = ref.abs().max().item()
     assert (logits - ref).abs().max().item() < 0.03 * scale
     assert (logits - ref).abs().mean().item() < 3e-3 * scale
+
+
+def test_unpack4(cuda):
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(4)
+    for signed in (True, False):
+        codes = rng.integers(-8 if signed else 0, 8 if signed else 16, size=(96, 352)).astype(np.int8 if signed else np.uint8)
+        u = codes.view(np.uint8)
+        packed = ((u[:, 0::2] & 0xF) | ((u[:, 1::2] & 0xF) << 4)).astype(np.uint8)
+        out = torch.empty(96, 352, dtype=torch.int8 if signed else torch.uint8, device=cuda)
+        K.unpack4(torch.from_numpy(packed).to(cuda), out)
+        assert np.array_equal(out.cpu().numpy(), codes)
+
+
+def test_engine_packed_int4_equals_unpacked(cuda):
+    """W4A8: weights packed two per byte in HBM + per-GEMM expansion == one code per byte, bit for bit (prefill and decode)."""
+    from mobilequant_b200.engine import IntEngine
+    g = load_golden("model_llama_w4_omni.pt")
+    model = product_model(g)
+    e_packed = IntEngine(model, g["qcfg"], g["act_dict"], cuda, pack4=True)
+    e_plain = IntEngine(model, g["qcfg"], g["act_dict"], cuda, pack4=False)
+    assert any(L[k]["codes"] is None for L in e_packed.layers for k in ("qkv", "o", "w13", "w2")), "nothing was packed"
+    assert e_packed.weight_bytes() < 0.75 * e_plain.weight_bytes()
+    ids = torch.cat(g["samples"][:2], dim=0).to(cuda)
+    B, T = ids.shape
+    h1 = e_packed.forward(ids, return_logits=False); h2 = e_plain.forward(ids, return_logits=False)
+    assert torch.equal(h1, h2)
+    c1, c2 = e_packed.new_cache(B, T), e_plain.new_cache(B, T)
+    e_packed.prefill(ids[:, :T - 2], c1); e_plain.prefill(ids[:, :T - 2], c2)
+    x1 = e_packed._embed(ids[:, T - 2]).contiguous(); x2 = x1.clone()
+    e_packed.decode_hidden(x1, c1); e_plain.decode_hidden(x2, c2)
+    assert torch.equal(x1, x2)
