@@ -122,6 +122,14 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
              const float* w_fq, const float* bias, float alpha, float eps, float s_out, float o_out, float qmax_out,
              uint8_t* codes, int32_t* rowsum, void* stream);
 
+/* mq_qnorm_resid (decode step): mq_qgemv_epilogue mode 2 (RESID) of the preceding skinny GEMM folded into the norm of the
+ * same rows: x[m, :] += dequant(Q_out(y)) from the s32 accumulator acc[rows, ldacc] (handed back zeroed; g_* are that
+ * GEMM's rowsum / sxw / ow / c0 / bias / output quantizer, N == H), then mq_qnorm of the updated rows.  rows <= 256.     */
+int mq_qnorm_resid(void* ctx, float* x, int rows, int H, int is_layernorm, float s_in, float o_in, float qmax_in, const float* w_fq,
+                   const float* bias, float alpha, float eps, float s_out, float o_out, float qmax_out, uint8_t* codes, int32_t* rowsum,
+                   int32_t* acc, int ldacc, const int32_t* g_rowsum, const float* g_sxw, const int32_t* g_ow, const int32_t* g_c0,
+                   const float* g_bias, const float* g_so, const float* g_oo, float g_qmax, int g_qgroup, void* stream);
+
 /* ---- K5: RoPE between two quantizers (hm:486-501 + qm:455-459) ------------------------------------------------------
  * qkv: u8 codes [B*T, ldq] of the fused q|k|v projection.  in_qparams / out_qparams are HOST arrays
  * {s_q,o_q,s_k,o_k,s_v,o_v}: projection output quantizers, then qk_bmm.input / qk_bmm.input2 / pv_bmm.input2.

@@ -2,6 +2,7 @@
 // Every kernel consumes and produces integer codes; the arithmetic is restated 1:1 in oracle/int_ref.py.
 #include "common.cuh"
 #include "ctx.h"
+#include "gv_epi.cuh"
 #include <string>
 #include <algorithm>
 #include <cstdlib>
@@ -121,8 +122,11 @@ __global__ void __launch_bounds__(128) qnorm_kernel(const NormArgs a) {
 // Few-row variant (decode step: rows == batch): one warp per row leaves a ~3 k-instruction dependent chain on a single
 // warp (17 us per launch for 8 rows); here one 256-thread CTA owns a row, statistics meet through shared memory.  Same
 // arithmetic: the integer sums are exact, so the reduction order does not matter.
-template <bool kLayerNorm>
-__global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a) {
+// FUSE: the residual-add epilogue of the preceding skinny GEMM (o_proj / w2 of the decode step) is applied to the row first
+// -- x[m, :] += dequant(Q_out(y)), accumulator handed back zeroed, exactly gv_epi_quad<GV_RESID> -- by the thread that
+// then normalises those columns: two launches per layer fewer in the decode chain.
+template <bool kLayerNorm, bool FUSE>
+__global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a, const GvEpiArgs e) {
   __shared__ unsigned long long s_s2[8];
   __shared__ long long s_s1[8];
   __shared__ int s_cs[8];
@@ -138,7 +142,13 @@ __global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a) {
   for (int it = 0; it < NR; ++it) {
     const int k = (it * 256 + tid) * 4;
     if (k < H) {
-      const float4 v = ldg4_stream(xr + k);
+      float4 v;
+      if (FUSE) {
+        gv_epi_quad<GV_RESID>(e, (int)row, k);            // updates x[row, k..k+3] in place (e.resid == a.x)
+        v = *reinterpret_cast<const float4*>(xr + k);      // this thread's own stores
+      } else {
+        v = ldg4_stream(xr + k);
+      }
       rr[it][0] = __fsub_rn(quant_magic<true>(v.x, qi), kRoundMagic); rr[it][1] = __fsub_rn(quant_magic<true>(v.y, qi), kRoundMagic);
       rr[it][2] = __fsub_rn(quant_magic<true>(v.z, qi), kRoundMagic); rr[it][3] = __fsub_rn(quant_magic<true>(v.w, qi), kRoundMagic);
 #pragma unroll
@@ -1143,8 +1153,9 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
   cudaStream_t st = (cudaStream_t)stream;
   NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
   if (rows <= 256 && H <= 8192) {                 // decode-sized inputs: one CTA per row
-    if (is_layernorm) qnorm_row_kernel<true><<<(unsigned)rows, 256, 0, st>>>(a);
-    else qnorm_row_kernel<false><<<(unsigned)rows, 256, 0, st>>>(a);
+    const GvEpiArgs none{};
+    if (is_layernorm) qnorm_row_kernel<true, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
+    else qnorm_row_kernel<false, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
     return check_launch(c, "mq_qnorm");
   }
   unsigned grid = (unsigned)((rows + 3) / 4);
@@ -1156,6 +1167,29 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
   }
 #undef MQ_NORM
   return check_launch(c, "mq_qnorm");
+}
+
+int mq_qnorm_resid(void* ctx, float* x, int rows, int H, int is_layernorm, float s_in, float o_in, float qmax_in, const float* w_fq,
+                   const float* bias, float alpha, float eps, float s_out, float o_out, float qmax_out, uint8_t* codes, int32_t* rowsum,
+                   int32_t* acc, int ldacc, const int32_t* g_rowsum, const float* g_sxw, const int32_t* g_ow, const int32_t* g_c0,
+                   const float* g_bias, const float* g_so, const float* g_oo, float g_qmax, int g_qgroup, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, x && w_fq && codes && rows > 0 && H > 0, "null pointer or empty input");
+  MQ_REQUIRE(c, rows <= 256 && H <= 8192 && H % 4 == 0, "the fused form covers decode-sized inputs (rows <= 256, H <= 8192, H % 4 == 0)");
+  MQ_REQUIRE(c, qmax_out <= 255.f && qmax_in <= 65535.f, "norm output codes are 8 bit, input codes at most 16 bit");
+  MQ_REQUIRE(c, o_in == rintf(o_in) && o_out == rintf(o_out), "integer engine kernels need integral offsets (qm:60)");
+  MQ_REQUIRE(c, acc && g_rowsum && g_sxw && g_ow && g_c0 && g_so && g_oo, "the fused residual epilogue needs acc / rowsum / sxw / ow / c0 / so / oo");
+  MQ_REQUIRE(c, ldacc >= H && ldacc % 4 == 0 && g_qgroup > 0 && g_qgroup % 4 == 0 && g_qmax < 4194304.f, "bad accumulator stride / qgroup / qmax");
+  MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_fq) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(acc) & 15) == 0, "x / w_fq / bias / acc must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
+  GvEpiArgs e{rows, H, acc, ldacc, g_rowsum, g_sxw, g_ow, g_c0, g_bias, g_so, g_oo, g_qgroup, g_qmax, nullptr, (int64_t)H, nullptr,
+              nullptr, 1.f, 0.f, 255.f, x, nullptr};
+  if (is_layernorm) qnorm_row_kernel<true, true><<<(unsigned)rows, 256, 0, st>>>(a, e);
+  else qnorm_row_kernel<false, true><<<(unsigned)rows, 256, 0, st>>>(a, e);
+  return check_launch(c, "mq_qnorm_resid");
 }
 
 int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int nkv, int hd, int rot, const float* in_qparams,

@@ -70,6 +70,8 @@ class IntEngine:
         # (TinyLlama, batch 8, graph replay): fused 1.76 ms/step, separate 1.67 ms/step -- the last-arriving CTA serialises
         # the group's epilogue while a graph node costs less than that -- so the two-launch form is the default.
         self.fused_gemv = os.environ.get("MQB200_GEMV_FUSED", "0") == "1"
+        # decode: the residual epilogues of o_proj / w2 ride on the following row norm (two launches per layer fewer)
+        self.fused_resid_norm = os.environ.get("MQB200_RESID_NORM", "1") != "0"
 
     # ---- build ------------------------------------------------------------------------------------------------------
     def _wq(self, w, c, want_fq=False):
@@ -368,6 +370,14 @@ class IntEngine:
                                    rs_act=torch.zeros(B, dtype=torch.int32, device=dev), acc=torch.zeros(B, nmax, dtype=torch.int32, device=dev))
         return self._bufs[key]
 
+    def _norm_dec(self, h, n, bufs, pending):
+        """Row norm of the decode step; `pending` = (GEMM, row sums) whose residual epilogue is applied to h first, in the
+        same launch."""
+        if pending is None:
+            return K.qnorm(h, n["qin"], n["w_fq"], n["bias"], n["qout"], self.layernorm, n["eps"], bufs["x"], bufs["rs"])
+        g, rs = pending
+        return K.qnorm_resid(h, n["qin"], n["w_fq"], n["bias"], n["qout"], self.layernorm, n["eps"], bufs["x"], bufs["rs"], bufs["acc"], g, rs)
+
     def _gemv(self, a, g, rowsum, mode, acc, **kw):
         if self.fused_gemv:
             return K.qgemv_fused(a, self._codes(g), acc, rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"],
@@ -384,18 +394,32 @@ class IntEngine:
         cos, sin = self._rope(cache.Tmax)
         pos = cache.length
         pkw = dict(pos_dev=cache.pos_dev, pos_bound=cache.Tmax - 1) if use_pos_dev else {}
+        fuse = self.fused_resid_norm
+        pending = None                      # (GEMM, its row sums): a residual epilogue still to be applied to h
         for i, L in enumerate(self.layers):
-            K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
+            self._norm_dec(h, L["n1"], bufs, pending)
             # code-sum buffers are cleared by an epilogue that runs between their consumer and their next producer
             self._gemv(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, bufs["acc"], out=bufs["qkv"], zero_out=bufs["rs_act"])
             K.qattn_decode(bufs["qkv"], B, self.nh, self.nkv, self.hd, self.rot, pos, L["rope_in"], L["rope_out"], cos, sin, cache.k[i], cache.v[i],
                            cache.rsk[i], L["attn"], L["attn_lut"], out=bufs["attn"], rowsum_out=bufs["rs_attn"], **pkw)
-            self._gemv(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, bufs["acc"], resid=h)
-            K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
+            if fuse:
+                K.qgemv(bufs["attn"], self._codes(L["o"]), bufs["acc"])
+                self._norm_dec(h, L["n2"], bufs, (L["o"], bufs["rs_attn"]))
+            else:
+                self._gemv(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, bufs["acc"], resid=h)
+                self._norm_dec(h, L["n2"], bufs, None)
             w2in = L["w2_in"]
             self._gemv(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, bufs["acc"], out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1],
                        qmax2=w2in[2], rowsum_out=bufs["rs_act"], zero_out=bufs["rs_attn"])
-            self._gemv(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, bufs["acc"], resid=h)
+            if fuse:
+                K.qgemv(bufs["act"], self._codes(L["w2"]), bufs["acc"])
+                pending = (L["w2"], bufs["rs_act"])
+            else:
+                self._gemv(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, bufs["acc"], resid=h)
+        if pending is not None:             # the last layer's w2 epilogue has no norm to ride on
+            g, rs = pending
+            K.qgemv_epilogue(bufs["acc"], B, g["N"], rs, g["sxw"], g["ow"], g["c0"], K.EPI_RESID, bias=g["bias"], so=g["so"], oo=g["oo"],
+                             qmax=g["qmax"], qgroup=g["qgroup"], resid=h)
         return h
 
     @torch.no_grad()

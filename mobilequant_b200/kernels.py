@@ -1,5 +1,6 @@
 """Tensor-level wrappers over the C ABI (include/mqb200.h).  These are the only callers of libmqb200 in the package."""
 import ctypes
+import math
 from ctypes import c_int, c_int32, c_int64, c_float, c_void_p
 import torch
 from . import _lib
@@ -26,6 +27,8 @@ def _protos():
                              c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P]
     lib.mq_qnorm.argtypes = [_P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float,
                              c_float, c_float, _P, _P, _P]
+    lib.mq_qnorm_resid.argtypes = [_P, _P, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float, c_float, c_float,
+                                   _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, c_int, _P]
     lib.mq_qrope.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
     lib.mq_qgemv.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]
@@ -255,6 +258,22 @@ def qnorm(x, qin, w_fq, bias, qout, layernorm=False, eps=1e-5, codes=None, rowsu
         check(_launch("qnorm", lib.mq_qnorm, h, ptr(x, F32), rows, H, int(layernorm), float(qin[0]), float(qin[1]), float(qin[2]), ptr(w_fq, F32),
                            ptr(bias), float(math.sqrt(H)), float(eps), float(qout[0]), float(qout[1]), float(qout[2]),
                            ptr(codes), ptr(rowsum), stream_ptr()), h)
+    return codes, rowsum
+
+
+def qnorm_resid(x, qin, w_fq, bias, qout, layernorm, eps, codes, rowsum, acc, g, g_rowsum):
+    """Decode step: x[rows, H] += dequant(Q_out(acc ...)) of the preceding skinny GEMM `g` (engine weight dict: sxw / ow / c0 /
+    bias / so / oo / qmax / qgroup), then qnorm of the updated rows -- one launch."""
+    lib = _protos()
+    rows, H = x.shape
+    assert g["N"] == H
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(_launch("qnorm_resid", lib.mq_qnorm_resid, h, ptr(x, F32), rows, H, int(layernorm), float(qin[0]), float(qin[1]), float(qin[2]),
+                           ptr(w_fq, F32), ptr(bias), float(math.sqrt(H)), float(eps), float(qout[0]), float(qout[1]), float(qout[2]),
+                           ptr(codes), ptr(rowsum), ptr(acc, torch.int32), int(acc.stride(0)), ptr(g_rowsum, torch.int32), ptr(g["sxw"], F32),
+                           ptr(g["ow"], torch.int32), ptr(g["c0"], torch.int32), ptr(g["bias"]), ptr(g["so"]), ptr(g["oo"]),
+                           float(g["qmax"]), int(g["qgroup"]), stream_ptr()), h)
     return codes, rowsum
 
 

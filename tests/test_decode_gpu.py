@@ -116,13 +116,15 @@ def test_qattn_decode_matches_oracle_rows(cuda, B, T, nh, nkv, hd, rot):
     assert np.array_equal(rsk[:, :, :T].cpu().numpy().astype(np.int64), k.sum(-1))
 
 
+@pytest.mark.parametrize("fused_norm", [True, False])
 @pytest.mark.parametrize("tag", MODEL_GOLDENS)
-def test_engine_prefill_decode_equals_full_forward(cuda, tag):
+def test_engine_prefill_decode_equals_full_forward(cuda, tag, fused_norm):
     """prefill(T0) + token-by-token decode reproduces, bit for bit, the residual stream of the CPU oracle's full-sequence
     forward at every decoded position, and the logits of the engine's own full forward."""
     from mobilequant_b200.engine import IntEngine
     g = load_golden(f"model_{tag}.pt")
     eng = IntEngine(product_model(g), g["qcfg"], g["act_dict"], cuda)
+    eng.fused_resid_norm = fused_norm          # residual epilogues inside the following row norm, or as their own launches
     ids = torch.cat(g["samples"][:2], dim=0).to(cuda)
     B, T = ids.shape
     T0 = T // 2
