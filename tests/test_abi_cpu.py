@@ -63,3 +63,40 @@ def test_product_never_imports_oracle():
                 if "import oracle" in txt or "from oracle" in txt or "/root/reference" in txt:
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def _header_prototypes():
+    """{function name: number of parameters} parsed from include/mqb200.h (comments stripped)."""
+    import re
+    txt = open(_lib.HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(mq_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        params = m.group(2).strip()
+        protos[m.group(1)] = 0 if params in ("", "void") else len(params.split(","))
+    return protos
+
+
+def test_ctypes_bindings_match_header(lib):
+    """Every binding in kernels.py passes exactly as many arguments as the header declares (a dropped or extra argument in
+    a ctypes prototype corrupts the call without any diagnostic)."""
+    from mobilequant_b200 import kernels
+    kernels._protos()
+    protos = _header_prototypes()
+    assert len(protos) >= 20
+    checked = 0
+    for name, n in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, f"{name}: header declares {n} parameters, ctypes binding passes {len(fn.argtypes)}"
+            checked += 1
+    assert checked >= 15
+
+
+def test_sim_export_key_set_matches_reference_golden():
+    """device/convert_sim.py: the parameter names let through for SimModel equal the reference's state-dict keys."""
+    import torch
+    from mobilequant_b200.device.convert_sim import sim_state_keys
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sim_export.pt"), weights_only=False)
+    for tag in ("llama_w8_slinear", "llama_w4", "gemma_w8_slinear"):
+        assert sim_state_keys(2, g[tag]["impl_sym_pch_as_slinear"]) == set(g[tag]["out_states"].keys())
