@@ -308,6 +308,13 @@ def roofline(eng, ids, B, T):
           "frac_of_burst_peak": (achieved / (2.0 * burst)) if burst else None,
           "avg_launch_ms": g["ms"] / g["n"], "launches_per_step": g["n"], "ops_per_step": ops,
           "int8_library_proxy_tops": lib, "frac_of_library_proxy": achieved / lib, "frac_of_spec_4500": achieved / 4500.0}
+    # the attention kernel is the larger share of the step but is neither HBM- nor tensor-bound: an exact 16-bit quantised
+    # softmax costs ~80 ALU instructions per score (DESIGN.md "qattn"); it is reported in its own units
+    at = per.get("qattn")
+    if at:
+        scores = B * eng.nh * T * (T + 1) / 2.0 * cfg.num_hidden_layers
+        shares["qattn"].update({"bound": "alu", "scores_per_s": scores / (at["ms"] / 1e3), "scores_per_step": scores,
+                                "ncu": "profiles/r1d_ncu_summary.md (issue slots 58 % busy, ALU pipe 47 %, tensor pipe 9 %)"})
     return rl, shares
 
 
