@@ -9,6 +9,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-I", os.path.join(HERE, "..", "include")]
+if os.environ.get("MQB200_MEASURE") == "1":      # enables result-destroying measurement knobs (MQ_QGEMM_DBG); never set for product builds
+    FLAGS.append("-DMQ_MEASURE_KNOBS")
 
 
 def _sources():

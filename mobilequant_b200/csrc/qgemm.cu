@@ -563,7 +563,10 @@ extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void
   QGemmArgs args;
   args.M = M; args.N = N; args.K = K; args.rowsum = rowsum; args.sxw = sxw; args.ow = ow; args.c0 = c0;
   args.bias = bias; args.so = so; args.oo = oo; args.qmax = qmax; args.out_bits = out_bits; args.out = out; args.ldo = ldo;
+  args.dbg = 0;
+#ifdef MQ_MEASURE_KNOBS   // measurement builds only (MQB200_MEASURE=1 python -m mobilequant_b200.build --force): dbg 1 drops the epilogue
   { const char* e = getenv("MQ_QGEMM_DBG"); args.dbg = e ? atoi(e) : 0; }
+#endif
   args.qgroup = qgroup > 0 ? qgroup : 32; args.rowsum_out = rowsum_out; args.lut = lut; args.s2 = s2; args.o2 = o2; args.qmax2 = qmax2;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
