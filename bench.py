@@ -171,7 +171,8 @@ def run_ours(args):
     model.eval()
     # activation ranges from a short calibration pass on synthetic ids (config 1 of BASELINE.json, on the GPU; with
     # several ranks the two samples are sharded and the packed ranges all-reduced, identical on every replica)
-    act = get_act_range(model, [synth_ids(1, T, cfg.vocab_size, 7 + i) for i in range(2)])
+    # (at least one sample per rank: the pass shards samples i % world == rank)
+    act = get_act_range(model, [synth_ids(1, T, cfg.vocab_size, 7 + i) for i in range(max(2, world))])
     from mobilequant_b200.ptq.generate_qcfg import default_qcfg
     wq = Q.QuantConfig(bitwidth=8) if args.wbits == 8 else Q.QuantConfig(bitwidth=4, is_symmetric=True, is_per_channel=True)
     qcfg = default_qcfg(cfg, wq, Q.QuantConfig(bitwidth=8))

@@ -61,6 +61,8 @@ def get_act_range(model, samples, per_channel=False):
             model(ids.to(device))
     for h in hooks:
         h.remove()
+    if world > 1 and len(samples) < world:
+        raise ValueError(f"sample-sharded act-range calibration needs at least one sample per rank ({len(samples)} samples, {world} ranks)")
     if world > 1 and not per_channel:
         from ..utils.dist import allreduce_ranges
         packed = allreduce_ranges(torch.stack([stats[k] for k in order]))   # [n, 2]; one exchange: max(-min), max(max)
