@@ -384,7 +384,12 @@ def calib_throughput(model, wq, act, cfg, T, dev, nsamples=96):
     A.e2equant(args, model, loader, _L(), device=dev)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"value": nsamples / dt, "unit": "samples/s", "samples": nsamples, "seconds": dt,
+    full = None
+    fpath = os.path.join(ROOT, "profiles", "r1d_calib512.json")        # the same recipe run on all 512 samples (scratch/calib512.py)
+    if os.path.exists(fpath):
+        fr = json.load(open(fpath))
+        full = {"samples": fr["samples"], "seconds": fr["seconds"], "samples_per_s": fr["samples_per_s"], "source": "profiles/r1d_calib512.json"}
+    return {"value": nsamples / dt, "unit": "samples/s", "samples": nsamples, "seconds": dt, "full_512_sample_run": full,
             "what": "e2equant LET+LWC+LRL, bs 1, seq %d, 1 epoch, includes FP-target pass, fuse and parameters.pth save" % T,
             "path": "fused quantizer / weight-prep kernels + cuBLAS TF32 GEMMs, whole step replayed as one CUDA graph; "
                     "512 samples at this rate: %.1f s (fixed costs included pro rata)" % (512 * dt / nsamples)}
