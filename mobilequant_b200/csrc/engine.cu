@@ -265,65 +265,71 @@ __device__ __forceinline__ void qrope_body(const RopeArgs& a, uint8_t* vs) {
     }
     const int b = tok / a.T, t = tok % a.T;
     const uint8_t* row = a.qkv + int64_t(tok) * a.ldq;
-    // cos/sin of this lane's head dims (shared by every head of the token)
+    // cos / sin of this lane's head dims (shared by every head of the token).  Dims beyond the rotary width (partial rotary,
+    // hm:489-501) use cos 1, sin 0 and themselves as partner -- x*1 + x*0 == x exactly -- so the head loops are branch
+    // free; the sign of rotate_half (hm:338-344: cat(-x2, x1)) is folded into sin (fmul(-y, s) == fmul(y, -s)).
     float cv[WPT][4], sv[WPT][4];
     int dpart[WPT];
-    bool rotd[WPT], neg[WPT];
 #pragma unroll
     for (int wi = 0; wi < WPT; ++wi) {
       const int d = (sub + wi * LPI) * 4;
-      rotd[wi] = d < a.rot;
-      neg[wi] = d < half;
-      dpart[wi] = d < half ? d + half : d - half;
-      if (rotd[wi]) {
+      if (d < a.rot) {
+        const bool neg = d < half;
+        dpart[wi] = neg ? d + half : d - half;
         const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
         cv[wi][0] = c.x; cv[wi][1] = c.y; cv[wi][2] = c.z; cv[wi][3] = c.w;
-        sv[wi][0] = sn.x; sv[wi][1] = sn.y; sv[wi][2] = sn.z; sv[wi][3] = sn.w;
+        sv[wi][0] = neg ? -sn.x : sn.x; sv[wi][1] = neg ? -sn.y : sn.y; sv[wi][2] = neg ? -sn.z : sn.z; sv[wi][3] = neg ? -sn.w : sn.w;
+      } else {
+        dpart[wi] = d;
+        cv[wi][0] = cv[wi][1] = cv[wi][2] = cv[wi][3] = 1.f;
+        sv[wi][0] = sv[wi][1] = sv[wi][2] = sv[wi][3] = 0.f;
       }
     }
-    // ---- q and k heads: HPW heads per iteration, LPI adjacent lanes per head
-    for (int hh0 = 0; hh0 < heads_qk; hh0 += HPW) {
-      const int hh = hh0 + grp;
-      const bool ok = hh < heads_qk;
-      const bool is_q = hh < a.nh;
-      int csum = 0;
-      if (ok) {
-        const uint8_t* src = row + hh * HD;              // q heads then k heads are contiguous in the row
-        const float s_in = is_q ? a.sq_in : a.sk_in, o_in = is_q ? a.oq_in : a.ok_in;
-        QParam qo;
-        qo.s = is_q ? qq.s : qk.s; qo.rs = is_q ? qq.rs : qk.rs; qo.lo = is_q ? qq.lo : qk.lo; qo.hi = is_q ? qq.hi : qk.hi;
-        qo.ioff = is_q ? qq.ioff : qk.ioff; qo.five = false;
-        uint8_t* dst = is_q ? a.q + ((int64_t(b) * a.nh + hh) * a.T + t) * HD
-                            : a.k + ((int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t) * HD;
+    // ---- q heads, then k heads: HPW heads per iteration, LPI adjacent lanes per head.  src0: codes of head 0 of the kind in
+    // the token's row; dst0 / rs0: head 0 of this token in the output layout (heads are T*HD / T elements apart)
+    const int64_t strideh = int64_t(a.T) * HD;
+    auto heads = [&](int nheads, const uint8_t* src0, float s_in, float o_in, const QParam& qo, uint8_t* dst0, int32_t* rs0) {
+      constexpr int U = 2;                               // heads in flight per lane group: the loop is load-latency bound
+      for (int hh0 = 0; hh0 < nheads; hh0 += U * HPW) {
+        uint32_t wx[U][WPT], wy[U][WPT];
+        bool ok[U];
 #pragma unroll
-        for (int wi = 0; wi < WPT; ++wi) {
-          const int d = (sub + wi * LPI) * 4;
-          float x[4], out[4];
-          unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + d)), s_in, o_in, x);
-          if (rotd[wi]) {
-            // q_embed = (q * cos) + (rotate_half(q) * sin); rotate_half = cat(-x2, x1)
-            float y[4];
-            unpack4(__ldg(reinterpret_cast<const uint32_t*>(src + dpart[wi])), s_in, o_in, y);
+        for (int u = 0; u < U; ++u) {
+          const int hh = hh0 + u * HPW + grp;
+          ok[u] = hh < nheads;
+          const uint8_t* src = src0 + (ok[u] ? hh : 0) * HD;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = fadd(fmul(x[j], cv[wi][j]), fmul(neg[wi] ? -y[j] : y[j], sv[wi][j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[j] = x[j];
+          for (int wi = 0; wi < WPT; ++wi) {
+            wx[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + (sub + wi * LPI) * 4));
+            wy[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + dpart[wi]));
           }
-          uint32_t packed = 0;
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<FIVE>(out[j], qo) << (8 * j);
-          *reinterpret_cast<uint32_t*>(dst + d) = packed;
-          csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+        for (int u = 0; u < U; ++u) {
+          const int hh = hh0 + u * HPW + grp;
+          int csum = 0;
+          uint8_t* dst = dst0 + hh * strideh;
+#pragma unroll
+          for (int wi = 0; wi < WPT; ++wi) {
+            const int d = (sub + wi * LPI) * 4;
+            float x[4], y[4];
+            unpack4(wx[u][wi], s_in, o_in, x);
+            unpack4(wy[u][wi], s_in, o_in, y);
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // q_embed = q * cos + rotate_half(q) * sin
+              packed |= (uint32_t)quant_int<FIVE>(fadd(fmul(x[j], cv[wi][j]), fmul(y[j], sv[wi][j])), qo) << (8 * j);
+            if (ok[u]) *reinterpret_cast<uint32_t*>(dst + d) = packed;
+            csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+          }
+#pragma unroll
+          for (int dd = LPI >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
+          if (ok[u] && sub == 0) rs0[int64_t(hh) * a.T] = csum;
         }
       }
-#pragma unroll
-      for (int dd = LPI >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
-      if (ok && sub == 0) {
-        if (is_q) a.rsq[(int64_t(b) * a.nh + hh) * a.T + t] = csum;
-        else a.rsk[(int64_t(b) * a.nkv + (hh - a.nh)) * a.T + t] = csum;
-      }
-    }
+    };
+    heads(a.nh, row, a.sq_in, a.oq_in, qq, a.q + (int64_t(b) * a.nh * a.T + t) * HD, a.rsq + int64_t(b) * a.nh * a.T + t);
+    heads(a.nkv, row + a.nh * HD, a.sk_in, a.ok_in, qk, a.k + (int64_t(b) * a.nkv * a.T + t) * HD, a.rsk + int64_t(b) * a.nkv * a.T + t);
     // ---- v: requant into the smem tile
     const uint8_t* vsrc = row + heads_qk * HD;
     for (int c = lane * 4; c < vw; c += 128) {
