@@ -146,7 +146,17 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def _trace(msg, _t0=[None]):
+    """MQB200_BENCH_TRACE=1: wall-clock phase marks on stderr (start-up diagnosis; nothing of this is inside a timed region)."""
+    if os.environ.get("MQB200_BENCH_TRACE") == "1":
+        now = time.perf_counter()
+        if _t0[0] is None:
+            _t0[0] = now
+        print(f"[bench rank {os.environ.get('RANK', '0')}] +{now - _t0[0]:7.1f} s  {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    _trace("start")
     import torch
     import torch.distributed as dist
     from mobilequant_b200 import kernels as K
@@ -162,6 +172,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    _trace("process group up")
     torch.backends.cuda.matmul.allow_tf32 = True          # as ptq/mobilequant.py:91 (only the fp lm_head / teacher use it)
     cfg = model_cfg(args)
     T, B = args.seqlen, args.batch
@@ -169,6 +180,7 @@ def run_ours(args):
     with torch.device(dev):
         model = HFForCausalLM(cfg).float()
     model.eval()
+    _trace("model built")
     # activation ranges from a short calibration pass on synthetic ids (config 1 of BASELINE.json, on the GPU; with
     # several ranks the two samples are sharded and the packed ranges all-reduced, identical on every replica)
     # (at least one sample per rank: the pass shards samples i % world == rank)
@@ -176,7 +188,9 @@ def run_ours(args):
     from mobilequant_b200.ptq.generate_qcfg import default_qcfg
     wq = Q.QuantConfig(bitwidth=8) if args.wbits == 8 else Q.QuantConfig(bitwidth=4, is_symmetric=True, is_per_channel=True)
     qcfg = default_qcfg(cfg, wq, Q.QuantConfig(bitwidth=8))
+    _trace("act ranges done")
     eng = IntEngine(model, qcfg, act, dev)
+    _trace("engine built")
     wtag = "W8A8" if args.wbits == 8 else "W4A8 per-channel symmetric (weights packed 2/byte in HBM, %.2f GB, expanded per layer into L2)" % (eng.weight_bytes() / 1e9)
     ids_host = synth_ids(B, T, cfg.vocab_size, 1000 + rank).pin_memory()
     ids_dev = ids_host.to(dev)
@@ -222,6 +236,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
+    _trace("warm-up done")
     K.reset_launch_count()
     with ClockSampler(local) as clk:
         ms = timed(step_resident, args.steps)
@@ -229,6 +244,7 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e_dev = timed(step_e2e, args.steps)
+    _trace("timed regions done")
     tokens_step = B * T * world
     value = tokens_step * args.steps / (ms / 1e3)
     e2e = tokens_step * args.steps / (ms_e2e_dev / 1e3)
@@ -256,9 +272,11 @@ def run_ours(args):
             torch.cuda.empty_cache()
             line["calib"] = calib_throughput(model, wq, act, cfg, T, dev, args.calib_samples)
         print(json.dumps(line), flush=True)
+    _trace("line printed")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    _trace("done")
 
 
 def roofline(eng, ids, B, T):
