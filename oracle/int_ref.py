@@ -183,6 +183,31 @@ def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
     return out.reshape(B * T, nh * hd)
 
 
+def qattn_decode_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
+    """mq_qattn_decode (attention part): the new token's row against every cached key, SimAttention.forward with k_cache /
+    v_cache (mobilellm/model/sim_model.py:271-330; the causal mask row of a decode step hides nothing, :222-223).
+    q [B,nh,hd] codes of the new token, k / v [B,nkv,Tk,hd] codes of positions 0..Tk-1 (the new token included).
+    Same arithmetic as qattn_int restricted to one query row.  Returns codes [B, nh*hd]."""
+    B, _, hd = q.shape
+    rep = nh // nkv
+    if lut is None:
+        lut = exp_tables(qs[0], hd)
+    sqk = f32(f32(qq[0]) * f32(qk[0])); spv = f32(f32(qp[0]) * f32(qv[0]))
+    out = np.zeros((B, nh, hd), np.int64)
+    for b in range(B):
+        for h in range(nh):
+            kv = h // rep
+            I = _mm_exact((q[b, h] - int(qq[1])).reshape(1, hd), (k[b, kv] - int(qk[1])).T)
+            c = quant_codes((I.astype(f32) * sqk).astype(f32), qs[0], qs[1], 0, qs[2]).astype(np.int64)
+            E = exp_eval(lut, np.clip(c.max() - c, 0, int(qs[2])))
+            S = E.sum(dtype=np.uint64)
+            p = (E.astype(f32) / f32(S)).astype(f32)
+            cp = quant_codes(p, qp[0], 0, 0, qp[2]).astype(np.int64)
+            A = _mm_exact(cp, v[b, kv] - int(qv[1]))
+            out[b, h] = quant_codes((A.astype(f32) * spv).astype(f32), qo[0], qo[1], 0, 255).astype(np.int64)[0]
+    return out.reshape(B, nh * hd)
+
+
 def act_lut(kind, q_w1out, q_in2, q_out):
     """256-entry table: w1-output code -> fq_out(act(x^)) as fp32 (QSiLU qm:739-753 / QGELU qm:790-799).  The
     transcendental is evaluated in float64 and rounded once to fp32."""
@@ -245,10 +270,10 @@ class IntModel:
         return qnorm_int(h, _sq(self.act, self.recipe, name, "input"), w_fq, self._bias(name), _sq(self.act, self.recipe, name, "output"),
                          self.layernorm, self.cfg.get("layer_norm_eps", 1e-5))
 
-    def block(self, h, i, B, T, cos, sin, trace=None):
+    def _qkv(self, h, i):
+        """input norm + fused q|k|v projection codes of block i; returns (x1, qkv, qin, qout)."""
         p = f"model.layers.{i}."
-        A, R = self.act, self.recipe
-        sq = lambda n, s: _sq(A, R, p + n, s)
+        sq = lambda n, s: _sq(self.act, self.recipe, p + n, s)
         x1 = self.norm(h, p + "input_layernorm")
         qx = sq("input_layernorm", "output")
         outs = []
@@ -259,9 +284,44 @@ class IntModel:
         qkv = np.concatenate(outs, axis=1)
         qin = [sq("self_attn." + n, "output")[:2] for n in ("q_proj", "k_proj", "v_proj")]
         qout = [sq("self_attn.qk_bmm", "input")[:2], sq("self_attn.qk_bmm", "input2")[:2], sq("self_attn.pv_bmm", "input2")[:2]]
+        return x1, qkv, qin, qout
+
+    def block(self, h, i, B, T, cos, sin, trace=None, cache=None):
+        """cache (optional): dict layer -> [k, v] code arrays [B, nkv, T, hd], filled for the decode steps that follow."""
+        p = f"model.layers.{i}."
+        sq = lambda n, s: _sq(self.act, self.recipe, p + n, s)
+        x1, qkv, qin, qout = self._qkv(h, i)
         q, k, v = qrope_int(qkv, B, T, self.nh, self.nkv, self.hd, self.rot, qin, qout, cos, sin)
+        if cache is not None:
+            cache[i] = [k, v]
         attn = qattn_int(q, k, v, self.nh, self.nkv, qout[0], qout[1], qout[2], sq("self_attn.qk_bmm", "output"),
                          sq("self_attn.pv_bmm", "input"), sq("self_attn.pv_bmm", "output")[:2])
+        return self._tail(h, attn, i, trace, dict(x1=x1, qkv=qkv, q=q, k=k, v=v))
+
+    def decode_block(self, h, i, pos, cache, cos, sin):
+        """One-token step of block i against the uint8 KV cache (SimBlock / SimAttention with k_cache, v_cache,
+        mobilellm/model/sim_model.py:271-330; capp/src/llm.cpp:545-653): h [B, H] rows of the new tokens at position pos;
+        the rotated k / v codes are appended to cache[i]."""
+        p = f"model.layers.{i}."
+        sq = lambda n, s: _sq(self.act, self.recipe, p + n, s)
+        B = h.shape[0]
+        _, qkv, qin, qout = self._qkv(h, i)
+        q, k, v = qrope_int(qkv, B, 1, self.nh, self.nkv, self.hd, self.rot, qin, qout, cos[pos:pos + 1], sin[pos:pos + 1])
+        cache[i] = [np.concatenate([cache[i][0], k], axis=2), np.concatenate([cache[i][1], v], axis=2)]     # sim_model.py:229-231
+        attn = qattn_decode_int(q[:, :, 0], cache[i][0], cache[i][1], self.nh, self.nkv, qout[0], qout[1], qout[2], sq("self_attn.qk_bmm", "output"),
+                                sq("self_attn.pv_bmm", "input"), sq("self_attn.pv_bmm", "output")[:2])
+        return self._tail(h, attn, i)
+
+    def decode(self, h, pos, cache, cos, sin):
+        for i in range(self.cfg["num_hidden_layers"]):
+            h = self.decode_block(h, i, pos, cache, cos, sin)
+        return h
+
+    def _tail(self, h, attn, i, trace=None, tr0=None):
+        """o_proj + residual, post-attention norm, gated MLP + residual (everything of the block after attention)."""
+        p = f"model.layers.{i}."
+        A, R = self.act, self.recipe
+        sq = lambda n, s: _sq(A, R, p + n, s)
         qa = sq("self_attn.pv_bmm", "output")
         y = self._lin_y(attn, qa, p + "self_attn.o_proj")
         qo = sq("self_attn.o_proj", "output")
@@ -281,16 +341,17 @@ class IntModel:
         qo = sq("mlp.w2", "output")
         h = (h + dequant(quant_codes(y, qo[0], qo[1], 0, qo[2]), qo[0], qo[1])).astype(f32)
         if trace is not None:
-            trace.update(x1=x1, qkv=qkv, q=q, k=k, v=v, attn=attn, h_mid=h_mid, x2=x2, act=act)
+            trace.update(tr0 or {})
+            trace.update(attn=attn, h_mid=h_mid, x2=x2, act=act)
         return h
 
-    def backbone(self, h, B, T, cos=None, sin=None, trace_layer=None):
+    def backbone(self, h, B, T, cos=None, sin=None, trace_layer=None, cache=None):
         if cos is None:
             cos, sin = rope_tables(T, self.rot, self.cfg.get("rope_theta", 10000.0))
         trace = None
         for i in range(self.cfg["num_hidden_layers"]):
             tr = {} if trace_layer == i else None
-            h = self.block(h, i, B, T, cos, sin, tr)
+            h = self.block(h, i, B, T, cos, sin, tr, cache)
             if tr is not None:
                 trace = tr
         return h, trace
