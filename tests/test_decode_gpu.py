@@ -94,6 +94,8 @@ def test_qattn_decode_matches_oracle_rows(cuda, B, T, nh, nkv, hd, rot):
     smax = 255 * 255 * hd * 0.033 * 0.029 * 0.12
     qs = (f32(2 * smax / 65535), f32(32768), f32(65535)); qp = (f32(1.0 / 65535), f32(0), f32(65535)); qo = (f32(0.7 / 255), f32(128), f32(255))
     ref = ir.qattn_int(q, k, v, nh, nkv, qout[0], qout[1], qout[2], qs, qp, qo).reshape(B, T, nh * hd)
+    # the oracle's own one-row (cache) form agrees with its causal form
+    assert np.array_equal(ir.qattn_decode_int(q[:, :, T - 1], k, v, nh, nkv, qout[0], qout[1], qout[2], qs, qp, qo), ref[:, T - 1])
     lut = torch.from_numpy(ir.exp_tables(qs[0], hd).view(np.int32)).to(cuda)
     params = [qout[0][1], qout[1][1], qout[2][1], f32(qout[0][0]) * f32(qout[1][0]), qs[0], qs[1], qs[2], qp[0], qp[2],
               f32(qp[0]) * f32(qout[2][0]), qo[0], qo[1]]
