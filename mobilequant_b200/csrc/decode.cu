@@ -3,17 +3,22 @@
 // The reference decodes with SimModel.generate (mobilellm/model/sim_model.py:181-235: context encoding, then one-token
 // steps that append to k_cache / v_cache [L, n_heads, T-1, head_dim]) and, on the phone, with the capp loop
 // (capp/src/llm.cpp:545-653, uint8 caches); both run the same static quantizers as the prefill, so the integer tensors
-// of a decode step equal row `pos` of a full-sequence forward.  Two kernels + one epilogue cover it here:
+// of a decode step equal row `pos` of a full-sequence forward.  Kernels of the step:
 //
 //   mq_qgemv          skinny GEMM  acc[b, n] += sum_k X[b, k] W[n, k]  for B <= 128 rows: the WEIGHTS are the 128-row
 //                     UMMA operand (tcgen05.mma kind::i8, M = 128, N = padded batch), every weight byte leaves HBM exactly
 //                     once, the K loop is split across CTAs so that all SMs stream, partial sums meet in an s32
 //                     accumulator with red.global.add (integer adds commute: the result is exact and deterministic)
 //   mq_qgemv_epilogue the requantisation epilogues of mq_qgemm (QUANT / ACTMUL / RESID) on that accumulator, same
-//                     arithmetic, and the accumulator is handed back zeroed
+//                     arithmetic (gv_epi.cuh), and the accumulator is handed back zeroed; mq_qgemv_fused runs it inside
+//                     the GEMV (last CTA of a column group); mq_qnorm_resid (engine.cu) folds RESID into the next norm
 //   mq_qattn_decode   RoPE + requant of the new token's q / k / v codes, append to the cache, exact quantised softmax
-//                     attention of the new row over keys 0..pos (same integer arithmetic as mq_qattn)
-// All three are HBM-bound (weights / cache streamed once); oracle: oracle/int_ref.py (full forward, row pos).
+//                     attention of the new row over keys 0..pos (same integer arithmetic as mq_qattn); a cluster of CTAs
+//                     splits the keys and exchanges exact integer partials through distributed shared memory
+//   mq_fgemv          the unquantised fp32 lm_head for <= 16 rows, one pass over the weights
+//   mq_unpack4        packed 4-bit weight codes -> one code per byte right before a GEMM (W4A8 weights stay packed in HBM)
+// All are HBM- or latency-bound (weights / cache streamed once); oracle: oracle/int_ref.py (IntModel.decode == row pos of
+// the full forward, tests/test_decode_oracle_cpu.py).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "ctx.h"
