@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "ctx.h"
 #include "gv_epi.cuh"
+#include "attn.cuh"
 #include <string>
 #include <algorithm>
 #include <cstdlib>
@@ -386,20 +387,6 @@ __global__ void __launch_bounds__(256) qrope_kernel(const RopeArgs a, const int 
 // materialises it ~9x per layer in fp32).  One CTA = 64 query rows of one head; each warp owns 16 rows.  K/V tiles are
 // double buffered with cp.async; every requantisation is the branch-free exact division of common.cuh.
 // =====================================================================================================================
-struct AttnArgs {
-  const uint8_t *q, *k, *vt;
-  const int32_t *rsq, *rsk;
-  int B, T, nh, nkv, hd;
-  float oq, ok, ov;            // integer zero points
-  float sqk;                   // sq*sk
-  float s_s, o_s, qmax_s;      // score quantizer
-  const uint32_t* lut;         // [512]: A[256] then B[256]
-  float s_p, qmax_p;           // prob quantizer (offset 0)
-  float spv;                   // s_p*s_v
-  float s_out, o_out;          // output quantizer (8 bit)
-  uint8_t* out;                // [B*T, nh*hd]
-  int32_t* rowsum_out;         // [B*T] atomically accumulated
-};
 
 __device__ __forceinline__ void mma_u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -1122,11 +1109,16 @@ static int launch_qattn4(Ctx* c, const AttnArgs& a, int cpw, size_t smem, cudaSt
   qattn4_kernel<HD, DV, FIVE><<<grid, 256, attr_smem, st>>>(a, cpw, (int)n_items);
   return check_launch(c, "mq_qattn");
 }
-// MQB200_QATTN=3pass forces the streaming three-pass kernel (the fallback for sequences whose score codes do not fit
-// in shared memory); read per call so that the tests can exercise both kernels in one process.
-static bool qattn_force_3pass() {
+// MQB200_QATTN picks the kernel (read per call so that the tests can exercise all of them in one process):
+//   unset / "tc"  tcgen05 + TMA + TMEM kernel (qattn_tc.cu) where the shape is covered (hd 64 / 128, T % 16 == 0)
+//   "smem"        mma.sync kernel with the score codes parked in shared memory (falls back to 3pass when they do not fit)
+//   "3pass"       streaming three-pass mma.sync kernel (any T)
+static int qattn_choice() {
   const char* e = getenv("MQB200_QATTN");
-  return e && e[0] == '3';
+  if (e && e[0] == '3') return 2;
+  if (e && e[0] == 's') return 1;
+  if (e && e[0] == 't' && e[1] == 'c' && e[2] == '!') return 3;       // "tc!": fail instead of falling back (tests)
+  return 0;
 }
 template <int HD, int DV>
 static int launch_qattn(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
@@ -1134,7 +1126,7 @@ static int launch_qattn(Ctx* c, const AttnArgs& a, dim3 grid, cudaStream_t st) {
   const bool five = mantissa_all_ones(a.s_s) || mantissa_all_ones(a.s_p) || mantissa_all_ones(a.s_out);
   const int cpw = ((a.T + 31) / 32 + 3) / 4;     // 32-key chunks per key-split warp
   const size_t smem4 = a4_smem_bytes<HD, DV>(cpw);
-  if (smem4 <= 227 * 1024 && !qattn_force_3pass())
+  if (smem4 <= 227 * 1024 && qattn_choice() != 2)
     return five ? launch_qattn4<HD, DV, true>(c, a, cpw, smem4, st) : launch_qattn4<HD, DV, false>(c, a, cpw, smem4, st);
   return five ? launch_qattn2<HD, DV, true>(c, a, grid, st) : launch_qattn2<HD, DV, false>(c, a, grid, st);
 }
@@ -1244,9 +1236,12 @@ int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, c
   a.o_out = qparams[11];
   MQ_REQUIRE(c, a.qmax_s <= 65535.f && a.qmax_p <= 65535.f, "score / probability codes are at most 16 bit");
   MQ_REQUIRE(c, a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out), "integer engine kernels need integral offsets (qm:60)");
-  a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
+  a.lut = lut; a.out = out; a.rowsum_out = rowsum_out; a.q_start = 0; a.Tq = T;
   dim3 grid((T + 63) / 64 * (hd == 256 ? 2 : 1), nh, B);
   cudaStream_t st = (cudaStream_t)stream;
+  const int choice = qattn_choice();
+  if ((choice == 0 || choice == 3) && qattn_tc_supported(a)) return launch_qattn_tc(c, a, st);
+  MQ_REQUIRE(c, choice != 3, "MQB200_QATTN=tc! but the shape is not covered by the tcgen05 kernel (hd 64/128, T % 16 == 0)");
   if (hd == 32) return launch_qattn<32, 32>(c, a, grid, st);
   if (hd == 64) return launch_qattn<64, 64>(c, a, grid, st);
   if (hd == 128) return launch_qattn<128, 128>(c, a, grid, st);

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "ctx.h"
+#include "tc_host.h"
 #include <string>
 #include <cstdlib>
 
@@ -422,37 +423,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
-// 2D row-major matrix [rows, cols] of `esize`-byte elements (cols contiguous, row pitch `pitch_bytes`), box = box_bytes
-// (128 or 64) x box_rows, swizzle span == box width
-static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int64_t rows, int64_t cols,
-                         int64_t pitch_bytes, int box_rows, int box_bytes = 128) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)pitch_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / esize), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  return enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int MODE, int CL, int NE>
 static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
                          cudaStream_t st) {

@@ -157,19 +157,26 @@ def exp_eval(tab, k):
     return (tab[k >> 8].astype(np.uint64) * tab[256 + (k & 255)].astype(np.uint64)) >> np.uint64(31)
 
 
-def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
-    """mq_qattn.  q [B,nh,T,hd], k/v [B,nkv,T,hd] codes; qq/qk/qv = (s,o); qs = (s,o,qmax) score quantizer;
-    qp = (s, o(=0), qmax) prob quantizer; qo = (s,o) output quantizer (8 bit).  Returns codes [B*T, nh*hd]."""
-    B, _, T, hd = q.shape
+def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None, heads=None, q_start=0):
+    """mq_qattn.  q [B,nh,Tq,hd], k/v [B,nkv,T,hd] codes; qq/qk/qv = (s,o); qs = (s,o,qmax) score quantizer;
+    qp = (s, o(=0), qmax) prob quantizer; qo = (s,o) output quantizer (8 bit).  Returns codes [B*Tq, nh*hd].
+    heads: optional iterable of (b, h) pairs -- only those are computed (the rest of the output stays 0; full-size
+    parity tests check a few heads against this oracle and the remaining ones against another kernel).
+    q_start: absolute position of query row 0 (sequence-sharded prefill: keys 0 .. q_start + Tq - 1 are visible)."""
+    B, _, Tq, hd = q.shape
+    T = k.shape[2]
     rep = nh // nkv
     if lut is None:
         lut = exp_tables(qs[0], hd)
     assert int(qp[1]) == 0
     sqk = f32(f32(qq[0]) * f32(qk[0])); spv = f32(f32(qp[0]) * f32(qv[0]))
-    out = np.zeros((B, T, nh, hd), np.int64)
-    causal = np.tril(np.ones((T, T), bool))
+    out = np.zeros((B, Tq, nh, hd), np.int64)
+    causal = np.arange(T)[None, :] <= (q_start + np.arange(Tq))[:, None]
+    todo = set((b, h) for b in range(B) for h in range(nh)) if heads is None else set(heads)
     for b in range(B):
         for h in range(nh):
+            if (b, h) not in todo:
+                continue
             kv = h // rep
             I = _mm_exact(q[b, h] - int(qq[1]), (k[b, kv] - int(qk[1])).T)
             c = quant_codes((I.astype(f32) * sqk).astype(f32), qs[0], qs[1], 0, qs[2]).astype(np.int64)
@@ -180,7 +187,7 @@ def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
             cp = np.where(causal, quant_codes(p, qp[0], 0, 0, qp[2]).astype(np.int64), 0)
             A = _mm_exact(cp, v[b, kv] - int(qv[1]))
             out[b, :, h, :] = quant_codes((A.astype(f32) * spv).astype(f32), qo[0], qo[1], 0, 255).astype(np.int64)
-    return out.reshape(B * T, nh * hd)
+    return out.reshape(B * Tq, nh * hd)
 
 
 def qattn_decode_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):

@@ -46,17 +46,27 @@ def test_qrope(cuda, B, T, nh, nkv, hd, rot):
     assert np.array_equal(out["rsk"].cpu().numpy().astype(np.int64), k.sum(-1))
 
 
-@pytest.mark.parametrize("impl", ["codes-in-smem", "3pass"])
+def _select_attn(monkeypatch, impl):
+    """tc: tcgen05/TMA/TMEM kernel ('tc!' = raise instead of falling back); smem / 3pass: the two mma.sync kernels."""
+    monkeypatch.setenv("MQB200_QATTN", {"tc": "tc!", "codes-in-smem": "smem", "3pass": "3pass"}[impl])
+
+
+def _tc_covers(T, hd):
+    return hd in (64, 128) and T % 16 == 0
+
+
+@pytest.mark.parametrize("impl", ["tc", "codes-in-smem", "3pass"])
 @pytest.mark.parametrize("B,T,nh,nkv,hd", [(1, 64, 2, 1, 64), (2, 100, 4, 2, 32), (1, 200, 4, 4, 64), (1, 130, 2, 1, 128), (1, 96, 2, 1, 256),
-                                           (1, 1, 2, 2, 64), (1, 33, 2, 1, 64), (1, 520, 2, 1, 64), (1, 391, 1, 1, 256)])
+                                           (1, 1, 2, 2, 64), (1, 33, 2, 1, 64), (1, 520, 2, 1, 64), (1, 391, 1, 1, 256),
+                                           (1, 16, 1, 1, 64), (2, 128, 4, 2, 64), (1, 144, 2, 2, 64), (2, 400, 4, 1, 64), (1, 640, 2, 1, 64),
+                                           (1, 128, 2, 1, 128), (2, 272, 2, 2, 128), (1, 528, 1, 1, 128)])
 def test_qattn(cuda, B, T, nh, nkv, hd, impl, monkeypatch):
-    """Both attention kernels (single-QK-pass with the score codes parked in shared memory; streaming three-pass
-    fallback for long sequences) against the integer oracle: ragged T, T = 1, multi-stage T, GQA, every head dim."""
+    """The three attention kernels (tcgen05 + TMA + TMEM; mma.sync with the score codes parked in shared memory; streaming
+    three-pass mma.sync) against the integer oracle: ragged T, T = 1, multi-tile T, GQA, every head dim."""
     from mobilequant_b200 import kernels as K
-    if impl == "3pass":
-        monkeypatch.setenv("MQB200_QATTN", "3pass")
-    else:
-        monkeypatch.delenv("MQB200_QATTN", raising=False)
+    if impl == "tc" and not _tc_covers(T, hd):
+        pytest.skip("shape not covered by the tcgen05 kernel (falls back to the mma.sync kernels, tested separately)")
+    _select_attn(monkeypatch, impl)
     rng = np.random.default_rng(T * hd)
     q = rng.integers(0, 256, size=(B, nh, T, hd)).astype(np.uint8)
     k = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)
@@ -77,6 +87,91 @@ def test_qattn(cuda, B, T, nh, nkv, hd, impl, monkeypatch):
     got = out.cpu().numpy().astype(np.int64)
     assert np.array_equal(got, ref), f"{(got != ref).mean():.4f} mismatching"
     assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+def _attn_problem(rng, B, T, nh, nkv, hd, spread=0.12):
+    q = rng.integers(0, 256, size=(B, nh, T, hd)).astype(np.uint8)
+    k = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)
+    v = rng.integers(0, 256, size=(B, nkv, T, hd)).astype(np.uint8)
+    qq, qk, qv = (f32(0.02), f32(126)), (f32(0.018), f32(131)), (f32(0.015), f32(124))
+    smax = 255 * 255 * hd * 0.02 * 0.018 * spread
+    qs = (f32(2 * smax / 65535), f32(32768), f32(65535))
+    qp = (f32(1.0 / 65535), f32(0), f32(65535))
+    qo = (f32(0.7 / 255), f32(128), f32(255))
+    params = [qq[1], qk[1], qv[1], f32(qq[0]) * f32(qk[0]), qs[0], qs[1], qs[2], qp[0], qp[2], f32(qp[0]) * f32(qv[0]), qo[0], qo[1]]
+    return q, k, v, (qq, qk, qv, qs, qp, qo), params
+
+
+@pytest.mark.parametrize("B,T,nh,nkv,hd,spread", [(2, 1024, 32, 4, 64, 0.12),      # TinyLlama-1.1B attention, seq 1024 (headline shape)
+                                                  (1, 2048, 8, 1, 256, 0.05),     # Gemma-2B attention, seq 2048
+                                                  (1, 2048, 4, 4, 64, 0.3),       # StableLM-style MHA, long sequence, wide score range
+                                                  (1, 1024, 4, 2, 128, 0.12)])
+def test_qattn_real_shapes(cuda, B, T, nh, nkv, hd, spread, monkeypatch):
+    """Parity at the benchmark's own shapes (the persistent multi-tile dispatch the bench runs): a few heads against the
+    numpy oracle (one head at T 1024 takes the oracle under a second), every head of every kernel against each other."""
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(B * T + hd)
+    q, k, v, qps, params = _attn_problem(rng, B, T, nh, nkv, hd, spread)
+    qq, qk, qv, qs, qp, qo = qps
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    bufs = dict(q=dev(q), k=dev(k), vt=dev(np.ascontiguousarray(v.transpose(0, 1, 3, 2))),
+                rsq=dev(q.astype(np.int32).sum(-1).astype(np.int32)), rsk=dev(k.astype(np.int32).sum(-1).astype(np.int32)))
+    lut = dev(ir.exp_tables(qs[0], hd).view(np.int32))
+    outs = {}
+    impls = (["tc"] if _tc_covers(T, hd) else []) + ["codes-in-smem", "3pass"]
+    for impl in impls:
+        _select_attn(monkeypatch, impl)
+        rs = torch.zeros(B * T, dtype=torch.int32, device=cuda)
+        out = K.qattn(bufs, B, T, nh, nkv, hd, params, lut, rowsum_out=rs)
+        outs[impl] = (out.cpu().numpy(), rs.cpu().numpy())
+    first = impls[0]
+    for impl in impls[1:]:
+        assert np.array_equal(outs[first][0], outs[impl][0]), f"{first} vs {impl}: {(outs[first][0] != outs[impl][0]).mean():.5f} of the codes differ"
+        assert np.array_equal(outs[first][1], outs[impl][1])
+    heads = [(0, 0), (B - 1, nh - 1), (0, nh // 2)]
+    ref = ir.qattn_int(q.astype(np.int64), k.astype(np.int64), v.astype(np.int64), nh, nkv, qq, qk, qv, qs, qp, qo, heads=heads)
+    got = outs[first][0].astype(np.int64).reshape(B, T, nh, hd)
+    ref = ref.reshape(B, T, nh, hd)
+    for b, h in set(heads):
+        assert np.array_equal(got[b, :, h], ref[b, :, h]), f"head {(b, h)}: {(got[b, :, h] != ref[b, :, h]).mean():.5f} mismatching"
+    assert np.array_equal(outs[first][1].astype(np.int64), outs[first][0].astype(np.int64).sum(1))
+
+
+@pytest.mark.parametrize("rows,H,layernorm", [(2048, 2048, False), (4096, 2048, True)])
+def test_qnorm_real_shapes(cuda, rows, H, layernorm):
+    """qnorm at the hidden size of all three evaluated families (H 2048), thousands of rows (warp-per-row kernel)."""
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(rows)
+    x = (rng.normal(0, 1.5, size=(rows, H)) * rng.uniform(0.2, 3, size=(rows, 1))).astype(f32)
+    w = rng.normal(0, 1, size=H).astype(f32)
+    bias = rng.normal(0, 0.1, size=H).astype(f32) if layernorm else None
+    qin = (f32((x.max() - x.min()) * 0.9 / 65535), f32(np.rint(-x.min() * 0.9 / ((x.max() - x.min()) * 0.9 / 65535))), f32(65535))
+    qout = (f32(8.0 / 255), f32(128), f32(255))
+    ref = ir.qnorm_int(x, qin, w, bias, qout, layernorm, 1e-5)
+    codes, rs = K.qnorm(torch.from_numpy(x).to(cuda), qin, torch.from_numpy(w).to(cuda), None if bias is None else torch.from_numpy(bias).to(cuda),
+                        qout, layernorm, 1e-5)
+    assert np.array_equal(codes.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
+@pytest.mark.parametrize("B,T,nh,nkv,hd,rot", [(2, 1024, 32, 4, 64, 64),       # TinyLlama
+                                               (1, 2048, 8, 1, 256, 256),     # Gemma-2B
+                                               (1, 1024, 32, 32, 64, 16)])    # StableLM-2 (partial rotary 0.25)
+def test_qrope_real_shapes(cuda, B, T, nh, nkv, hd, rot):
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(T + hd + nkv)
+    N = (nh + 2 * nkv) * hd
+    qkv = rng.integers(0, 256, size=(B * T, N)).astype(np.uint8)
+    qin = [(f32(0.031), f32(120)), (f32(0.027), f32(131)), (f32(0.011), f32(127))]
+    qout = [(f32(0.033), f32(125)), (f32(0.029), f32(128)), (f32(0.012), f32(126))]
+    cos, sin = ir.rope_tables(T, rot)
+    q, k, v = ir.qrope_int(qkv, B, T, nh, nkv, hd, rot, qin, qout, cos, sin)
+    out = K.qrope(torch.from_numpy(qkv).to(cuda), B, T, nh, nkv, hd, rot, qin, qout, torch.from_numpy(cos).to(cuda), torch.from_numpy(sin).to(cuda))
+    assert np.array_equal(out["q"].cpu().numpy().astype(np.int64), q)
+    assert np.array_equal(out["k"].cpu().numpy().astype(np.int64), k)
+    assert np.array_equal(out["vt"].cpu().numpy().astype(np.int64), v.transpose(0, 1, 3, 2))
+    assert np.array_equal(out["rsq"].cpu().numpy().astype(np.int64), q.sum(-1))
+    assert np.array_equal(out["rsk"].cpu().numpy().astype(np.int64), k.sum(-1))
 
 
 @pytest.mark.parametrize("tag", MODEL_GOLDENS)
