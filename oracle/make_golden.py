@@ -138,6 +138,40 @@ def ref_act_range(model, samples):
     return act
 
 
+def ref_code_trace(qmodel_fwd, sample, layers):
+    """Integer codes of the reference's own fake-quant forward (the unmodified Quantizer.forward, qm:251-295), captured by
+    forward hooks on the Quantizer submodules of the given decoder layers: code = rne(y / scale) + offset (exact: y is
+    (code - offset) * scale).  Also the fp32 residual stream entering the post-attention norm and leaving the block.
+    These pin the LSB-flip rate of the integer engine against the reference itself (tests/test_engine_gpu.py)."""
+    trace = {i: {} for i in layers}
+    hooks = []
+
+    def qhook(i, key):
+        def fn(mod, inp, out):
+            s, o = mod.scale.detach(), mod.offset.detach()
+            c = torch.round(out.detach() / s) + o
+            trace[i][key] = c.to(torch.int32).clone()
+        return fn
+
+    want = {"input_layernorm.output_quantizer": "x1", "self_attn.q_proj.output_quantizer": "q_proj", "self_attn.k_proj.output_quantizer": "k_proj",
+            "self_attn.v_proj.output_quantizer": "v_proj", "self_attn.qk_bmm.input_quantizer": "q", "self_attn.qk_bmm.input2_quantizer": "kT",
+            "self_attn.pv_bmm.input2_quantizer": "v", "self_attn.pv_bmm.output_quantizer": "attn",
+            "post_attention_layernorm.output_quantizer": "x2", "mlp.w2.input_quantizer": "act"}
+    for i in layers:
+        layer = qmodel_fwd.model.layers[i]
+        for name, key in want.items():
+            m = layer.get_submodule(name)
+            hooks.append(m.register_forward_hook(qhook(i, key)))
+        hooks.append(layer.post_attention_layernorm.register_forward_hook(
+            lambda mod, inp, out, i=i: trace[i].__setitem__("h_mid", inp[0].detach().clone())))
+        hooks.append(layer.register_forward_hook(lambda mod, inp, out, i=i: trace[i].__setitem__("h_out", out[0].detach().clone())))
+    with torch.no_grad():
+        qmodel_fwd(sample)
+    for h in hooks:
+        h.remove()
+    return trace
+
+
 def make_args(**kw):
     a = types.SimpleNamespace(nsamples=4, seqlen=32, batch_size=1, epochs=2, warmup_epochs=0, deactive_amp=True,
                               let=True, lwc=True, lrl=True, use_shift=False, aug_loss=False, let_lr=1e-3, lwc_lr=1e-2,
@@ -182,6 +216,7 @@ def golden_model(tag, cfgd, w_bits, w_sym, w_pc, mode, T=32, nsamples=2, epochs=
         qm_fwd = copy.deepcopy(qmodel)
         out_ref = qm_fwd(samples[0])
         logits_ref, = (out_ref.logits,)
+        ref_trace = ref_code_trace(qm_fwd, samples[0], [0, cd["num_hidden_layers"] - 1])
     qs = mr.QState(recipe, act)
     with torch.no_grad():
         logits_o, hid_o = mr.model_forward(sd0, cd, samples[0], qs, quant=True)
@@ -267,6 +302,9 @@ def golden_model(tag, cfgd, w_bits, w_sym, w_pc, mode, T=32, nsamples=2, epochs=
         alg.omniquant(args, qmodel, loader, logger, device="cpu")
         learned = torch.load(os.path.join(args.output_dir, "quant_parameters.pth"), weights_only=False)
     act_after = qm.export_act_range(qmodel)
+    # the fused model the reference hands to create_fp_model / save_pretrained (alg:147-184, ptq/mobilequant.py:240-246):
+    # LET folded into the weights, every weight clamped to its learned LWC range, zero-shift bias buffers registered
+    fused_sd = {k: v.detach().clone() for k, v in qmodel.state_dict().items() if "quantizer" not in k and "smooth" not in k}
     res = mr.calibrate(sd0, cd, recipe, act, embeds, mode=mode, epochs=epochs, let_lr=args.let_lr, lwc_lr=args.lwc_lr,
                        lrl_lr=args.lrl_lr, let_min_lr=args.let_min_lr, lwc_min_lr=args.lwc_min_lr, lrl_min_lr=args.lrl_min_lr)
     worst = dict(let=0.0, lwc=0.0, lrl=0.0)
@@ -283,12 +321,43 @@ def golden_model(tag, cfgd, w_bits, w_sym, w_pc, mode, T=32, nsamples=2, epochs=
     torch.save(dict(cfg=cd, state_dict=sd0, samples=samples, act_dict=act, qcfg=qcfg, logits_fq=logits_ref, hidden_fq=hid_o,
                     mode=mode, epochs=epochs, hp=dict(let_lr=args.let_lr, lwc_lr=args.lwc_lr, lrl_lr=args.lrl_lr,
                                                       let_min_lr=args.let_min_lr, lwc_min_lr=args.lwc_min_lr, lrl_min_lr=args.lrl_min_lr),
-                    learned=learned, act_after=act_after, losses=res["losses"], let0=let0, grads0=grads0, loss0=loss0.item(),
+                    learned=learned, act_after=act_after, fused_state_dict=fused_sd, ref_trace=ref_trace, losses=res["losses"], let0=let0, grads0=grads0, loss0=loss0.item(),
                     w_cfg=dict(bits=w_bits, sym=w_sym, per_channel=w_pc)),
                os.path.join(GOLD, f"model_{tag}.pt"))
 
 
+def golden_trace(tag, cfgd, T):
+    """Forward-only fixture at a longer sequence (several attention tiles, head_dim 64): weights, ranges, qcfg and the
+    reference's fake-quant codes of the first and last block."""
+    model, cfg = build_ref_model(cfgd)
+    g = gen(4242)
+    samples = [torch.randint(3, cfgd["vocab_size"], (1, T), generator=g) for _ in range(2)]
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cd = cfg_to_dict(cfgd)
+    act = ref_act_range(model, samples)
+    qmodel = qm.create_sim_qmodel(model, qm.QuantConfig(bitwidth=8), qm.QuantConfig(bitwidth=8))
+    for p in qmodel.parameters():
+        p.requires_grad = False
+    ref_update_quant_cfg(qm, qmodel)
+    qm.set_scale_and_offset(qmodel, act, "parameter")
+    qcfg = qm.export_qcfg(qmodel)
+    with torch.no_grad():
+        logits_ref = qmodel(samples[0]).logits
+    ref_trace = ref_code_trace(qmodel, samples[0], [0, cd["num_hidden_layers"] - 1])
+    qs = mr.QState(mr.recipe_from_qcfg_json(qcfg), act)
+    with torch.no_grad():
+        logits_o, _ = mr.model_forward(sd0, cd, samples[0], qs, quant=True)
+    d = (logits_o - logits_ref).abs().max().item()
+    print(f"[{tag}] fake-quant forward oracle-vs-reference max |dlogits| = {d:.3e}")
+    assert d == 0.0
+    torch.save(dict(cfg=cd, state_dict=sd0, samples=samples, act_dict=act, qcfg=qcfg, logits_fq=logits_ref, ref_trace=ref_trace,
+                    w_cfg=dict(bits=8, sym=False, per_channel=False)), os.path.join(GOLD, f"trace_{tag}.pt"))
+
+
+TINY_HD64 = dict(TINY, num_attention_heads=2, num_key_value_heads=1)      # head_dim 64: the tcgen05 attention kernel's shape class
+
 if __name__ == "__main__":
+    golden_trace("llama_hd64_t256", TINY_HD64, 256)
     golden_model("llama_w8_e2e", TINY, 8, False, False, "e2e")
     golden_model("llama_w4_omni", TINY, 4, True, True, "omniquant")
     golden_model("stablelm_w8_omni", TINY_MHA, 8, False, False, "omniquant")
