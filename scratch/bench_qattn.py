@@ -1,12 +1,17 @@
-"""qattn micro-bench: single-QK-pass (score codes in smem) vs streaming three-pass kernel, CUDA events."""
+"""qattn micro-bench: tcgen05 kernel vs the two mma.sync kernels, CUDA events.  usage: bench_qattn.py [impl,...] [iters]"""
 import os, sys, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mobilequant_b200 import kernels as K
 from oracle import int_ref as ir
 cuda = torch.device("cuda:0")
 f32 = np.float32
+impls = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tc", "smem"]
+iters0 = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+shapes = [tuple(int(x) for x in s.split("x")) for s in sys.argv[3].split(",")] if len(sys.argv) > 3 else \
+    [(8, 1024, 32, 4, 64), (32, 1024, 32, 4, 64), (8, 1024, 32, 32, 64), (2, 2048, 32, 4, 64), (1, 4096, 32, 4, 64), (4, 1024, 16, 4, 128)]
 
-def run(B, T, nh, nkv, hd, iters=10):
+
+def run(B, T, nh, nkv, hd, iters):
     q = torch.randint(0, 256, (B, nh, T, hd), dtype=torch.uint8, device=cuda)
     k = torch.randint(0, 256, (B, nkv, T, hd), dtype=torch.uint8, device=cuda)
     vt = torch.randint(0, 256, (B, nkv, hd, T), dtype=torch.uint8, device=cuda)
@@ -19,24 +24,19 @@ def run(B, T, nh, nkv, hd, iters=10):
     out = torch.empty(B * T, nh * hd, dtype=torch.uint8, device=cuda)
     rs = torch.zeros(B * T, dtype=torch.int32, device=cuda)
     res = {}
-    for impl in ("smem", "3pass"):
-        if impl == "3pass": os.environ["MQB200_QATTN"] = "3pass"
-        else: os.environ.pop("MQB200_QATTN", None)
-        for _ in range(3): K.qattn(bufs, B, T, nh, nkv, hd, params, lut, out=out, rowsum_out=rs)
+    for impl in impls:
+        os.environ["MQB200_QATTN"] = {"tc": "tc!", "smem": "smem", "3pass": "3pass"}[impl]
+        for _ in range(2): K.qattn(bufs, B, T, nh, nkv, hd, params, lut, out=out, rowsum_out=rs)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters): K.qattn(bufs, B, T, nh, nkv, hd, params, lut, out=out, rowsum_out=rs)
         e1.record(); torch.cuda.synchronize()
         res[impl] = (e0.elapsed_time(e1) / iters, out.clone())
-    same = torch.equal(res["smem"][1], res["3pass"][1])
+    same = all(torch.equal(res[impls[0]][1], res[i][1]) for i in impls[1:])
     el = B * nh * T * (T + 1) / 2
-    print(f"B={B} T={T} nh={nh} nkv={nkv} hd={hd}: smem {res['smem'][0]*1e3:.1f} us ({el/res['smem'][0]/1e6:.1f} G scores/s)  "
-          f"3pass {res['3pass'][0]*1e3:.1f} us  same={same}", flush=True)
+    print(f"B={B} T={T} nh={nh} nkv={nkv} hd={hd}: " + "  ".join(f"{i} {res[i][0]*1e3:.1f} us ({el/res[i][0]/1e6:.1f} G scores/s)" for i in impls) + f"  same={same}", flush=True)
 
-run(8, 1024, 32, 4, 64)
-run(32, 1024, 32, 4, 64, iters=4)
-run(8, 1024, 32, 32, 64)
-run(4, 2048, 8, 1, 256)
-run(2, 2048, 32, 4, 64)
-run(1, 4096, 32, 4, 64)
+
+for s in shapes:
+    run(*s, iters=iters0)
