@@ -358,7 +358,7 @@ def decode_throughput(eng, ids, B, T, nsteps):
     tokens.copy_(logits.argmax(-1))
     for _ in range(3):                                   # warm replays, then rewind the position
         graph.replay()
-    cache.pos_dev.fill_(T0)
+    graph.rewind(T0)
     tokens.copy_(logits.argmax(-1))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -214,6 +214,7 @@ struct AttnDecArgs {
   const uint8_t* qkv; int ldq;
   int B, nh, nkv, hd, rot, Tmax, pos;
   const int* pos_dev;
+  int pos_max;                                        // largest position this launch was sized for (< Tmax)
   float sq_in, oq_in, sk_in, ok_in, sv_in, ov_in;     // projection output quantizers
   float sq, oq, sk, ok, sv, ov;                       // qk_bmm.input / input2, pv_bmm.input2
   const float* cos; const float* sin;                 // [>= pos + 1, rot]
@@ -294,6 +295,9 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   const int grp = blockIdx.x / CS;
   const int b = grp / a.nkv, kvh = grp % a.nkv;
   const int pos = a.pos_dev ? *a.pos_dev : a.pos;
+  // a replayed graph increments *pos_dev on the device: a step beyond the position the launch was sized for (cache capacity,
+  // score slab, cos / sin tables) must not touch memory.  Every CTA of every cluster sees the same pos: uniform exit.
+  if (pos < 0 || pos > a.pos_max) return;
   const int Tk = pos + 1;
   const int per = (Tk + CS - 1) / CS;
   const int j_lo = min(Tk, cr * per), j_hi = min(Tk, j_lo + per);
@@ -762,7 +766,7 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
                     (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(cos) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(sin) & 15) == 0, "qkv must be 4-byte, caches and cos/sin 16-byte aligned");
   AttnDecArgs a;
-  a.qkv = qkv; a.ldq = ldq; a.B = B; a.nh = nh; a.nkv = nkv; a.hd = hd; a.rot = rot; a.Tmax = Tmax; a.pos = pos; a.pos_dev = pos_dev;
+  a.qkv = qkv; a.ldq = ldq; a.B = B; a.nh = nh; a.nkv = nkv; a.hd = hd; a.rot = rot; a.Tmax = Tmax; a.pos = pos; a.pos_dev = pos_dev; a.pos_max = pos_bound;
   a.sq_in = rope_in_qparams[0]; a.oq_in = rope_in_qparams[1]; a.sk_in = rope_in_qparams[2]; a.ok_in = rope_in_qparams[3];
   a.sv_in = rope_in_qparams[4]; a.ov_in = rope_in_qparams[5];
   a.sq = rope_out_qparams[0]; a.oq = rope_out_qparams[1]; a.sk = rope_out_qparams[2]; a.ok = rope_out_qparams[3];

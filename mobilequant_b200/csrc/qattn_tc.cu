@@ -308,8 +308,14 @@ qattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[sb]);
-        if (kind != 2) {
-          const int4* ck4 = reinterpret_cast<const int4*>(s_ck + c8 * kTN + cg * 32);
+        const int4* ck4 = reinterpret_cast<const int4*>(s_ck + c8 * kTN + cg * 32);
+        if (kind == 0) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int4 c = ck4[j4];
+            mx = max(mx, max(max((int)r[4 * j4] + c.x, (int)r[4 * j4 + 1] + c.y), max((int)r[4 * j4 + 2] + c.z, (int)r[4 * j4 + 3] + c.w)));
+          }
+        } else if (kind == 1) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const int4 c = ck4[j4];
@@ -317,8 +323,7 @@ qattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = 4 * j4 + e;
-              const int v = (int)r[j] + cc[e];
-              if (kind == 0 || j <= lane) mx = max(mx, v);
+              if (j <= lane) mx = max(mx, (int)r[j] + cc[e]);
             }
           }
         }

@@ -128,8 +128,13 @@ class IntEngine:
                                 x1[0], x1[1], self.H, qo, [getattr(at.q_proj, "bias", None), getattr(at.k_proj, "bias", None), getattr(at.v_proj, "bias", None)])
         qk_in, qk_in2, qk_out = (_sq(act, qcfg, pa + "qk_bmm", s) for s in ("input", "input2", "output"))
         pv_in, pv_in2, pv_out = (_sq(act, qcfg, pa + "pv_bmm", s) for s in ("input", "input2", "output"))
-        if pv_in[1] != 0.0:
-            raise NotImplementedError("pv_bmm.input_quantizer offset must be 0 (softmax output range starts at 0)")
+        # pv_bmm.input_quantizer: p >= 0, so with an offset o_p >= 0 the de-offset code clamp(rne(p/s)+o_p, 0, qmax) - o_p is
+        # clamp(rne(p/s), 0, qmax - o_p): the kernels work on de-offset codes with the upper bound lowered by o_p.  A negative
+        # offset (learned range minimum above 0) would give every masked position the weight |o_p|*s_p in the reference's
+        # fake-quant simulation (it quantises the full [T,T] matrix, hm:527-534) -- not a causal computation; not supported.
+        if pv_in[1] < 0.0:
+            raise NotImplementedError("pv_bmm.input_quantizer offset must be >= 0 (softmax output range must include 0)")
+        pv_in = (pv_in[0], 0.0, pv_in[2] - pv_in[1])
         L["rope_in"] = [(q[0], q[1]) for q in qo]
         L["rope_out"] = [(qk_in[0], qk_in[1]), (qk_in2[0], qk_in2[1]), (pv_in2[0], pv_in2[1])]
         f = np.float32
@@ -460,7 +465,7 @@ class IntEngine:
         with torch.cuda.graph(g):
             step()
         cache.pos_dev.fill_(keep)
-        return g, tokens, state["logits"]
+        return DecodeGraph(g, tokens, state["logits"], cache)
 
     @torch.no_grad()
     def generate(self, context_ids, max_new_tokens, eos_token_id=None, pad_token_id=0, do_sample=False, temperature=0.5, Tmax=None):
@@ -489,6 +494,29 @@ class IntEngine:
                 break
             logits = self.decode_step(nxt, cache)
         return torch.cat(out, dim=1)
+
+
+class DecodeGraph:
+    """The captured greedy decode step + its static buffers.  replay() refuses to step past the cache capacity (the device
+    position is incremented by the graph itself) and keeps cache.length in step with the device position.  Unpacks as
+    (graph, tokens, logits) for callers that only need the buffers."""
+
+    def __init__(self, graph, tokens, logits, cache):
+        self.graph, self.tokens, self.logits, self.cache = graph, tokens, logits, cache
+
+    def replay(self):
+        if self.cache.length >= self.cache.Tmax:
+            raise RuntimeError(f"KV cache is full ({self.cache.Tmax} positions): cannot decode another token")
+        self.graph.replay()
+        self.cache.length += 1
+
+    def rewind(self, length):
+        """Set the host and device position (benchmarks replay the same steps several times)."""
+        self.cache.length = int(length)
+        self.cache.pos_dev.fill_(int(length))
+
+    def __iter__(self):
+        return iter((self, self.tokens, self.logits))
 
 
 class KVCache:

@@ -97,13 +97,22 @@ def main(argv=None):
     p.add_argument("--num_samples", type=int, default=512)
     p.add_argument("--per_channel", default=False, action="store_true")
     p.add_argument("--use_rand_samples", default=False, action="store_true")
+    p.add_argument("--samples_path", default=None, type=str,
+                   help="torch-saved list of LongTensor [1, T] token ids (the reference tokenises the Pile validation split, "
+                        "generate_act_range.py:97-104; there is no dataset / tokenizer access here)")
     p.add_argument("--output_dir", default=None, type=str)
     args = p.parse_args(argv)
+    if args.samples_path is None and not args.use_rand_samples:
+        raise FileNotFoundError("no calibration text available offline: pass --samples_path <token-id list> or --use_rand_samples "
+                                "(uniformly random token ids, the reference's own convention for its extra samples)")
     out_dir = args.output_dir or args.hf_path
     torch.manual_seed(1337)
     model = HFForCausalLM.from_pretrained(args.hf_path, use_matmul_as_module=True, l2norm_as_rmsnorm=True).float().cuda()
-    # no tokenizer / dataset access offline: the calibration set is the reference's own random-id convention
-    samples = random_samples(args.num_samples, args.seq_len, model.config.vocab_size, model.config.bos_token_id or 1)
+    samples = []
+    if args.samples_path is not None:
+        samples += [t.view(1, -1)[:, :args.seq_len].long() for t in torch.load(args.samples_path, weights_only=False)][:args.num_samples]
+    if args.use_rand_samples:     # generate_act_range.py:105-108: one random-id sample per text sample (all of them without text)
+        samples += random_samples(len(samples) or args.num_samples, args.seq_len, model.config.vocab_size, model.config.bos_token_id or 1)
     act_dict = get_act_range(model, samples, args.per_channel)
     os.makedirs(out_dir, exist_ok=True)
     if not args.per_channel:

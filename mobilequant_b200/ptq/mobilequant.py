@@ -3,9 +3,12 @@
     python -m mobilequant_b200.ptq.mobilequant --hf_path <dir> --mode e2e --lwc --let --lrl \\
         --weight_bitwidth 8 --act_bitwidth 8 --nsamples 512 --seqlen 1024 --epochs 1 --output_dir out
 
-Offline differences: no tokenizer/dataset/lm-eval (calibration uses random token ids of the reference's own
-convention, generate_act_range.py:106-108 / device/export.py:116); under torchrun the calibration set is sharded
-over ranks (sample-parallel) instead of the reference's layer-sharding.
+Calibration data: the reference's cached loader `{cache_dir}/dataloader_{family}_{calib_dataset}_{nsamples}.cache`
+(ptq/mobilequant.py:221-227, a torch-saved list of (input_ids [1, seqlen], target)) is used when it exists.  There is
+no tokenizer / dataset access here, so without that cache only `--calib_dataset random` (random token ids of the
+reference's own convention, generate_act_range.py:106-108 / device/export.py:116) can run -- any other choice raises
+instead of silently calibrating on random tokens.  Evaluation (--tasks) needs the lm-eval fork and is rejected.
+Under torchrun the calibration set is sharded over ranks (sample-parallel) instead of the reference's layer-sharding.
 """
 import argparse, os, random, time
 import torch
@@ -51,7 +54,7 @@ def build_parser():
     p.add_argument("--deactive_amp", action="store_true")
     p.add_argument("--batch_size", type=int, default=1)
     p.add_argument("--num_fewshot", type=int, default=0)
-    p.add_argument("--tasks", default="", type=str)
+    p.add_argument("--tasks", default="", type=str, help="not supported (lm-eval); must stay empty")
     p.add_argument("--mode", default="omniquant", type=str, choices=["e2e", "omniquant"])
     p.add_argument("--original_omniquant", default=False, action="store_true")
     p.add_argument("--cache_in_gpu", default=False, action="store_true")
@@ -89,8 +92,28 @@ def quantize(args, model, dataloader, logger, act_dict):
     return model, act_out, qcfg_out
 
 
+def load_calibration_set(args, config, logger, seed=1337):
+    """ptq/mobilequant.py:221-227: the cached dataloader when present; random ids only when asked for by name."""
+    family = os.path.basename(os.path.normpath(args.hf_path or "model")).split("-")[0]                 # ptq/mobilequant.py:78
+    cache = os.path.join(args.cache_dir or ".", f"dataloader_{family}_{args.calib_dataset}_{args.nsamples}.cache")
+    if os.path.exists(cache):
+        logger.info(f"load calibration set from {cache}")
+        return torch.load(cache, weights_only=False)
+    if args.calib_dataset != "random":
+        raise FileNotFoundError(
+            f"calibration set {cache!r} not found and --calib_dataset {args.calib_dataset} cannot be built here (no tokenizer / "
+            "dataset access): create the cache with the reference's get_loaders (ptq/mobilequant.py:221-227) and point --cache_dir "
+            "at it, or pass --calib_dataset random to calibrate on uniformly random token ids")
+    logger.info("calibrating on uniformly random token ids (--calib_dataset random)")
+    samples = random_samples(args.nsamples, args.seqlen, config.vocab_size, config.bos_token_id or 1, seed)
+    return [(s, None) for s in samples]
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    if args.tasks:
+        raise NotImplementedError("--tasks needs the lm-eval fork of the reference (eval/harness_eval.py); run it on the exported "
+                                  "artefacts (act_dict.json, default_qcfg.json, fp checkpoint)")
     if args.epochs > 0:
         assert args.lwc or args.let or args.lrl
     if (8 <= args.weight_bitwidth < 16) or (8 <= args.act_bitwidth < 16):
@@ -108,8 +131,7 @@ def main(argv=None):
     args.dtype = torch.float32 if args.dtype is None else STR_TO_DTYPE[args.dtype]
     act_path = args.act_dict_path or os.path.join(args.hf_path, "act_dict.json")
     act_dict = json_load(act_path) if act_path.endswith(".json") else torch.load(act_path)
-    samples = random_samples(args.nsamples, args.seqlen, model.config.vocab_size, model.config.bos_token_id or 1, seed)
-    dataloader = [(s, None) for s in samples]
+    dataloader = load_calibration_set(args, model.config, logger, seed)
     quantize(args, model, dataloader, logger, act_dict)
 
 

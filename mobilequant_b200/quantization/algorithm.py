@@ -374,6 +374,19 @@ def _drop_learned(layer):
         delattr(obj, parts[-1])
 
 
+def _load_learned(layer, state, use_shift):
+    """--resume (alg:497-498, 707-709).  The checkpoints hold only the learnable quantisation parameters (quant_state_dict),
+    so the load cannot be strict over the whole block; instead every key of the checkpoint must exist in the block and
+    every learnable the block registered must be in the checkpoint -- a silent partial resume is an error."""
+    res = layer.load_state_dict(state, strict=False)
+    if res.unexpected_keys:
+        raise KeyError(f"--resume: unexpected keys {res.unexpected_keys[:4]}...")
+    want = set(quant_state_dict(layer, use_shift=use_shift).keys())
+    missing = sorted(want - set(state.keys()))
+    if missing:
+        raise KeyError(f"--resume: the checkpoint lacks learnable parameters {missing[:4]}...")
+
+
 def _allreduce_grads(params, world):
     """Data-parallel exchange: SUM of the learnable-scalar gradients over NCCL, then the batch mean (alg:459)."""
     from ..utils.dist import allreduce_grads
@@ -507,7 +520,7 @@ def omniquant(args, model, dataloader, logger, device=None):
     if model.config.num_linears_per_mlp == 3 and not args.original_omniquant:
         pairs["w2"] = "fc2"
     layers[0] = layers[0].to(device)
-    if not (args.deactive_amp and args.epochs > 0):
+    if args.epochs > 0 and not args.deactive_amp:
         raise NotImplementedError("the B200 path calibrates in fp32 (the reference's W8A8/W4A8 recipes all set "
                                   "--deactive_amp, ptq/mobilequant.py:122-123)")
     dtype = torch.float32
@@ -539,7 +552,7 @@ def omniquant(args, model, dataloader, logger, device=None):
         if args.let:
             _register_let(qlayer, pairs, device, dtype)
         if args.resume:
-            qlayer.load_state_dict(omni_parameters[i], strict=False)
+            _load_learned(qlayer, omni_parameters[i], args.use_shift)
         if args.epochs > 0:
             groups = [{"params": let_parameters(qlayer, args.use_shift), "lr": args.let_lr},
                       {"params": lwc_parameters(qlayer), "lr": args.lwc_lr}]
@@ -613,7 +626,7 @@ def e2equant(args, model, dataloader, logger, device=None):
         pairs["o_proj"] = "out"
     if model.config.num_linears_per_mlp == 3:
         pairs["w2"] = "fc2"
-    if not (args.deactive_amp and args.epochs > 0):
+    if args.epochs > 0 and not args.deactive_amp:
         raise NotImplementedError("the B200 path calibrates in fp32 (--deactive_amp)")
     dtype = torch.float32
     inps, attention_mask, position_ids = _catch_first_layer_inputs(model, layers, dataloader, args.nsamples, args.seqlen, device, dtype)
@@ -643,7 +656,7 @@ def e2equant(args, model, dataloader, logger, device=None):
         for i in range(len(layers)):
             _register_let(layers[i], pairs, device, dtype)
             if args.resume:
-                layers[i].load_state_dict(e2e_parameters[i], strict=False)
+                _load_learned(layers[i], e2e_parameters[i], args.use_shift)
 
     optimizer = None
     if args.epochs > 0:

@@ -167,7 +167,12 @@ class Quantizer(nn.Module):
         self._check_supported()
         x = input_
         dynamic = self.qcfg.is_dynamic or self.lwc or not hasattr(self, "scale") or not hasattr(self, "offset")
-        if dynamic or let is not None:
+        if let is not None and not (self.qcfg.is_dynamic or self.lwc):
+            # --let without --lwc: the reference quantises the materialised temp_weight with a range it caches on the
+            # first forward and reuses afterwards (qm:262-277); only the LWC / dynamic path recomputes the range per step
+            x = materialize_let(x, let)
+            let = None
+        if dynamic:
             x2 = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
             if x.dim() == 1:
                 x2 = x.reshape(1, -1)
@@ -182,7 +187,7 @@ class Quantizer(nn.Module):
                 scale, offset = scale.reshape(-1, 1), offset.reshape(-1, 1)
             else:
                 scale, offset = scale.reshape(()), offset.reshape(())
-            if self.qcfg.is_dynamic or self.lwc or let is not None:
+            if self.qcfg.is_dynamic or self.lwc:
                 if isinstance(getattr(self, "scale", None), nn.Parameter):
                     raise TypeError("cannot assign a dynamic scale over a cached nn.Parameter (reference qm:244)")
                 self.scale, self.offset = scale, offset
@@ -607,8 +612,8 @@ def set_scale_and_offset(model, act_dict, use_scale_offset_as="buffer"):
 
 
 def update_quant_cfg(model, use_8bit_softmax_input=False, use_8bit_softmax_output=False):
-    """The mixed-precision recipe that ptq/mobilequant.py:175-201 and ptq/generate_qcfg.py:85-113 apply (a script-local
-    closure in the reference; a library function here so both entry points share it)."""
+    """The mixed-precision recipe ptq/mobilequant.py:175-201 applies before calibration (a script-local closure in the
+    reference).  ptq/generate_qcfg.py has its own, different rule set: ptq/generate_qcfg.py:create_mixed_precision_model."""
     for name, module in reversed(list(model._modules.items())):
         if isinstance(module, QLinear):
             if any(k in name for k in _NO_INPUT_Q):

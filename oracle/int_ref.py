@@ -168,7 +168,9 @@ def qattn_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None, heads=None, q_
     rep = nh // nkv
     if lut is None:
         lut = exp_tables(qs[0], hd)
-    assert int(qp[1]) == 0
+    # de-offset prob codes: clamp(rne(p/s)+o_p, 0, qmax) - o_p == clamp(rne(p/s), 0, qmax - o_p) for p >= 0, o_p >= 0
+    assert int(qp[1]) >= 0
+    qp = (qp[0], 0, f32(qp[2]) - f32(qp[1]))
     sqk = f32(f32(qq[0]) * f32(qk[0])); spv = f32(f32(qp[0]) * f32(qv[0]))
     out = np.zeros((B, Tq, nh, hd), np.int64)
     causal = np.arange(T)[None, :] <= (q_start + np.arange(Tq))[:, None]
@@ -199,6 +201,8 @@ def qattn_decode_int(q, k, v, nh, nkv, qq, qk, qv, qs, qp, qo, lut=None):
     rep = nh // nkv
     if lut is None:
         lut = exp_tables(qs[0], hd)
+    assert int(qp[1]) >= 0
+    qp = (qp[0], 0, f32(qp[2]) - f32(qp[1]))
     sqk = f32(f32(qq[0]) * f32(qk[0])); spv = f32(f32(qp[0]) * f32(qv[0]))
     out = np.zeros((B, nh, hd), np.int64)
     for b in range(B):

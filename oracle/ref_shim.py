@@ -79,3 +79,31 @@ def ref_update_quant_cfg(qm, model, use_8bit_softmax_input=False, use_8bit_softm
         elif len(list(module.children())) > 1:
             ref_update_quant_cfg(qm, module, use_8bit_softmax_input, use_8bit_softmax_output)
     return model
+
+
+def ref_create_mixed_precision_model(qm, model, use_16bit_output_for_mlp=False, use_16bit_softmax_input=False, use_16bit_softmax_output=False):
+    """Restatement of the script-local closure ptq/generate_qcfg.py:85-113 (the script parses argv and loads a tokenizer at
+    import time, so it cannot be imported); the Q* classes it touches are the reference's own."""
+    for name, module in reversed(model._modules.items()):
+        if isinstance(module, qm.QLinear):
+            if "w2" in name:
+                model._modules[name].weight_quantizer.qcfg.is_per_channel = True
+                model._modules[name].output_quantizer.qcfg.bitwidth = 16
+            elif "o_proj" in name:
+                model._modules[name].output_quantizer.qcfg.bitwidth = 16
+            if use_16bit_output_for_mlp and ("w1" in name or "w3" in name):
+                model._modules[name].output_quantizer.qcfg.bitwidth = 16
+        elif isinstance(module, (qm.QRMSNorm, qm.QLayerNorm)):
+            model._modules[name].input_quantizer.qcfg.bitwidth = 16
+            model._modules[name].weight_quantizer.qcfg.bitwidth = 16
+        elif isinstance(module, qm.QMatMul):
+            if "qk_bmm" in name and use_16bit_softmax_input:
+                model._modules[name].output_quantizer.qcfg.bitwidth = 16
+            if "pv_bmm" in name and use_16bit_softmax_output:
+                model._modules[name].input_quantizer.qcfg.bitwidth = 16
+        elif isinstance(module, (qm.QSiLU, qm.QGELU)):
+            if model._modules[name].input_quantizer is not None:
+                model._modules[name].input_quantizer.enable = False
+        elif len(list(module.children())) > 1:
+            ref_create_mixed_precision_model(qm, module, use_16bit_output_for_mlp, use_16bit_softmax_input, use_16bit_softmax_output)
+    return model

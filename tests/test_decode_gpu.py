@@ -174,6 +174,17 @@ def test_engine_generate_and_graph_replay(cuda):
         graph.replay()
         got.append(tokens.clone())
     assert torch.equal(torch.stack(got, dim=1), ids[:, 12:])
+    # capacity guard: the wrapper refuses to step past Tmax and keeps cache.length in step with the device position;
+    # a raw replay past the capacity is a no-op for the caches (the kernel exits on pos > pos_bound)
+    assert cache.length == 12 + new - 1 and int(cache.pos_dev.item()) == cache.length
+    graph.replay()
+    assert cache.length == cache.Tmax
+    with pytest.raises(RuntimeError, match="KV cache is full"):
+        graph.replay()
+    snap = [t.clone() for t in cache.k + cache.v + cache.rsk]
+    graph.graph.replay()                      # what a caller bypassing the wrapper would do
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(snap, cache.k + cache.v + cache.rsk))
 
 
 def test_fgemv_lm_head(cuda):

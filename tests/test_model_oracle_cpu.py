@@ -79,3 +79,49 @@ def test_json_artifact_format(tmp_path):
     txt = p.read_text()
     assert txt.index('"a"') < txt.index('"b"') and "\n    " in txt       # sort_keys + indent=4 (io.py:34-36)
     assert json_load(str(p))["a"]["input"] == [-1.5, 2.0]
+
+
+def test_generate_qcfg_matches_reference_script():
+    """ptq/generate_qcfg.py: same flags and the same default_qcfg.json as the reference's script for the flag sets its
+    experiment scripts use (golden written by oracle/make_golden_qcfg.py with the reference's own Q* classes)."""
+    import os
+    from helpers import GOLDEN
+    from mobilequant_b200.model import HFConfig, HFForCausalLM
+    from mobilequant_b200.quantization.qmodule import QuantConfig
+    from mobilequant_b200.ptq import generate_qcfg as G
+    gold = json.load(open(os.path.join(GOLDEN, "generate_qcfg.json")))
+    assert len(gold) >= 5
+    for name, case in gold.items():
+        model = HFForCausalLM(HFConfig(**case["cfg"], use_cache=False, use_matmul_as_module=True, l2norm_as_rmsnorm=True))
+        wb, wg, wpc, wsym = case["weight"]
+        ab, asym, adyn = case["act"]
+        got = G.generate_qcfg(model, QuantConfig(bitwidth=wb, group_size=wg, is_per_channel=wpc, is_symmetric=wsym),
+                              QuantConfig(bitwidth=ab, is_symmetric=asym, is_dynamic=adyn), *case["switches"])
+        assert got == case["default_qcfg"], name
+    # the reference's command lines parse unchanged (experiments/*: --use_16bit_softmax_input --use_16bit_softmax_output)
+    a = G.build_parser().parse_args(["--hf_path", "x", "--use_16bit_softmax_input", "--use_16bit_softmax_output", "--use_16bit_output_for_mlp"])
+    assert a.weight_bitwidth == 8 and a.act_bitwidth == 8 and a.use_16bit_output_for_mlp
+    with pytest.raises(SystemExit):
+        G.build_parser().parse_args(["--hf_path", "x", "--use_8bit_softmax_input"])      # that flag belongs to ptq/mobilequant.py
+
+
+def test_calibration_set_is_never_silently_random(tmp_path):
+    """ptq/mobilequant.py: a cached dataloader is used when present; without it only --calib_dataset random runs."""
+    import types, logging
+    from mobilequant_b200.ptq import mobilequant as M
+    cfg = types.SimpleNamespace(vocab_size=100, bos_token_id=1)
+    log = logging.getLogger("t")
+    args = M.build_parser().parse_args(["--hf_path", "/x/llama-1.1b-chat", "--nsamples", "3", "--seqlen", "8", "--cache_dir", str(tmp_path)])
+    assert args.calib_dataset == "pile"
+    with pytest.raises(FileNotFoundError, match="calib_dataset random"):
+        M.load_calibration_set(args, cfg, log)
+    saved = [(torch.full((1, 8), i), None) for i in range(3)]
+    torch.save(saved, tmp_path / "dataloader_llama_pile_3.cache")                      # ptq/mobilequant.py:221
+    got = M.load_calibration_set(args, cfg, log)
+    assert len(got) == 3 and torch.equal(got[2][0], saved[2][0])
+    args.calib_dataset = "random"
+    args.nsamples = 4
+    got = M.load_calibration_set(args, cfg, log)
+    assert len(got) == 4 and got[0][0].shape == (1, 8) and int(got[0][0].min()) >= 2
+    with pytest.raises(NotImplementedError, match="lm-eval"):
+        M.main(["--hf_path", "/x", "--tasks", "wikitext"])
