@@ -156,7 +156,8 @@ def test_fuse_matches_reference_fused_weights(cuda, tag, tmp_path):
     else:
         A.omniquant(args, m, loader, _Log(), device=cuda)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if "quantizer" not in k and "smooth" not in k}
-    ref = g["fused_state_dict"]
+    # (the reference leaves `temp_weight` aliases of untransformed weights registered as parameters, alg:222-233: not an artefact)
+    ref = {k: v for k, v in g["fused_state_dict"].items() if not k.endswith(("temp_weight", "temp_bias"))}
     assert set(ref) <= set(sd) | {"lm_head.weight"}, sorted(set(ref) - set(sd))[:5]
     for k, r in ref.items():
         if k == "lm_head.weight" and k not in sd:
