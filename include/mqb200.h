@@ -203,6 +203,18 @@ int mq_unpack4(void* ctx, const uint8_t* packed, int64_t n_codes, int is_signed,
  * 2: all-ones significands.                                                                                         */
 int mq_selftest_div(void* ctx, int64_t n, uint64_t seed, int mode, float fixed_scale, uint64_t* mismatches, void* stream);
 
+/* ---- optimiser step of the calibration loops (alg:513,716-722 torch.optim.AdamW + mobilellm/utils/optim.py:28-41) ----
+ * One flat fp32 buffer holds every learnable (LET scales, LWC bound factors, LRL scales / offsets); `grads`,
+ * `exp_avg`, `exp_avg_sq` are buffers of the same length n.  Elements [seg_end[i-1], seg_end[i]) use learning rate
+ * lr[i] (device array, ngroups <= 8; seg_end is a HOST array).  Two launches: (1) global L2 norm of grads (double
+ * accumulation, fixed order) -> state[1]; a non-finite norm sets state[2] = 1, counts a skipped step in state[5] and
+ * leaves parameters, moments and the step counter untouched (GradScaler.step semantics); (2) AdamW update with
+ * betas / eps / decoupled weight decay, bias corrections from the step counter state[0] (kept on the device so that
+ * the whole training step can be replayed as a CUDA graph).  state: device float[8], zero-initialised by the caller. */
+int mq_adamw_step(void* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int ngroups,
+                  const int64_t* seg_end, const float* lr, float beta1, float beta2, float eps, float weight_decay,
+                  float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ def _protos():
     lib.mq_qattn_decode.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P]
     lib.mq_selftest_div.argtypes = [_P, c_int64, ctypes.c_uint64, c_int, c_float, _P, _P]
+    lib.mq_adamw_step.argtypes = [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, c_float, c_float, c_float, c_float, _P, _P]
     _protos_done = True
     return lib
 
@@ -407,6 +408,20 @@ def qattn_decode(qkv, B, nh, nkv, hd, rot, pos, qin, qout, cos, sin, k_cache, v_
                            ptr(cos, F32), ptr(sin, F32), ptr(k_cache), ptr(v_cache), ptr(rsk_cache, torch.int32), ctypes.cast(pq, _P),
                            ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
     return out
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, seg_end, lr, state, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """Global grad norm + skip-on-non-finite + AdamW over flat fp32 buffers (include/mqb200.h:mq_adamw_step).
+    seg_end: python ints (ascending, last == params.numel()); lr: float32 CUDA tensor [len(seg_end)]; state: float32[8]."""
+    lib = _protos()
+    n = params.numel()
+    seg = (c_int64 * len(seg_end))(*[int(v) for v in seg_end])
+    h = _h(params)
+    with torch.cuda.device(params.device):
+        check(_launch("adamw_step", lib.mq_adamw_step, h, ptr(params, F32), ptr(grads, F32), ptr(exp_avg, F32), ptr(exp_avg_sq, F32), n,
+                      len(seg_end), ctypes.cast(seg, _P), ptr(lr, F32), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                      ptr(state, F32), stream_ptr()), h)
+    return state
 
 
 def selftest_div(n, seed=1, mode=0, fixed_scale=1.0, device=None):

@@ -179,3 +179,43 @@ def test_div_rn_exact(cuda, mode, scale):
     pseudo-random operand pairs per case, including all-ones significands (the Markstein exception)."""
     from mobilequant_b200 import kernels as K
     assert K.selftest_div(1 << 28, seed=7 + mode, mode=mode, fixed_scale=scale) == 0
+
+
+def test_flat_adamw_matches_torch_adamw(cuda):
+    """mq_adamw_step (global grad norm + skip-on-non-finite + AdamW over a flat buffer, three learning-rate groups) against
+    torch.optim.AdamW on the CPU (what the reference constructs, alg:513,716-722) and the scaler's norm (optim.py:5-25)."""
+    from mobilequant_b200.utils.optim import FlatAdamW, ampscaler_get_grad_norm
+    g = torch.Generator().manual_seed(11)
+    shapes = [(), (), (37,), (64, 1), (1,), (130,), ()]
+    lrs = [1e-3, 1e-2, 1e-6]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    dev_p = [torch.nn.Parameter(p.detach().clone().to(cuda)) for p in ref_p]
+    grouping = [[0, 2, 5], [3, 4], [1, 6]]
+    ref = torch.optim.AdamW([{"params": [ref_p[i] for i in grp], "lr": lr} for grp, lr in zip(grouping, lrs)], weight_decay=0.01)
+    opt = FlatAdamW([{"params": [dev_p[i] for i in grp], "lr": lr} for grp, lr in zip(grouping, lrs)], weight_decay=0.01, device=cuda)
+    for p, q in zip(ref_p, dev_p):
+        assert torch.equal(p.detach(), q.detach().cpu())                 # re-pointing kept the values
+    for it in range(6):
+        grads = [torch.randn(s, generator=g) * (10.0 ** (it - 3)) for s in shapes]
+        opt.zero_grad()
+        for p, q, gr in zip(ref_p, dev_p, grads):
+            p.grad = gr.clone()
+            q.grad.add_(gr.to(cuda))                                      # autograd accumulates in place into the flat views
+        for i, lr in enumerate(lrs):
+            ref.param_groups[i]["lr"] = lr * (1 + it)
+            opt.set_lr(i, lr * (1 + it))
+        opt.sync_lr()
+        norm_ref = ampscaler_get_grad_norm(ref_p)
+        ref.step()
+        norm = opt.step()
+        assert norm.item() == pytest.approx(norm_ref.item(), rel=1e-6)
+        for p, q in zip(ref_p, dev_p):
+            assert torch.allclose(q.detach().cpu(), p.detach(), rtol=2e-6, atol=1e-9), it
+    # a non-finite gradient skips the step entirely (GradScaler.step semantics)
+    before = [q.detach().clone() for q in dev_p]
+    step_before = opt.state[0].item()
+    opt.zero_grad()
+    dev_p[2].grad[3] = float("inf")
+    norm = opt.step()
+    assert not torch.isfinite(norm)
+    assert all(torch.equal(a, b.detach()) for a, b in zip(before, dev_p)) and opt.state[0].item() == step_before and opt.skipped_steps == 1
