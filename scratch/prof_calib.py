@@ -44,5 +44,12 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print(f"e2equant {nsamples} samples {layers} layers: {dt:.2f} s -> {nsamples/dt:.2f} samples/s (under profiler)")
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=35, max_name_column_width=70))
-print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=70))
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        a = agg[e.name[:90]]; a[0] += 1; a[1] += e.device_time / 1e3
+tot = sum(v[1] for v in agg.values())
+print(f"GPU kernel time total {tot:.1f} ms over {nsamples} samples = {tot/nsamples:.1f} ms/sample (FP pass + training step + fuse)")
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    print(f"{t/nsamples:8.3f} ms/sample {c/nsamples:8.1f} launches/sample  {k}")

@@ -210,7 +210,7 @@ def test_flat_adamw_matches_torch_adamw(cuda):
         norm = opt.step()
         assert norm.item() == pytest.approx(norm_ref.item(), rel=1e-6)
         for p, q in zip(ref_p, dev_p):
-            assert torch.allclose(q.detach().cpu(), p.detach(), rtol=2e-6, atol=1e-9), it
+            assert torch.allclose(q.detach().cpu(), p.detach(), rtol=1e-5, atol=1e-7), it
     # a non-finite gradient skips the step entirely (GradScaler.step semantics)
     before = [q.detach().clone() for q in dev_p]
     step_before = opt.state[0].item()
