@@ -149,6 +149,15 @@ int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, c
              int T, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out, int32_t* rowsum_out,
              void* stream);
 
+/* mq_qattn_shard: the same attention for a SHARD of the queries (sequence-sharded prefill): q / rsq / out /
+ * rowsum_out hold Tq query rows per (batch, head) whose absolute positions are q_start .. q_start + Tq - 1; k / vt / rsk
+ * hold all T keys of the sequence (the shards' K/V codes are exchanged by the caller, 2 * hd + 4 bytes per token and kv
+ * head); query i sees keys 0 .. q_start + i.  q_start must be a multiple of 128 and the shape must be covered by the
+ * tcgen05 kernel (hd 64 / 128, T % 16 == 0); mq_qattn is the case q_start = 0, Tq = T.                                  */
+int mq_qattn_shard(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, const int32_t* rsq, const int32_t* rsk, int B,
+                   int Tq, int T, int q_start, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out,
+                   int32_t* rowsum_out, void* stream);
+
 /* ---- decode step: one new token per sequence against an int8 KV cache ---------------------------------------------
  * Reference: SimModel.generate / SimModel.forward with k_cache, v_cache (mobilellm/model/sim_model.py:105-132,181-235) and
  * the on-device loop capp/src/llm.cpp:545-653 (uint8 caches [L, n_heads, T-1, head_dim]).  The static quantizers are the

@@ -1221,6 +1221,29 @@ int mq_qrope(void* ctx, const uint8_t* qkv, int ldq, int B, int T, int nh, int n
   return check_launch(c, "mq_qrope");
 }
 
+static int fill_attn_args(Ctx* c, AttnArgs& a, const float* qparams) {
+  a.oq = qparams[0]; a.ok = qparams[1]; a.ov = qparams[2]; a.sqk = qparams[3]; a.s_s = qparams[4]; a.o_s = qparams[5];
+  a.qmax_s = qparams[6]; a.s_p = qparams[7]; a.qmax_p = qparams[8]; a.spv = qparams[9]; a.s_out = qparams[10];
+  a.o_out = qparams[11];
+  MQ_REQUIRE(c, a.qmax_s <= 65535.f && a.qmax_p <= 65535.f, "score / probability codes are at most 16 bit");
+  MQ_REQUIRE(c, a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out), "integer engine kernels need integral offsets (qm:60)");
+  return MQ_NO_ERROR;
+}
+
+int mq_qattn_shard(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, const int32_t* rsq, const int32_t* rsk, int B,
+                   int Tq, int T, int q_start, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out,
+                   int32_t* rowsum_out, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, q && k && vt && rsq && rsk && qparams && lut && out, "null pointer");
+  MQ_REQUIRE(c, B > 0 && T > 0 && Tq > 0 && q_start >= 0 && q_start + Tq <= T && nh > 0 && nkv > 0 && nh % nkv == 0, "bad shape");
+  AttnArgs a;
+  a.q = q; a.k = k; a.vt = vt; a.rsq = rsq; a.rsk = rsk; a.B = B; a.T = T; a.nh = nh; a.nkv = nkv; a.hd = hd;
+  if (int rc = fill_attn_args(c, a, qparams)) return rc;
+  a.lut = lut; a.out = out; a.rowsum_out = rowsum_out; a.q_start = q_start; a.Tq = Tq;
+  MQ_REQUIRE(c, qattn_tc_supported(a), "mq_qattn_shard needs hd 64 / 128, T % 16 == 0, q_start % 128 == 0 and 16-byte aligned buffers");
+  return launch_qattn_tc(c, a, (cudaStream_t)stream);
+}
+
 int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, const int32_t* rsq, const int32_t* rsk, int B,
              int T, int nh, int nkv, int hd, const float* qparams, const uint32_t* lut, uint8_t* out, int32_t* rowsum_out,
              void* stream) {
@@ -1231,11 +1254,7 @@ int mq_qattn(void* ctx, const uint8_t* q, const uint8_t* k, const uint8_t* vt, c
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0, "q/k must be 16-byte aligned");
   AttnArgs a;
   a.q = q; a.k = k; a.vt = vt; a.rsq = rsq; a.rsk = rsk; a.B = B; a.T = T; a.nh = nh; a.nkv = nkv; a.hd = hd;
-  a.oq = qparams[0]; a.ok = qparams[1]; a.ov = qparams[2]; a.sqk = qparams[3]; a.s_s = qparams[4]; a.o_s = qparams[5];
-  a.qmax_s = qparams[6]; a.s_p = qparams[7]; a.qmax_p = qparams[8]; a.spv = qparams[9]; a.s_out = qparams[10];
-  a.o_out = qparams[11];
-  MQ_REQUIRE(c, a.qmax_s <= 65535.f && a.qmax_p <= 65535.f, "score / probability codes are at most 16 bit");
-  MQ_REQUIRE(c, a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out), "integer engine kernels need integral offsets (qm:60)");
+  if (int rc = fill_attn_args(c, a, qparams)) return rc;
   a.lut = lut; a.out = out; a.rowsum_out = rowsum_out; a.q_start = 0; a.Tq = T;
   dim3 grid((T + 63) / 64 * (hd == 256 ? 2 : 1), nh, B);
   cudaStream_t st = (cudaStream_t)stream;

@@ -58,8 +58,15 @@ class IntEngine:
         self.H, self.I = cfg.hidden_size, cfg.intermediate_size
         self.Ipad = (self.I + 127) // 128 * 128
         self.layernorm = cfg.norm_class.lower() == "layernorm"
-        if cfg.num_linears_per_mlp != 3 or cfg.shared_attention_norm or cfg.parallel_residual:
-            raise NotImplementedError("IntEngine covers the gated-MLP pre-norm block of the three evaluated families")
+        # block variants (hm:1171-1172, 1257-1263): sequential pre-norm (llama / gemma / stablelm) and the parallel block with
+        # one shared norm (phi: attention and MLP both read input_layernorm's codes).  The two mixed combinations make the MLP
+        # consume either post_attention_layernorm(input_layernorm(x)) or the unquantised residual -- no model family the
+        # reference converts uses them (scripts/convert_ckpt.py) and the second is not an integer computation at all.
+        self.parallel = bool(cfg.parallel_residual)
+        if bool(cfg.shared_attention_norm) != self.parallel:
+            raise NotImplementedError("IntEngine covers parallel_residual == shared_attention_norm (both False: llama / gemma / "
+                                      "stablelm; both True: phi)")
+        self.gated = cfg.num_linears_per_mlp == 3
         self.embed = model.model.embed_tokens.weight.detach().float().to(dev)
         self.final_norm = model.model.norm.to(dev).float()
         self.lm_head = model.lm_head.weight.detach().float().to(dev)
@@ -115,7 +122,10 @@ class IntEngine:
     def _build_layer(self, layer, p, qcfg, act):
         L = {}
         at, mlp = layer.self_attn, layer.mlp
-        for tag, mod, name in (("n1", layer.input_layernorm, p + ".input_layernorm"), ("n2", layer.post_attention_layernorm, p + ".post_attention_layernorm")):
+        norms = [("n1", layer.input_layernorm, p + ".input_layernorm")]
+        if not self.parallel:
+            norms.append(("n2", layer.post_attention_layernorm, p + ".post_attention_layernorm"))
+        for tag, mod, name in norms:
             wq = self._wq(mod.weight, qcfg[name]["weight"], want_fq=True)
             b = getattr(mod, "bias", None)
             b = None if b is None or float(b.detach().abs().max()) == 0.0 else b.detach().float().to(self.device).contiguous()
@@ -149,11 +159,21 @@ class IntEngine:
                               [_sq(act, qcfg, pa + "o_proj", "output")], [getattr(at.o_proj, "bias", None)])
         # ---- MLP: w1 || w3 interleaved per 128 rows (padded to a multiple of 128), activation folded into a LUT
         pm = p + ".mlp."
-        x2 = L["n2"]["qout"]
-        q1, q3 = _sq(act, qcfg, pm + "w1", "output"), _sq(act, qcfg, pm + "w3", "output")
-        w1 = self._wq(mlp.w1.weight, qcfg[pm + "w1"]["weight"]); w3 = self._wq(mlp.w3.weight, qcfg[pm + "w3"]["weight"])
+        x2 = L["n1"]["qout"] if self.parallel else L["n2"]["qout"]
+        q1 = _sq(act, qcfg, pm + "w1", "output")
+        w1 = self._wq(mlp.w1.weight, qcfg[pm + "w1"]["weight"])
         pc1 = self._percol([w1], x2[0], x2[1], self.H, [q1], [getattr(mlp.w1, "bias", None)])
-        pc3 = self._percol([w3], x2[0], x2[1], self.H, [q3], [getattr(mlp.w3, "bias", None)])
+        if self.gated:
+            q3 = _sq(act, qcfg, pm + "w3", "output")
+            w3 = self._wq(mlp.w3.weight, qcfg[pm + "w3"]["weight"])
+            pc3 = self._percol([w3], x2[0], x2[1], self.H, [q3], [getattr(mlp.w3, "bias", None)])
+        else:
+            # two-linear MLP (hm:1057-1062 with num_linears_per_mlp == 2): the gate operand of the fused activation epilogue
+            # is the constant 1.0 -- zero weight codes, bias 1, "output quantizer" (scale 1, offset 0): code 1 -> 1.0 exactly
+            q3 = (1.0, 0.0, 255.0)
+            one = torch.ones(self.I, device=self.device)
+            pc3 = dict(pc1, codes=torch.zeros_like(pc1["codes"]), sxw=torch.zeros_like(pc1["sxw"]), ow=torch.zeros_like(pc1["ow"]),
+                       c0=torch.zeros_like(pc1["c0"]), bias=one, so=torch.ones_like(pc1["so"]), oo=torch.zeros_like(pc1["oo"]))
         L["w13"] = self._interleave(pc1, pc3)
         act_q = qcfg[pm + "act_fn"]
         q_aout = _sq(act, qcfg, pm + "act_fn", "output")
@@ -276,14 +296,35 @@ class IntEngine:
         return K.qgemm(a, self._codes(g), rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
                        qgroup=g["qgroup"], **kw)
 
+    def _attn_inputs(self, h, L, B, T, bufs, cos, sin):
+        """Input norm, fused q|k|v projection, RoPE + re-quantisation into the attention layouts (token-local work)."""
+        K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
+        self._gemm(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, out=bufs["qkv"], out_bits=8)
+        K.qrope(bufs["qkv"], B, T, self.nh, self.nkv, self.hd, self.rot, L["rope_in"], L["rope_out"], cos, sin, bufs["rope"])
+
+    def _block_tail(self, h, L, bufs, trace=None):
+        """o_proj + residual, (post-attention norm,) MLP + residual.  Sequential block: the MLP reads the norm of the updated
+        residual stream; parallel block with shared norm (phi): it reads the input norm's codes, still in bufs["x"]."""
+        self._gemm(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, resid=h)
+        if trace is not None:
+            trace.update(h_mid=h.clone())
+        if not self.parallel:
+            K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
+        bufs["rs_act"].zero_()
+        w2in = L["w2_in"]
+        self._gemm(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1], qmax2=w2in[2],
+                   rowsum_out=bufs["rs_act"])
+        if trace is not None:
+            trace.update(x2=bufs["x"].clone(), act=bufs["act"].clone())
+        self._gemm(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, resid=h)
+        return h
+
     @torch.no_grad()
     def block(self, h, L, B, T, bufs, trace=None, cache=None):
         """One decoder block on the fp32 residual stream h [B*T, H] (updated in place).  cache = (KVCache, layer index):
         the rotated k / v codes of the T tokens are also written to the decode cache."""
         cos, sin = self._rope(T)
-        K.qnorm(h, L["n1"]["qin"], L["n1"]["w_fq"], L["n1"]["bias"], L["n1"]["qout"], self.layernorm, L["n1"]["eps"], bufs["x"], bufs["rs"])
-        self._gemm(bufs["x"], L["qkv"], bufs["rs"], K.EPI_QUANT, out=bufs["qkv"], out_bits=8)
-        K.qrope(bufs["qkv"], B, T, self.nh, self.nkv, self.hd, self.rot, L["rope_in"], L["rope_out"], cos, sin, bufs["rope"])
+        self._attn_inputs(h, L, B, T, bufs, cos, sin)
         if cache is not None:
             kv, li = cache
             kv.k[li][:, :, :T].copy_(bufs["rope"]["k"])
@@ -294,18 +335,98 @@ class IntEngine:
         if trace is not None:
             trace.update(x1=bufs["x"].clone(), qkv=bufs["qkv"].clone(), q=bufs["rope"]["q"].clone(), k=bufs["rope"]["k"].clone(),
                          vt=bufs["rope"]["vt"].clone(), attn=bufs["attn"].clone())
-        self._gemm(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, resid=h)
-        if trace is not None:
-            trace.update(h_mid=h.clone())
-        K.qnorm(h, L["n2"]["qin"], L["n2"]["w_fq"], L["n2"]["bias"], L["n2"]["qout"], self.layernorm, L["n2"]["eps"], bufs["x"], bufs["rs"])
-        bufs["rs_act"].zero_()
-        w2in = L["w2_in"]
-        self._gemm(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1], qmax2=w2in[2],
-                   rowsum_out=bufs["rs_act"])
-        if trace is not None:
-            trace.update(x2=bufs["x"].clone(), act=bufs["act"].clone())
-        self._gemm(bufs["act"], L["w2"], bufs["rs_act"], K.EPI_RESID, resid=h)
-        return h
+        return self._block_tail(h, L, bufs, trace)
+
+    # ---- sequence-sharded prefill (north star: "inference shards the KV/sequence across GPUs") -----------
+    @staticmethod
+    def seq_shard_plan(T, rank, world):
+        """Zig-zag ownership of 2*world equal chunks: rank r owns chunks r and 2*world-1-r, which gives every rank the same
+        number of causally visible (query, key) pairs.  Returns (chunk length, [chunk ids], absolute positions of the local tokens)."""
+        if T % (2 * world * 128):
+            raise ValueError(f"sequence-sharded prefill needs T % (256 * world) == 0 (T {T}, world {world})")
+        Tc = T // (2 * world)
+        chunks = [rank, 2 * world - 1 - rank]
+        pos = torch.cat([torch.arange(c * Tc, (c + 1) * Tc) for c in chunks])
+        return Tc, chunks, pos
+
+    def _shard_buffers(self, B, Tl, T):
+        dev = self.device
+        u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+        b = dict(x=u8(B * Tl, self.H), rs=i32(B * Tl), qkv=u8(B * Tl, (self.nh + 2 * self.nkv) * self.hd),
+                 rope=dict(q=u8(B, self.nh, Tl, self.hd), k=u8(B, self.nkv, Tl, self.hd), vt=u8(B, self.nkv, self.hd, Tl),
+                           rsq=i32(B, self.nh, Tl), rsk=i32(B, self.nkv, Tl)),
+                 attn=u8(B * Tl, self.nh * self.hd), rs_attn=i32(B * Tl), act=u8(B * Tl, self.Ipad), rs_act=i32(B * Tl),
+                 k_all=u8(B, self.nkv, T, self.hd), vt_all=u8(B, self.nkv, self.hd, T), rsk_all=i32(B, self.nkv, T))
+        return b
+
+    @torch.no_grad()
+    def seq_sharded_steps(self, input_ids, rank, world):
+        """Generator form of the sequence-sharded prefill of rank `rank`: per layer it yields the packed K | V^T | key-code-sum
+        codes of the local tokens (one uint8 tensor, 2*hd + 4 bytes per token and kv head) and expects the list of all ranks'
+        packed tensors back (`send`); everything else is token-local.  Finishes by returning the fp32 hidden state of the
+        local tokens [B, Tl, H] and their absolute positions.  Drivers: prefill_seq_sharded (torch.distributed all_gather) and
+        the single-process lock-step simulation of the tests."""
+        B, T = input_ids.shape
+        if self.hd not in (64, 128):
+            raise NotImplementedError("sequence-sharded attention runs on the tcgen05 kernel (head_dim 64 / 128)")
+        Tc, chunks, pos = self.seq_shard_plan(T, rank, world)
+        Tl = 2 * Tc
+        pos_d = pos.to(self.device)
+        h = self._embed(input_ids.to(self.device)[:, pos_d]).reshape(B * Tl, self.H).contiguous()
+        cos, sin = self._rope(T)
+        cosl, sinl = cos[pos_d].contiguous(), sin[pos_d].contiguous()
+        bufs = self._shard_buffers(B, Tl, T)
+        rope = bufs["rope"]
+        nk, nr = rope["k"].numel(), rope["rsk"].numel() * 4
+        for L in self.layers:
+            self._attn_inputs(h, L, B, Tl, bufs, cosl, sinl)
+            packed = torch.cat([rope["k"].reshape(-1), rope["vt"].reshape(-1), rope["rsk"].view(torch.uint8).reshape(-1)])
+            gathered = yield packed
+            for r, buf in enumerate(gathered):                        # place every rank's two chunks at their sequence positions
+                k_r = buf[:nk].view(B, self.nkv, Tl, self.hd)
+                v_r = buf[nk:2 * nk].view(B, self.nkv, self.hd, Tl)
+                s_r = buf[2 * nk:2 * nk + nr].view(torch.int32).view(B, self.nkv, Tl)
+                for s, c in enumerate((r, 2 * world - 1 - r)):
+                    bufs["k_all"][:, :, c * Tc:(c + 1) * Tc].copy_(k_r[:, :, s * Tc:(s + 1) * Tc])
+                    bufs["vt_all"][:, :, :, c * Tc:(c + 1) * Tc].copy_(v_r[:, :, :, s * Tc:(s + 1) * Tc])
+                    bufs["rsk_all"][:, :, c * Tc:(c + 1) * Tc].copy_(s_r[:, :, s * Tc:(s + 1) * Tc])
+            attn3 = bufs["attn"].view(B, Tl, self.nh * self.hd)
+            rs2 = bufs["rs_attn"].view(B, Tl)
+            for s, c in enumerate(chunks):                             # one causal call per owned chunk: queries c*Tc .. (c+1)*Tc-1
+                q_s = rope["q"][:, :, s * Tc:(s + 1) * Tc].contiguous()
+                rsq_s = rope["rsq"][:, :, s * Tc:(s + 1) * Tc].contiguous()
+                rs_s = torch.zeros(B * Tc, dtype=torch.int32, device=self.device)
+                out_s = K.qattn_shard(q_s, rsq_s, bufs["k_all"], bufs["vt_all"], bufs["rsk_all"], B, Tc, T, c * Tc, self.nh, self.nkv,
+                                      self.hd, L["attn"], L["attn_lut"], rowsum_out=rs_s)
+                attn3[:, s * Tc:(s + 1) * Tc].copy_(out_s.view(B, Tc, -1))
+                rs2[:, s * Tc:(s + 1) * Tc].copy_(rs_s.view(B, Tc))
+            self._block_tail(h, L, bufs)
+        return h.view(B, Tl, self.H), pos
+
+    @torch.no_grad()
+    def prefill_seq_sharded(self, input_ids, group=None):
+        """Sequence-sharded integer prefill over the ranks of a torch.distributed (NCCL) process group: every rank holds the
+        weights, owns 2 of 2*world sequence chunks (zig-zag) and exchanges only the int8 K / V codes of its tokens, one
+        all_gather per layer.  Returns (hidden [B, Tl, H] of the local tokens, their absolute positions); the logits of the
+        last position live on rank 0 (it owns the last chunk): `last_token_logits`."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        gen = self.seq_sharded_steps(input_ids, rank, world)
+        packed = next(gen)
+        try:
+            while True:
+                out = [torch.empty_like(packed) for _ in range(world)]
+                dist.all_gather(out, packed, group=group)
+                packed = gen.send(out)
+        except StopIteration as e:
+            return e.value
+
+    def last_token_logits(self, h_local, pos):
+        """Logits of the sequence's last position from a rank's local hidden state (None on ranks that do not own it)."""
+        T_last = int(pos.max().item())
+        idx = int((pos == T_last).nonzero()[0])
+        return self._head(h_local[:, idx, :])
 
     @torch.no_grad()
     def backbone(self, h, B, T, trace_layer=None, cache=None):
@@ -399,7 +520,7 @@ class IntEngine:
         cos, sin = self._rope(cache.Tmax)
         pos = cache.length
         pkw = dict(pos_dev=cache.pos_dev, pos_bound=cache.Tmax - 1) if use_pos_dev else {}
-        fuse = self.fused_resid_norm
+        fuse = self.fused_resid_norm and not self.parallel
         pending = None                      # (GEMM, its row sums): a residual epilogue still to be applied to h
         for i, L in enumerate(self.layers):
             self._norm_dec(h, L["n1"], bufs, pending)
@@ -412,7 +533,8 @@ class IntEngine:
                 self._norm_dec(h, L["n2"], bufs, (L["o"], bufs["rs_attn"]))
             else:
                 self._gemv(bufs["attn"], L["o"], bufs["rs_attn"], K.EPI_RESID, bufs["acc"], resid=h)
-                self._norm_dec(h, L["n2"], bufs, None)
+                if not self.parallel:                # (parallel block: the MLP reads the input norm's codes, still in bufs["x"])
+                    self._norm_dec(h, L["n2"], bufs, None)
             w2in = L["w2_in"]
             self._gemv(bufs["x"], L["w13"], bufs["rs"], K.EPI_ACTMUL, bufs["acc"], out=bufs["act"], lut=L["act_lut"], s2=w2in[0], o2=w2in[1],
                        qmax2=w2in[2], rowsum_out=bufs["rs_act"], zero_out=bufs["rs_attn"])

@@ -31,6 +31,7 @@ def _protos():
                                    _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, c_int, _P]
     lib.mq_qrope.argtypes = [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qattn.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
+    lib.mq_qattn_shard.argtypes = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]
     lib.mq_qgemv.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]
     lib.mq_qgemv_epilogue.argtypes = [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float, _P, c_int64, _P, _P,
                                       c_float, c_float, c_float, _P, c_int, _P, _P]
@@ -306,6 +307,20 @@ def qattn(bufs, B, T, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
     with torch.cuda.device(dev):
         check(_launch("qattn", lib.mq_qattn, h, ptr(bufs["q"]), ptr(bufs["k"]), ptr(bufs["vt"]), ptr(bufs["rsq"]), ptr(bufs["rsk"]), B, T, nh, nkv, hd,
                            ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
+    return out
+
+
+def qattn_shard(q, rsq, k, vt, rsk, B, Tq, T, q_start, nh, nkv, hd, qparams, lut, out=None, rowsum_out=None):
+    """Attention of a query shard (absolute positions q_start .. q_start + Tq - 1) against all T keys; include/mqb200.h:mq_qattn_shard."""
+    lib = _protos()
+    dev = q.device
+    if out is None:
+        out = torch.empty(B * Tq, nh * hd, dtype=torch.uint8, device=dev)
+    h = _h(out)
+    pq = _host_floats(qparams)
+    with torch.cuda.device(dev):
+        check(_launch("qattn", lib.mq_qattn_shard, h, ptr(q), ptr(k), ptr(vt), ptr(rsq, torch.int32), ptr(rsk, torch.int32), B, Tq, T, q_start,
+                      nh, nkv, hd, ctypes.cast(pq, _P), ptr(lut), ptr(out), ptr(rowsum_out), stream_ptr()), h)
     return out
 
 

@@ -307,7 +307,7 @@ class IntModel:
             cache[i] = [k, v]
         attn = qattn_int(q, k, v, self.nh, self.nkv, qout[0], qout[1], qout[2], sq("self_attn.qk_bmm", "output"),
                          sq("self_attn.pv_bmm", "input"), sq("self_attn.pv_bmm", "output")[:2])
-        return self._tail(h, attn, i, trace, dict(x1=x1, qkv=qkv, q=q, k=k, v=v))
+        return self._tail(h, attn, i, x1, trace, dict(x1=x1, qkv=qkv, q=q, k=k, v=v))
 
     def decode_block(self, h, i, pos, cache, cos, sin):
         """One-token step of block i against the uint8 KV cache (SimBlock / SimAttention with k_cache, v_cache,
@@ -316,20 +316,22 @@ class IntModel:
         p = f"model.layers.{i}."
         sq = lambda n, s: _sq(self.act, self.recipe, p + n, s)
         B = h.shape[0]
-        _, qkv, qin, qout = self._qkv(h, i)
+        x1, qkv, qin, qout = self._qkv(h, i)
         q, k, v = qrope_int(qkv, B, 1, self.nh, self.nkv, self.hd, self.rot, qin, qout, cos[pos:pos + 1], sin[pos:pos + 1])
         cache[i] = [np.concatenate([cache[i][0], k], axis=2), np.concatenate([cache[i][1], v], axis=2)]     # sim_model.py:229-231
         attn = qattn_decode_int(q[:, :, 0], cache[i][0], cache[i][1], self.nh, self.nkv, qout[0], qout[1], qout[2], sq("self_attn.qk_bmm", "output"),
                                 sq("self_attn.pv_bmm", "input"), sq("self_attn.pv_bmm", "output")[:2])
-        return self._tail(h, attn, i)
+        return self._tail(h, attn, i, x1)
 
     def decode(self, h, pos, cache, cos, sin):
         for i in range(self.cfg["num_hidden_layers"]):
             h = self.decode_block(h, i, pos, cache, cos, sin)
         return h
 
-    def _tail(self, h, attn, i, trace=None, tr0=None):
-        """o_proj + residual, post-attention norm, gated MLP + residual (everything of the block after attention)."""
+    def _tail(self, h, attn, i, x1=None, trace=None, tr0=None):
+        """o_proj + residual, post-attention norm, MLP + residual (everything of the block after attention).  Block variants
+        of hm:1257-1263: sequential (MLP reads the norm of the updated residual) and parallel with shared norm (phi: the MLP
+        reads input_layernorm's codes x1); two-linear MLP (num_linears_per_mlp == 2): no gate."""
         p = f"model.layers.{i}."
         A, R = self.act, self.recipe
         sq = lambda n, s: _sq(A, R, p + n, s)
@@ -338,14 +340,23 @@ class IntModel:
         qo = sq("self_attn.o_proj", "output")
         h = (h + dequant(quant_codes(y, qo[0], qo[1], 0, qo[2]), qo[0], qo[1])).astype(f32)
         h_mid = h
-        x2 = self.norm(h, p + "post_attention_layernorm")
-        qx2 = sq("post_attention_layernorm", "output")
-        q1, q3 = sq("mlp.w1", "output"), sq("mlp.w3", "output")
+        parallel = bool(self.cfg.get("parallel_residual"))
+        assert parallel == bool(self.cfg.get("shared_attention_norm")), "mixed parallel / shared-norm blocks are not integer paths"
+        if parallel:
+            x2, qx2 = x1, sq("input_layernorm", "output")
+        else:
+            x2 = self.norm(h, p + "post_attention_layernorm")
+            qx2 = sq("post_attention_layernorm", "output")
+        q1 = sq("mlp.w1", "output")
         c1 = quant_codes(self._lin_y(x2, qx2, p + "mlp.w1"), q1[0], q1[1], 0, q1[2]).astype(np.int64)
-        c3 = quant_codes(self._lin_y(x2, qx2, p + "mlp.w3"), q3[0], q3[1], 0, q3[2])
         kind = "silu" if "input2" in R[p + "mlp.act_fn"] else "gelu"
         lut = act_lut(kind, q1, sq("mlp.act_fn", "input2") if kind == "silu" else None, sq("mlp.act_fn", "output"))
-        prod = (lut[c1] * dequant(c3, q3[0], q3[1])).astype(f32)
+        if self.cfg.get("num_linears_per_mlp", 3) == 3:
+            q3 = sq("mlp.w3", "output")
+            c3 = quant_codes(self._lin_y(x2, qx2, p + "mlp.w3"), q3[0], q3[1], 0, q3[2])
+            prod = (lut[c1] * dequant(c3, q3[0], q3[1])).astype(f32)
+        else:
+            prod = lut[c1].astype(f32)
         qw2 = sq("mlp.w2", "input")
         act = quant_codes(prod, qw2[0], qw2[1], 0, qw2[2]).astype(np.int64)
         y = self._lin_y(act, qw2, p + "mlp.w2")

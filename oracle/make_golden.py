@@ -160,9 +160,13 @@ def ref_code_trace(qmodel_fwd, sample, layers):
     for i in layers:
         layer = qmodel_fwd.model.layers[i]
         for name, key in want.items():
-            m = layer.get_submodule(name)
+            try:
+                m = layer.get_submodule(name)
+            except AttributeError:                     # shared_attention_norm: no post_attention_layernorm
+                continue
             hooks.append(m.register_forward_hook(qhook(i, key)))
-        hooks.append(layer.post_attention_layernorm.register_forward_hook(
+        # residual stream after attention == second operand-free input of resid_add_2 (hm:1257,1270)
+        hooks.append(layer.resid_add_2.register_forward_hook(
             lambda mod, inp, out, i=i: trace[i].__setitem__("h_mid", inp[0].detach().clone())))
         hooks.append(layer.register_forward_hook(lambda mod, inp, out, i=i: trace[i].__setitem__("h_out", out[0].detach().clone())))
     with torch.no_grad():
@@ -355,9 +359,13 @@ def golden_trace(tag, cfgd, T):
 
 
 TINY_HD64 = dict(TINY, num_attention_heads=2, num_key_value_heads=1)      # head_dim 64: the tcgen05 attention kernel's shape class
+# phi-like (scripts/convert_ckpt.py:28): parallel residual, one shared LayerNorm, two-linear GELU MLP, biases, partial rotary
+TINY_PHI = dict(TINY, num_key_value_heads=4, norm_class="layernorm", attention_bias=True, mlp_bias=True, hidden_act="gelu",
+                num_linears_per_mlp=2, shared_attention_norm=True, parallel_residual=True, partial_rotary_factor=0.5)
 
 if __name__ == "__main__":
     golden_trace("llama_hd64_t256", TINY_HD64, 256)
+    golden_trace("phi_t64", TINY_PHI, 64)
     golden_model("llama_w8_e2e", TINY, 8, False, False, "e2e")
     golden_model("llama_w4_omni", TINY, 4, True, True, "omniquant")
     golden_model("stablelm_w8_omni", TINY_MHA, 8, False, False, "omniquant")

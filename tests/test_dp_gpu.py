@@ -114,3 +114,58 @@ def test_two_gpu_calibration_matches_single_gpu(tmp_path):
     # batch-of-2 backward, and Adam's normalisation amplifies that on near-zero gradients); the contract is BASELINE.json's
     # "within 1e-3 on the learned scales/ranges"
     assert worst < 1e-3, worst
+
+
+def _seq_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from helpers import load_golden, product_model
+        from mobilequant_b200.engine import IntEngine
+        g = load_golden("trace_llama_hd64_t256.pt")
+        eng = IntEngine(product_model(g), g["qcfg"], g["act_dict"], dev)
+        T = 256 * world
+        ids = torch.randint(3, g["cfg"]["vocab_size"], (2, T), generator=torch.Generator().manual_seed(world))
+        h_local, pos = eng.prefill_seq_sharded(ids)
+        full = eng.forward(ids.to(dev), return_logits=False)
+        ok = torch.equal(h_local, full[:, pos.to(dev)])
+        if rank == 0:
+            ok = ok and torch.equal(eng.last_token_logits(h_local, pos), eng._head(full[:, -1, :]))
+        t = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            q.put(int(t.item()))
+            q.close(); q.join_thread()
+        torch.cuda.synchronize()
+        dist.barrier()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    os._exit(0)
+
+
+def test_two_gpu_sequence_sharded_prefill():
+    """prefill_seq_sharded over NCCL (one all_gather of the int8 K / V codes per layer) == the single-GPU forward, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seq_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        ok = q.get(timeout=600)
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert ok == 1

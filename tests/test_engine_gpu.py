@@ -137,6 +137,27 @@ def test_qattn_real_shapes(cuda, B, T, nh, nkv, hd, spread, monkeypatch):
     assert np.array_equal(outs[first][1].astype(np.int64), outs[first][0].astype(np.int64).sum(1))
 
 
+@pytest.mark.parametrize("B,T,Tq,q_start,nh,nkv,hd", [(1, 512, 256, 256, 2, 1, 64), (2, 640, 128, 384, 4, 2, 64), (1, 384, 256, 128, 2, 2, 128),
+                                                      (1, 272, 144, 128, 2, 1, 64)])
+def test_qattn_shard(cuda, B, T, Tq, q_start, nh, nkv, hd):
+    """mq_qattn_shard: a shard of the queries (absolute positions q_start ..) against all keys == the same rows of the full
+    causal attention (oracle with q_start)."""
+    from mobilequant_b200 import kernels as K
+    rng = np.random.default_rng(T + q_start)
+    q, k, v, qps, params = _attn_problem(rng, B, T, nh, nkv, hd)
+    qq, qk, qv, qs, qp, qo = qps
+    qsh = np.ascontiguousarray(q[:, :, q_start:q_start + Tq])
+    ref = ir.qattn_int(qsh.astype(np.int64), k.astype(np.int64), v.astype(np.int64), nh, nkv, qq, qk, qv, qs, qp, qo, q_start=q_start)
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    lut = dev(ir.exp_tables(qs[0], hd).view(np.int32))
+    rs = torch.zeros(B * Tq, dtype=torch.int32, device=cuda)
+    out = K.qattn_shard(dev(qsh), dev(qsh.astype(np.int32).sum(-1).astype(np.int32)), dev(k), dev(np.ascontiguousarray(v.transpose(0, 1, 3, 2))),
+                        dev(k.astype(np.int32).sum(-1).astype(np.int32)), B, Tq, T, q_start, nh, nkv, hd, params, lut, rowsum_out=rs)
+    got = out.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, ref), f"{(got != ref).mean():.4f} mismatching"
+    assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
+
+
 @pytest.mark.parametrize("rows,H,layernorm", [(2048, 2048, False), (4096, 2048, True)])
 def test_qnorm_real_shapes(cuda, rows, H, layernorm):
     """qnorm at the hidden size of all three evaluated families (H 2048), thousands of rows (warp-per-row kernel)."""
@@ -174,12 +195,13 @@ def test_qrope_real_shapes(cuda, B, T, nh, nkv, hd, rot):
     assert np.array_equal(out["rsk"].cpu().numpy().astype(np.int64), k.sum(-1))
 
 
-@pytest.mark.parametrize("tag", MODEL_GOLDENS)
+@pytest.mark.parametrize("tag", MODEL_GOLDENS + ["trace:llama_hd64_t256", "trace:phi_t64"])
 def test_engine_bit_exact_vs_integer_oracle(cuda, tag):
     """Every integer tensor of a block (norm / qkv / rope / attention / activation codes) and the fp32 residual stream
-    after all layers are bit-identical to the CPU restatement."""
+    after all layers are bit-identical to the CPU restatement (four calibrated families + a multi-tile hd-64 sequence on the
+    tcgen05 attention kernel + the phi-like parallel block with a shared LayerNorm and a two-linear MLP)."""
     from mobilequant_b200.engine import IntEngine
-    g = load_golden(f"model_{tag}.pt")
+    g = load_golden(f"trace_{tag[6:]}.pt" if tag.startswith("trace:") else f"model_{tag}.pt")
     model = product_model(g)
     eng = IntEngine(model, g["qcfg"], g["act_dict"], cuda)
     ids = torch.cat(g["samples"][:2], dim=0)
@@ -204,7 +226,63 @@ def test_engine_bit_exact_vs_integer_oracle(cuda, tag):
     assert np.array_equal(h.cpu().numpy(), h_ref)
 
 
-@pytest.mark.parametrize("fixture", ["trace_llama_hd64_t256.pt"] + [f"model_{t}.pt" for t in MODEL_GOLDENS])
+def test_engine_decode_parallel_block(cuda):
+    """Decode step of the phi-like block variant (parallel residual, shared norm, two-linear MLP) == row `pos` of the full
+    integer forward."""
+    from mobilequant_b200.engine import IntEngine
+    g = load_golden("trace_phi_t64.pt")
+    eng = IntEngine(product_model(g), g["qcfg"], g["act_dict"], cuda)
+    ids = torch.cat(g["samples"][:2], dim=0)
+    B, T = ids.shape
+    im = ir.IntModel(g["state_dict"], g["cfg"], mr.recipe_from_qcfg_json(g["qcfg"]), g["act_dict"])
+    cos, sin = ir.rope_tables(T, im.rot, g["cfg"].get("rope_theta", 10000.0))
+    h_ref, _ = im.backbone(im.embed(ids.numpy()), B, T, cos, sin)
+    for Tset in (T, T - 3):
+        eng.set_rope_tables(Tset, torch.from_numpy(cos[:Tset]), torch.from_numpy(sin[:Tset]))
+    cache = eng.new_cache(B, T)
+    eng.prefill(ids[:, :T - 3].to(cuda), cache)
+    for t in range(T - 3, T):
+        hd = eng._embed(ids[:, t].to(cuda)).contiguous()
+        eng.decode_hidden(hd, cache)
+        cache.length += 1
+        assert np.array_equal(hd.cpu().numpy(), h_ref.reshape(B, T, -1)[:, t]), t
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_seq_sharded_prefill_matches_full_forward(cuda, world):
+    """Sequence-sharded prefill (zig-zag chunks, per-layer exchange of the int8 K / V codes) simulated in one process: all
+    ranks' generators advance in lock-step and the 'all_gather' is a Python list.  With static per-tensor quantizers every
+    token's integer tensors are independent of how the sequence is split, so the merged hidden state must equal the
+    single-GPU forward bit for bit."""
+    from mobilequant_b200.engine import IntEngine
+    g = load_golden("trace_llama_hd64_t256.pt")
+    eng = IntEngine(product_model(g), g["qcfg"], g["act_dict"], cuda)
+    T = 256 * world
+    gen = torch.Generator().manual_seed(world)
+    ids = torch.randint(3, g["cfg"]["vocab_size"], (2, T), generator=gen)
+    full = eng.forward(ids.to(cuda), return_logits=False)
+    gens = [eng.seq_sharded_steps(ids, r, world) for r in range(world)]
+    packed = [next(gn) for gn in gens]
+    results = [None] * world
+    while any(r is None for r in results):
+        nxt = []
+        for r, gn in enumerate(gens):
+            try:
+                nxt.append(gn.send([p.clone() for p in packed]))
+            except StopIteration as e:
+                results[r] = e.value
+        packed = nxt
+    merged = torch.empty_like(full)
+    for h_local, pos in results:
+        merged[:, pos.to(cuda)] = h_local
+    assert torch.equal(merged, full)
+    # the last position lives on rank 0 (zig-zag: it owns the last chunk)
+    h0, pos0 = results[0]
+    assert int(pos0.max()) == T - 1
+    assert torch.equal(eng.last_token_logits(h0, pos0), eng._head(full[:, -1, :]))
+
+
+@pytest.mark.parametrize("fixture", ["trace_llama_hd64_t256.pt", "trace_phi_t64.pt"] + [f"model_{t}.pt" for t in MODEL_GOLDENS])
 def test_engine_lsb_flip_rate_vs_reference(cuda, fixture):
     """Per-tensor LSB-flip rate of the sm_100a engine against the integer codes of the UNMODIFIED reference's fake-quant
     forward (golden `ref_trace`, first and last block): 8-bit codes within one LSB at a rate <= 1e-3 (measured: identical),

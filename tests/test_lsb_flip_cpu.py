@@ -13,7 +13,7 @@ import torch
 from helpers import load_golden
 from oracle import int_ref as ir, model_ref as mr
 
-FIXTURES = ["trace_llama_hd64_t256.pt", "model_llama_w8_e2e.pt", "model_llama_w4_omni.pt", "model_stablelm_w8_omni.pt", "model_gemma_w8_e2e.pt"]
+FIXTURES = ["trace_llama_hd64_t256.pt", "trace_phi_t64.pt", "model_llama_w8_e2e.pt", "model_llama_w4_omni.pt", "model_stablelm_w8_omni.pt", "model_gemma_w8_e2e.pt"]
 MAX_FLIP_RATE_8BIT = 1e-3       # measured: 0 on every fixture (every 8-bit code tensor identical to the reference's)
 MAX_FLIP_RATE_16BIT = 5e-3      # o_proj output (16 bit): measured <= 1.7e-3, never more than one LSB
 
@@ -21,16 +21,18 @@ MAX_FLIP_RATE_16BIT = 5e-3      # o_proj output (16 bit): measured <= 1.7e-3, ne
 def reference_pairs(tr, rt, B, T, nh, nkv):
     """(integer-forward tensor, reference code tensor) per traced name, brought to the integer forward's layouts."""
     rep = nh // nkv
-    return {
+    pairs = {
         "input_layernorm.output": (tr["x1"], rt["x1"].reshape(B * T, -1)),
         "q|k|v_proj.output": (tr["qkv"], torch.cat([rt["q_proj"], rt["k_proj"], rt["v_proj"]], -1).reshape(B * T, -1)),
         "qk_bmm.input": (tr["q"], rt["q"]),
         "qk_bmm.input2": (tr["k"], rt["kT"].transpose(-1, -2)[:, ::rep]),
         "pv_bmm.input2": (tr["v"], rt["v"][:, ::rep]),
         "pv_bmm.output": (tr["attn"], rt["attn"].transpose(1, 2).reshape(B * T, -1)),
-        "post_attention_layernorm.output": (tr["x2"], rt["x2"].reshape(B * T, -1)),
         "w2.input": (tr["act"], rt["act"].reshape(B * T, -1)),
     }
+    if "x2" in rt:              # absent with shared_attention_norm (phi-like blocks have no post-attention norm)
+        pairs["post_attention_layernorm.output"] = (tr["x2"], rt["x2"].reshape(B * T, -1))
+    return pairs
 
 
 def check_against_reference(tr, rt, B, T, nh, nkv, s_oproj, where):
