@@ -70,6 +70,8 @@ class IntEngine:
         self.embed = model.model.embed_tokens.weight.detach().float().to(dev)
         self.final_norm = model.model.norm.to(dev).float()
         self.lm_head = model.lm_head.weight.detach().float().to(dev)
+        b = getattr(model.lm_head, "bias", None)                   # hm:1682: the head carries a bias when config.mlp_bias (phi)
+        self.lm_head_bias = None if b is None else b.detach().float().to(dev)
         self.layers = [self._build_layer(model.model.layers[i], f"model.layers.{i}", qcfg, act_dict) for i in range(cfg.num_hidden_layers)]
         self._rope_cache = {}
         self._bufs = {}
@@ -453,7 +455,7 @@ class IntEngine:
         if last_token_only:
             h = h[:, -1:, :]
         hn = self.final_norm(h)
-        return torch.nn.functional.linear(hn, self.lm_head)
+        return torch.nn.functional.linear(hn, self.lm_head, self.lm_head_bias)
 
     __call__ = forward
 
@@ -470,8 +472,9 @@ class IntEngine:
     def _head(self, h):
         hn = self.final_norm(h)
         if hn.dim() == 2 and hn.shape[0] <= 16:        # decode step: HBM-bound fp32 GEMV instead of a library SGEMM
-            return K.fgemv(hn.contiguous(), self.lm_head)
-        return torch.nn.functional.linear(hn, self.lm_head)
+            out = K.fgemv(hn.contiguous(), self.lm_head)
+            return out if self.lm_head_bias is None else out.add_(self.lm_head_bias)
+        return torch.nn.functional.linear(hn, self.lm_head, self.lm_head_bias)
 
     @torch.no_grad()
     def prefill(self, input_ids, cache):

@@ -225,7 +225,7 @@ class HFForCausalLM(nn.Module):
         super().__init__()
         self.config = config
         self.model = HFModel(config)
-        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=config.mlp_bias)        # hm:1682
         self.apply(self._init_weights)
         if config.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight

@@ -125,3 +125,30 @@ def test_calibration_set_is_never_silently_random(tmp_path):
     assert len(got) == 4 and got[0][0].shape == (1, 8) and int(got[0][0].min()) >= 2
     with pytest.raises(NotImplementedError, match="lm-eval"):
         M.main(["--hf_path", "/x", "--tasks", "wikitext"])
+
+
+def test_encodings_writer_matches_reference_functions():
+    """device/encodings.py against the UNMODIFIED text of the reference's update_encodings & co (device/utils.py:278-560, executed by
+    oracle/make_golden_encodings.py on synthetic AIMET-style files) and the kv-cache block of device/calibrate.py:275-285."""
+    import copy, os
+    from helpers import GOLDEN
+    from mobilequant_b200.device import encodings as E
+    gold = json.load(open(os.path.join(GOLDEN, "encodings.json")))
+    assert len(gold) >= 3
+    for tag, c in gold.items():
+        got, untouched = E.update_encodings(copy.deepcopy(c["ori_encodings"]), c["act_dict"], c["num_blocks"], c["q_proj_factor"],
+                                            c["impl_sym_pch_as_slinear"])
+        assert got == c["updated"], tag
+        assert untouched == ["module_add_mask", "module_embedding"], tag
+        assert E.kv_cache_encodings(c["act_dict"], c["num_blocks"], 8) == c["kv_cache"], tag
+    # self-contained writer: same numbers under canonical node names, bitwidths taken from default_qcfg.json
+    c = gold["llama_plain"]
+    mods = {k: {f: {"bitwidth": "16" if ("norm" in k and f == "input") or k.endswith("o_proj") or k.endswith("w2") and f == "output" else "8"}
+                for f in ("input", "input2", "output")} for k in c["act_dict"]}
+    enc = E.encodings_from_act_dict(c["act_dict"], mods, c["num_blocks"], head_dim=64)
+    e = enc["activation_encodings"]["module_matmul_1"]["input"]["1"]
+    mn, mx = c["act_dict"]["model.layers.0.self_attn.pv_bmm"]["input2"]
+    assert e["min"] == mn and e["max"] == mx and e["scale"] == (mx - mn) / 255 and e["offset"] == int(mn * 255 / (mx - mn))
+    q = enc["activation_encodings"]["layers.0.self_attn.q_proj"]["output"]["0"]
+    assert q["max"] == c["act_dict"]["model.layers.0.self_attn.q_proj"]["output"][1] * 0.125       # attention scaling folded into q_proj
+    assert enc["activation_encodings"]["layers.0.input_layernorm.module_normalize"]["input"]["0"]["bitwidth"] == 16
