@@ -123,7 +123,11 @@ def update_encodings(ori_encodings, new_act_dict, num_blocks, q_proj_factor, imp
         has_sigmoid = any(k.startswith(f"layers.{i}.mlp.act.sigmoid") for k in act)
         for node, exact, src, sf, tf, slot, q in block_rules(i, impl_sym_pch_as_slinear, has_sigmoid):
             name = _resolve(act, node, exact)
-            fmin, fmax = new_act_dict[f"model.layers.{i}.{src}"][sf]
+            entry = new_act_dict[f"model.layers.{i}.{src}"]
+            if sf not in entry and sf == "input2" and src.endswith("act_fn"):
+                fmin, fmax = 0.0, 1.0              # sigmoid output: the range QSiLU.set_scale_offset assumes when none was recorded (qm:731-734)
+            else:
+                fmin, fmax = entry[sf]
             f = q_proj_factor if q else 1.0
             enc = act[name][tf][slot]
             enc.update(encoding_from_min_max(fmin * f, fmax * f, enc["bitwidth"]))
