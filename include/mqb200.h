@@ -115,6 +115,18 @@ int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, 
              const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo, int32_t* rowsum_out,
              const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup, void* stream);
 
+/* mq_qgemm_w4a8: the same GEMM with the weight operand PACKED, two 4-bit codes per byte (b_packed [N, K/2] bytes, the code
+ * of column 2j in the low nibble of byte j, UNSIGNED nibbles 0..15; K % 32 == 0).  Symmetric 4-bit weights (codes -8..7,
+ * experiments/w4a8/main/e2e_llama-s1024-ep60-sym.sh:26) are passed in offset-binary form code + 8 with ow[n] = 8: the zero-
+ * point algebra above is unchanged (c0 is invariant under that shift).  The packed k-slices are staged by TMA and expanded
+ * to one code per byte INSIDE the kernel (four warps write the 128B-swizzled operand rows the tensor core reads), so the
+ * weights stream from HBM at 4 bits per code and no unpacked copy ever exists in global memory (BASELINE config 3).       */
+int mq_qgemm_w4a8(void* ctx, const void* a_codes, int a_signed, const void* b_packed, int M, int N, int K,
+                  const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                  int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
+                  int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                  void* stream);
+
 /* ---- K4: QRMSNorm.forward (qm:515-531, L2-norm form hm:187-195) / QLayerNorm.forward (qm:625-642) on codes ---------
  * x fp32 residual stream [rows, H] -> 16-bit input quantizer -> norm with the fake-quantised weight w_fq (from
  * mq_wprep_fwd) -> 8-bit output quantizer: codes u8 [rows, H] and rowsum[rows] = sum of the codes.               */

@@ -65,33 +65,42 @@ struct QGemmArgs {
 // CTA and k-slice 16 KB of A + 8 KB of B leave the L2 instead of 16 + 32 (single) / 16 + 16 (pair).  At 128 MMA cycles
 // per 32 bytes of K the single-CTA kernel asks the L2 for 96 B/clk/SM, more than twice what it sustains chip-wide
 // (~43-50 B/clk/SM): the operand traffic, not the tensor pipe, was the ceiling of the first two variants.
-template <int MODE, int CL, int NE>
+// W4: the weight operand arrives PACKED (two 4-bit codes per byte, [N, K/2], unsigned nibbles): the TMA stages 64-byte packed
+// rows into a small ring, four extra warps expand the nibbles into the 128B-swizzled operand rows the MMA reads (the fused
+// int4 x int8 matmul of BASELINE config 3: the weights never exist one-code-per-byte outside shared memory).  CL 1 only.
+template <int MODE, int CL, int NE, bool W4 = false>
 struct SmemLayout {
   static constexpr bool PAIR = CL >= 2;
+  static_assert(!W4 || CL == 1, "the packed-weight path is built for the single-CTA variant");
+  static constexpr int kPStages = W4 ? 2 : 0;                // packed-B ring
+  static constexpr int kPBytes = 256 * 64;                   // 256 rows x 64 packed bytes (one k-slice of 128 codes)
   static constexpr int kCW = NE == 16 ? 16 : 32;             // accumulator columns per tcgen05.ld / per staging tile
   static constexpr int kOutTile = 32 * kCW * 4;              // RESID: one fp32 staging tile (32 rows x kCW columns)
-  static constexpr int kStages = PAIR ? (MODE == EPI_RESID ? 4 : 6) : (MODE == EPI_RESID ? 3 : 4);
+  static constexpr int kStages = W4 ? (MODE == EPI_RESID ? 2 : 3) : (PAIR ? (MODE == EPI_RESID ? 4 : 6) : (MODE == EPI_RESID ? 3 : 4));
   static constexpr int kABytes = kBM * kBK;
   static constexpr int kBRows = PAIR ? kBN / 2 : kBN;       // B rows resident per CTA
   static constexpr int kBBoxRows = CL == 4 ? kBRows / 2 : kBRows;   // B rows per TMA box
   static constexpr int kBBytes = kBRows * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kColpOff = kStages * kStageBytes;                 // 2 x CP_COUNT x 256 x 4 B
+  static constexpr int kPackOff = kStages * kStageBytes;                 // [kPStages][kPBytes] packed weight k-slices (W4)
+  static constexpr int kColpOff = kPackOff + kPStages * kPBytes;         // 2 x CP_COUNT x 256 x 4 B
   static constexpr int kLutOff = kColpOff + 2 * CP_COUNT * kBN * 4;      // 256 floats
   static constexpr int kOutOff = kLutOff + 1024;                         // RESID: per-warp 32x32 fp32 staging tiles
   static constexpr int kOutBufs = 2;                                     // staging tiles per warp
   static constexpr int kOutBytes = MODE == EPI_RESID ? NE * kOutBufs * kOutTile : 0;
   static constexpr int kBarOff = kOutOff + kOutBytes;
   static constexpr int kTotal = kBarOff + 256;
-  static_assert(kOutOff % 1024 == 0, "staging tiles must keep the 128B-swizzle phase");
+  static_assert(kOutOff % 1024 == 0 && kPackOff % 1024 == 0, "staging tiles must keep the swizzle phase");
   static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
-template <int MODE, int CL, int NE>
-__global__ void __launch_bounds__(64 + NE * 32, 1)
+constexpr int kUnpackWarps = 4;
+
+template <int MODE, int CL, int NE, bool W4 = false>
+__global__ void __launch_bounds__(64 + NE * 32 + (W4 ? kUnpackWarps * 32 : 0), 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_r, const QGemmArgs p, const uint32_t idesc) {
-  using L = SmemLayout<MODE, CL, NE>;
+  using L = SmemLayout<MODE, CL, NE, W4>;
   constexpr bool PAIR = CL >= 2, QUAD = CL == 4;
   constexpr int kNE = NE, kParts = NE / 4, CW = L::kCW;        // kParts = column parts per TMEM lane quarter
   constexpr int kCtas = CL;                                     // CTAs (128-row blocks) per scheduling unit
@@ -109,7 +118,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tfull_bar = empty_bar + L::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* pfull_bar = tempty_bar + 2;                      // W4: packed k-slice landed / consumed by the unpack warps
+  uint64_t* pempty_bar = pfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty_bar + 2);
+  uint8_t* smem_p = smem + L::kPackOff;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kCtas * kBM - 1) / (kCtas * kBM), n_tiles = (p.N + BN - 1) / BN;
@@ -122,12 +134,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     prefetch_tmap(&tmap_b);
     if (MODE == EPI_RESID) prefetch_tmap(&tmap_r);
     // QUAD: a stage is free once BOTH pairs have retired the MMAs that read it (the B quarters are written across pairs)
-    for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], QUAD ? 2 : 1); }
+    // W4: a stage is full once the A tile has landed (1 arrival + tx bytes) AND the four unpack warps have written the B tile
+    for (int i = 0; i < L::kStages; ++i) { mbar_init(&full_bar[i], W4 ? 1 + kUnpackWarps : 1); mbar_init(&empty_bar[i], QUAD ? 2 : 1); }
+    if (W4) for (int i = 0; i < L::kPStages; ++i) { mbar_init(&pfull_bar[i], 1); mbar_init(&pempty_bar[i], kUnpackWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNE * (PAIR ? 2 : 1)); }
     fence_barrier_init();
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
-  if (MODE == EPI_ACTMUL && threadIdx.x >= 64) {
+  if (MODE == EPI_ACTMUL && threadIdx.x >= 64 && threadIdx.x < 64 + kNE * 32) {
     for (int i = threadIdx.x - 64; i < 256; i += kNE * 32) lut_s[i] = __ldg(p.lut + i);
   }
   tc_fence_before();
@@ -140,6 +154,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int pstage = 0; uint32_t pphase = 0;
+      (void)pstage; (void)pphase;
       for (int t = unit; t < num_tiles; t += num_units) {
         const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + pair_rank * L::kBRows;
         for (int k = 0; k < k_iters; ++k) {
@@ -153,6 +169,14 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                                   n0 + pair_id * L::kBBoxRows, (uint16_t)(0x5u << pair_rank));
             else
               tma_load_2d_pair(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+          } else if (W4) {
+            // A into the operand stage; the packed B k-slice (64 bytes per row) into the packed ring for the unpack warps
+            mbar_expect_tx(&full_bar[stage], L::kABytes);
+            tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
+            mbar_wait(&pempty_bar[pstage], pphase ^ 1);
+            mbar_expect_tx(&pfull_bar[pstage], L::kPBytes);
+            tma_load_2d(smem_p + pstage * L::kPBytes, &tmap_b, &pfull_bar[pstage], k * (kBK / 2), n0);
+            if (++pstage == L::kPStages) { pstage = 0; pphase ^= 1; }
           } else {
             mbar_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
@@ -196,7 +220,45 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 2) {
+  } else if (W4 && warp >= 2 + kNE) {
+    // ===================== nibble expansion (W4) =====================
+    // packed ring slot: 256 rows x 64 B, TMA SWIZZLE_64B (16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3)); operand
+    // slot: 256 rows x 128 B, SWIZZLE_128B (chunk c at c ^ (r & 7)).  A thread expands 16 packed bytes (32 codes, low nibble
+    // first) of one row per step: 8 consecutive lanes take 8 consecutive rows, so loads and stores are bank-conflict free.
+    const int ut = threadIdx.x - (64 + kNE * 32);
+    int stage = 0; uint32_t phase = 0;
+    int pstage = 0; uint32_t pphase = 0;
+    for (int t = unit; t < num_tiles; t += num_units) {
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);            // the MMAs that read this operand slot have retired
+        mbar_wait(&pfull_bar[pstage], pphase);              // the packed k-slice has landed
+        const uint8_t* src = smem_p + pstage * L::kPBytes;
+        uint8_t* dst = smem_b + stage * L::kBBytes;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int task = it * (kUnpackWarps * 32) + ut;
+          const int r = task & 255, c = task >> 8;          // row, packed 16-byte chunk (4 per row)
+          const uint4 pk = *reinterpret_cast<const uint4*>(src + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+          const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = w[j] & 0x0F0F0F0Fu, hi = (w[j] >> 4) & 0x0F0F0F0Fu;
+            o[2 * j] = __byte_perm(lo, hi, 0x5140);         // codes 0..3 of the word: lo0 hi0 lo1 hi1
+            o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);     // codes 4..7:             lo2 hi2 lo3 hi3
+          }
+          uint8_t* drow = dst + r * 128;
+          *reinterpret_cast<uint4*>(drow + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(drow + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&full_bar[stage]); mbar_arrive(&pempty_bar[pstage]); }
+        if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        if (++pstage == L::kPStages) { pstage = 0; pphase ^= 1; }
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + kNE) {
     // ===================== epilogue =====================
     const int ew = warp - 2;                 // 0..kNE-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
@@ -423,24 +485,26 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
-template <int MODE, int CL, int NE>
+template <int MODE, int CL, int NE, bool W4 = false>
 static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& args, float* resid, int a_signed, int b_signed,
                          cudaStream_t st) {
-  using L = SmemLayout<MODE, CL, NE>;
+  using L = SmemLayout<MODE, CL, NE, W4>;
   constexpr bool PAIR = CL >= 2;
-  constexpr int kThreads = 64 + NE * 32;
+  constexpr int kThreads = 64 + NE * 32 + (W4 ? kUnpackWarps * 32 : 0);
   CUtensorMap ta, tb, tr;
+  // W4: b is the packed matrix [N, K/2] (64-byte boxes, SWIZZLE_64B) -- it is expanded inside the kernel
   if (!make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, a, args.M, args.K, args.K, kBM) ||
-      !make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBBoxRows))
+      !(W4 ? make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K / 2, args.K / 2, kBN, 64)
+           : make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBBoxRows)))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
   tr = ta;
   if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32, L::kCW * 4))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the residual stream (16B-aligned pointer, ldo % 4 == 0)");
   static int max_units = -1;                    // co-resident clusters of this variant (GPC boundaries can cost a few)
   if (max_units < 0) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    if (CL > 2 && (e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess)
+    if (CL > 2 && (e = cudaFuncSetAttribute(qgemm_kernel<MODE, CL, NE, W4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess)
       return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute(cluster): ") + cudaGetErrorString(e));
     max_units = c->sm_count / CL;
     if (PAIR) {
@@ -451,7 +515,7 @@ static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& 
       qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, qgemm_kernel<MODE, CL, NE>, &q) == cudaSuccess && n > 0 && n < max_units) max_units = n;
+      if (cudaOccupancyMaxActiveClusters(&n, qgemm_kernel<MODE, CL, NE, W4>, &q) == cudaSuccess && n > 0 && n < max_units) max_units = n;
       cudaGetLastError();
     }
   }
@@ -465,7 +529,7 @@ static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = PAIR ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, CL, NE>, ta, tb, tr, args, idesc);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, CL, NE, W4>, ta, tb, tr, args, idesc);
   if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemm launch: ") + cudaGetErrorString(e));
   return check_launch(c, "mq_qgemm");
 }
@@ -510,14 +574,15 @@ static int launch_qgemm(Ctx* c, const void* a, const void* b, const QGemmArgs& a
 
 using namespace mq;
 
-extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
-                        const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
-                        int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
-                        int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
-                        void* stream) {
+static int qgemm_entry(void* ctx, bool w4, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
+                       const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                       int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
+                       int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                       void* stream) {
   MQ_CTX(c, ctx);
   MQ_REQUIRE(c, a_codes && b_codes && M > 0 && N > 0 && K > 0, "null operand or empty problem");
   MQ_REQUIRE(c, K % 16 == 0, "K must be a multiple of 16 bytes (TMA row pitch)");
+  MQ_REQUIRE(c, !w4 || K % 32 == 0, "packed 4-bit weights: K must be a multiple of 32 (16-byte rows of packed codes)");
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(a_codes) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_codes) & 15) == 0,
              "operands must be 16-byte aligned");
   MQ_REQUIRE(c, rowsum && sxw && ow && c0, "rowsum / sxw / ow / c0 are required");
@@ -539,6 +604,15 @@ extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void
 #endif
   args.qgroup = qgroup > 0 ? qgroup : 32; args.rowsum_out = rowsum_out; args.lut = lut; args.s2 = s2; args.o2 = o2; args.qmax2 = qmax2;
   cudaStream_t st = (cudaStream_t)stream;
+  if (w4) {          // packed weights: single-CTA variant, 8 epilogue warps + 4 nibble-expansion warps; codes are unsigned nibbles
+    switch (mode) {
+      case EPI_QUANT: return launch_qgemm2<EPI_QUANT, 1, 8, true>(c, a_codes, b_codes, args, resid, a_signed, 0, st);
+      case EPI_ACTMUL: return launch_qgemm2<EPI_ACTMUL, 1, 8, true>(c, a_codes, b_codes, args, resid, a_signed, 0, st);
+      case EPI_RESID: return launch_qgemm2<EPI_RESID, 1, 8, true>(c, a_codes, b_codes, args, resid, a_signed, 0, st);
+      case EPI_F32: return launch_qgemm2<EPI_F32, 1, 8, true>(c, a_codes, b_codes, args, resid, a_signed, 0, st);
+      default: return launch_qgemm2<EPI_I32, 1, 8, true>(c, a_codes, b_codes, args, resid, a_signed, 0, st);
+    }
+  }
   switch (mode) {
     case EPI_QUANT: return launch_qgemm<EPI_QUANT>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
     case EPI_ACTMUL: return launch_qgemm<EPI_ACTMUL>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
@@ -546,4 +620,22 @@ extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void
     case EPI_F32: return launch_qgemm<EPI_F32>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
     default: return launch_qgemm<EPI_I32>(c, a_codes, b_codes, args, resid, a_signed, b_signed, st);
   }
+}
+
+extern "C" int mq_qgemm(void* ctx, const void* a_codes, int a_signed, const void* b_codes, int b_signed, int M, int N, int K,
+                        const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                        int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
+                        int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                        void* stream) {
+  return qgemm_entry(ctx, false, a_codes, a_signed, b_codes, b_signed, M, N, K, rowsum, sxw, ow, c0, bias, mode, so, oo, qmax, out_bits, out,
+                     ldo, rowsum_out, lut, s2, o2, qmax2, resid, qgroup, stream);
+}
+
+extern "C" int mq_qgemm_w4a8(void* ctx, const void* a_codes, int a_signed, const void* b_packed, int M, int N, int K,
+                             const int32_t* rowsum, const float* sxw, const int32_t* ow, const int32_t* c0, const float* bias,
+                             int mode, const float* so, const float* oo, float qmax, int out_bits, void* out, int64_t ldo,
+                             int32_t* rowsum_out, const float* lut, float s2, float o2, float qmax2, float* resid, int qgroup,
+                             void* stream) {
+  return qgemm_entry(ctx, true, a_codes, a_signed, b_packed, 0, M, N, K, rowsum, sxw, ow, c0, bias, mode, so, oo, qmax, out_bits, out,
+                     ldo, rowsum_out, lut, s2, o2, qmax2, resid, qgroup, stream);
 }

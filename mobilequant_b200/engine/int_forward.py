@@ -79,6 +79,8 @@ class IntEngine:
         # (TinyLlama, batch 8, graph replay): fused 1.76 ms/step, separate 1.67 ms/step -- the last-arriving CTA serialises
         # the group's epilogue while a graph node costs less than that -- so the two-launch form is the default.
         self.fused_gemv = os.environ.get("MQB200_GEMV_FUSED", "0") == "1"
+        # prefill with packed 4-bit weights: fused int4 x int8 GEMM (default) or mq_unpack4 into scratch + the W8 GEMM ("0")
+        self.fused_w4 = os.environ.get("MQB200_W4_FUSED", "1") != "0"
         # decode: the residual epilogues of o_proj / w2 ride on the following row norm (two launches per layer fewer)
         self.fused_resid_norm = os.environ.get("MQB200_RESID_NORM", "1") != "0"
 
@@ -202,13 +204,19 @@ class IntEngine:
         return L
 
     def _pack(self, g):
-        """4-bit matrix (already arranged: fused / interleaved / K-padded) -> two codes per byte; the int8 copy is dropped."""
+        """4-bit matrix (already arranged: fused / interleaved / K-padded) -> two UNSIGNED codes per byte (low nibble first); the
+        int8 copy is dropped.  Symmetric weights (codes -8..7) are stored in offset-binary form code + 8 with the per-column
+        zero point raised by 8 -- c0 = K*ox*ow - ox*colsum is invariant under that shift -- so one format serves the fused
+        int4 x int8 GEMM (mq_qgemm_w4a8: nibbles expanded inside the kernel) and the decode path (mq_unpack4)."""
         c = g["codes"]
-        if g["wbits"] > 4 or (c.shape[0] * c.shape[1]) % 32 or c.shape[1] % 2:
+        if g["wbits"] > 4 or (c.shape[0] * c.shape[1]) % 32 or c.shape[1] % 32:
             return
         u = c.view(torch.uint8)
+        if c.dtype == torch.int8:
+            u = (u + 8) & 0xF
+            g["ow"] = (g["ow"] + 8).contiguous()
         g["packed"] = ((u[:, 0::2] & 0xF) | ((u[:, 1::2] & 0xF) << 4)).contiguous()
-        g["shape"], g["dtype"] = tuple(c.shape), c.dtype
+        g["shape"], g["dtype"] = tuple(c.shape), torch.uint8
         g["codes"] = None
 
     def _codes(self, g):
@@ -295,6 +303,9 @@ class IntEngine:
         return self._bufs[key]
 
     def _gemm(self, a, g, rowsum, mode, **kw):
+        if g["codes"] is None and self.fused_w4:        # packed 4-bit weights: expanded inside the GEMM (no scratch copy)
+            return K.qgemm(a, g["packed"], rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
+                           qgroup=g["qgroup"], packed4=True, **kw)
         return K.qgemm(a, self._codes(g), rowsum, g["sxw"], g["ow"], g["c0"], mode, bias=g["bias"], so=g["so"], oo=g["oo"], qmax=g["qmax"],
                        qgroup=g["qgroup"], **kw)
 

@@ -25,6 +25,8 @@ def _protos():
                                  _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qgemm.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
                              c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P]
+    lib.mq_qgemm_w4a8.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
+                                  c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P]
     lib.mq_qnorm.argtypes = [_P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float,
                              c_float, c_float, _P, _P, _P]
     lib.mq_qnorm_resid.argtypes = [_P, _P, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float, c_float, c_float,
@@ -206,13 +208,14 @@ EPI_QUANT, EPI_ACTMUL, EPI_RESID, EPI_F32, EPI_I32 = 0, 1, 2, 3, 4
 
 
 def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255.0, out_bits=8, out=None, ldo=None,
-          rowsum_out=None, lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None):
+          rowsum_out=None, lut=None, s2=1.0, o2=0.0, qmax2=255.0, resid=None, qgroup=None, packed4=False):
     """a: [M,K] uint8/int8 codes, b: [N,K] uint8/int8 codes.  so/oo: one entry per `qgroup` columns (default: one
-    entry for the whole N when they have a single element).  See include/mqb200.h:mq_qgemm."""
+    entry for the whole N when they have a single element).  See include/mqb200.h:mq_qgemm.
+    packed4: b is [N, K/2] uint8 holding two unsigned 4-bit codes per byte (mq_qgemm_w4a8: expanded inside the kernel)."""
     lib = _protos()
     M, K = a.shape
     N = b.shape[0]
-    assert b.shape[1] == K
+    assert b.shape[1] == (K // 2 if packed4 else K)
     dev = a.device
     if out is None and mode != EPI_RESID:
         if mode == EPI_QUANT:
@@ -232,11 +235,14 @@ def qgemm(a, b, rowsum, sxw, ow, c0, mode, bias=None, so=None, oo=None, qmax=255
     if so is not None and mode in (EPI_QUANT, EPI_ACTMUL, EPI_RESID):
         assert qgroup > 0 and so.numel() == (N + qgroup - 1) // qgroup == oo.numel(), "so/oo need one entry per qgroup columns"
     h = _h(a)
+    tail = (ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias), int(mode), ptr(so), ptr(oo),
+            float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out), ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid),
+            int(qgroup), stream_ptr())
     with torch.cuda.device(dev):
-        check(_launch("qgemm", lib.mq_qgemm, h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K,
-                           ptr(rowsum, torch.int32), ptr(sxw, F32), ptr(ow, torch.int32), ptr(c0, torch.int32), ptr(bias),
-                           int(mode), ptr(so), ptr(oo), float(qmax), int(out_bits), ptr(out), int(ldo), ptr(rowsum_out),
-                           ptr(lut), float(s2), float(o2), float(qmax2), ptr(resid), int(qgroup), stream_ptr()), h)
+        if packed4:
+            check(_launch("qgemm", lib.mq_qgemm_w4a8, h, ptr(a), int(a.dtype == torch.int8), ptr(b, torch.uint8), M, N, K, *tail), h)
+        else:
+            check(_launch("qgemm", lib.mq_qgemm, h, ptr(a), int(a.dtype == torch.int8), ptr(b), int(b.dtype == torch.int8), M, N, K, *tail), h)
     return resid if mode == EPI_RESID else out
 
 

@@ -146,3 +146,46 @@ def test_qgemm_cluster_variants(cuda, cl, ne, M, N, K, monkeypatch):
     got = run_all()
     for x, y in zip(base, got):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(300, 512, 256, "quant"), (1024, 2560, 2048, "quant"), (257, 768, 1056, "i32"), (512, 2048, 5632, "resid"),
+                                        (384, 1024, 2048, "actmul")])
+def test_qgemm_w4a8_packed_equals_unpacked(cuda, M, N, K, mode):
+    """mq_qgemm_w4a8 (nibbles expanded inside the kernel) == mq_qgemm on the one-code-per-byte matrix, bit for bit, for every
+    epilogue, ragged M, K not a multiple of the 128-code k-slice, multi-tile N; plus the exact int64 accumulator."""
+    from mobilequant_b200 import kernels as K_
+    rng = np.random.default_rng(M + N + K)
+    a = rng.integers(0, 256, size=(M, K)).astype(np.uint8)
+    wu = rng.integers(0, 16, size=(N, K)).astype(np.uint8)                   # unsigned 4-bit codes (offset-binary for symmetric weights)
+    packed = (wu[:, 0::2] | (wu[:, 1::2] << 4)).astype(np.uint8)
+    ow = rng.integers(6, 10, size=N).astype(np.int32)
+    ox = 117
+    colsum = wu.astype(np.int64).sum(1)
+    c0 = (K * ox * ow.astype(np.int64) - ox * colsum).astype(np.int32)
+    sxw = (rng.uniform(0.5, 1.5, size=N) * 1e-3).astype(np.float32)
+    dev = lambda x: torch.from_numpy(x).to(cuda)
+    A, Wd, Pd = dev(a), dev(wu), dev(packed)
+    rowsum = dev(a.astype(np.int64).sum(1).astype(np.int32))
+    common = dict(rowsum=rowsum, sxw=dev(sxw), ow=dev(ow), c0=dev(c0))
+    if mode == "i32":
+        ref = K_.qgemm(A, Wd, mode=K_.EPI_I32, **common)
+        got = K_.qgemm(A, Pd, mode=K_.EPI_I32, packed4=True, **common)
+        exact = (a.astype(np.int64) - ox) @ (wu.astype(np.int64) - ow[:, None]).T
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), exact)
+    elif mode == "quant":
+        so, oo = torch.tensor([0.02], device=cuda), torch.tensor([131.0], device=cuda)
+        rs1 = torch.zeros(M, dtype=torch.int32, device=cuda); rs2 = torch.zeros_like(rs1)
+        ref = K_.qgemm(A, Wd, mode=K_.EPI_QUANT, so=so, oo=oo, rowsum_out=rs1, **common)
+        got = K_.qgemm(A, Pd, mode=K_.EPI_QUANT, so=so, oo=oo, rowsum_out=rs2, packed4=True, **common)
+        assert torch.equal(rs1, rs2)
+    elif mode == "resid":
+        so, oo = torch.tensor([3e-4], device=cuda), torch.tensor([32768.0], device=cuda)
+        h0 = torch.randn(M, N, generator=torch.Generator().manual_seed(1)).to(cuda)
+        ref = K_.qgemm(A, Wd, mode=K_.EPI_RESID, so=so, oo=oo, qmax=65535.0, resid=h0.clone(), **common)
+        got = K_.qgemm(A, Pd, mode=K_.EPI_RESID, so=so, oo=oo, qmax=65535.0, resid=h0.clone(), packed4=True, **common)
+    else:
+        so = torch.full((N // 128,), 0.02, device=cuda); oo = torch.full((N // 128,), 128.0, device=cuda)
+        lut = torch.linspace(-1, 3, 256, device=cuda)
+        ref = K_.qgemm(A, Wd, mode=K_.EPI_ACTMUL, so=so, oo=oo, lut=lut, s2=0.05, o2=120.0, **common)
+        got = K_.qgemm(A, Pd, mode=K_.EPI_ACTMUL, so=so, oo=oo, lut=lut, s2=0.05, o2=120.0, packed4=True, **common)
+    assert torch.equal(got, ref)
