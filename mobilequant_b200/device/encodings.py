@@ -188,7 +188,8 @@ def export_quantized_weights(model, qcfg, pack4=True):
             raise RuntimeError("export_quantized_weights runs on a CUDA device (no CPU fallback)")
         do_pack = pack4 and bits == 4 and w.shape[1] % 2 == 0 and (w.shape[0] * w.shape[1]) % 32 == 0
         out = K.wprep_fwd(w, bits, sym, pc, want_fq=False, want_codes=True, pack4=do_pack)
-        weights[name] = {"codes": out["codes"].cpu(), "scale": out["scale"].cpu(), "offset": out["offset"].cpu(), "bitwidth": bits,
+        codes = out["codes"].view(torch.uint8) if do_pack else out["codes"]        # packed bytes are raw nibble pairs (two's complement for symmetric)
+        weights[name] = {"codes": codes.cpu(), "scale": out["scale"].cpu(), "offset": out["offset"].cpu(), "bitwidth": bits,
                          "is_symmetric": sym, "is_per_channel": pc, "packed": bool(do_pack), "shape": tuple(w.shape)}
         qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if sym else (0, 2 ** bits - 1)
         rows = []
