@@ -53,6 +53,7 @@ struct QGemmArgs {
   int32_t* rowsum_out;     // [M] atomically accumulated sum of the emitted codes (or null)
   const float* lut;        // [256] EPI_ACTMUL: act(w1 code) as fp32 (QSiLU/QGELU folded, qm:739-753)
   float s2, o2, qmax2;     // EPI_ACTMUL: w2.input_quantizer
+  int split_f;             // tail wave: the tiles of the last, partial wave are split into split_f column slices (1, 2 or 4)
   int dbg;                 // measurement only (MQ_QGEMM_DBG): 1 = epilogue releases the accumulator without reading it
 };
 
@@ -99,7 +100,8 @@ constexpr int kUnpackWarps = 4;
 template <int MODE, int CL, int NE, bool W4 = false>
 __global__ void __launch_bounds__(64 + NE * 32 + (W4 ? kUnpackWarps * 32 : 0), 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ CUtensorMap tmap_r, const QGemmArgs p, const uint32_t idesc) {
+             const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_b2, const QGemmArgs p,
+             const uint32_t idesc, const uint32_t idesc2) {
   using L = SmemLayout<MODE, CL, NE, W4>;
   constexpr bool PAIR = CL >= 2, QUAD = CL == 4;
   constexpr int kNE = NE, kParts = NE / 4, CW = L::kCW;        // kParts = column parts per TMEM lane quarter
@@ -127,11 +129,24 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int m_tiles = (p.M + kCtas * kBM - 1) / (kCtas * kBM), n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_iters = (p.K + kBK - 1) / kBK;
+  // Tail-wave splitting: the persistent units walk whole 128(x CL) x 256 tiles for every complete wave; the tiles of the last,
+  // partial wave are cut into split_f column slices (own TMA box / UMMA N), so that e.g. 68 left-over tiles keep 136 of 148
+  // SMs busy for half a tile time instead of 68 SMs for a whole one (o_proj at batch 8 x seq 1024: 4 -> 3.5 waves).
+  const int SF = p.split_f;
+  const int full_tiles = SF > 1 ? (num_tiles / num_units) * num_units : num_tiles;
+  const int num_items = full_tiles + (num_tiles - full_tiles) * SF;
+  const int sub_cols = BN / SF;
+  // work item -> (tile, first column inside the tile, columns)
+  auto item_tile = [&](int w, int& t, int& c0, int& nc) {
+    if (w < full_tiles) { t = w; c0 = 0; nc = BN; }
+    else { const int s2 = w - full_tiles; t = full_tiles + s2 / SF; c0 = (s2 % SF) * sub_cols; nc = sub_cols; }
+  };
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();                 // the swizzle math below assumes a 1024B-aligned window
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_b2);
     if (MODE == EPI_RESID) prefetch_tmap(&tmap_r);
     // QUAD: a stage is free once BOTH pairs have retired the MMAs that read it (the B quarters are written across pairs)
     // W4: a stage is full once the A tile has landed (1 arrival + tx bytes) AND the four unpack warps have written the B tile
@@ -156,19 +171,22 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int pstage = 0; uint32_t pphase = 0;
       (void)pstage; (void)pphase;
-      for (int t = unit; t < num_tiles; t += num_units) {
-        const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + pair_rank * L::kBRows;
+      for (int w = unit; w < num_items; w += num_units) {
+        int t, c0, nc; item_tile(w, t, c0, nc);
+        const bool sub = nc != BN;                           // column slice of a tail-wave tile: smaller B box (tmap_b2)
+        const int brows = PAIR ? nc / 2 : nc;                // B rows this CTA loads
+        const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + c0 + pair_rank * brows;
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
             // the pair leader's barrier collects the bytes of both CTAs
-            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (L::kABytes + brows * kBK));
             tma_load_2d_pair(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
             if (QUAD)   // this CTA's quarter of the B tile, delivered to the same half of both pairs
               tma_load_2d_pair_mc(smem_b + stage * L::kBBytes + pair_id * (L::kBBoxRows * kBK), &tmap_b, &full_bar[stage], k * kBK,
                                   n0 + pair_id * L::kBBoxRows, (uint16_t)(0x5u << pair_rank));
             else
-              tma_load_2d_pair(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+              tma_load_2d_pair(smem_b + stage * L::kBBytes, sub ? &tmap_b2 : &tmap_b, &full_bar[stage], k * kBK, n0);
           } else if (W4) {
             // A into the operand stage; the packed B k-slice (64 bytes per row) into the packed ring for the unpack warps
             mbar_expect_tx(&full_bar[stage], L::kABytes);
@@ -178,9 +196,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tma_load_2d(smem_p + pstage * L::kPBytes, &tmap_b, &pfull_bar[pstage], k * (kBK / 2), n0);
             if (++pstage == L::kPStages) { pstage = 0; pphase ^= 1; }
           } else {
-            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            mbar_expect_tx(&full_bar[stage], L::kABytes + brows * kBK);
             tma_load_2d(smem_a + stage * L::kABytes, &tmap_a, &full_bar[stage], k * kBK, m0);
-            tma_load_2d(smem_b + stage * L::kBBytes, &tmap_b, &full_bar[stage], k * kBK, n0);
+            tma_load_2d(smem_b + stage * L::kBBytes, sub ? &tmap_b2 : &tmap_b, &full_bar[stage], k * kBK, n0);
           }
           if (++stage == L::kStages) { stage = 0; phase ^= 1; }
         }
@@ -191,7 +209,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint16_t pair_mask = (uint16_t)(0x3u << (2 * pair_id)), all_mask = (uint16_t)((1u << CL) - 1u);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
+    for (int w = unit; w < num_items; w += num_units) {
+      int t, c0, nc; item_tile(w, t, c0, nc);
+      const uint32_t idesc_w = nc != BN ? idesc2 : idesc;  // UMMA N of a column slice
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -204,8 +224,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
             // advance both descriptors by kk*32 bytes inside the 128B swizzle row (address field is in 16B units)
-            if (PAIR) mma_i8_pair(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc, (k | kk) != 0);
-            else mma_i8(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc, (k | kk) != 0);
+            if (PAIR) mma_i8_pair(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc_w, (k | kk) != 0);
+            else mma_i8(tmem_d, adesc + uint64_t(kk * (kUmmaK >> 4)), bdesc + uint64_t(kk * (kUmmaK >> 4)), idesc_w, (k | kk) != 0);
           }
           if (PAIR) {
             tc_commit_pair(&empty_bar[stage], all_mask);                       // smem slot free once these MMAs retire
@@ -228,7 +248,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int ut = threadIdx.x - (64 + kNE * 32);
     int stage = 0; uint32_t phase = 0;
     int pstage = 0; uint32_t pphase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
+    for (int w = unit; w < num_items; w += num_units) {
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(&empty_bar[stage], phase ^ 1);            // the MMAs that read this operand slot have retired
         mbar_wait(&pfull_bar[pstage], pphase);              // the packed k-slice has landed
@@ -268,8 +288,9 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint8_t* stage_out = smem + L::kOutOff + ew * L::kOutBufs * L::kOutTile;
     int out_buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = unit; t < num_tiles; t += num_units) {
-      const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN;
+    for (int w = unit; w < num_items; w += num_units) {
+      int t, c0s, nc; item_tile(w, t, c0s, nc);
+      const int m0 = (t / n_tiles) * (kCtas * kBM) + cta_rank * kBM, n0 = (t % n_tiles) * BN + c0s;
       // stage the per-column parameters of this tile (double buffered with the accumulator)
       float* cp = colp + acc * CP_COUNT * BN;
       int* cpi = reinterpret_cast<int*>(cp);
@@ -367,7 +388,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         }
         });
       } else {
-        constexpr int W = BN / kParts;
+        const int W = nc / kParts;                       // a column slice of a tail-wave tile is narrower (nc a multiple of kParts * CW)
         for (int cc = part * W; cc < (part + 1) * W; cc += CW) {
           if (n0 + cc >= p.N) break;
           uint32_t r[CW];
@@ -498,6 +519,7 @@ static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& 
            : make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBBoxRows)))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed (pointers must be 16B aligned, K a multiple of 16)");
   tr = ta;
+  CUtensorMap tb2 = tb;
   if (MODE == EPI_RESID && !make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, resid, args.M, args.N, args.ldo * 4, 32, L::kCW * 4))
     return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the residual stream (16B-aligned pointer, ldo % 4 == 0)");
   static int max_units = -1;                    // co-resident clusters of this variant (GPC boundaries can cost a few)
@@ -522,14 +544,27 @@ static int launch_qgemm2(Ctx* c, const void* a, const void* b, const QGemmArgs& 
   const int m_tiles = (args.M + CL * kBM - 1) / (CL * kBM), n_tiles = (args.N + kBN - 1) / kBN;
   int units = m_tiles * n_tiles;
   if (units > max_units) units = max_units;
+  // tail-wave splitting (see the kernel): column slices for the tiles of the last, partial wave.  MQ_QGEMM_SPLIT=0 disables it.
+  QGemmArgs args2 = args;
+  args2.split_f = 1;
+  {
+    const char* e = getenv("MQ_QGEMM_SPLIT");
+    const int rem = (m_tiles * n_tiles) % units;
+    if (!(e && e[0] == '0') && MODE != EPI_ACTMUL && !W4 && CL <= 2 && rem > 0) {
+      if (rem * 4 <= units) args2.split_f = 4; else if (rem * 2 <= units) args2.split_f = 2;
+    }
+    if (args2.split_f > 1 && !make_tmap_2d(&tb2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, b, args.N, args.K, args.K, L::kBBoxRows / args2.split_f))
+      return fail(c, MQ_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the tail-wave column slices");
+  }
   const uint32_t idesc = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, (PAIR ? 2 : 1) * kBM, kBN);
+  const uint32_t idesc2 = make_idesc(2u, a_signed ? 1u : 0u, b_signed ? 1u : 0u, 0u, 0u, (PAIR ? 2 : 1) * kBM, kBN / args2.split_f);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CL); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = PAIR ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, CL, NE, W4>, ta, tb, tr, args, idesc);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm_kernel<MODE, CL, NE, W4>, ta, tb, tr, tb2, args2, idesc, idesc2);
   if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemm launch: ") + cudaGetErrorString(e));
   return check_launch(c, "mq_qgemm");
 }
@@ -598,7 +633,7 @@ static int qgemm_entry(void* ctx, bool w4, const void* a_codes, int a_signed, co
   QGemmArgs args;
   args.M = M; args.N = N; args.K = K; args.rowsum = rowsum; args.sxw = sxw; args.ow = ow; args.c0 = c0;
   args.bias = bias; args.so = so; args.oo = oo; args.qmax = qmax; args.out_bits = out_bits; args.out = out; args.ldo = ldo;
-  args.dbg = 0;
+  args.dbg = 0; args.split_f = 1;
 #ifdef MQ_MEASURE_KNOBS   // measurement builds only (MQB200_MEASURE=1 python -m mobilequant_b200.build --force): dbg 1 drops the epilogue
   { const char* e = getenv("MQ_QGEMM_DBG"); args.dbg = e ? atoi(e) : 0; }
 #endif

@@ -1,7 +1,10 @@
-import os, sys, torch, time
-sys.path.insert(0, "/root/repo")
+"""qgemm micro-bench: the four GEMMs of a TinyLlama block at batch 8 x seq 1024, default dispatch, with / without tail-wave splitting."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mobilequant_b200 import kernels as Kn
 cuda = torch.device("cuda:0")
+
+
 def run(M, N, K, mode=Kn.EPI_QUANT, iters=20):
     a = torch.randint(0, 256, (M, K), dtype=torch.uint8, device=cuda)
     b = torch.randint(0, 256, (N, K), dtype=torch.uint8, device=cuda)
@@ -12,27 +15,22 @@ def run(M, N, K, mode=Kn.EPI_QUANT, iters=20):
     kw = dict(so=so, oo=oo, qmax=255.0, qgroup=128)
     if mode == Kn.EPI_ACTMUL: kw.update(lut=lut, s2=0.01, o2=128.0)
     if mode == Kn.EPI_RESID: kw.update(resid=torch.zeros(M, N, device=cuda), qmax=65535.0)
-    out = None
-    for _ in range(3): out = Kn.qgemm(a, b, rowsum, sxw, ow, c0, mode, **kw)
+    for _ in range(3): Kn.qgemm(a, b, rowsum, sxw, ow, c0, mode, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters): Kn.qgemm(a, b, rowsum, sxw, ow, c0, mode, **kw)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print(f"M={M} N={N} K={K} mode={mode}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TOP/s")
-for spec in (sys.argv[1:] or ["1/8", "1/16", "2/8", "2/16", "4/16"]):
-    cl, ne = spec.split("/")
-    os.environ["MQ_QGEMM_CL"] = cl; os.environ["MQ_QGEMM_NE"] = ne
-    print("== cluster", cl, "epilogue warps", ne, flush=True)
-    for M in (8192,):
-        run(M, 2560, 2048); run(M, 2048, 2048, Kn.EPI_RESID); run(M, 11264, 2048, Kn.EPI_ACTMUL); run(M, 2048, 5632, Kn.EPI_RESID)
-        run(M, 8192, 8192, Kn.EPI_I32)
-# library proxy for the INT8 peak
-a = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=cuda); b = torch.randint(-128, 127, (8192, 8192), dtype=torch.int8, device=cuda)
-for _ in range(3): torch._int_mm(a, b.t())
-torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20): torch._int_mm(a, b.t())
-e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 20
-print(f"torch._int_mm 8192^3: {ms*1e3:.1f} us {2*8192**3/ms/1e9:.1f} TOP/s")
+    print(f"  N={N:6d} K={K:5d} mode={mode}: {ms*1e3:7.1f} us  {2*M*N*K/ms/1e9:7.1f} TOP/s", flush=True)
+    return ms, 2.0 * M * N * K
+
+
+for split in (sys.argv[1:] or ["1", "0"]):
+    os.environ["MQ_QGEMM_SPLIT"] = split
+    print("== tail-wave splitting", "on" if split != "0" else "off", flush=True)
+    tot_ms, tot_ops = 0.0, 0.0
+    for N, K, mode in ((2560, 2048, Kn.EPI_QUANT), (2048, 2048, Kn.EPI_RESID), (11264, 2048, Kn.EPI_ACTMUL), (2048, 5632, Kn.EPI_RESID)):
+        ms, ops = run(8192, N, K, mode)
+        tot_ms += ms; tot_ops += ops
+    print(f"  block total {tot_ms*1e3:.1f} us -> {tot_ops/tot_ms/1e9:.1f} TOP/s", flush=True)
