@@ -34,7 +34,7 @@ constexpr int kUmmaK = 32;        // 8-bit operands: 32 elements per MMA
 // that 576 threads fit the register file).
 
 enum { EPI_QUANT = 0, EPI_ACTMUL = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_I32 = 4 };
-enum { CP_NEGOW = 0, CP_C0, CP_SXW, CP_BIAS, CP_COUNT };
+enum { CP_NEGOW = 0, CP_C0, CP_SXW, CP_BIAS, CP_Q, CP_COUNT };   // CP_Q: output quantizer (scale [0..8), offset [8..16)) per 32-column chunk
 
 struct QGemmArgs {
   int M, N, K;
@@ -302,12 +302,20 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         cp[CP_SXW * BN + c] = ok ? __ldg(p.sxw + n) : 0.f;
         cp[CP_BIAS * BN + c] = (ok && has_bias) ? __ldg(p.bias + n) : 0.f;
       }
+      // the output quantizer of every 32-column chunk of the tile (so / oo are per column group): staged with the column
+      // parameters so that no global load sits between the accumulator's arrival and the first requantisation
+      if (etid < BN / 32 && MODE != EPI_F32 && MODE != EPI_I32) {
+        const int g = min((n0 + etid * 32) / p.qgroup, (p.N - 1) / p.qgroup);
+        cp[CP_Q * BN + etid] = __ldg(p.so + g);
+        cp[CP_Q * BN + 8 + etid] = __ldg(p.oo + g);
+      }
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M && p.dbg != 1;
+      const int rs = row_ok ? __ldg(p.rowsum + row) : 0;      // (issued before the wait: its latency hides behind the MMAs)
       asm volatile("bar.sync 1, %0;" ::"n"(kNE * 32) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M && p.dbg != 1;
       if (p.dbg == 1) {
         tc_fence_before();
         __syncwarp();
@@ -315,7 +323,6 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      const int rs = row_ok ? __ldg(p.rowsum + row) : 0;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
       const int4* v_negow = reinterpret_cast<const int4*>(cpi + CP_NEGOW * BN);
       const int4* v_c0 = reinterpret_cast<const int4*>(cpi + CP_C0 * BN);
@@ -340,9 +347,8 @@ qgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           y[0] = __fadd_rn(y[0], b.x); y[1] = __fadd_rn(y[1], b.y); y[2] = __fadd_rn(y[2], b.z); y[3] = __fadd_rn(y[3], b.w);
         }
       };
-      auto group_q = [&](int col /* tile column */, float qmax) {
-        const int g = min((n0 + col) / p.qgroup, (p.N - 1) / p.qgroup);
-        return make_qparam(__ldg(p.so + g), __ldg(p.oo + g), qmax);
+      auto group_q = [&](int col /* tile column, multiple of 32 */, float qmax) {
+        return make_qparam(cp[CP_Q * BN + (col >> 5)], cp[CP_Q * BN + 8 + (col >> 5)], qmax);
       };
 
       if (MODE == EPI_ACTMUL) {
