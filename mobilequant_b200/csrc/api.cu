@@ -12,6 +12,30 @@ int fail(Ctx* c, int code, const std::string& what) {
   return code;
 }
 
+void* stream_ws(Ctx* c, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(c->ws_mutex);
+  for (auto& e : c->ws_by_stream)
+    if (e.first == st) return e.second;
+  void* p = nullptr;
+  if (c->ws_by_stream.empty()) {
+    p = c->ws;                                  // the buffer mq_setup allocated goes to the first stream
+  } else {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&p, c->ws_bytes);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fail(c, MQ_FAILED_ALLOCATION, std::string("per-stream workspace cudaMalloc: ") + cudaGetErrorString(e) +
+                                        " (a stream must be used once outside graph capture before it is captured)");
+      return nullptr;
+    }
+  }
+  c->ws_by_stream.emplace_back(st, p);
+  return p;
+}
+
 int check_launch(Ctx* c, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
@@ -97,6 +121,8 @@ int mq_ref_context(void* ctx) {
 int mq_release(void* ctx) {
   MQ_CTX(c, ctx);
   if (c->refs.fetch_sub(1) == 1) {
+    for (auto& e : c->ws_by_stream)
+      if (e.second && e.second != c->ws) cudaFree(e.second);
     if (c->ws) cudaFree(c->ws);
     if (c->counters) cudaFree(c->counters);
     c->magic = 0;

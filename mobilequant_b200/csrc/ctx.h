@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <string>
 #include <atomic>
+#include <mutex>
+#include <vector>
+#include <utility>
 #include "mqb200.h"
 
 namespace mq {
@@ -16,8 +19,13 @@ struct Ctx {
   std::atomic<int> refs{1};
   int device = 0;
   int sm_count = 148;
-  void* ws = nullptr;      // device scratch (deterministic two-stage reductions, split-K partials)
-  size_t ws_bytes = 0;
+  void* ws = nullptr;      // device scratch of the first stream seen (deterministic two-stage reductions, split-K partials)
+  size_t ws_bytes = 0;     // size of EVERY per-stream scratch buffer
+  // One scratch buffer per stream: kernels of different streams (the calibration step runs its weight pass on a side stream)
+  // must not share reduction partials.  Buffers are created on first use of a stream (never during a graph capture: the
+  // eager warm-up step of the calibration loops touches every stream first) and live as long as the context.
+  std::mutex ws_mutex;
+  std::vector<std::pair<cudaStream_t, void*>> ws_by_stream;
   int* counters = nullptr; // zero-initialised arrival counters of the fused skinny-GEMM epilogue (self-resetting)
   int n_counters = 0;
   std::string last_error[6];
@@ -29,6 +37,7 @@ inline Ctx* as_ctx(void* p) {
 }
 
 int fail(Ctx* c, int code, const std::string& what);
+void* stream_ws(Ctx* c, cudaStream_t st);      // scratch buffer (ws_bytes) owned by `st`; nullptr when it cannot be allocated
 int check_launch(Ctx* c, const char* what);
 
 }  // namespace mq

@@ -122,7 +122,8 @@ extern "C" int mq_adamw_step(void* ctx, float* params, const float* grads, float
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.state = state;
   // the optimiser owns the tail of the context's counter array (the skinny-GEMM epilogue uses the head) and the workspace
   // for the duration of its two launches (single stream per context, include/mqb200.h "Threading")
-  a.partial = reinterpret_cast<double*>(c->ws);
+  a.partial = reinterpret_cast<double*>(stream_ws(c, (cudaStream_t)stream));
+  if (!a.partial) return MQ_FAILED_ALLOCATION;
   a.ticket = reinterpret_cast<unsigned*>(c->counters + c->n_counters - 1);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t want = (n / 4 + kOptThreads - 1) / kOptThreads;

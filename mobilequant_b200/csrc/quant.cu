@@ -750,7 +750,9 @@ int mq_fq_bwd(void* ctx, const float* x, const float* g, float* gx, int64_t n, c
   }
   bool vec = (n % 4 == 0) && aligned16(x) && aligned16(g) && (!gx || aligned16(gx)) && (group % 4 == 0);
   int grid = grid_for(c, vec ? n / 4 : n, 256, 8);
-  double* partial = want ? reinterpret_cast<double*>(c->ws) : nullptr;
+  void* wsp = want ? stream_ws(c, st) : nullptr;
+  if (want && !wsp) return MQ_FAILED_ALLOCATION;
+  double* partial = reinterpret_cast<double*>(wsp);
   if (vec) fq_bwd_kernel<true><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial);
   else fq_bwd_kernel<false><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial);
   if (want) fq_bwd_final_kernel<<<1, 32, 0, st>>>(partial, grid, gscale, goffset);
@@ -763,7 +765,8 @@ int mq_minmax(void* ctx, const float* x, int64_t n, float* minmax, int accumulat
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = (n % 4 == 0) && aligned16(x);
   int grid = grid_for(c, vec ? n / 4 : n, 256 * 4, 8);
-  float* partial = reinterpret_cast<float*>(c->ws);
+  float* partial = reinterpret_cast<float*>(stream_ws(c, st));
+  if (!partial) return MQ_FAILED_ALLOCATION;
   if (vec) minmax_kernel<true><<<grid, 256, 0, st>>>(x, n, partial);
   else minmax_kernel<false><<<grid, 256, 0, st>>>(x, n, partial);
   minmax_final_kernel<<<1, 32, 0, st>>>(partial, grid, minmax, accumulate);
@@ -779,7 +782,8 @@ int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_
     minmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, cols, out_min, out_max, accumulate);
   } else {
     MQ_REQUIRE(c, size_t(cols) * 2 * sizeof(int) <= c->ws_bytes, "too many columns for the workspace");
-    int* ws = reinterpret_cast<int*>(c->ws);
+    int* ws = reinterpret_cast<int*>(stream_ws(c, st));
+    if (!ws) return MQ_FAILED_ALLOCATION;
     unsigned gx = (unsigned)((cols + 255) / 256);
     int seg = (int)((int64_t(c->sm_count) * 4 + gx - 1) / gx);
     if (seg > rows) seg = (int)rows;
@@ -818,7 +822,8 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
   MQ_REQUIRE(c, !pack4 || (cfg.bitwidth <= 4 && cols % 2 == 0), "pack4 needs bitwidth <= 4 and even cols");
   cudaStream_t st = (cudaStream_t)stream;
   LetArgs la{col_fac, row_fac, col_mode, row_mode};
-  float* row_mn = reinterpret_cast<float*>(c->ws);
+  float* row_mn = reinterpret_cast<float*>(stream_ws(c, st));
+  if (!row_mn) return MQ_FAILED_ALLOCATION;
   float* row_mx = row_mn + rows;
   const bool vec = wprep_vec_ok(cols, w, col_fac, w_fq, wt_out, codes, pack4);
   if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
@@ -847,7 +852,9 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   cudaStream_t st = (cudaStream_t)stream;
   LetArgs la{col_fac, row_fac, col_mode, row_mode};
   // workspace carve-up (all sized by rows): mn, mx | gs (double) | cmn, cmx | GroupGrad
-  char* p = reinterpret_cast<char*>(c->ws);
+  char* const ws0 = reinterpret_cast<char*>(stream_ws(c, st));
+  if (!ws0) return MQ_FAILED_ALLOCATION;
+  char* p = ws0;
   float* row_mn = reinterpret_cast<float*>(p); p += rows * sizeof(float);
   float* row_mx = reinterpret_cast<float*>(p); p += rows * sizeof(float);
   p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
@@ -857,7 +864,9 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   GroupGrad* gg = reinterpret_cast<GroupGrad*>(p); p += rows * sizeof(GroupGrad);
   p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   float* partial = reinterpret_cast<float*>(p);
-  size_t partial_cap = (c->ws_bytes - size_t(p - reinterpret_cast<char*>(c->ws))) / sizeof(float);
+  // (wprep_check bounds rows * 32 bytes; the carve-up above adds at most 32 bytes of alignment padding per context -- checked)
+  MQ_REQUIRE(c, size_t(p - ws0) + 16 <= c->ws_bytes, "too many rows for the workspace");
+  size_t partial_cap = (c->ws_bytes - size_t(p - ws0)) / sizeof(float);
 
   const bool vec = wprep_vec_ok(cols, w, col_fac, g, g_wt, scratch, 0);
   if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);

@@ -407,6 +407,33 @@ def _use_graphs(device):
     return device.type == "cuda" and os.environ.get("MQ_CUDA_GRAPH", "1") != "0"
 
 
+def _weight_stream(device):
+    """Side stream of the weight pass (MQ_WPREP_STREAM=0 keeps everything on one stream)."""
+    if device.type != "cuda" or os.environ.get("MQ_WPREP_STREAM", "1") == "0":
+        return None
+    return torch.cuda.Stream(device=device)
+
+
+def _prefetch_weights(layers, side):
+    """Run the LET + LWC + fake-quant pass of every weight of `layers` (mq_wprep_fwd: min/max, clip, quantise -- 8 bytes of
+    HBM traffic per weight, independent of the activations) on `side`, ahead of the forward pass that consumes them on the
+    current stream; each module picks its tensor up after waiting for its own event (qmodule.py:_fq_weight), so layer k's
+    GEMMs overlap the weight pass of the layers behind it.  autograd runs each backward on the stream of its forward, so
+    the gradient reductions of the weight pass (mq_wprep_bwd) overlap the activation backward the same way."""
+    if side is None:
+        return
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)                          # LET / LWC parameters of this step are final
+    with torch.cuda.stream(side):
+        for layer in layers:
+            for m in layer.modules():
+                if isinstance(m, (QLinear, QRMSNorm, QLayerNorm)):
+                    w = m._fq_weight_now()
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    m._prepared_weight = (w, ev)
+
+
 def _make_optimizer(groups, wd, device):
     """AdamW of the reference (alg:513,716-722).  On the GPU: utils/optim.py:FlatAdamW -- every learnable becomes a view of
     one flat buffer and grad norm + skip-on-non-finite (GradScaler semantics, optim.py:37-38) + AdamW are one fused kernel
@@ -464,7 +491,7 @@ def _no_grad_replay(fn, example, device):
     return _Replay(body, [example], _use_graphs(device))
 
 
-def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, world, device, example_inputs):
+def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, world, device, example_inputs, side=None):
     """One optimiser step as a replayable unit: forward, MSE against the FP target(s), backward, (all-reduce,) global
     grad norm, AdamW.  Returns step(x, y[, y2]) -> (loss, norm), both detached 0-d tensors."""
     flat = isinstance(optimizer, FlatAdamW)
@@ -480,6 +507,8 @@ def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, w
         if not flat:
             return loss.detach(), _train_step(args, loss, optimizer, loss_scaler, params_fn, world).detach()
         loss.backward()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)     # the weight pass's gradient reductions ran on the side stream
         optimizer.allreduce_grads(world)             # one SUM all-reduce of the flat buffer (no-op on one rank)
         norm = optimizer.step()                      # grad norm, skip-on-non-finite and AdamW on the device
         return loss.detach(), norm
@@ -556,14 +585,17 @@ def omniquant(args, model, dataloader, logger, device=None):
             max_iters = args.epochs * gsteps
             warmup_iters = args.warmup_epochs * gsteps
 
-            def forward_fn(x, qlayer=qlayer):
+            side = _weight_stream(device)
+
+            def forward_fn(x, qlayer=qlayer, side=side):
                 smooth_lm_temporary(qlayer, model.config, args.let, args.use_shift, args.original_omniquant)
+                _prefetch_weights([qlayer], side)
                 return qlayer(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0]
 
             bs = args.batch_size
             example = [quant_inps[:bs], fp_inps[:bs]] + ([fp_inps_2[:bs]] if args.aug_loss else [])
             step = _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, lambda qlayer=qlayer: get_parameters(qlayer, args.use_shift),
-                              world, device, example)
+                              world, device, example, side)
             for epochs in range(args.epochs):
                 loss_list, norm_list = [], []
                 for g, j in enumerate(my_batches):
@@ -660,13 +692,17 @@ def e2equant(args, model, dataloader, logger, device=None):
         max_iters = args.epochs * gsteps
         warmup_iters = args.warmup_epochs * gsteps
 
+        side = _weight_stream(device)
+
         def forward_fn(x):
             for k in range(len(layers)):
                 smooth_lm_temporary(layers[k], model.config, args.let, args.use_shift)
+            _prefetch_weights(layers, side)
             return backbone(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0]
 
         example = [quant_inps[:batch_size], fp_inps[:batch_size]] + ([fp_inps_2[:batch_size]] if args.aug_loss else [])
-        step = _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, lambda: get_parameters(model, args.use_shift), world, device, example)
+        step = _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, lambda: get_parameters(model, args.use_shift), world, device, example,
+                          side)
         for epochs in range(args.epochs):
             loss_list, norm_list = [], []
             for g, j in enumerate(my_batches):

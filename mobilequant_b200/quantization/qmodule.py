@@ -249,6 +249,28 @@ class _QBase:
             else:
                 q.set_scale_offset_from_minmax(act_scale[s][0], act_scale[s][1], use_scale_offset_as, device)
 
+    def _fq_weight(self):
+        """The (LET-transformed,) fake-quantised weight of a QLinear / QRMSNorm / QLayerNorm forward.  The calibration loops may
+        compute it ahead of time on a side stream (algorithm.py:_prefetch_weights: the weight pass is HBM-bound and independent
+        of the activations, the rest of a step is a chain of small kernels); the stashed tensor is picked up here after waiting
+        for its event."""
+        pre = getattr(self, "_prepared_weight", None)
+        if pre is not None:
+            self._prepared_weight = None
+            w, ev = pre
+            torch.cuda.current_stream().wait_event(ev)
+            w.record_stream(torch.cuda.current_stream())
+            return w
+        return self._fq_weight_now()
+
+    def _fq_weight_now(self):
+        weight, let = self._let_weight(self.weight)
+        if self.weight_quantizer is not None:
+            return self.weight_quantizer(weight, let=let) if let is not None else self.weight_quantizer(weight)
+        if let is not None:
+            return materialize_let(weight, let)
+        return weight
+
     def _let_weight(self, raw_weight):
         """weight fed to the weight quantizer + the fused LET description (None when not under smooth_lm_temporary)."""
         if not getattr(self, "use_temporary_parameter", False):
@@ -276,12 +298,8 @@ class QLinear(nn.Linear, _QBase):
         self._set_ranges(act_scale, use_scale_offset_as, self.weight.device)
 
     def forward(self, input_):
-        weight, let = self._let_weight(self.weight)
         bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
-        if self.weight_quantizer is not None:
-            weight = self.weight_quantizer(weight, let=let) if let is not None else self.weight_quantizer(weight)
-        elif let is not None:
-            weight = materialize_let(weight, let)
+        weight = self._fq_weight()
         if self.input_quantizer is not None:
             input_ = self.input_quantizer(input_)
         out = nn.functional.linear(input_, weight, bias=bias)
@@ -356,12 +374,7 @@ class QRMSNorm(HFRMSNorm, _QBase):
         self._set_ranges(act_scale, use_scale_offset_as, self.weight.device)
 
     def _qweight(self):
-        weight, let = self._let_weight(self.weight)
-        if self.weight_quantizer is not None:
-            weight = self.weight_quantizer(weight, let=let) if let is not None else self.weight_quantizer(weight)
-        elif let is not None:
-            weight = materialize_let(weight, let)
-        return weight
+        return self._fq_weight()
 
     def forward(self, input_):
         weight = self._qweight()
@@ -411,12 +424,8 @@ class QLayerNorm(nn.LayerNorm, _QBase):
         self._set_ranges(act_scale, use_scale_offset_as, self.weight.device)
 
     def forward(self, input_):
-        weight, let = self._let_weight(self.weight)
         bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
-        if self.weight_quantizer is not None:
-            weight = self.weight_quantizer(weight, let=let) if let is not None else self.weight_quantizer(weight)
-        elif let is not None:
-            weight = materialize_let(weight, let)
+        weight = self._fq_weight()
         if self.input_quantizer is not None:
             input_ = self.input_quantizer(input_)
         out = nn.functional.layer_norm(input_, input_.shape[-1:], weight=weight, bias=bias, eps=self.eps)
