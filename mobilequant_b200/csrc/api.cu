@@ -32,6 +32,8 @@ void* stream_ws(Ctx* c, cudaStream_t st) {
       return nullptr;
     }
   }
+  // the last 64 bytes of every scratch buffer are self-resetting arrival counters (zero between launches)
+  cudaMemsetAsync(static_cast<char*>(p) + c->ws_bytes - 64, 0, 64, st);
   c->ws_by_stream.emplace_back(st, p);
   return p;
 }

@@ -74,8 +74,11 @@ __global__ void __launch_bounds__(256) fq_bwd_kernel(const float* __restrict__ x
                                                       float* __restrict__ gx, int64_t n,
                                                       const float* __restrict__ scale,
                                                       const float* __restrict__ offset, int64_t group, float qmin,
-                                                      float qmax, double* __restrict__ partial /*[2*grid] or NULL*/) {
+                                                      float qmax, double* __restrict__ partial /*[2*grid] or NULL*/,
+                                                      unsigned* __restrict__ ticket, float* __restrict__ gscale,
+                                                      float* __restrict__ goffset) {
   __shared__ float red[32];
+  __shared__ bool s_last;
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthr = int64_t(gridDim.x) * blockDim.x;
   float s = 0.f, o = 0.f;
@@ -104,19 +107,26 @@ __global__ void __launch_bounds__(256) fq_bwd_kernel(const float* __restrict__ x
   if (partial) {
     float bs = block_reduce(acc_s, OpSum(), red);
     float bo = block_reduce(acc_o, OpSum(), red);
-    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = bs; partial[2 * blockIdx.x + 1] = bo; }
-  }
-}
-
-__global__ void fq_bwd_final_kernel(const double* __restrict__ partial, int nblocks, float* gscale, float* goffset) {
-  // single warp, fixed order -> deterministic
-  double s = 0., o = 0.;
-  for (int i = threadIdx.x; i < nblocks; i += 32) { s += partial[2 * i]; o += partial[2 * i + 1]; }
-  s = warp_reduce(s, OpSum());
-  o = warp_reduce(o, OpSum());
-  if (threadIdx.x == 0) {
-    if (gscale) *gscale = (float)s;
-    if (goffset) *goffset = (float)o;
+    // the block that arrives last folds the per-block partials in block order (fixed order: deterministic) -- no second launch
+    if (threadIdx.x == 0) {
+      partial[2 * blockIdx.x] = bs; partial[2 * blockIdx.x + 1] = bo;
+      __threadfence();
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+      __threadfence();
+      const volatile double* vp = partial;
+      double s2 = 0., o2 = 0.;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) { s2 += vp[2 * i]; o2 += vp[2 * i + 1]; }
+      s2 = warp_reduce(s2, OpSum());
+      o2 = warp_reduce(o2, OpSum());
+      if (threadIdx.x == 0) {
+        if (gscale) *gscale = (float)s2;
+        if (goffset) *goffset = (float)o2;
+        *ticket = 0u;
+      }
+    }
   }
 }
 
@@ -753,9 +763,9 @@ int mq_fq_bwd(void* ctx, const float* x, const float* g, float* gx, int64_t n, c
   void* wsp = want ? stream_ws(c, st) : nullptr;
   if (want && !wsp) return MQ_FAILED_ALLOCATION;
   double* partial = reinterpret_cast<double*>(wsp);
-  if (vec) fq_bwd_kernel<true><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial);
-  else fq_bwd_kernel<false><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial);
-  if (want) fq_bwd_final_kernel<<<1, 32, 0, st>>>(partial, grid, gscale, goffset);
+  unsigned* ticket = want ? reinterpret_cast<unsigned*>(static_cast<char*>(wsp) + c->ws_bytes - 64) : nullptr;
+  if (vec) fq_bwd_kernel<true><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial, ticket, gscale, goffset);
+  else fq_bwd_kernel<false><<<grid, 256, 0, st>>>(x, g, gx, n, scale, offset, group, qmin, qmax, partial, ticket, gscale, goffset);
   return check_launch(c, "mq_fq_bwd");
 }
 
@@ -781,7 +791,7 @@ int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_
   if (per_row) {
     minmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, cols, out_min, out_max, accumulate);
   } else {
-    MQ_REQUIRE(c, size_t(cols) * 2 * sizeof(int) <= c->ws_bytes, "too many columns for the workspace");
+    MQ_REQUIRE(c, size_t(cols) * 2 * sizeof(int) + 64 <= c->ws_bytes, "too many columns for the workspace");
     int* ws = reinterpret_cast<int*>(stream_ws(c, st));
     if (!ws) return MQ_FAILED_ALLOCATION;
     unsigned gx = (unsigned)((cols + 255) / 256);
@@ -808,7 +818,7 @@ static int wprep_check(Ctx* c, const float* w, int64_t rows, int64_t cols, const
   MQ_REQUIRE(c, (col_mode == 0) || col_fac, "col_mode set but col_fac is NULL");
   MQ_REQUIRE(c, (row_mode == 0) || row_fac, "row_mode set but row_fac is NULL");
   MQ_REQUIRE(c, cfg.bitwidth >= 2 && cfg.bitwidth <= 16, "bitwidth must be in [2,16]");
-  MQ_REQUIRE(c, size_t(rows) * 32 <= c->ws_bytes, "too many rows for the workspace");
+  MQ_REQUIRE(c, size_t(rows) * 32 + 128 <= c->ws_bytes, "too many rows for the workspace");
   return MQ_NO_ERROR;
 }
 
@@ -865,8 +875,8 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   float* partial = reinterpret_cast<float*>(p);
   // (wprep_check bounds rows * 32 bytes; the carve-up above adds at most 32 bytes of alignment padding per context -- checked)
-  MQ_REQUIRE(c, size_t(p - ws0) + 16 <= c->ws_bytes, "too many rows for the workspace");
-  size_t partial_cap = (c->ws_bytes - size_t(p - ws0)) / sizeof(float);
+  MQ_REQUIRE(c, size_t(p - ws0) + 80 <= c->ws_bytes, "too many rows for the workspace");
+  size_t partial_cap = (c->ws_bytes - 64 - size_t(p - ws0)) / sizeof(float);      // (the last 64 bytes are arrival counters)
 
   const bool vec = wprep_vec_ok(cols, w, col_fac, g, g_wt, scratch, 0);
   if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
