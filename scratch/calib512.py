@@ -43,4 +43,4 @@ res = {"config": "TinyLlama-1.1B shapes, W8A8, e2equant LET+LWC+LRL, bs 1, seq 1
        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "last_log": msgs[-3:]}
 print(json.dumps(res))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/r1d_calib512.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/r2_calib512.json", "w"), indent=1)
