@@ -79,8 +79,12 @@ class IntEngine:
         # (TinyLlama, batch 8, graph replay): fused 1.76 ms/step, separate 1.67 ms/step -- the last-arriving CTA serialises
         # the group's epilogue while a graph node costs less than that -- so the two-launch form is the default.
         self.fused_gemv = os.environ.get("MQB200_GEMV_FUSED", "0") == "1"
-        # prefill with packed 4-bit weights: fused int4 x int8 GEMM (default) or mq_unpack4 into scratch + the W8 GEMM ("0")
-        self.fused_w4 = os.environ.get("MQB200_W4_FUSED", "1") != "0"
+        # prefill with packed 4-bit weights: mq_unpack4 into an L2-resident scratch + the W8 GEMM (default), or the fused
+        # int4 x int8 GEMM mq_qgemm_w4a8 (MQB200_W4_FUSED=1).  Both are bit-identical; measured on B200 at batch 32 x seq 1024
+        # (profiles/r2_bench_w4a8_b32*.json) the fused kernel's GEMMs take 45.6 ms per step against 25.0 + 0.8 ms: expanding
+        # nibbles through shared memory (16 KB read + 32 KB written per k-slice) competes with the tensor core's own operand
+        # fetch (96 B/clk of the 128 B/clk shared-memory port), while the scratch copy costs only L2 traffic.
+        self.fused_w4 = os.environ.get("MQB200_W4_FUSED", "0") == "1"
         # decode: the residual epilogues of o_proj / w2 ride on the following row norm (two launches per layer fewer)
         self.fused_resid_norm = os.environ.get("MQB200_RESID_NORM", "1") != "0"
 

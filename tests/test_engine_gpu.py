@@ -346,18 +346,16 @@ def test_engine_packed_int4_equals_unpacked(cuda):
     ids = torch.cat(g["samples"][:2], dim=0).to(cuda)
     B, T = ids.shape
     from mobilequant_b200 import kernels as K
-    assert e_packed.fused_w4
+    h2 = e_plain.forward(ids, return_logits=False)
+    assert torch.equal(e_packed.forward(ids, return_logits=False), h2)      # default: mq_unpack4 into scratch + the W8 GEMM
+    e_packed.fused_w4 = True                                                # fused int4 x int8 GEMM: nibbles expanded inside the kernel
     K.enable_event_timing(True)
     h1 = e_packed.forward(ids, return_logits=False)
     torch.cuda.synchronize()
     launched = set(K.collect_event_timing().keys())
     K.enable_event_timing(False)
-    assert "unpack4" not in launched and "qgemm" in launched, launched      # prefill: nibbles are expanded inside the GEMM
-    h2 = e_plain.forward(ids, return_logits=False)
+    assert "unpack4" not in launched and "qgemm" in launched, launched
     assert torch.equal(h1, h2)
-    e_packed.fused_w4 = False                                               # the scratch-expansion path stays bit-identical
-    assert torch.equal(e_packed.forward(ids, return_logits=False), h2)
-    e_packed.fused_w4 = True
     c1, c2 = e_packed.new_cache(B, T), e_plain.new_cache(B, T)
     e_packed.prefill(ids[:, :T - 2], c1); e_plain.prefill(ids[:, :T - 2], c2)
     x1 = e_packed._embed(ids[:, T - 2]).contiguous(); x2 = x1.clone()
