@@ -25,7 +25,7 @@ def num(v):
 
 
 out_md, title, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
-lines = [f"# {title}\n", "`ncu --set full --clock-control none --import-source on`; one column per captured launch; GB/s = (dram read + write) / duration.\n"]
+lines = [f"# {title}\n", "`ncu --set full --clock-control none`; one column per captured launch; GB/s = (dram read + write) / duration.\n"]
 for rep in reps:
     hdr, units, data = raw(rep)
     kn = hdr.index("Kernel Name")
