@@ -4,6 +4,7 @@
 #include "ctx.h"
 #include "gv_epi.cuh"
 #include "attn.cuh"
+#include "tc_common.cuh"
 #include <string>
 #include <algorithm>
 #include <cstdlib>
@@ -118,6 +119,114 @@ __global__ void __launch_bounds__(128) qnorm_kernel(const NormArgs a) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
   if (lane == 0 && a.rowsum) a.rowsum[row] = csum;
+}
+
+// Pipelined variant for the prefill (thousands of rows, H == 128*NV): persistent CTAs, one warp per row, the row's 4*H bytes
+// arrive by ONE bulk async copy (cp.async.bulk + mbarrier) into the warp's shared-memory slot; pass 1 pulls the row into
+// registers, after which the slot is refilled with the warp's next row underneath pass 2 (the longer pass), so the exact
+// requantisation chain (~25 instructions per element: this kernel is ALU-bound, not HBM-bound) no longer
+// waits for its loads.  Same arithmetic as qnorm_kernel; w_fq / bias are staged once per CTA.
+template <bool kLayerNorm, int NV>
+__global__ void __launch_bounds__(128) qnorm_pipe_kernel(const NormArgs a) {
+  constexpr int H = NV * 128;
+  constexpr int kRowBytes = H * 4;
+  extern __shared__ __align__(128) uint8_t qn_smem[];
+  float* s_w = reinterpret_cast<float*>(qn_smem);                           // [H]
+  float* s_b = s_w + H;                                                     // [H] (zeros without a bias)
+  float* s_x = s_b + H;                                                     // [4 warps][H]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + 4 * H);               // [4 warps]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x * 4; k < H; k += 128 * 4) {
+    *reinterpret_cast<float4*>(s_w + k) = ldg4(a.w_fq + k);
+    *reinterpret_cast<float4*>(s_b + k) = a.bias ? ldg4(a.bias + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float* xb = s_x + warp * H;
+  uint64_t* bar = s_bar + warp;
+  if (lane == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const QParam qi = make_qparam(a.s_in, a.o_in, a.qmax_in);
+  const QParam qo = make_qparam(a.s_out, a.o_out, a.qmax_out);
+  const int64_t nwarps = int64_t(gridDim.x) * 4;
+  int64_t row = int64_t(blockIdx.x) * 4 + warp;
+  auto issue = [&](int64_t r) {                                             // lane 0 only
+    tc::mbar_expect_tx(bar, kRowBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(xb)), "l"(a.x + r * H), "r"(kRowBytes), "r"(tc::smem_u32(bar)) : "memory");
+  };
+  if (row < a.rows && lane == 0) issue(row);
+  for (int it = 0; row < a.rows; ++it, row += nwarps) {
+    tc::mbar_wait(bar, it & 1);
+    const float* xr = xb;
+    float rr[NV][4];
+    unsigned long long s2 = 0; long long s1 = 0;
+    auto stats = [&](auto five_tag) {
+      constexpr bool FIVE = decltype(five_tag)::value;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + j * 128 + lane * 4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float m = quant_magic<FIVE>(vv[e], qi);
+          rr[j][e] = __fsub_rn(m, kRoundMagic);
+          const int i = __float_as_int(m) - kRoundMagicBits;        // == int(rr): no F2I
+          s2 += (unsigned long long)((long long)i * i);
+          if (kLayerNorm) s1 += i;
+        }
+      }
+    };
+    dispatch_five(qi.five, stats);
+    __syncwarp();                                     // the row is in registers: refill the slot underneath pass 2
+    if (row + nwarps < a.rows && lane == 0) issue(row + nwarps);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+      if (kLayerNorm) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    }
+    float denom = 1.f, rdenom = 1.f, mean = 0.f, rstd = 1.f;
+    bool five = qo.five | qi.five;
+    if (kLayerNorm) {
+      const double m = (double)s1 / (double)H;
+      const double var = (double)s2 / (double)H - m * m;
+      mean = (float)(m * (double)a.s_in);
+      rstd = (float)(1.0 / sqrt(var * (double)a.s_in * (double)a.s_in + (double)a.eps));
+    } else {
+      denom = fmaxf(fmul(__fsqrt_rn(__ull2float_rn(s2)), a.s_in), 1e-12f);
+      rdenom = __frcp_rn(denom);
+      five |= mantissa_all_ones(denom);
+    }
+    int csum = 0;
+    const bool has_bias = a.bias != nullptr;
+    auto emit = [&](auto five_tag) {
+      constexpr bool FIVE = decltype(five_tag)::value;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int k = j * 128 + lane * 4;
+        const float4 w = *reinterpret_cast<const float4*>(s_w + k);
+        const float4 bb = *reinterpret_cast<const float4*>(s_b + k);
+        const float wv[4] = {w.x, w.y, w.z, w.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xh = fmul(rr[j][e], a.s_in);
+          float t;
+          if (kLayerNorm) t = fmul(fmul(fsub(xh, mean), rstd), wv[e]);
+          else t = fmul(wv[e], fmul(a.alpha, div_rn<FIVE>(xh, denom, rdenom)));
+          if (has_bias) t = fadd(t, bv[e]);
+          packed |= (uint32_t)quant_int<FIVE>(t, qo) << (8 * e);
+        }
+        csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+        *reinterpret_cast<uint32_t*>(a.codes + row * H + k) = packed;
+      }
+    };
+    dispatch_five(five, emit);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
+    if (lane == 0 && a.rowsum) a.rowsum[row] = csum;
+  }
 }
 
 // Few-row variant (decode step: rows == batch): one warp per row leaves a ~3 k-instruction dependent chain on a single
@@ -1155,6 +1264,25 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
     if (is_layernorm) qnorm_row_kernel<true, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
     else qnorm_row_kernel<false, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
     return check_launch(c, "mq_qnorm");
+  }
+  // prefill-sized inputs with H 1024 / 2048: the pipelined persistent kernel (MQB200_QNORM=simple keeps the one-shot kernel)
+  {
+    const char* e = getenv("MQB200_QNORM");
+    if ((H == 2048 || H == 1024) && rows >= 1024 && !(e && e[0] == 's')) {
+      const size_t smem = size_t(H) * 4 * (2 + 4) + 64;
+      const int per_sm = (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024));
+      const unsigned g = (unsigned)std::min<int64_t>((rows + 3) / 4, int64_t(c->sm_count) * per_sm);
+#define MQ_NORMP(LN, NV)                                                                                                   \
+  do {                                                                                                                     \
+    static bool attr = false;                                                                                              \
+    if (!attr) { cudaFuncSetAttribute(qnorm_pipe_kernel<LN, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+    qnorm_pipe_kernel<LN, NV><<<g, 128, smem, st>>>(a);                                                                    \
+  } while (0)
+      if (is_layernorm) { if (H == 2048) MQ_NORMP(true, 16); else MQ_NORMP(true, 8); }
+      else { if (H == 2048) MQ_NORMP(false, 16); else MQ_NORMP(false, 8); }
+#undef MQ_NORMP
+      return check_launch(c, "mq_qnorm");
+    }
   }
   unsigned grid = (unsigned)((rows + 3) / 4);
 #define MQ_NORM(LN, NV) qnorm_kernel<LN, NV><<<grid, 128, 0, st>>>(a)

@@ -158,7 +158,7 @@ def test_qattn_shard(cuda, B, T, Tq, q_start, nh, nkv, hd):
     assert np.array_equal(rs.cpu().numpy().astype(np.int64), ref.sum(1))
 
 
-@pytest.mark.parametrize("rows,H,layernorm", [(2048, 2048, False), (4096, 2048, True)])
+@pytest.mark.parametrize("rows,H,layernorm", [(2048, 2048, False), (4096, 2048, True), (1100, 1024, False), (1027, 1024, True), (8192, 2048, False)])
 def test_qnorm_real_shapes(cuda, rows, H, layernorm):
     """qnorm at the hidden size of all three evaluated families (H 2048), thousands of rows (warp-per-row kernel)."""
     from mobilequant_b200 import kernels as K
