@@ -62,6 +62,23 @@ int mq_fq_bwd(void* ctx, const float* x, const float* g, float* gx, int64_t n, c
               const float* offset, int64_t group, float qmin, float qmax, float* gscale, float* goffset,
               void* stream);
 
+/* ---- Calibration attention core, the element-wise chain between the two batched matmuls of HFAttention.forward
+ * (hm:514-534) with the QMatMul quantizers around it (qm:453-466), fused:
+ *   P = fq2( softmax( fq1(S) * mul + causal_mask ) )      S, P: [rows, T] fp32, rows = B*nh*Tq
+ * fq1 = qk_bmm.output_quantizer, fq2 = pv_bmm.input_quantizer (per-tensor static; a NULL scale/offset pair disables one),
+ * mul = fp32 1/sqrt(head_dim), causal != 0: row r sees columns <= (r % Tq) + (T - Tq) (finfo.min elsewhere, as
+ * _prepare_4d_causal_attention_mask builds it, hm:1548-1555).  stats[rows][2] receives (row max, sum of exp) for the
+ * backward.  T % 4 == 0 and T <= 2048 (mq_attn_probs_supported); one launch each way, nothing else materialised.
+ * Backward: dS from g = dL/dP; gparams (may be NULL) = DEVICE float[4] OVERWRITTEN with d/dscale1, d/doffset1,
+ * d/dscale2, d/doffset2 (deterministic fixed-order reduction in the ctx workspace of `stream`).                  */
+int mq_attn_probs_supported(int T);
+int mq_attn_probs_fwd(void* ctx, const float* S, float* P, float* stats, int64_t rows, int T, int Tq, int causal, float mul,
+                      const float* scale1, const float* offset1, float qmin1, float qmax1, const float* scale2,
+                      const float* offset2, float qmin2, float qmax2, void* stream);
+int mq_attn_probs_bwd(void* ctx, const float* S, const float* stats, const float* g, float* dS, int64_t rows, int T, int Tq,
+                      int causal, float mul, const float* scale1, const float* offset1, float qmin1, float qmax1,
+                      const float* scale2, const float* offset2, float qmin2, float qmax2, float* gparams, void* stream);
+
 /* ---- K8: range statistics, generate_act_range.py:55-69 (per tensor) / :57-63 (per channel) -------------------
  * minmax[0] = min(minmax[0], min x), minmax[1] = max(minmax[1], max x) when accumulate != 0, else overwritten.
  * rows variant: x is [rows, cols]; per_row != 0 reduces over cols (weights, qm:30) else over rows (per-channel

@@ -3,6 +3,7 @@
 // deterministic two-stage reductions (no float atomics) so that repeated runs give identical bits.
 #include "common.cuh"
 #include "ctx.h"
+#include "fq_math.cuh"
 
 namespace mq {
 
@@ -54,21 +55,6 @@ __global__ void __launch_bounds__(256) fq_fwd_kernel(const float* __restrict__ x
 // K1 backward.  Element-wise terms exactly as autograd evaluates them for qm:286-290:
 //   t5 = clamp(rne(x/s)+o) - o ; g_t1 = g*s*m ; gx = g_t1 / s ; gs = g*t5 - g_t1*((x/s)/s) ; go = g_t1 - g*s
 // ================================================================================================================
-struct FqGrad { float gx, gs, go; };
-__device__ __forceinline__ FqGrad fq_bwd_elem(float x, float g, float s, float o, float qmin, float qmax) {
-  float u = fdiv(x, s);
-  float t3 = fadd(rintf(u), o);
-  bool m = (t3 >= qmin) && (t3 <= qmax);
-  float t5 = fsub(fminf(fmaxf(t3, qmin), qmax), o);
-  float gs5 = fmul(g, s);
-  float gt1 = m ? gs5 : 0.f;
-  FqGrad r;
-  r.gx = fdiv(gt1, s);
-  r.gs = fsub(fmul(g, t5), fmul(gt1, fdiv(u, s)));
-  r.go = fsub(gt1, gs5);
-  return r;
-}
-
 template <bool kVec>
 __global__ void __launch_bounds__(256) fq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       float* __restrict__ gx, int64_t n,
@@ -448,10 +434,6 @@ __global__ void __launch_bounds__(256) wprep_bwd_apply_kernel(const float* __res
 // Same arithmetic, bit for bit, with 128-bit loads/stores and the branch-free exact division of common.cuh for every
 // division by the group scale / the row factor (the divisor is uniform over a CTA, so its reciprocal and the FIVE
 // variant are chosen once).  Divisions by a per-column LET factor (only norm weights, rows == 1) keep __fdiv_rn.
-struct RowDiv { float r, rr; bool five; };
-__device__ __forceinline__ RowDiv make_rowdiv(float r) { RowDiv d; d.r = r; d.rr = __frcp_rn(r); d.five = mantissa_all_ones(r); return d; }
-__device__ __forceinline__ float div_any(float a, const RowDiv& d) { return d.five ? div_rn<true>(a, d.r, d.rr) : div_rn<false>(a, d.r, d.rr); }
-
 __device__ __forceinline__ float let_apply_v(float w, float c, const RowDiv& rd, int col_mode, int row_mode) {
   float t = w;
   if (col_mode == 2) t = fmul(t, c); else if (col_mode == 1) t = fdiv(t, c);
@@ -464,31 +446,6 @@ __device__ __forceinline__ float4 let_apply4(float4 w, const float* col_fac, int
   return make_float4(let_apply_v(w.x, c.x, rd, la.col_mode, la.row_mode), let_apply_v(w.y, c.y, rd, la.col_mode, la.row_mode),
                      let_apply_v(w.z, c.z, rd, la.col_mode, la.row_mode), let_apply_v(w.w, c.w, rd, la.col_mode, la.row_mode));
 }
-// rintf(u) for the purposes of a quantizer whose code range lies inside +-2^22: |u| is clamped first, which cannot change
-// clamp(rne(u) + o, qmin, qmax) nor the in-range test
-__device__ __forceinline__ float rne_magic(float u) {
-  const float uc = fminf(fmaxf(u, -4194303.f), 4194303.f);
-  return __fsub_rn(__fadd_rn(uc, kRoundMagic), kRoundMagic);
-}
-template <bool FIVE>
-__device__ __forceinline__ float quant_code_v(float x, float s, float rs, float o, float qmin, float qmax) {
-  return fminf(fmaxf(fadd(rne_magic(div_rn<FIVE>(x, s, rs)), o), qmin), qmax);
-}
-template <bool FIVE>
-__device__ __forceinline__ FqGrad fq_bwd_elem_v(float x, float g, float s, float rs, float o, float qmin, float qmax) {
-  const float u = div_rn<FIVE>(x, s, rs);
-  const float t3 = fadd(rne_magic(u), o);
-  const bool m = (t3 >= qmin) && (t3 <= qmax);
-  const float t5 = fsub(fminf(fmaxf(t3, qmin), qmax), o);
-  const float gs5 = fmul(g, s);
-  const float gt1 = m ? gs5 : 0.f;
-  FqGrad r;
-  r.gx = div_rn<FIVE>(gt1, s, rs);
-  r.gs = fsub(fmul(g, t5), fmul(gt1, div_rn<FIVE>(u, s, rs)));
-  r.go = fsub(gt1, gs5);
-  return r;
-}
-
 __global__ void __launch_bounds__(256) wprep_rowminmax_v_kernel(const float* __restrict__ w, int64_t cols, LetArgs la,
                                                                  float* __restrict__ row_mn, float* __restrict__ row_mx) {
   __shared__ float red[32];

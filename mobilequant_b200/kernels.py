@@ -17,6 +17,11 @@ def _protos():
     lib = _lib.load()
     lib.mq_fq_fwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_float, c_float, _P]
     lib.mq_fq_bwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_float, c_float, _P, _P, _P]
+    lib.mq_attn_probs_supported.argtypes = [c_int]
+    lib.mq_attn_probs_fwd.argtypes = [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P, _P, c_float, c_float, _P, _P, c_float,
+                                      c_float, _P]
+    lib.mq_attn_probs_bwd.argtypes = [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P, _P, c_float, c_float, _P, _P,
+                                      c_float, c_float, _P, _P]
     lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
     lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
@@ -120,6 +125,43 @@ def fq_bwd(x, g, scale, offset, qmin, qmax, group=0, want_gx=True, want_gparams=
         check(_launch("fq_bwd", lib.mq_fq_bwd, h, ptr(x, F32), ptr(g, F32), ptr(gx), x.numel(), ptr(scale, F32), ptr(offset, F32),
                             int(group), float(qmin), float(qmax), ptr(gs), ptr(go), stream_ptr()), h)
     return gx, gs, go
+
+
+def attn_probs_supported(T):
+    return bool(_protos().mq_attn_probs_supported(int(T)))
+
+
+def attn_probs_fwd(S, Tq, causal, mul, q1, q2):
+    """P = fq2(softmax(fq1(S) * mul + causal mask)) over the last dim of S [..., Tq, T] (contiguous fp32).  q1 / q2: None or
+    (scale, offset, qmin, qmax) with 0-d CUDA scale / offset.  Returns (P, stats)."""
+    lib = _protos()
+    T = S.shape[-1]
+    rows = S.numel() // T
+    P = torch.empty_like(S)
+    stats = torch.empty((rows, 2), dtype=F32, device=S.device)
+    h = _h(S)
+    s1, o1, lo1, hi1 = q1 if q1 is not None else (None, None, 0.0, 0.0)
+    s2, o2, lo2, hi2 = q2 if q2 is not None else (None, None, 0.0, 0.0)
+    with torch.cuda.device(S.device):
+        check(_launch("attn_probs_fwd", lib.mq_attn_probs_fwd, h, ptr(S, F32), ptr(P), ptr(stats), rows, T, int(Tq), int(causal), float(mul),
+                      ptr(s1), ptr(o1), float(lo1), float(hi1), ptr(s2), ptr(o2), float(lo2), float(hi2), stream_ptr()), h)
+    return P, stats
+
+
+def attn_probs_bwd(S, stats, g, Tq, causal, mul, q1, q2, want_gparams=True):
+    lib = _protos()
+    T = S.shape[-1]
+    rows = S.numel() // T
+    dS = torch.empty_like(S)
+    gp = torch.empty(4, dtype=F32, device=S.device) if want_gparams else None
+    h = _h(S)
+    s1, o1, lo1, hi1 = q1 if q1 is not None else (None, None, 0.0, 0.0)
+    s2, o2, lo2, hi2 = q2 if q2 is not None else (None, None, 0.0, 0.0)
+    with torch.cuda.device(S.device):
+        check(_launch("attn_probs_bwd", lib.mq_attn_probs_bwd, h, ptr(S, F32), ptr(stats, F32), ptr(g, F32), ptr(dS), rows, T, int(Tq),
+                      int(causal), float(mul), ptr(s1), ptr(o1), float(lo1), float(hi1), ptr(s2), ptr(o2), float(lo2), float(hi2),
+                      ptr(gp), stream_ptr()), h)
+    return dS, gp
 
 
 # ---- K8 ---------------------------------------------------------------------------------------------------------

@@ -115,11 +115,16 @@ class HFAttention(nn.Module):
             k = torch.cat((kr, k[..., self.rotary_dim:]), dim=-1)
         k = repeat_kv(k, self.num_key_value_groups)
         v = repeat_kv(v, self.num_key_value_groups)
-        attn = self.qk_bmm(q, k.transpose(2, 3)) / math.sqrt(self.head_dim)
-        if attention_mask is not None:
-            attn = attn + attention_mask
-        attn = nn.functional.softmax(attn, dim=-1, dtype=torch.float32).to(q.dtype)
-        out = self.pv_bmm(attn, v)
+        fused = getattr(self.qk_bmm, "fused_probs", None)          # QMatMul pair: one kernel for the element-wise attention core
+        attn = fused(q, k.transpose(2, 3), self.head_dim, attention_mask, self.pv_bmm) if fused is not None else None
+        if attn is not None:
+            out = self.pv_bmm(attn, v, input_quantized=True)
+        else:
+            attn = self.qk_bmm(q, k.transpose(2, 3)) / math.sqrt(self.head_dim)
+            if attention_mask is not None:
+                attn = attn + attention_mask
+            attn = nn.functional.softmax(attn, dim=-1, dtype=torch.float32).to(q.dtype)
+            out = self.pv_bmm(attn, v)
         out = out.transpose(1, 2).contiguous().view(bsz, q_len, -1)
         return self.o_proj(out), None, None
 

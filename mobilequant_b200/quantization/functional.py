@@ -68,3 +68,40 @@ class LetLwcWeightQuantFn(torch.autograd.Function):
                 g_row.reshape(rshape) if (n[3] and g_row is not None) else None, None,
                 g_up.reshape(ushape) if (n[5] and g_up is not None) else None,
                 g_low.reshape(lshape) if (n[6] and g_low is not None) else None, None, None, None)
+
+
+class AttnProbsFn(torch.autograd.Function):
+    """fq2(softmax(fq1(S) / sqrt(hd) + causal mask)): the element-wise attention core between qk_bmm and pv_bmm (hm:514-534 with
+    qk_bmm.output_quantizer and pv_bmm.input_quantizer, qm:453-466) as one kernel forward and one backward
+    (csrc/calib_attn.cu).  Saves S and two floats per row; scale / offset gradients of both quantizers come out of the same
+    backward pass.  q1 / q2 are (scale, offset, qmin, qmax) or scale None for a disabled quantizer."""
+
+    @staticmethod
+    def forward(ctx, S, mul, s1, o1, qmin1, qmax1, s2, o2, qmin2, qmax2):
+        Sc = S.detach().contiguous()
+        f = lambda t: None if t is None else t.detach().reshape(()).float().contiguous()
+        q1 = None if s1 is None else (f(s1), f(o1), qmin1, qmax1)
+        q2 = None if s2 is None else (f(s2), f(o2), qmin2, qmax2)
+        Tq = Sc.shape[-2]
+        P, stats = K.attn_probs_fwd(Sc, Tq, True, mul, q1, q2)
+        ctx.save_for_backward(Sc, stats, *(t for q in (q1, q2) if q is not None for t in q[:2]))
+        ctx.meta = (mul, Tq, None if q1 is None else (qmin1, qmax1), None if q2 is None else (qmin2, qmax2),
+                    None if s1 is None else (s1.shape, o1.shape), None if s2 is None else (s2.shape, o2.shape))
+        return P
+
+    @staticmethod
+    def backward(ctx, g):
+        Sc, stats, *qs = ctx.saved_tensors
+        mul, Tq, r1, r2, sh1, sh2 = ctx.meta
+        q1 = q2 = None
+        if r1 is not None:
+            q1 = (qs[0], qs[1], r1[0], r1[1]); qs = qs[2:]
+        if r2 is not None:
+            q2 = (qs[0], qs[1], r2[0], r2[1])
+        n = ctx.needs_input_grad
+        want = n[2] or n[3] or n[6] or n[7]
+        dS, gp = K.attn_probs_bwd(Sc, stats, g.float().contiguous(), Tq, True, mul, q1, q2, want_gparams=want)
+        pick = lambda need, i, shape: gp[i].reshape(shape) if (need and shape is not None) else None
+        return (dS if n[0] else None, None,
+                pick(n[2], 0, sh1 and sh1[0]), pick(n[3], 1, sh1 and sh1[1]), None, None,
+                pick(n[6], 2, sh2 and sh2[0]), pick(n[7], 3, sh2 and sh2[1]), None, None)

@@ -8,13 +8,15 @@ There is no CPU execution path: tensors must live on a CUDA device (host logic -
 works anywhere).
 """
 import math
+import os
 from copy import deepcopy
 from dataclasses import dataclass
 import torch
 import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
-from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn
+from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn
+from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
 CLIPMAX = 1e6    # qm:12
@@ -223,6 +225,28 @@ def materialize_let(w, let):
     return t.reshape(w.shape)
 
 
+_causal_cache = {}
+
+
+def is_causal_mask(mask, tq, tk):
+    """True when `mask` is the additive causal mask transformers builds for a full prompt (hm:1548-1555: finfo.min above the
+    diagonal, 0 elsewhere, [B, 1, T, T]).  Checked by content once per mask tensor (never during stream capture: an unknown
+    mask then counts as not causal)."""
+    if mask is None or tq != tk or mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[-2:] != (tq, tk) or mask.dtype != torch.float32:
+        return False
+    key = (mask.data_ptr(), tuple(mask.shape), tuple(mask.stride()), mask._version)
+    hit = _causal_cache.get(key)
+    if hit is None:
+        if mask.is_cuda and torch.cuda.is_current_stream_capturing():
+            return False
+        ref = torch.triu(torch.full((tq, tk), torch.finfo(mask.dtype).min, dtype=mask.dtype, device=mask.device), diagonal=1)
+        hit = bool((mask == ref).all())
+        if len(_causal_cache) > 64:
+            _causal_cache.clear()
+        _causal_cache[key] = hit
+    return hit
+
+
 # ---------------------------------------------------------------------------------------------------------------
 class _QBase:
     """Shared (de)serialisation of the quantizer triplets (qm:314-339 and friends)."""
@@ -346,8 +370,8 @@ class QMatMul(nn.Module, _QBase):
     def set_scale_offset(self, act_scale, use_scale_offset_as="parameter"):
         self._set_ranges(act_scale, use_scale_offset_as)
 
-    def forward(self, x1, x2):
-        if self.input_quantizer is not None:
+    def forward(self, x1, x2, input_quantized=False):
+        if self.input_quantizer is not None and not input_quantized:
             x1 = self.input_quantizer(x1)
         if self.input2_quantizer is not None:
             x2 = self.input2_quantizer(x2)
@@ -355,6 +379,34 @@ class QMatMul(nn.Module, _QBase):
         if self.output_quantizer is not None:
             out = self.output_quantizer(out)
         return out
+
+    def fused_probs(self, q, kt, head_dim, attention_mask, pv_bmm):
+        """The attention core of HFAttention.forward (hm:514-534) with this module as qk_bmm:
+            pv_bmm.input_quantizer(softmax(self(q, kt) / sqrt(head_dim) + attention_mask))
+        as matmul + ONE fused kernel (csrc/calib_attn.cu) instead of the element-wise chain over [B, nh, T, T].  Returns None
+        when the fused kernel does not cover the case (non-causal mask, cached ranges missing, dynamic / per-channel quantizers,
+        reduced precision, T > 2048): the caller then runs the chain op by op."""
+        oq, pq = self.output_quantizer, getattr(pv_bmm, "input_quantizer", None)
+        if os.environ.get("MQB200_FUSED_PROBS", "1") == "0":
+            return None
+        if not isinstance(pv_bmm, QMatMul) or not q.is_cuda or q.dtype != torch.float32 or kt.dtype != torch.float32:
+            return None
+        if not is_causal_mask(attention_mask, q.shape[-2], kt.shape[-1]) or not K.attn_probs_supported(kt.shape[-1]):
+            return None
+        params = []
+        for quant in (oq, pq):
+            if quant is None or not quant.enable or quant.qcfg.bitwidth > 16:
+                params += [None, None, 0.0, 0.0]
+                continue
+            if quant.qcfg.is_dynamic or quant.lwc or quant.qcfg.is_per_channel or quant.qcfg.group_size != -1 \
+                    or not hasattr(quant, "scale") or not hasattr(quant, "offset") or quant.scale.numel() != 1:
+                return None
+            params += [quant.scale, quant.offset, quant.qmin, quant.qmax]
+        x1 = self.input_quantizer(q) if self.input_quantizer is not None else q
+        x2 = self.input2_quantizer(kt) if self.input2_quantizer is not None else kt
+        scores = torch.matmul(x1, x2)
+        mul = (torch.ones((), dtype=torch.float32) / torch.tensor(math.sqrt(head_dim), dtype=torch.float32)).item()
+        return AttnProbsFn.apply(scores, mul, *params)
 
 
 class QRMSNorm(HFRMSNorm, _QBase):

@@ -219,3 +219,64 @@ def test_flat_adamw_matches_torch_adamw(cuda):
     norm = opt.step()
     assert not torch.isfinite(norm)
     assert all(torch.equal(a, b.detach()) for a, b in zip(before, dev_p)) and opt.state[0].item() == step_before and opt.skipped_steps == 1
+
+
+def _probs_chain(S, hd, q1, q2):
+    """The op-by-op attention core of HFAttention.forward (hm:514-534) with StaticFakeQuantFn as the quantizers."""
+    import math
+    from mobilequant_b200.quantization.functional import StaticFakeQuantFn
+    from mobilequant_b200.model.hf_model import causal_mask_4d
+    T = S.shape[-1]
+    a = S if q1 is None else StaticFakeQuantFn.apply(S, *q1)
+    a = a / math.sqrt(hd) + causal_mask_4d(S.shape[0], T, torch.float32, S.device)
+    p = torch.nn.functional.softmax(a, dim=-1, dtype=torch.float32)
+    return p if q2 is None else StaticFakeQuantFn.apply(p, *q2)
+
+
+@pytest.mark.parametrize("T,hd,bits1,pmin", [(64, 64, 16, 0.0), (256, 80, 8, 0.0), (1024, 64, 16, 0.0), (2048, 256, 16, 0.0),
+                                             (512, 64, 16, 0.05), (36, 64, 16, 0.0), (1024, 64, None, 0.0)])
+def test_attn_probs_fused_matches_chain(cuda, T, hd, bits1, pmin):
+    """csrc/calib_attn.cu (forward + backward incl. the LRL scale / offset gradients) against the element-wise chain it
+    replaces.  pmin > 0 puts fq2's offset outside its code range (masked columns then contribute to the gradients)."""
+    import math
+    from mobilequant_b200.quantization.functional import AttnProbsFn
+    from mobilequant_b200.quantization.qmodule import compute_scale_offset_from_min_max
+    torch.manual_seed(T + hd)
+    B, nh = (1, 2) if T >= 1024 else (2, 3)
+    S0 = (torch.randn(B, nh, T, T, device=cuda) * 6.0)
+    W = torch.randn(B, nh, T, T, device=cuda)
+
+    def qparams(mn, mx, bits):
+        if bits is None:
+            return None
+        s, o, _, _, lo, hi = compute_scale_offset_from_min_max(mn, mx, bits, False)
+        return [torch.nn.Parameter(s.to(cuda)), torch.nn.Parameter(o.to(cuda)), lo, hi]
+
+    outs = []
+    for fused in (False, True):
+        S = S0.clone().requires_grad_(True)
+        q1, q2 = qparams(-20.0, 18.0, bits1), qparams(pmin, 1.0, 16)
+        if fused:
+            mul = (torch.ones(()) / torch.tensor(math.sqrt(hd))).item()
+            f1 = q1 if q1 is not None else [None, None, 0.0, 0.0]
+            out = AttnProbsFn.apply(S, mul, *f1, *q2)
+        else:
+            out = _probs_chain(S, hd, q1, q2)
+        (out * W).sum().backward()
+        outs.append((out.detach(), S.grad, q1, q2))
+    (o0, g0, a1, a2), (o1, g1, b1, b2) = outs
+    lsb = a2[0].item()
+    d = (o0 - o1).abs()
+    assert d.max().item() <= 1.01 * lsb                       # at most one code apart (exp / summation order), and rarely
+    assert (d > 0).float().mean().item() < 1e-3
+    gs = g0.abs().max().item()
+    assert (g0 - g1).abs().max().item() < 2e-3 * gs
+    assert (g0 - g1).abs().mean().item() < 1e-5 * gs
+    assert (g1[..., 0, 1:] == 0).all()                         # masked columns get an exact zero
+    for ref, got in ((a1, b1), (a2, b2)):
+        if ref is None:
+            continue
+        for i in (0, 1):
+            r, g = ref[i].grad.item(), got[i].grad.item()
+            scale = max(abs(r), 1e-3 * W.numel() ** 0.5 * (lsb if ref is a2 else ref[0].item()))
+            assert abs(r - g) <= 0.02 * scale, (i, r, g)
