@@ -273,10 +273,15 @@ def test_attn_probs_fused_matches_chain(cuda, T, hd, bits1, pmin):
     assert (g0 - g1).abs().max().item() < 2e-3 * gs
     assert (g0 - g1).abs().mean().item() < 1e-5 * gs
     assert (g1[..., 0, 1:] == 0).all()                         # masked columns get an exact zero
+    # fq2's scale gradient is a cancelling sum of g * (rounding residual): every probability that lands on the other side of a
+    # rounding boundary (exp / summation order; counted above) moves it by ~|g|, so the bound grows with sqrt(#flips)
+    nflip = int((d > 0).sum().item())
     for ref, got in ((a1, b1), (a2, b2)):
         if ref is None:
             continue
         for i in (0, 1):
             r, g = ref[i].grad.item(), got[i].grad.item()
-            scale = max(abs(r), 1e-3 * W.numel() ** 0.5 * (lsb if ref is a2 else ref[0].item()))
-            assert abs(r - g) <= 0.02 * scale, (i, r, g)
+            tol = 0.02 * abs(r) + 1e-3 * W.numel() ** 0.5 * (lsb if ref is a2 else ref[0].item())
+            if ref is a2 and i == 0:
+                tol += 4.0 * (nflip + 1) ** 0.5
+            assert abs(r - g) <= tol, (i, r, g, nflip)
