@@ -79,6 +79,18 @@ int mq_attn_probs_bwd(void* ctx, const float* S, const float* stats, const float
                       int causal, float mul, const float* scale1, const float* offset1, float qmin1, float qmax1,
                       const float* scale2, const float* offset2, float qmin2, float qmax2, float* gparams, void* stream);
 
+/* ---- Calibration MLP core of a gated-SiLU block (hm:1042-1062 with QSiLU, qm:691-753, and w2.input_quantizer), fused:
+ *   out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b )        a = w1(x) (already quantised by w1), b = w3(x); n elements, n % 4 == 0
+ * scales / offsets: HOST arrays of 3 DEVICE pointers in the order fq_s (QSiLU.input2_quantizer), fq_o (QSiLU.output_quantizer),
+ * fq_w (w2.input_quantizer); a NULL pair disables that quantizer; qmins / qmaxs: HOST float[3].
+ * Backward: da, db from g = dL/dout; gparams (may be NULL) = DEVICE float[6] OVERWRITTEN with (d/dscale, d/doffset) of fq_s,
+ * fq_o, fq_w (deterministic fixed-order reduction in the ctx workspace of `stream`).                                      */
+int mq_silu_gate_fwd(void* ctx, const float* a, const float* b, float* out, int64_t n, const float* const* scales,
+                     const float* const* offsets, const float* qmins, const float* qmaxs, void* stream);
+int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, const float* g, float* da, float* db, int64_t n,
+                     const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs,
+                     float* gparams, void* stream);
+
 /* ---- K8: range statistics, generate_act_range.py:55-69 (per tensor) / :57-63 (per channel) -------------------
  * minmax[0] = min(minmax[0], min x), minmax[1] = max(minmax[1], max x) when accumulate != 0, else overwritten.
  * rows variant: x is [rows, cols]; per_row != 0 reduces over cols (weights, qm:30) else over rows (per-channel

@@ -4,9 +4,11 @@
 // runs this as ~8 element-wise launches forward and ~12 backward over [B, nh, T, T] fp32 tensors (134 MB each at T 1024);
 // here the forward is ONE pass (read S below the diagonal, write P^) and the backward ONE pass (read dP^ and S below the
 // diagonal, write dS), the row statistics (max, sum) being the only thing kept in between.  One warp per row, the row
-// lives in registers.  Arithmetic is the reference's op for op (explicit _rn intrinsics; divisions by a launch- or
-// row-uniform divisor through the exact div_rn of common.cuh); the two quantizers' scale / offset gradients (LRL) are
-// accumulated in the same pass and folded in fixed block order by the last block to arrive (deterministic).
+// lives in registers.  The forward arithmetic is the reference's op for op with explicit _rn intrinsics (x / scale through the
+// exact div_rn of common.cuh), except that a probability is exp * RN(1 / sum) instead of exp / sum (<= 1 ulp apart; forward
+// and backward use the same value).  The backward evaluates the quantizer gradients in the cancellation-free form of
+// fq_math.cuh (fq_bwd_elem_c); both quantizers' scale / offset gradients (LRL) are accumulated in the same pass and folded in
+// fixed block order by the last block to arrive (deterministic).
 // Columns above the diagonal: A == 0 exactly (exp(finfo.min - max) underflows to 0 as in the reference), so P^ = fq_2(0),
 // dS == 0, and their fq_2 gradient terms vanish whenever 0 is inside fq_2's code range -- they are skipped then, and
 // processed like every other column otherwise.
@@ -15,30 +17,6 @@
 #include "fq_math.cuh"
 
 namespace mq {
-
-struct FqP {
-  float s, rs, o, qmin, qmax;
-  bool five, on;
-};
-__device__ __forceinline__ FqP load_fqp(const float* scale, const float* offset, float qmin, float qmax) {
-  FqP q;
-  q.on = scale != nullptr;
-  q.s = q.on ? __ldg(scale) : 1.f;
-  q.o = q.on ? __ldg(offset) : 0.f;
-  q.rs = __frcp_rn(q.s);
-  q.five = mantissa_all_ones(q.s);
-  q.qmin = qmin; q.qmax = qmax;
-  return q;
-}
-__device__ __forceinline__ float fq_apply(float x, const FqP& q) {
-  if (!q.on) return x;
-  const float c = q.five ? quant_code_v<true>(x, q.s, q.rs, q.o, q.qmin, q.qmax) : quant_code_v<false>(x, q.s, q.rs, q.o, q.qmin, q.qmax);
-  return dequant(c, q.s, q.o);
-}
-__device__ __forceinline__ FqGrad fq_grad(float x, float g, const FqP& q) {
-  if (!q.on) { FqGrad r; r.gx = g; r.gs = 0.f; r.go = 0.f; return r; }
-  return q.five ? fq_bwd_elem_v<true>(x, g, q.s, q.rs, q.o, q.qmin, q.qmax) : fq_bwd_elem_v<false>(x, g, q.s, q.rs, q.o, q.qmin, q.qmax);
-}
 
 struct ProbArgs {
   const float* S; float* P; float* stats;        // stats[rows][2] = (row max of the scaled scores, sum of exp)
@@ -52,9 +30,10 @@ struct ProbArgs {
 };
 
 constexpr int kRowsPerCta = 8;
+constexpr float kNegInf = -INFINITY;               // masked score: exp(-inf - max) == 0 exactly, like exp(finfo.min - max)
 
 template <int NV>
-__global__ void __launch_bounds__(256) attn_probs_fwd_kernel(const ProbArgs a) {
+__global__ void __launch_bounds__(256, NV <= 8 ? 4 : 2) attn_probs_fwd_kernel(const ProbArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= a.rows) return;
@@ -62,45 +41,54 @@ __global__ void __launch_bounds__(256) attn_probs_fwd_kernel(const ProbArgs a) {
   const int ncol = a.causal ? int(row % a.Tq) + 1 + (T - a.Tq) : T;
   const FqP q1 = load_fqp(a.s1, a.o1, a.qmin1, a.qmax1), q2 = load_fqp(a.s2, a.o2, a.qmin2, a.qmax2);
   const float* sr = a.S + row * T;
-  float v[NV][4];
-  float mx = -FLT_MAX;
+  float* pr = a.P + row * T;
+  float mx, sum;
+  auto body = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    float v[NV][4];
+    mx = kNegInf;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int k0 = j * 128 + lane * 4;
-    if (k0 < ncol) {
-      const float4 x = ldg4_stream(sr + k0);
-      const float xv[4] = {x.x, x.y, x.z, x.w};
+    for (int j = 0; j < NV; ++j) {
+      const int k0 = j * 128 + lane * 4;
+      v[j][0] = v[j][1] = v[j][2] = v[j][3] = kNegInf;
+      if (k0 < ncol) {
+        const float4 x = ldg4_stream(sr + k0);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[j][e] = fmul(fq_apply(xv[e], q1), a.mul);
-        if (k0 + e < ncol) mx = fmaxf(mx, v[j][e]);
+        for (int e = 0; e < 4; ++e) {
+          const float t = fmul(fq_apply<FIVE>(xv[e], q1), a.mul);
+          v[j][e] = (k0 + e < ncol) ? t : kNegInf;
+          mx = fmaxf(mx, v[j][e]);
+        }
       }
     }
-  }
-  mx = warp_reduce(mx, OpFMax());
-  float sum = 0.f;
+    mx = warp_reduce(mx, OpFMax());
+    sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int k0 = j * 128 + lane * 4;
+    for (int j = 0; j < NV; ++j) {
+      if (j * 128 + lane * 4 >= ncol) continue;                     // fully masked chunk: exp(-inf) == 0
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      v[j][e] = (k0 + e < ncol) ? expf(fsub(v[j][e], mx)) : 0.f;
-      sum += v[j][e];
+      for (int e = 0; e < 4; ++e) {
+        v[j][e] = expf(fsub(v[j][e], mx));
+        sum += v[j][e];
+      }
     }
-  }
-  sum = warp_reduce(sum, OpSum());
-  const RowDiv rd = make_rowdiv(sum);
-  const float pz = fq_apply(0.f, q2);
-  float* pr = a.P + row * T;
+    sum = warp_reduce(sum, OpSum());
+    const float rsum = __frcp_rn(sum);
+    const float pz = fq_apply<FIVE>(0.f, q2);
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int k0 = j * 128 + lane * 4;
-    if (k0 >= T) continue;
-    float o4[4];
+    for (int j = 0; j < NV; ++j) {
+      const int k0 = j * 128 + lane * 4;
+      if (k0 >= T) continue;
+      float o4[4] = {pz, pz, pz, pz};
+      if (k0 < ncol) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o4[e] = (k0 + e < ncol) ? fq_apply(div_any(v[j][e], rd), q2) : pz;
-    *reinterpret_cast<float4*>(pr + k0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-  }
+        for (int e = 0; e < 4; ++e) o4[e] = fq_apply<FIVE>(fmul(v[j][e], rsum), q2);
+      }
+      *reinterpret_cast<float4*>(pr + k0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  };
+  dispatch_five(q1.five | q2.five, body);
   if (lane == 0) { a.stats[2 * row] = mx; a.stats[2 * row + 1] = sum; }
 }
 
@@ -114,82 +102,73 @@ __global__ void __launch_bounds__(256) attn_probs_bwd_kernel(const ProbArgs a) {
   // fq_2 at a masked column: x = 0 -> t3 = o2; its (gs, go) terms are identically 0 iff o2 is inside the code range
   const bool neutral = !q2.on || (q2.o >= q2.qmin && q2.o <= q2.qmax);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};            // gs1, go1, gs2, go2
-  for (int64_t row = int64_t(blockIdx.x) * kRowsPerCta + (threadIdx.x >> 5); row < a.rows; row += int64_t(gridDim.x) * kRowsPerCta) {
-    const int ncol = a.causal ? int(row % a.Tq) + 1 + (T - a.Tq) : T;
-    const int nproc = neutral ? ncol : T;
-    const float* sr = a.S + row * T;
-    const float* gr = a.g + row * T;
-    const float mx = __ldg(a.stats + 2 * row);
-    const RowDiv rd = make_rowdiv(__ldg(a.stats + 2 * row + 1));
-    float p[NV][4], gp[NV][4];
-    float dot = 0.f;
+  auto body = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    for (int64_t row = int64_t(blockIdx.x) * kRowsPerCta + (threadIdx.x >> 5); row < a.rows; row += int64_t(gridDim.x) * kRowsPerCta) {
+      const int ncol = a.causal ? int(row % a.Tq) + 1 + (T - a.Tq) : T;
+      const int nproc = neutral ? ncol : T;
+      const float* sr = a.S + row * T;
+      const float* gr = a.g + row * T;
+      const float mx = __ldg(a.stats + 2 * row);
+      const float rsum = __frcp_rn(__ldg(a.stats + 2 * row + 1));
+      // With y = softmax row, h = dL/dy (after fq_2's backward) and dot = sum(y*h), the gradient that reaches fq_1's output is
+      // g1_i = mul * (y_i*h_i - dot*y_i).  Everything fq_1's backward needs from element i besides g1_i is known in this
+      // pass -- c_i = dy/dscale = t5 - m*u and the in-range bit m -- so its row sums are accumulated as
+      //   sum g1_i*c_i = mul * (A - dot*B),  A = sum y*h*c, B = sum y*c     and   sum_{!m} g1_i = mul * (C - dot*D)
+      // and the second pass only scales: dS_i = m ? g1_i : 0 from the stashed y_i*h_i and y_i (both zeroed where !m).
+      float pm[NV][4], wm[NV][4];
+      float dot = 0.f, A = 0.f, Bq = 0.f, C = 0.f, D = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int k0 = j * 128 + lane * 4;
-      if (k0 < nproc) {
-        const float4 g4 = ldg4_stream(gr + k0);
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-        float xv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (k0 < ncol) { const float4 x = ldg4(sr + k0); xv[0] = x.x; xv[1] = x.y; xv[2] = x.z; xv[3] = x.w; }
+      for (int j = 0; j < NV; ++j) {
+        const int k0 = j * 128 + lane * 4;
+        pm[j][0] = pm[j][1] = pm[j][2] = pm[j][3] = 0.f;
+        wm[j][0] = wm[j][1] = wm[j][2] = wm[j][3] = 0.f;
+        if (k0 < nproc) {
+          const float4 g4 = ldg4_stream(gr + k0);
+          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+          float xv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (k0 < ncol) { const float4 x = ldg4_stream(sr + k0); xv[0] = x.x; xv[1] = x.y; xv[2] = x.z; xv[3] = x.w; }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float pe = 0.f;
-          if (k0 + e < ncol) pe = div_any(expf(fsub(fmul(fq_apply(xv[e], q1), a.mul), mx)), rd);
-          const FqGrad r = fq_grad(pe, gv[e], q2);
-          p[j][e] = pe; gp[j][e] = r.gx;
-          acc[2] += r.gs; acc[3] += r.go;
-          dot = fmaf(pe, r.gx, dot);
-        }
-      }
-    }
-    dot = warp_reduce(dot, OpSum());
-    float* dr = a.dS + row * T;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int k0 = j * 128 + lane * 4;
-      if (k0 >= T) continue;
-      float d4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (k0 < ncol) {
-        const float4 x = ldg4(sr + k0);
-        const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (k0 + e < ncol) {
-            const float da = fmul(fsub(gp[j][e], dot), p[j][e]);          // softmax backward: (g - sum(g*y)) * y
-            const FqGrad r = fq_grad(xv[e], fmul(da, a.mul), q1);
-            d4[e] = r.gx; acc[0] += r.gs; acc[1] += r.go;
+          for (int e = 0; e < 4; ++e) {
+            float sq = xv[e], c1 = 0.f;
+            bool m1 = true;
+            if (q1.on) {
+              const float u = div_rn<FIVE>(xv[e], q1.s, q1.rs);
+              const float t3 = fadd(rne_magic(u), q1.o);
+              m1 = (t3 >= q1.qmin) && (t3 <= q1.qmax);
+              const float t5 = fsub(fminf(fmaxf(t3, q1.qmin), q1.qmax), q1.o);
+              sq = fmul(t5, q1.s);
+              c1 = fsub(t5, m1 ? u : 0.f);
+            }
+            const float t = (k0 + e < ncol) ? fmul(sq, a.mul) : kNegInf;
+            const float pe = fmul(expf(fsub(t, mx)), rsum);
+            const FqGrad r = fq_grad<FIVE>(pe, gv[e], q2);
+            acc[2] += r.gs; acc[3] += r.go;
+            const float w = fmul(pe, r.gx);
+            dot += w;
+            A = fmaf(w, c1, A); Bq = fmaf(pe, c1, Bq);
+            C += m1 ? 0.f : w; D += m1 ? 0.f : pe;
+            pm[j][e] = m1 ? pe : 0.f; wm[j][e] = m1 ? w : 0.f;
           }
         }
       }
-      *reinterpret_cast<float4*>(dr + k0) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      dot = warp_reduce(dot, OpSum());
+      acc[0] += fmul(a.mul, fmaf(-dot, Bq, A));
+      acc[1] -= fmul(fmul(q1.s, a.mul), fmaf(-dot, D, C));
+      float* dr = a.dS + row * T;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int k0 = j * 128 + lane * 4;
+        if (k0 >= T) continue;
+        float d4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d4[e] = fmul(a.mul, fmaf(-dot, pm[j][e], wm[j][e]));
+        *reinterpret_cast<float4*>(dr + k0) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      }
     }
-  }
-  if (!a.gout) return;
-  float b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = block_reduce(acc[i], OpSum(), red);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a.partial[4 * blockIdx.x + i] = b[i];
-    __threadfence();
-    s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < 32) {
-    __threadfence();
-    const volatile double* vp = a.partial;
-    double t[4] = {0., 0., 0., 0.};
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) t[k] += vp[4 * i + k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = warp_reduce(t[k], OpSum());
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) a.gout[k] = (float)t[k];
-      *a.ticket = 0u;
-    }
-  }
+  };
+  dispatch_five(q1.five | q2.five, body);
+  if (a.gout) grid_fold<4>(acc, a.partial, a.ticket, a.gout, red, &s_last);
 }
 
 static int probs_nv(int T) {

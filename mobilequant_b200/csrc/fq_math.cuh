@@ -53,4 +53,86 @@ __device__ __forceinline__ FqGrad fq_bwd_elem_v(float x, float g, float s, float
   return r;
 }
 
+// The same gradients in the cancellation-free form  dy/dx = m,  dy/ds = t5 - m*u,  dy/do = (m - 1)*s   (u = x/s,
+// t5 = clamp(rne(u)+o) - o, m = in-range).  The op-by-op form above evaluates dy/ds as g*t5 - (g*s*m)*(u/s): two products of
+// magnitude |g|*|u| whose difference is at most |g|/2, each carrying an fp32 rounding error of |g|*|u|*2^-24 (about 1 % of
+// the result for 16-bit codes); here t5 - u is exact (both are within 1/2 of each other), there is one exact division instead
+// of three, and the two forms differ by that rounding noise only (and gx by the <= 1 ulp of (g*s)/s versus g).
+template <bool FIVE>
+__device__ __forceinline__ FqGrad fq_bwd_elem_c(float x, float g, float s, float rs, float o, float qmin, float qmax) {
+  const float u = div_rn<FIVE>(x, s, rs);
+  const float t3 = fadd(rne_magic(u), o);
+  const bool m = (t3 >= qmin) && (t3 <= qmax);
+  const float t5 = fsub(fminf(fmaxf(t3, qmin), qmax), o);
+  FqGrad r;
+  r.gx = m ? g : 0.f;
+  r.gs = fmul(g, fsub(t5, m ? u : 0.f));
+  r.go = m ? 0.f : -fmul(g, s);
+  return r;
+}
+
+// ---- a per-tensor static quantizer as the fused calibration kernels (calib_attn.cu, calib_act.cu) carry it ---------------
+struct FqP {
+  float s, rs, o, qmin, qmax;
+  bool five, on;
+};
+__device__ __forceinline__ FqP load_fqp(const float* scale, const float* offset, float qmin, float qmax) {
+  FqP q;
+  q.on = scale != nullptr;
+  q.s = q.on ? __ldg(scale) : 1.f;
+  q.o = q.on ? __ldg(offset) : 0.f;
+  q.rs = __frcp_rn(q.s);
+  q.five = mantissa_all_ones(q.s);
+  q.qmin = qmin; q.qmax = qmax;
+  return q;
+}
+// FIVE is chosen once per launch (true when any of the launch's scales needs the second Newton step; the longer variant is
+// exact for every divisor).  fq_grad is the cancellation-free form (fq_bwd_elem_c).
+template <bool FIVE>
+__device__ __forceinline__ float fq_apply(float x, const FqP& q) {
+  if (!q.on) return x;
+  return dequant(quant_code_v<FIVE>(x, q.s, q.rs, q.o, q.qmin, q.qmax), q.s, q.o);
+}
+template <bool FIVE>
+__device__ __forceinline__ FqGrad fq_grad(float x, float g, const FqP& q) {
+  if (!q.on) { FqGrad r; r.gx = g; r.gs = 0.f; r.go = 0.f; return r; }
+  return fq_bwd_elem_c<FIVE>(x, g, q.s, q.rs, q.o, q.qmin, q.qmax);
+}
+
+
+// Deterministic grid-wide fold of NACC per-thread float accumulators (quantizer scale / offset gradients): block sums go to
+// double partial[NACC * gridDim.x]; the block whose ticket shows it arrived last adds them in block order and writes
+// gout[NACC]; the ticket resets itself.  `red` = 32 floats of shared memory, `s_last` one shared bool.
+template <int NACC>
+__device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* partial, unsigned* ticket, float* gout, float* red,
+                                          bool* s_last) {
+  float b[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) b[i] = block_reduce(acc[i], OpSum(), red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) partial[NACC * blockIdx.x + i] = b[i];
+    __threadfence();
+    *s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (*s_last && threadIdx.x < 32) {
+    __threadfence();
+    const volatile double* vp = partial;
+    double t[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) t[k] = 0.;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32)
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) t[k] += vp[NACC * i + k];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) t[k] = warp_reduce(t[k], OpSum());
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) gout[k] = (float)t[k];
+      *ticket = 0u;
+    }
+  }
+}
+
 }  // namespace mq

@@ -22,6 +22,8 @@ def _protos():
                                       c_float, _P]
     lib.mq_attn_probs_bwd.argtypes = [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P, _P, c_float, c_float, _P, _P,
                                       c_float, c_float, _P, _P]
+    lib.mq_silu_gate_fwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]
+    lib.mq_silu_gate_bwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]
     lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
     lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
@@ -162,6 +164,39 @@ def attn_probs_bwd(S, stats, g, Tq, causal, mul, q1, q2, want_gparams=True):
                       int(causal), float(mul), ptr(s1), ptr(o1), float(lo1), float(hi1), ptr(s2), ptr(o2), float(lo2), float(hi2),
                       ptr(gp), stream_ptr()), h)
     return dS, gp
+
+
+def _qarrays(qs):
+    """[(scale, offset, qmin, qmax) | None, ...] -> host arrays of device pointers / bounds for the fused calibration kernels."""
+    n = len(qs)
+    sc = (c_void_p * n)(*[ptr(q[0], F32) if q is not None else c_void_p(0) for q in qs])
+    of = (c_void_p * n)(*[ptr(q[1], F32) if q is not None else c_void_p(0) for q in qs])
+    lo = (c_float * n)(*[float(q[2]) if q is not None else 0.0 for q in qs])
+    hi = (c_float * n)(*[float(q[3]) if q is not None else 0.0 for q in qs])
+    return sc, of, lo, hi
+
+
+def silu_gate_fwd(a, b, qs):
+    """fq_w(fq_o(a * fq_s(sigmoid(a))) * b); qs = [fq_s, fq_o, fq_w], each None or (scale, offset, qmin, qmax)."""
+    lib = _protos()
+    out = torch.empty_like(a)
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(a)
+    with torch.cuda.device(a.device):
+        check(_launch("silu_gate_fwd", lib.mq_silu_gate_fwd, h, ptr(a, F32), ptr(b, F32), ptr(out), a.numel(), sc, of, lo, hi, stream_ptr()), h)
+    return out
+
+
+def silu_gate_bwd(a, b, g, qs, want_gparams=True):
+    lib = _protos()
+    da, db = torch.empty_like(a), torch.empty_like(a)
+    gp = torch.empty(6, dtype=F32, device=a.device) if want_gparams else None
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(a)
+    with torch.cuda.device(a.device):
+        check(_launch("silu_gate_bwd", lib.mq_silu_gate_bwd, h, ptr(a, F32), ptr(b, F32), ptr(g, F32), ptr(da), ptr(db), a.numel(), sc, of, lo, hi,
+                      ptr(gp), stream_ptr()), h)
+    return da, db, gp
 
 
 # ---- K8 ---------------------------------------------------------------------------------------------------------

@@ -143,6 +143,13 @@ class HFMLP(nn.Module):
         self.act_fn = _ACT[config.hidden_act]()
 
     def forward(self, x):
+        fused = getattr(self.act_fn, "fused_gate", None) if self.num_linears_per_mlp == 3 else None
+        if fused is not None:                               # QSiLU + gate product + w2's input quantizer as one kernel
+            a, b = self.w1(x), self.w3(x)
+            h = fused(a, b, self.w2)
+            if h is not None:
+                return self.w2(h, input_quantized=True)
+            return self.w2(self.elementwisemul(self.act_fn(a), b))
         h = self.act_fn(self.w1(x))
         if self.num_linears_per_mlp == 3:
             h = self.elementwisemul(h, self.w3(x))

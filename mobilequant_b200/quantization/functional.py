@@ -105,3 +105,56 @@ class AttnProbsFn(torch.autograd.Function):
         return (dS if n[0] else None, None,
                 pick(n[2], 0, sh1 and sh1[0]), pick(n[3], 1, sh1 and sh1[1]), None, None,
                 pick(n[6], 2, sh2 and sh2[0]), pick(n[7], 3, sh2 and sh2[1]), None, None)
+
+
+def _pack_q(params):
+    """flat [s, o, qmin, qmax] * n (s None = disabled) -> kernel-side list + the tensors to save + shapes for the gradients."""
+    qs, saved, shapes = [], [], []
+    for i in range(0, len(params), 4):
+        s, o, lo, hi = params[i:i + 4]
+        if s is None:
+            qs.append(None); shapes.append(None)
+            continue
+        sd, od = s.detach().reshape(()).float().contiguous(), o.detach().reshape(()).float().contiguous()
+        qs.append((sd, od, lo, hi)); saved += [sd, od]; shapes.append((s.shape, o.shape))
+    return qs, saved, shapes
+
+
+def _unpack_q(saved, bounds):
+    qs, k = [], 0
+    for b in bounds:
+        if b is None:
+            qs.append(None)
+        else:
+            qs.append((saved[k], saved[k + 1], b[0], b[1])); k += 2
+    return qs
+
+
+class SiluGateFn(torch.autograd.Function):
+    """fq_w(fq_o(a * fq_s(sigmoid(a))) * b): QSiLU (qm:691-753) on a = w1(x), the gate product with b = w3(x) (hm:1059) and
+    w2.input_quantizer as one kernel forward and one backward (csrc/calib_act.cu).  params = (scale, offset, qmin, qmax) of
+    fq_s, fq_o, fq_w flattened; scale None disables a quantizer."""
+
+    @staticmethod
+    def forward(ctx, a, b, *params):
+        ac, bc = a.detach().contiguous(), b.detach().contiguous()
+        qs, saved, shapes = _pack_q(params)
+        out = K.silu_gate_fwd(ac, bc, qs)
+        ctx.save_for_backward(ac, bc, *saved)
+        ctx.meta = ([None if q is None else (q[2], q[3]) for q in qs], shapes)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ac, bc, *saved = ctx.saved_tensors
+        bounds, shapes = ctx.meta
+        qs = _unpack_q(saved, bounds)
+        n = ctx.needs_input_grad
+        want = any(n[2 + 4 * i] or n[3 + 4 * i] for i in range(3))
+        da, db, gp = K.silu_gate_bwd(ac, bc, g.float().contiguous(), qs, want_gparams=want)
+        out = [da if n[0] else None, db if n[1] else None]
+        for i in range(3):
+            sh = shapes[i]
+            out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[2 + 4 * i]) else None,
+                    gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[3 + 4 * i]) else None, None, None]
+        return tuple(out)

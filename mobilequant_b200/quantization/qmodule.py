@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
-from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn
+from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn
 from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
@@ -225,6 +225,25 @@ def materialize_let(w, let):
     return t.reshape(w.shape)
 
 
+def _static_params(quant, device):
+    """[scale, offset, qmin, qmax] of a per-tensor static quantizer for the fused calibration kernels ([None, None, 0, 0] when it
+    is absent / disabled); False when the fused kernels do not cover it (dynamic, LWC, per-channel, range not cached yet)."""
+    if quant is None or not quant.enable or quant.qcfg.bitwidth > 16:
+        return [None, None, 0.0, 0.0]
+    if quant.qcfg.is_dynamic or quant.lwc or quant.qcfg.is_per_channel or quant.qcfg.group_size != -1 \
+            or not hasattr(quant, "scale") or not hasattr(quant, "offset") or quant.scale.numel() != 1:
+        return False
+    for t in (quant.scale, quant.offset):                          # same lazy move as Quantizer.forward
+        if t.device != device:
+            t.data = t.to(device)
+    return [quant.scale, quant.offset, quant.qmin, quant.qmax]
+
+
+def _fused_enabled(name):
+    """MQB200_FUSED_<NAME>=0 runs that piece of the calibration block op by op (A/B checks)."""
+    return os.environ.get(f"MQB200_FUSED_{name}", "1") != "0"
+
+
 _causal_cache = {}
 
 
@@ -321,10 +340,10 @@ class QLinear(nn.Linear, _QBase):
     def set_scale_offset(self, act_scale, use_scale_offset_as="parameter"):
         self._set_ranges(act_scale, use_scale_offset_as, self.weight.device)
 
-    def forward(self, input_):
+    def forward(self, input_, input_quantized=False):
         bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
         weight = self._fq_weight()
-        if self.input_quantizer is not None:
+        if self.input_quantizer is not None and not input_quantized:
             input_ = self.input_quantizer(input_)
         out = nn.functional.linear(input_, weight, bias=bias)
         if self.output_quantizer is not None:
@@ -386,22 +405,17 @@ class QMatMul(nn.Module, _QBase):
         as matmul + ONE fused kernel (csrc/calib_attn.cu) instead of the element-wise chain over [B, nh, T, T].  Returns None
         when the fused kernel does not cover the case (non-causal mask, cached ranges missing, dynamic / per-channel quantizers,
         reduced precision, T > 2048): the caller then runs the chain op by op."""
-        oq, pq = self.output_quantizer, getattr(pv_bmm, "input_quantizer", None)
-        if os.environ.get("MQB200_FUSED_PROBS", "1") == "0":
-            return None
-        if not isinstance(pv_bmm, QMatMul) or not q.is_cuda or q.dtype != torch.float32 or kt.dtype != torch.float32:
+        if not _fused_enabled("PROBS") or not isinstance(pv_bmm, QMatMul) or not q.is_cuda or q.dtype != torch.float32 \
+                or kt.dtype != torch.float32:
             return None
         if not is_causal_mask(attention_mask, q.shape[-2], kt.shape[-1]) or not K.attn_probs_supported(kt.shape[-1]):
             return None
         params = []
-        for quant in (oq, pq):
-            if quant is None or not quant.enable or quant.qcfg.bitwidth > 16:
-                params += [None, None, 0.0, 0.0]
-                continue
-            if quant.qcfg.is_dynamic or quant.lwc or quant.qcfg.is_per_channel or quant.qcfg.group_size != -1 \
-                    or not hasattr(quant, "scale") or not hasattr(quant, "offset") or quant.scale.numel() != 1:
+        for quant in (self.output_quantizer, pv_bmm.input_quantizer):
+            pq = _static_params(quant, q.device)
+            if pq is False:
                 return None
-            params += [quant.scale, quant.offset, quant.qmin, quant.qmax]
+            params += pq
         x1 = self.input_quantizer(q) if self.input_quantizer is not None else q
         x2 = self.input2_quantizer(kt) if self.input2_quantizer is not None else kt
         scores = torch.matmul(x1, x2)
@@ -533,6 +547,24 @@ class QSiLU(nn.Module, _QBase):
         if self.output_quantizer is not None:
             out = self.output_quantizer(out)
         return out
+
+
+    def fused_gate(self, a, b, w2):
+        """HFMLP.forward's element-wise core with this module as act_fn (hm:1057-1061):
+            w2.input_quantizer(self(a) * b)
+        as ONE fused kernel (csrc/calib_act.cu).  None when not covered; the caller then goes op by op."""
+        if not _fused_enabled("GATE") or not isinstance(w2, QLinear) or not a.is_cuda or a.dtype != torch.float32 \
+                or b.dtype != torch.float32 or a.shape != b.shape or a.numel() % 4 != 0:
+            return None
+        if self.input_quantizer is not None and self.input_quantizer.enable and self.input_quantizer.qcfg.bitwidth <= 16:
+            return None                                    # a separate quantizer on a: not the MobileQuant recipe (qm:853-858)
+        params = []
+        for quant in (self.input2_quantizer, self.output_quantizer, w2.input_quantizer):
+            pq = _static_params(quant, a.device)
+            if pq is False:
+                return None
+            params += pq
+        return SiluGateFn.apply(a, b, *params)
 
 
 class QGELU(nn.Module, _QBase):

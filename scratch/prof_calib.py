@@ -39,7 +39,7 @@ class L:
 
 from torch.profiler import profile, ProfilerActivity
 torch.cuda.synchronize(); t0 = time.perf_counter()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     A.e2equant(args, model, loader, L(), device=dev)
     torch.cuda.synchronize()
 dt = time.perf_counter() - t0
@@ -53,3 +53,8 @@ tot = sum(v[1] for v in agg.values())
 print(f"GPU kernel time total {tot:.1f} ms over {nsamples} samples = {tot/nsamples:.1f} ms/sample (FP pass + training step + fuse)")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{t/nsamples:8.3f} ms/sample {c/nsamples:8.1f} launches/sample  {k}")
+
+print("---- by aten op and input shape (self device time)")
+rows = sorted(prof.key_averages(group_by_input_shape=True), key=lambda e: -e.self_device_time_total)[:60]
+for e in rows:
+    print(f"{e.self_device_time_total/1e3/nsamples:8.3f} ms/sample {e.count/nsamples:8.1f} calls/sample  {e.key[:40]:40s} {str(e.input_shapes)[:110]}")

@@ -285,3 +285,44 @@ def test_attn_probs_fused_matches_chain(cuda, T, hd, bits1, pmin):
             if ref is a2 and i == 0:
                 tol += 4.0 * (nflip + 1) ** 0.5
             assert abs(r - g) <= tol, (i, r, g, nflip)
+
+
+@pytest.mark.parametrize("on", [(True, True, True), (False, True, True), (True, False, False), (False, False, False)])
+def test_silu_gate_fused_matches_chain(cuda, on):
+    """csrc/calib_act.cu silu_gate (forward, backward, the three quantizers' LRL gradients) against the module chain it
+    replaces: w2.input_quantizer(QSiLU(a) * b)."""
+    from mobilequant_b200.quantization.functional import SiluGateFn, StaticFakeQuantFn
+    from mobilequant_b200.quantization.qmodule import compute_scale_offset_from_min_max
+    torch.manual_seed(5)
+    a0 = torch.randn(3, 257, 64, device=cuda) * 3.0
+    b0 = torch.randn(3, 257, 64, device=cuda) * 2.0
+    W = torch.randn_like(a0)
+
+    def qparams(mn, mx, bits, enabled):
+        if not enabled:
+            return [None, None, 0.0, 0.0]
+        s, o, _, _, lo, hi = compute_scale_offset_from_min_max(mn, mx, bits, False)
+        return [torch.nn.Parameter(s.to(cuda)), torch.nn.Parameter(o.to(cuda)), lo, hi]
+
+    res = []
+    for fused in (False, True):
+        a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        qs = [qparams(0.0, 1.0, 8, on[0]), qparams(-0.3, 6.0, 8, on[1]), qparams(-9.0, 11.0, 8, on[2])]
+        if fused:
+            out = SiluGateFn.apply(a, b, *[v for q in qs for v in q])
+        else:
+            fq = lambda x, q: x if q[0] is None else StaticFakeQuantFn.apply(x, *q)
+            out = fq(fq(a * fq(torch.sigmoid(a), qs[0]), qs[1]) * b, qs[2])
+        (out * W).sum().backward()
+        res.append((out.detach(), a.grad, b.grad, qs))
+    (o0, ga0, gb0, q0), (o1, ga1, gb1, q1) = res
+    assert torch.equal(o0, o1)
+    assert torch.allclose(ga0, ga1, rtol=1e-5, atol=1e-6) and torch.allclose(gb0, gb1, rtol=1e-5, atol=1e-6)
+    for r, g in zip(q0, q1):
+        if r[0] is None:
+            continue
+        for i in (0, 1):
+            ref, got = r[i].grad.item(), g[i].grad.item()
+            # the chain evaluates d/dscale as g*t5 - (g*s*m)*(u/s) (rounding noise |g|*|u|*2^-24 per element), the fused kernel
+            # as g*(t5 - m*u)
+            assert abs(ref - got) <= 1e-3 * abs(ref) + 2e-2, (i, ref, got)
