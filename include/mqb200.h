@@ -91,6 +91,20 @@ int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, const float* g, 
                      const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs,
                      float* gparams, void* stream);
 
+/* ---- Calibration QRMSNorm in its L2-norm form (qm:515-531 over hm:187-195 / F.normalize), fused with both quantizers:
+ *   out = fq_out( w * (alpha * xq / max(||xq||_2, eps)) + bias ),  xq = fq_in(x)      x, out: [rows, H] fp32, H % 4 == 0, H <= 8192
+ * w = the (already fake-quantised) norm weight [H], bias may be NULL; nrm[rows] receives ||xq||_2 for the backward.
+ * scales / offsets: HOST arrays of 2 DEVICE pointers (input, output quantizer; NULL pair = disabled), qmins / qmaxs HOST float[2].
+ * Backward: dx [rows, H], dw [H], dbias [H] (may be NULL) from g = dL/dout; gparams (may be NULL) = DEVICE float[4] OVERWRITTEN
+ * with (d/dscale, d/doffset) of the input and the output quantizer.  All reductions are fixed-order (deterministic).         */
+int mq_rmsnorm_l2_supported(int H);
+int mq_rmsnorm_l2_fwd(void* ctx, const float* x, const float* w, const float* bias, float* out, float* nrm, int64_t rows, int H,
+                      float alpha, float eps, const float* const* scales, const float* const* offsets, const float* qmins,
+                      const float* qmaxs, void* stream);
+int mq_rmsnorm_l2_bwd(void* ctx, const float* x, const float* w, const float* bias, const float* nrm, const float* g, float* dx,
+                      float* dw, float* dbias, int64_t rows, int H, float alpha, float eps, const float* const* scales,
+                      const float* const* offsets, const float* qmins, const float* qmaxs, float* gparams, void* stream);
+
 /* ---- K8: range statistics, generate_act_range.py:55-69 (per tensor) / :57-63 (per channel) -------------------
  * minmax[0] = min(minmax[0], min x), minmax[1] = max(minmax[1], max x) when accumulate != 0, else overwritten.
  * rows variant: x is [rows, cols]; per_row != 0 reduces over cols (weights, qm:30) else over rows (per-channel

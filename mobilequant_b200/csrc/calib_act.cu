@@ -3,6 +3,10 @@
 // folded deterministically; arithmetic as in fq_math.cuh):
 //   * gated SiLU MLP core (hm:1042-1062 with QSiLU qm:691-753 and w2.input_quantizer):
 //       out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b ),   a = w1(x) (already quantised by w1), b = w3(x)
+//   * QRMSNorm in its L2-norm form (qm:515-531 over hm:187-195, F.normalize):
+//       out = fq_out( w * (alpha * xq / max(||xq||_2, eps)) + bias ),   xq = fq_in(x)
+//     one CTA per row (row statistics through shared memory), dL/dw and dL/dbias accumulated per thread over the rows of a
+//     CTA and folded over CTAs in fixed order by a second tiny kernel.
 #include "common.cuh"
 #include "ctx.h"
 #include "fq_math.cuh"
@@ -84,6 +88,157 @@ __global__ void __launch_bounds__(256) silu_gate_bwd_kernel(const GateArgs p) {
   if (p.gout) grid_fold<6>(acc, p.partial, p.ticket, p.gout, red, &s_last);
 }
 
+
+struct NormCArgs {
+  const float *x, *w, *b; float *out, *nrm; int64_t rows; int H; float alpha, eps;
+  const float *s_i, *o_i; float qmin_i, qmax_i;      // input quantizer
+  const float *s_o, *o_o; float qmin_o, qmax_o;      // output quantizer
+  const float* g; float *dx, *pdw, *pdb;             // backward: pdw / pdb = per-CTA column partials [gridDim.x][H]
+  double* partial; unsigned* ticket; float* gout;    // gout[4] = d/d(scale, offset) of the input, output quantizer
+};
+
+// thread t of the CTA owns columns (k*256 + t)*4 .. +3, k < NVT
+template <int NVT>
+__global__ void __launch_bounds__(256) rmsnorm_l2_fwd_kernel(const NormCArgs p) {
+  __shared__ float red[32];
+  const FqP qi = load_fqp(p.s_i, p.o_i, p.qmin_i, p.qmax_i), qo = load_fqp(p.s_o, p.o_o, p.qmin_o, p.qmax_o);
+  const int H = p.H;
+  auto body = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+      const float* xr = p.x + row * H;
+      float xq[NVT][4];
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < NVT; ++k) {
+        const int c = (k * 256 + threadIdx.x) * 4;
+        xq[k][0] = xq[k][1] = xq[k][2] = xq[k][3] = 0.f;
+        if (c < H) {
+          const float4 v = ldg4_stream(xr + c);
+          xq[k][0] = fq_apply<FIVE>(v.x, qi); xq[k][1] = fq_apply<FIVE>(v.y, qi);
+          xq[k][2] = fq_apply<FIVE>(v.z, qi); xq[k][3] = fq_apply<FIVE>(v.w, qi);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ss = fmaf(xq[k][e], xq[k][e], ss);
+        }
+      }
+      ss = block_reduce(ss, OpSum(), red);
+      const float raw = __fsqrt_rn(ss), nrm = fmaxf(raw, p.eps), rn = __frcp_rn(nrm);
+      if (threadIdx.x == 0) p.nrm[row] = raw;
+#pragma unroll
+      for (int k = 0; k < NVT; ++k) {
+        const int c = (k * 256 + threadIdx.x) * 4;
+        if (c >= H) continue;
+        const float4 w4 = ldg4(p.w + c);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.b) b4 = ldg4(p.b + c);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float y = fmul(wv[e], fmul(p.alpha, div_rn<true>(xq[k][e], nrm, rn)));
+          if (p.b) y = fadd(y, bv[e]);
+          o[e] = fq_apply<FIVE>(y, qo);
+        }
+        *reinterpret_cast<float4*>(p.out + row * H + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  };
+  dispatch_five(qi.five | qo.five, body);
+}
+
+template <int NVT>
+__global__ void __launch_bounds__(256) rmsnorm_l2_bwd_kernel(const NormCArgs p) {
+  __shared__ float red[32];
+  __shared__ bool s_last;
+  const FqP qi = load_fqp(p.s_i, p.o_i, p.qmin_i, p.qmax_i), qo = load_fqp(p.s_o, p.o_o, p.qmin_o, p.qmax_o);
+  const int H = p.H;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float dw[NVT][4], db[NVT][4];
+#pragma unroll
+  for (int k = 0; k < NVT; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dw[k][e] = db[k][e] = 0.f;
+  auto body = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+      const float* xr = p.x + row * H;
+      const float* gr = p.g + row * H;
+      const float raw = __ldg(p.nrm + row), nrm = fmaxf(raw, p.eps), rn = __frcp_rn(nrm);
+      const bool clamped = raw < p.eps;                       // clamp_min passes no gradient to the norm then
+      float nv[NVT][4], dn[NVT][4];
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NVT; ++k) {
+        const int c = (k * 256 + threadIdx.x) * 4;
+        nv[k][0] = nv[k][1] = nv[k][2] = nv[k][3] = 0.f;
+        dn[k][0] = dn[k][1] = dn[k][2] = dn[k][3] = 0.f;
+        if (c < H) {
+          const float4 v = ldg4(xr + c), g4 = ldg4_stream(gr + c), w4 = ldg4(p.w + c);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.b) b4 = ldg4(p.b + c);
+          const float xv[4] = {v.x, v.y, v.z, v.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w},
+                      bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float n = div_rn<true>(fq_apply<FIVE>(xv[e], qi), nrm, rn);
+            const float t = fmul(p.alpha, n);
+            float y = fmul(wv[e], t);
+            if (p.b) y = fadd(y, bv[e]);
+            const FqGrad ro = fq_grad<FIVE>(y, gv[e], qo);
+            acc[2] += ro.gs; acc[3] += ro.go;
+            dw[k][e] = fmaf(ro.gx, t, dw[k][e]);
+            db[k][e] += ro.gx;
+            nv[k][e] = n;
+            dn[k][e] = fmul(p.alpha, fmul(ro.gx, wv[e]));
+            dot = fmaf(dn[k][e], n, dot);
+          }
+        }
+      }
+      dot = block_reduce(dot, OpSum(), red);
+      if (clamped) dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NVT; ++k) {
+        const int c = (k * 256 + threadIdx.x) * 4;
+        if (c >= H) continue;
+        const float4 v = ldg4(xr + c);
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float dxq = fmul(fmaf(-nv[k][e], dot, dn[k][e]), rn);
+          const FqGrad ri = fq_grad<FIVE>(xv[e], dxq, qi);
+          d[e] = ri.gx; acc[0] += ri.gs; acc[1] += ri.go;
+        }
+        *reinterpret_cast<float4*>(p.dx + row * H + c) = make_float4(d[0], d[1], d[2], d[3]);
+      }
+    }
+  };
+  dispatch_five(qi.five | qo.five, body);
+#pragma unroll
+  for (int k = 0; k < NVT; ++k) {
+    const int c = (k * 256 + threadIdx.x) * 4;
+    if (c >= H) continue;
+    *reinterpret_cast<float4*>(p.pdw + int64_t(blockIdx.x) * H + c) = make_float4(dw[k][0], dw[k][1], dw[k][2], dw[k][3]);
+    if (p.pdb) *reinterpret_cast<float4*>(p.pdb + int64_t(blockIdx.x) * H + c) = make_float4(db[k][0], db[k][1], db[k][2], db[k][3]);
+  }
+  if (p.gout) grid_fold<4>(acc, p.partial, p.ticket, p.gout, red, &s_last);
+}
+
+// out[c] = sum over blocks (in block order) of part[blk][c]
+__global__ void __launch_bounds__(256) fold_cols_kernel(const float* __restrict__ part, int nblk, int H, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[int64_t(b) * H + c];
+  out[c] = s;
+}
+
+static int norm_nvt(int H) {
+  if (H % 4 != 0 || H < 4 || H > 8192) return 0;
+  const int chunks = (H / 4 + 255) / 256;
+  return chunks <= 1 ? 1 : chunks <= 2 ? 2 : chunks <= 4 ? 4 : 8;
+}
+
 }  // namespace mq
 
 using namespace mq;
@@ -133,6 +288,76 @@ int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, const float* g, 
   }
   silu_gate_bwd_kernel<<<grid_for_elems(c, n / 4, 4), 256, 0, st>>>(p);
   return check_launch(c, "mq_silu_gate_bwd");
+}
+
+int mq_rmsnorm_l2_supported(int H) { return norm_nvt(H) != 0; }
+
+static void norm_fill(NormCArgs& p, const float* x, const float* w, const float* b, int64_t rows, int H, float alpha, float eps,
+                      const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs) {
+  p.x = x; p.w = w; p.b = b; p.rows = rows; p.H = H; p.alpha = alpha; p.eps = eps;
+  p.s_i = scales[0]; p.o_i = offsets[0]; p.qmin_i = qmins[0]; p.qmax_i = qmaxs[0];
+  p.s_o = scales[1]; p.o_o = offsets[1]; p.qmin_o = qmins[1]; p.qmax_o = qmaxs[1];
+}
+
+int mq_rmsnorm_l2_fwd(void* ctx, const float* x, const float* w, const float* bias, float* out, float* nrm, int64_t rows, int H,
+                      float alpha, float eps, const float* const* scales, const float* const* offsets, const float* qmins,
+                      const float* qmaxs, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, x && w && out && nrm && rows >= 0 && scales && offsets && qmins && qmaxs, "null pointer or negative size");
+  const int nvt = norm_nvt(H);
+  MQ_REQUIRE(c, nvt != 0, "H must be a multiple of 4 and <= 8192");
+  MQ_REQUIRE(c, al16(x) && al16(w) && al16(out) && (!bias || al16(bias)), "tensors must be 16-byte aligned");
+  for (int i = 0; i < 2; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
+  if (rows == 0) return MQ_NO_ERROR;
+  NormCArgs p{};
+  norm_fill(p, x, w, bias, rows, H, alpha, eps, scales, offsets, qmins, qmaxs);
+  p.out = out; p.nrm = nrm;
+  const int64_t cap = int64_t(c->sm_count) * 8;
+  const unsigned grid = (unsigned)(rows < cap ? rows : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nvt) {
+    case 1: rmsnorm_l2_fwd_kernel<1><<<grid, 256, 0, st>>>(p); break;
+    case 2: rmsnorm_l2_fwd_kernel<2><<<grid, 256, 0, st>>>(p); break;
+    case 4: rmsnorm_l2_fwd_kernel<4><<<grid, 256, 0, st>>>(p); break;
+    default: rmsnorm_l2_fwd_kernel<8><<<grid, 256, 0, st>>>(p); break;
+  }
+  return check_launch(c, "mq_rmsnorm_l2_fwd");
+}
+
+int mq_rmsnorm_l2_bwd(void* ctx, const float* x, const float* w, const float* bias, const float* nrm, const float* g, float* dx,
+                      float* dw, float* dbias, int64_t rows, int H, float alpha, float eps, const float* const* scales,
+                      const float* const* offsets, const float* qmins, const float* qmaxs, float* gparams, void* stream) {
+  MQ_CTX(c, ctx);
+  MQ_REQUIRE(c, x && w && nrm && g && dx && dw && rows > 0 && scales && offsets && qmins && qmaxs, "null pointer or empty input");
+  MQ_REQUIRE(c, !dbias || bias, "dbias without a bias");
+  const int nvt = norm_nvt(H);
+  MQ_REQUIRE(c, nvt != 0, "H must be a multiple of 4 and <= 8192");
+  MQ_REQUIRE(c, al16(x) && al16(w) && al16(g) && al16(dx) && (!bias || al16(bias)), "tensors must be 16-byte aligned");
+  for (int i = 0; i < 2; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormCArgs p{};
+  norm_fill(p, x, w, bias, rows, H, alpha, eps, scales, offsets, qmins, qmaxs);
+  p.nrm = const_cast<float*>(nrm); p.g = g; p.dx = dx; p.gout = gparams;
+  const int64_t cap = int64_t(c->sm_count) * 2;
+  const unsigned grid = (unsigned)(rows < cap ? rows : cap);
+  // workspace of this stream: [grid_fold partials (64 KB)] [pdw: grid*H floats] [pdb: grid*H floats] ... [tickets: last 64 B]
+  char* wsp = static_cast<char*>(stream_ws(c, st));
+  if (!wsp) return MQ_FAILED_ALLOCATION;
+  const size_t part_bytes = size_t(grid) * H * sizeof(float);
+  MQ_REQUIRE(c, 65536 + 2 * part_bytes + 64 <= c->ws_bytes, "workspace too small");
+  p.partial = reinterpret_cast<double*>(wsp);
+  p.ticket = reinterpret_cast<unsigned*>(wsp + c->ws_bytes - 64);
+  p.pdw = reinterpret_cast<float*>(wsp + 65536);
+  p.pdb = dbias ? reinterpret_cast<float*>(wsp + 65536 + part_bytes) : nullptr;
+  switch (nvt) {
+    case 1: rmsnorm_l2_bwd_kernel<1><<<grid, 256, 0, st>>>(p); break;
+    case 2: rmsnorm_l2_bwd_kernel<2><<<grid, 256, 0, st>>>(p); break;
+    case 4: rmsnorm_l2_bwd_kernel<4><<<grid, 256, 0, st>>>(p); break;
+    default: rmsnorm_l2_bwd_kernel<8><<<grid, 256, 0, st>>>(p); break;
+  }
+  fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdw, (int)grid, H, dw);
+  if (dbias) fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdb, (int)grid, H, dbias);
+  return check_launch(c, "mq_rmsnorm_l2_bwd");
 }
 
 }  // extern "C"

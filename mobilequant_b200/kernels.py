@@ -24,6 +24,9 @@ def _protos():
                                       c_float, c_float, _P, _P]
     lib.mq_silu_gate_fwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]
     lib.mq_silu_gate_bwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]
+    lib.mq_rmsnorm_l2_supported.argtypes = [c_int]
+    lib.mq_rmsnorm_l2_fwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P]
+    lib.mq_rmsnorm_l2_bwd.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]
     lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
     lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
@@ -197,6 +200,41 @@ def silu_gate_bwd(a, b, g, qs, want_gparams=True):
         check(_launch("silu_gate_bwd", lib.mq_silu_gate_bwd, h, ptr(a, F32), ptr(b, F32), ptr(g, F32), ptr(da), ptr(db), a.numel(), sc, of, lo, hi,
                       ptr(gp), stream_ptr()), h)
     return da, db, gp
+
+
+def rmsnorm_l2_supported(H):
+    return bool(_protos().mq_rmsnorm_l2_supported(int(H)))
+
+
+def rmsnorm_l2_fwd(x, w, bias, alpha, eps, qs):
+    """fq_out(w * (alpha * fq_in(x) / max(||fq_in(x)||, eps)) + bias) over the last dim; qs = [fq_in, fq_out].  Returns (out, nrm)."""
+    lib = _protos()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    out = torch.empty_like(x)
+    nrm = torch.empty(rows, dtype=F32, device=x.device)
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(_launch("rmsnorm_l2_fwd", lib.mq_rmsnorm_l2_fwd, h, ptr(x, F32), ptr(w, F32), ptr(bias), ptr(out), ptr(nrm), rows, H, float(alpha),
+                      float(eps), sc, of, lo, hi, stream_ptr()), h)
+    return out, nrm
+
+
+def rmsnorm_l2_bwd(x, w, bias, nrm, g, alpha, eps, qs, want_dbias=False, want_gparams=True):
+    lib = _protos()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    dx = torch.empty_like(x)
+    dw = torch.empty(H, dtype=F32, device=x.device)
+    dbias = torch.empty(H, dtype=F32, device=x.device) if want_dbias else None
+    gp = torch.empty(4, dtype=F32, device=x.device) if want_gparams else None
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(x)
+    with torch.cuda.device(x.device):
+        check(_launch("rmsnorm_l2_bwd", lib.mq_rmsnorm_l2_bwd, h, ptr(x, F32), ptr(w, F32), ptr(bias), ptr(nrm, F32), ptr(g, F32), ptr(dx), ptr(dw),
+                      ptr(dbias), rows, H, float(alpha), float(eps), sc, of, lo, hi, ptr(gp), stream_ptr()), h)
+    return dx, dw, dbias, gp
 
 
 # ---- K8 ---------------------------------------------------------------------------------------------------------

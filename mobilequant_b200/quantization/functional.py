@@ -158,3 +158,38 @@ class SiluGateFn(torch.autograd.Function):
             out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[2 + 4 * i]) else None,
                     gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[3 + 4 * i]) else None, None, None]
         return tuple(out)
+
+
+class RmsNormL2Fn(torch.autograd.Function):
+    """QRMSNorm.forward in its L2-norm form (qm:515-531, hm:187-195): input quantizer, F.normalize, alpha, weight, bias and
+    output quantizer as one kernel forward, one backward plus the fixed-order fold of dL/dweight (csrc/calib_act.cu).
+    params = (scale, offset, qmin, qmax) of the input and the output quantizer, flattened."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, alpha, eps, *params):
+        xc = x.detach().contiguous()
+        wc = w.detach().reshape(-1).float().contiguous()
+        bc = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+        qs, saved, shapes = _pack_q(params)
+        out, nrm = K.rmsnorm_l2_fwd(xc, wc, bc, alpha, eps, qs)
+        ctx.save_for_backward(xc, wc, nrm, *([bc] if bc is not None else []), *saved)
+        ctx.meta = (alpha, eps, bc is not None, [None if q is None else (q[2], q[3]) for q in qs], shapes, w.shape,
+                    None if bias is None else bias.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, eps, has_b, bounds, shapes, wshape, bshape = ctx.meta
+        xc, wc, nrm, *rest = ctx.saved_tensors
+        bc = rest.pop(0) if has_b else None
+        qs = _unpack_q(rest, bounds)
+        n = ctx.needs_input_grad
+        want = any(n[5 + 4 * i] or n[6 + 4 * i] for i in range(2))
+        dx, dw, db, gp = K.rmsnorm_l2_bwd(xc, wc, bc, nrm, g.float().contiguous(), alpha, eps, qs, want_dbias=has_b and n[2],
+                                          want_gparams=want)
+        out = [dx if n[0] else None, dw.reshape(wshape) if n[1] else None, db.reshape(bshape) if (has_b and n[2]) else None, None, None]
+        for i in range(2):
+            sh = shapes[i]
+            out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[5 + 4 * i]) else None,
+                    gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[6 + 4 * i]) else None, None, None]
+        return tuple(out)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
-from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn
+from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn
 from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
@@ -442,11 +442,30 @@ class QRMSNorm(HFRMSNorm, _QBase):
     def _qweight(self):
         return self._fq_weight()
 
+    def _fused(self, input_, weight, bias):
+        """The whole forward as one kernel (csrc/calib_act.cu) when it is the L2-norm form with per-tensor static quantizers."""
+        if not _fused_enabled("NORM") or not self.l2norm_as_rmsnorm or not input_.is_cuda or input_.dtype != torch.float32 \
+                or weight.dtype != torch.float32 or not K.rmsnorm_l2_supported(input_.shape[-1]):
+            return None
+        l2 = self.l2norm
+        if l2.p != 2 or l2.dim not in (-1, input_.dim() - 1):
+            return None
+        params = []
+        for quant in (self.input_quantizer, self.output_quantizer):
+            pq = _static_params(quant, input_.device)
+            if pq is False:
+                return None
+            params += pq
+        return RmsNormL2Fn.apply(input_, weight, bias, self.alpha, l2.eps, *params)
+
     def forward(self, input_):
         weight = self._qweight()
+        bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
+        out = self._fused(input_, weight, bias)
+        if out is not None:
+            return out
         if self.input_quantizer is not None:
             input_ = self.input_quantizer(input_)
-        bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
         out = self.forward_impl(input_, weight, bias)
         if self.output_quantizer is not None:
             out = self.output_quantizer(out)

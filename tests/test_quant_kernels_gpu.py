@@ -326,3 +326,47 @@ def test_silu_gate_fused_matches_chain(cuda, on):
             # the chain evaluates d/dscale as g*t5 - (g*s*m)*(u/s) (rounding noise |g|*|u|*2^-24 per element), the fused kernel
             # as g*(t5 - m*u)
             assert abs(ref - got) <= 1e-3 * abs(ref) + 2e-2, (i, ref, got)
+
+
+@pytest.mark.parametrize("H,bias,on", [(2048, False, (True, True)), (2560, True, (True, True)), (64, False, (False, True)),
+                                       (1024, True, (False, False))])
+def test_rmsnorm_l2_fused_matches_chain(cuda, H, bias, on):
+    """csrc/calib_act.cu rmsnorm_l2 (forward, dx, dweight, dbias, LRL gradients) against QRMSNorm's op-by-op forward."""
+    from mobilequant_b200.quantization import qmodule as Q
+    torch.manual_seed(H)
+    x0 = torch.randn(2, 37, H, device=cuda) * 2.0
+    Wt = torch.randn_like(x0)
+    res = []
+    for fused in (False, True):
+        os.environ["MQB200_FUSED_NORM"] = "1" if fused else "0"
+        try:
+            m = Q.QRMSNorm(dict(dim=H, eps=1e-6, device=cuda, dtype=torch.float32, l2norm_as_rmsnorm=True),
+                           Q.QuantConfig(bitwidth=16), None, Q.QuantConfig(bitwidth=8))
+            torch.manual_seed(1); m.weight.data = torch.randn(H, device=cuda)
+            if bias:
+                m.bias = torch.nn.Parameter(torch.randn(H, device=cuda) * 0.1)
+            m.set_scale_offset({"input": [-7.0, 8.0], "output": [-60.0, 70.0]}, "parameter")
+            if not on[0]:
+                m.input_quantizer = None
+            if not on[1]:
+                m.output_quantizer.enable = False
+            x = x0.clone().requires_grad_(True)
+            out = m(x)
+            (out * Wt).sum().backward()
+            res.append((out.detach(), x.grad, m.weight.grad, None if not bias else m.bias.grad,
+                        [0.0 if q.grad is None else q.grad.item() for q in m.parameters() if q.dim() == 0]))
+        finally:
+            os.environ.pop("MQB200_FUSED_NORM", None)
+    (o0, gx0, gw0, gb0, gq0), (o1, gx1, gw1, gb1, gq1) = res
+    lsb = 130.0 / 255
+    d = (o0 - o1).abs()
+    assert d.max().item() <= (1.01 * lsb if on[1] else 1e-4)      # ||x|| summation order: at most one output code apart, rarely
+    assert (d > 1e-5).float().mean().item() < 2e-3
+    gs = gx0.abs().max().item()
+    assert (gx0 - gx1).abs().max().item() < 0.05 * gs and (gx0 - gx1).abs().mean().item() < 2e-4 * gs
+    assert torch.allclose(gw0, gw1, rtol=2e-3, atol=2e-3 * gw0.abs().max().item())
+    if bias:
+        assert torch.allclose(gb0, gb1, rtol=2e-3, atol=2e-3 * gb0.abs().max().item())
+    assert len(gq0) == len(gq1)
+    for r, g in zip(gq0, gq1):
+        assert abs(r - g) <= 0.03 * abs(r) + 0.05 * max(abs(v) for v in gq0), (gq0, gq1)
