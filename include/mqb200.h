@@ -79,17 +79,20 @@ int mq_attn_probs_bwd(void* ctx, const float* S, const float* stats, const float
                       int causal, float mul, const float* scale1, const float* offset1, float qmin1, float qmax1,
                       const float* scale2, const float* offset2, float qmin2, float qmax2, float* gparams, void* stream);
 
-/* ---- Calibration MLP core of a gated-SiLU block (hm:1042-1062 with QSiLU, qm:691-753, and w2.input_quantizer), fused:
- *   out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b )        a = w1(x) (already quantised by w1), b = w3(x); n elements, n % 4 == 0
- * scales / offsets: HOST arrays of 3 DEVICE pointers in the order fq_s (QSiLU.input2_quantizer), fq_o (QSiLU.output_quantizer),
- * fq_w (w2.input_quantizer); a NULL pair disables that quantizer; qmins / qmaxs: HOST float[3].
- * Backward: da, db from g = dL/dout; gparams (may be NULL) = DEVICE float[6] OVERWRITTEN with (d/dscale, d/doffset) of fq_s,
- * fq_o, fq_w (deterministic fixed-order reduction in the ctx workspace of `stream`).                                      */
-int mq_silu_gate_fwd(void* ctx, const float* a, const float* b, float* out, int64_t n, const float* const* scales,
-                     const float* const* offsets, const float* qmins, const float* qmaxs, void* stream);
-int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, const float* g, float* da, float* db, int64_t n,
-                     const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs,
-                     float* gparams, void* stream);
+/* ---- Calibration MLP core of a gated-SiLU block (hm:1042-1062 with QSiLU, qm:691-753, the output quantizers of w1 / w3 and
+ * w2.input_quantizer), fused:
+ *   out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b ),   a = fq_a(ya), b = fq_b(yb)      ya = w1 x + b1, yb = w3 x + b3
+ * ya, yb: [rows, cols] fp32 with row stride ld (the two halves of ONE [rows, 2*cols] GEMM result, or two tensors with ld == cols);
+ * out: [rows, cols] contiguous; cols % 4 == 0.  scales / offsets: HOST arrays of 5 DEVICE pointers in the order fq_a
+ * (w1.output_quantizer), fq_b (w3.output_quantizer), fq_s (QSiLU.input2_quantizer), fq_o (QSiLU.output_quantizer), fq_w
+ * (w2.input_quantizer); a NULL pair disables that quantizer; qmins / qmaxs: HOST float[5].
+ * Backward: dya, dyb (row stride ldd) from g = dL/dout; gparams (may be NULL) = DEVICE float[10] OVERWRITTEN with
+ * (d/dscale, d/doffset) of the five quantizers in that order (deterministic fixed-order reduction, ctx workspace of `stream`). */
+int mq_silu_gate_fwd(void* ctx, const float* ya, const float* yb, int64_t ld, float* out, int64_t rows, int cols,
+                     const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs, void* stream);
+int mq_silu_gate_bwd(void* ctx, const float* ya, const float* yb, int64_t ld, const float* g, float* dya, float* dyb, int64_t ldd,
+                     int64_t rows, int cols, const float* const* scales, const float* const* offsets, const float* qmins,
+                     const float* qmaxs, float* gparams, void* stream);
 
 /* ---- Calibration QRMSNorm in its L2-norm form (qm:515-531 over hm:187-195 / F.normalize), fused with both quantizers:
  *   out = fq_out( w * (alpha * xq / max(||xq||_2, eps)) + bias ),  xq = fq_in(x)      x, out: [rows, H] fp32, H % 4 == 0, H <= 8192

@@ -2,7 +2,8 @@
 // ATen launches the module graph produces (the quantizers' scale / offset gradients come out of the same backward pass,
 // folded deterministically; arithmetic as in fq_math.cuh):
 //   * gated SiLU MLP core (hm:1042-1062 with QSiLU qm:691-753 and w2.input_quantizer):
-//       out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b ),   a = w1(x) (already quantised by w1), b = w3(x)
+//       out = fq_w( fq_o( a * fq_s(sigmoid(a)) ) * b ),   a = fq_a(w1 x + b1), b = fq_b(w3 x + b3)
+//     fq_a / fq_b = the output quantizers of w1 / w3; a and b may be the two halves of one [rows, 2*I] GEMM result (row stride)
 //   * QRMSNorm in its L2-norm form (qm:515-531 over hm:187-195, F.normalize):
 //       out = fq_out( w * (alpha * xq / max(||xq||_2, eps)) + bias ),   xq = fq_in(x)
 //     one CTA per row (row statistics through shared memory), dL/dw and dL/dbias accumulated per thread over the rows of a
@@ -20,74 +21,88 @@ static inline int grid_for_elems(Ctx* c, int64_t n4, int waves) {
 }
 
 struct GateArgs {
-  const float *a, *b; float* out; int64_t n;
-  const float *s_s, *o_s; float qmin_s, qmax_s;      // fq_s: QSiLU.input2_quantizer (on sigmoid(a))
-  const float *s_o, *o_o; float qmin_o, qmax_o;      // fq_o: QSiLU.output_quantizer
-  const float *s_w, *o_w; float qmin_w, qmax_w;      // fq_w: w2.input_quantizer
-  const float* g; float *da, *db;
-  double* partial; unsigned* ticket; float* gout;    // gout[6] = d/d(scale, offset) of fq_s, fq_o, fq_w
+  const float *a, *b; float* out; int64_t rows; int cols; int64_t ld;   // a, b: [rows, cols] with row stride ld; out: [rows, cols]
+  const float *sc[5], *of[5]; float qmin[5], qmax[5];  // fq_a (w1.output), fq_b (w3.output), fq_s, fq_o (QSiLU), fq_w (w2.input)
+  const float* g; float *da, *db; int64_t ldd;         // backward: da, db with row stride ldd
+  double* partial; unsigned* ticket; float* gout;      // gout[10] = (d/dscale, d/doffset) of the five quantizers
 };
 
 // ATen: sigmoid(x) = 1 / (1 + exp(-x)) in fp32
 __device__ __forceinline__ float sigmoid_rn(float x) { return __frcp_rn(fadd(1.f, expf(-x))); }
 
 __global__ void __launch_bounds__(256) silu_gate_fwd_kernel(const GateArgs p) {
-  const FqP qs = load_fqp(p.s_s, p.o_s, p.qmin_s, p.qmax_s), qo = load_fqp(p.s_o, p.o_o, p.qmin_o, p.qmax_o),
-            qw = load_fqp(p.s_w, p.o_w, p.qmin_w, p.qmax_w);
-  const int64_t n4 = p.n >> 2, nthr = int64_t(gridDim.x) * blockDim.x;
+  FqP q[5];
+  bool five = false;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { q[i] = load_fqp(p.sc[i], p.of[i], p.qmin[i], p.qmax[i]); five |= q[i].five; }
+  const int c4 = p.cols >> 2;
+  const int64_t n4 = p.rows * c4, nthr = int64_t(gridDim.x) * blockDim.x;
   auto body = [&](auto five_tag) {
     constexpr bool FIVE = decltype(five_tag)::value;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += nthr) {
-      const float4 a4 = ldg4_stream(p.a + (i << 2)), b4 = ldg4_stream(p.b + (i << 2));
+      const int64_t r = i / c4;
+      const int c = int(i - r * c4) << 2;
+      const float4 a4 = ldg4_stream(p.a + r * p.ld + c), b4 = ldg4_stream(p.b + r * p.ld + c);
       const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float y = fq_apply<FIVE>(sigmoid_rn(av[e]), qs);
-        const float h = fq_apply<FIVE>(fmul(av[e], y), qo);
-        o[e] = fq_apply<FIVE>(fmul(h, bv[e]), qw);
+        const float a = fq_apply<FIVE>(av[e], q[0]), b = fq_apply<FIVE>(bv[e], q[1]);
+        const float y = fq_apply<FIVE>(sigmoid_rn(a), q[2]);
+        const float h = fq_apply<FIVE>(fmul(a, y), q[3]);
+        o[e] = fq_apply<FIVE>(fmul(h, b), q[4]);
       }
-      *reinterpret_cast<float4*>(p.out + (i << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(p.out + r * p.cols + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
   };
-  dispatch_five(qs.five | qo.five | qw.five, body);
+  dispatch_five(five, body);
 }
 
 __global__ void __launch_bounds__(256) silu_gate_bwd_kernel(const GateArgs p) {
   __shared__ float red[32];
   __shared__ bool s_last;
-  const FqP qs = load_fqp(p.s_s, p.o_s, p.qmin_s, p.qmax_s), qo = load_fqp(p.s_o, p.o_o, p.qmin_o, p.qmax_o),
-            qw = load_fqp(p.s_w, p.o_w, p.qmin_w, p.qmax_w);
-  const int64_t n4 = p.n >> 2, nthr = int64_t(gridDim.x) * blockDim.x;
-  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  FqP q[5];
+  bool five = false;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { q[i] = load_fqp(p.sc[i], p.of[i], p.qmin[i], p.qmax[i]); five |= q[i].five; }
+  const int c4 = p.cols >> 2;
+  const int64_t n4 = p.rows * c4, nthr = int64_t(gridDim.x) * blockDim.x;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
   auto body = [&](auto five_tag) {
     constexpr bool FIVE = decltype(five_tag)::value;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += nthr) {
-      const float4 a4 = ldg4_stream(p.a + (i << 2)), b4 = ldg4_stream(p.b + (i << 2)), g4 = ldg4_stream(p.g + (i << 2));
+      const int64_t r = i / c4;
+      const int c = int(i - r * c4) << 2;
+      const float4 a4 = ldg4_stream(p.a + r * p.ld + c), b4 = ldg4_stream(p.b + r * p.ld + c), g4 = ldg4_stream(p.g + r * p.cols + c);
       const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
       float da[4], db[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float sg = sigmoid_rn(av[e]);
-        const float y = fq_apply<FIVE>(sg, qs);
-        const float hh = fmul(av[e], y);
-        const float h = fq_apply<FIVE>(hh, qo);
-        const FqGrad rw = fq_grad<FIVE>(fmul(h, bv[e]), gv[e], qw);          // through w2.input_quantizer
-        db[e] = fmul(rw.gx, h);
-        const FqGrad ro = fq_grad<FIVE>(hh, fmul(rw.gx, bv[e]), qo);         // through QSiLU.output_quantizer
-        const FqGrad rs = fq_grad<FIVE>(sg, fmul(ro.gx, av[e]), qs);         // through QSiLU.input2_quantizer
+        const float a = fq_apply<FIVE>(av[e], q[0]), b = fq_apply<FIVE>(bv[e], q[1]);
+        const float sg = sigmoid_rn(a);
+        const float y = fq_apply<FIVE>(sg, q[2]);
+        const float hh = fmul(a, y);
+        const float h = fq_apply<FIVE>(hh, q[3]);
+        const FqGrad rw = fq_grad<FIVE>(fmul(h, b), gv[e], q[4]);           // through w2.input_quantizer
+        const FqGrad rb = fq_grad<FIVE>(bv[e], fmul(rw.gx, h), q[1]);        // gate operand, through w3.output_quantizer
+        const FqGrad ro = fq_grad<FIVE>(hh, fmul(rw.gx, b), q[3]);          // through QSiLU.output_quantizer
+        const FqGrad rs = fq_grad<FIVE>(sg, fmul(ro.gx, a), q[2]);          // through QSiLU.input2_quantizer
         // a feeds the product directly and through the sigmoid (ATen sigmoid_backward: g * (1 - y) * y)
-        da[e] = fadd(fmul(ro.gx, y), fmul(fmul(rs.gx, fsub(1.f, sg)), sg));
-        acc[0] += rs.gs; acc[1] += rs.go; acc[2] += ro.gs; acc[3] += ro.go; acc[4] += rw.gs; acc[5] += rw.go;
+        const float ga = fadd(fmul(ro.gx, y), fmul(fmul(rs.gx, fsub(1.f, sg)), sg));
+        const FqGrad ra = fq_grad<FIVE>(av[e], ga, q[0]);                    // through w1.output_quantizer
+        da[e] = ra.gx; db[e] = rb.gx;
+        acc[0] += ra.gs; acc[1] += ra.go; acc[2] += rb.gs; acc[3] += rb.go; acc[4] += rs.gs; acc[5] += rs.go;
+        acc[6] += ro.gs; acc[7] += ro.go; acc[8] += rw.gs; acc[9] += rw.go;
       }
-      *reinterpret_cast<float4*>(p.da + (i << 2)) = make_float4(da[0], da[1], da[2], da[3]);
-      *reinterpret_cast<float4*>(p.db + (i << 2)) = make_float4(db[0], db[1], db[2], db[3]);
+      *reinterpret_cast<float4*>(p.da + r * p.ldd + c) = make_float4(da[0], da[1], da[2], da[3]);
+      *reinterpret_cast<float4*>(p.db + r * p.ldd + c) = make_float4(db[0], db[1], db[2], db[3]);
     }
   };
-  dispatch_five(qs.five | qo.five | qw.five, body);
-  if (p.gout) grid_fold<6>(acc, p.partial, p.ticket, p.gout, red, &s_last);
+  dispatch_five(five, body);
+  if (p.gout) grid_fold<10>(acc, p.partial, p.ticket, p.gout, red, &s_last);
 }
-
 
 struct NormCArgs {
   const float *x, *w, *b; float *out, *nrm; int64_t rows; int H; float alpha, eps;
@@ -247,46 +262,48 @@ extern "C" {
 
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-int mq_silu_gate_fwd(void* ctx, const float* a, const float* b, float* out, int64_t n, const float* const* scales,
-                     const float* const* offsets, const float* qmins, const float* qmaxs, void* stream) {
+static void gate_fill(GateArgs& p, const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs) {
+  for (int i = 0; i < 5; ++i) { p.sc[i] = scales[i]; p.of[i] = offsets[i]; p.qmin[i] = qmins[i]; p.qmax[i] = qmaxs[i]; }
+}
+
+int mq_silu_gate_fwd(void* ctx, const float* a, const float* b, int64_t ld, float* out, int64_t rows, int cols,
+                     const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs, void* stream) {
   MQ_CTX(c, ctx);
-  MQ_REQUIRE(c, a && b && out && n >= 0 && n % 4 == 0 && scales && offsets && qmins && qmaxs, "null pointer or n % 4 != 0");
+  MQ_REQUIRE(c, a && b && out && rows >= 0 && cols > 0 && cols % 4 == 0 && ld >= cols && ld % 4 == 0 && scales && offsets && qmins && qmaxs,
+             "null pointer or cols / ld not a multiple of 4");
   MQ_REQUIRE(c, al16(a) && al16(b) && al16(out), "a / b / out must be 16-byte aligned");
-  for (int i = 0; i < 3; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
-  if (n == 0) return MQ_NO_ERROR;
+  for (int i = 0; i < 5; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
+  if (rows == 0) return MQ_NO_ERROR;
   GateArgs p{};
-  p.a = a; p.b = b; p.out = out; p.n = n;
-  p.s_s = scales[0]; p.o_s = offsets[0]; p.qmin_s = qmins[0]; p.qmax_s = qmaxs[0];
-  p.s_o = scales[1]; p.o_o = offsets[1]; p.qmin_o = qmins[1]; p.qmax_o = qmaxs[1];
-  p.s_w = scales[2]; p.o_w = offsets[2]; p.qmin_w = qmins[2]; p.qmax_w = qmaxs[2];
-  silu_gate_fwd_kernel<<<grid_for_elems(c, n / 4, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  p.a = a; p.b = b; p.ld = ld; p.out = out; p.rows = rows; p.cols = cols;
+  gate_fill(p, scales, offsets, qmins, qmaxs);
+  silu_gate_fwd_kernel<<<grid_for_elems(c, rows * (cols / 4), 8), 256, 0, (cudaStream_t)stream>>>(p);
   return check_launch(c, "mq_silu_gate_fwd");
 }
 
-int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, const float* g, float* da, float* db, int64_t n,
-                     const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs,
-                     float* gparams, void* stream) {
+int mq_silu_gate_bwd(void* ctx, const float* a, const float* b, int64_t ld, const float* g, float* da, float* db, int64_t ldd,
+                     int64_t rows, int cols, const float* const* scales, const float* const* offsets, const float* qmins,
+                     const float* qmaxs, float* gparams, void* stream) {
   MQ_CTX(c, ctx);
-  MQ_REQUIRE(c, a && b && g && da && db && n >= 0 && n % 4 == 0 && scales && offsets && qmins && qmaxs, "null pointer or n % 4 != 0");
+  MQ_REQUIRE(c, a && b && g && da && db && rows >= 0 && cols > 0 && cols % 4 == 0 && ld >= cols && ld % 4 == 0 && ldd >= cols && ldd % 4 == 0 &&
+                 scales && offsets && qmins && qmaxs, "null pointer or cols / ld / ldd not a multiple of 4");
   MQ_REQUIRE(c, al16(a) && al16(b) && al16(g) && al16(da) && al16(db), "tensors must be 16-byte aligned");
-  for (int i = 0; i < 3; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
+  for (int i = 0; i < 5; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
   cudaStream_t st = (cudaStream_t)stream;
-  if (n == 0) {
-    if (gparams) cudaMemsetAsync(gparams, 0, 6 * sizeof(float), st);
+  if (rows == 0) {
+    if (gparams) cudaMemsetAsync(gparams, 0, 10 * sizeof(float), st);
     return MQ_NO_ERROR;
   }
   GateArgs p{};
-  p.a = a; p.b = b; p.g = g; p.da = da; p.db = db; p.n = n; p.gout = gparams;
-  p.s_s = scales[0]; p.o_s = offsets[0]; p.qmin_s = qmins[0]; p.qmax_s = qmaxs[0];
-  p.s_o = scales[1]; p.o_o = offsets[1]; p.qmin_o = qmins[1]; p.qmax_o = qmaxs[1];
-  p.s_w = scales[2]; p.o_w = offsets[2]; p.qmin_w = qmins[2]; p.qmax_w = qmaxs[2];
+  p.a = a; p.b = b; p.ld = ld; p.g = g; p.da = da; p.db = db; p.ldd = ldd; p.rows = rows; p.cols = cols; p.gout = gparams;
+  gate_fill(p, scales, offsets, qmins, qmaxs);
   if (gparams) {
     void* wsp = stream_ws(c, st);
     if (!wsp) return MQ_FAILED_ALLOCATION;
     p.partial = reinterpret_cast<double*>(wsp);
     p.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(wsp) + c->ws_bytes - 64);
   }
-  silu_gate_bwd_kernel<<<grid_for_elems(c, n / 4, 4), 256, 0, st>>>(p);
+  silu_gate_bwd_kernel<<<grid_for_elems(c, rows * (cols / 4), 4), 256, 0, st>>>(p);
   return check_launch(c, "mq_silu_gate_bwd");
 }
 

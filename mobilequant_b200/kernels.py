@@ -22,8 +22,8 @@ def _protos():
                                       c_float, _P]
     lib.mq_attn_probs_bwd.argtypes = [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _P, _P, c_float, c_float, _P, _P,
                                       c_float, c_float, _P, _P]
-    lib.mq_silu_gate_fwd.argtypes = [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]
-    lib.mq_silu_gate_bwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]
+    lib.mq_silu_gate_fwd.argtypes = [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, _P]
+    lib.mq_silu_gate_bwd.argtypes = [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, _P]
     lib.mq_rmsnorm_l2_supported.argtypes = [c_int]
     lib.mq_rmsnorm_l2_fwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P]
     lib.mq_rmsnorm_l2_bwd.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]
@@ -179,27 +179,51 @@ def _qarrays(qs):
     return sc, of, lo, hi
 
 
-def silu_gate_fwd(a, b, qs):
-    """fq_w(fq_o(a * fq_s(sigmoid(a))) * b); qs = [fq_s, fq_o, fq_w], each None or (scale, offset, qmin, qmax)."""
+def _gate_operands(y, a, b):
+    """(pointer a, pointer b, row stride, rows, cols) of the gate operands: the two halves of y [rows, 2*cols], or a / b [.., cols]."""
+    if y is not None:
+        cols = y.shape[-1] // 2
+        rows = y.numel() // (2 * cols)
+        base = ptr(y, F32)
+        return base, c_void_p(y.data_ptr() + 4 * cols), 2 * cols, rows, cols
+    cols = a.shape[-1]
+    return ptr(a, F32), ptr(b, F32), cols, a.numel() // cols, cols
+
+
+def silu_gate_fwd(qs, y=None, a=None, b=None):
+    """fq_w(fq_o(A * fq_s(sigmoid(A))) * B), A = fq_a(ya), B = fq_b(yb); qs = [fq_a, fq_b, fq_s, fq_o, fq_w], each None or
+    (scale, offset, qmin, qmax).  Operands: y [.., 2*I] (ya | yb side by side, one GEMM result) or separate a, b [.., I]."""
     lib = _protos()
-    out = torch.empty_like(a)
+    pa, pb, ld, rows, cols = _gate_operands(y, a, b)
+    src = y if y is not None else a
+    out = torch.empty(src.shape[:-1] + (cols,), dtype=F32, device=src.device)
     sc, of, lo, hi = _qarrays(qs)
-    h = _h(a)
-    with torch.cuda.device(a.device):
-        check(_launch("silu_gate_fwd", lib.mq_silu_gate_fwd, h, ptr(a, F32), ptr(b, F32), ptr(out), a.numel(), sc, of, lo, hi, stream_ptr()), h)
+    h = _h(src)
+    with torch.cuda.device(src.device):
+        check(_launch("silu_gate_fwd", lib.mq_silu_gate_fwd, h, pa, pb, ld, ptr(out), rows, cols, sc, of, lo, hi, stream_ptr()), h)
     return out
 
 
-def silu_gate_bwd(a, b, g, qs, want_gparams=True):
+def silu_gate_bwd(g, qs, y=None, a=None, b=None, want_gparams=True):
+    """Returns (dy, None, gparams) for the side-by-side layout, (da, db, gparams) otherwise."""
     lib = _protos()
-    da, db = torch.empty_like(a), torch.empty_like(a)
-    gp = torch.empty(6, dtype=F32, device=a.device) if want_gparams else None
+    pa, pb, ld, rows, cols = _gate_operands(y, a, b)
+    src = y if y is not None else a
+    if y is not None:
+        dy = torch.empty_like(y)
+        pda, pdb, ldd = ptr(dy), c_void_p(dy.data_ptr() + 4 * cols), 2 * cols
+        res = (dy, None)
+    else:
+        da, db = torch.empty_like(a), torch.empty_like(a)
+        pda, pdb, ldd = ptr(da), ptr(db), cols
+        res = (da, db)
+    gp = torch.empty(10, dtype=F32, device=src.device) if want_gparams else None
     sc, of, lo, hi = _qarrays(qs)
-    h = _h(a)
-    with torch.cuda.device(a.device):
-        check(_launch("silu_gate_bwd", lib.mq_silu_gate_bwd, h, ptr(a, F32), ptr(b, F32), ptr(g, F32), ptr(da), ptr(db), a.numel(), sc, of, lo, hi,
-                      ptr(gp), stream_ptr()), h)
-    return da, db, gp
+    h = _h(src)
+    with torch.cuda.device(src.device):
+        check(_launch("silu_gate_bwd", lib.mq_silu_gate_bwd, h, pa, pb, ld, ptr(g, F32), pda, pdb, ldd, rows, cols, sc, of, lo, hi, ptr(gp),
+                      stream_ptr()), h)
+    return res + (gp,)
 
 
 def rmsnorm_l2_supported(H):

@@ -143,13 +143,11 @@ class HFMLP(nn.Module):
         self.act_fn = _ACT[config.hidden_act]()
 
     def forward(self, x):
-        fused = getattr(self.act_fn, "fused_gate", None) if self.num_linears_per_mlp == 3 else None
-        if fused is not None:                               # QSiLU + gate product + w2's input quantizer as one kernel
-            a, b = self.w1(x), self.w3(x)
-            h = fused(a, b, self.w2)
+        fused = getattr(self.act_fn, "fused_mlp", None) if self.num_linears_per_mlp == 3 else None
+        if fused is not None:                               # Q* modules: one GEMM for w1 | w3 + one kernel for the element-wise core
+            h = fused(x, self.w1, self.w3, self.w2)
             if h is not None:
                 return self.w2(h, input_quantized=True)
-            return self.w2(self.elementwisemul(self.act_fn(a), b))
         h = self.act_fn(self.w1(x))
         if self.num_linears_per_mlp == 3:
             h = self.elementwisemul(h, self.w3(x))

@@ -131,32 +131,33 @@ def _unpack_q(saved, bounds):
 
 
 class SiluGateFn(torch.autograd.Function):
-    """fq_w(fq_o(a * fq_s(sigmoid(a))) * b): QSiLU (qm:691-753) on a = w1(x), the gate product with b = w3(x) (hm:1059) and
-    w2.input_quantizer as one kernel forward and one backward (csrc/calib_act.cu).  params = (scale, offset, qmin, qmax) of
-    fq_s, fq_o, fq_w flattened; scale None disables a quantizer."""
+    """fq_w(fq_o(A * fq_s(sigmoid(A))) * B) with A = fq_a(ya), B = fq_b(yb): the output quantizers of w1 / w3, QSiLU (qm:691-753),
+    the gate product (hm:1059) and w2.input_quantizer as one kernel forward and one backward (csrc/calib_act.cu).  `y` holds
+    ya | yb side by side ([.., 2*I], the result of ONE GEMM over the concatenated w1 / w3 weights).  params = (scale, offset,
+    qmin, qmax) of fq_a, fq_b, fq_s, fq_o, fq_w flattened; scale None disables a quantizer."""
 
     @staticmethod
-    def forward(ctx, a, b, *params):
-        ac, bc = a.detach().contiguous(), b.detach().contiguous()
+    def forward(ctx, y, *params):
+        yc = y.detach().contiguous()
         qs, saved, shapes = _pack_q(params)
-        out = K.silu_gate_fwd(ac, bc, qs)
-        ctx.save_for_backward(ac, bc, *saved)
+        out = K.silu_gate_fwd(qs, y=yc)
+        ctx.save_for_backward(yc, *saved)
         ctx.meta = ([None if q is None else (q[2], q[3]) for q in qs], shapes)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        ac, bc, *saved = ctx.saved_tensors
+        yc, *saved = ctx.saved_tensors
         bounds, shapes = ctx.meta
         qs = _unpack_q(saved, bounds)
         n = ctx.needs_input_grad
-        want = any(n[2 + 4 * i] or n[3 + 4 * i] for i in range(3))
-        da, db, gp = K.silu_gate_bwd(ac, bc, g.float().contiguous(), qs, want_gparams=want)
-        out = [da if n[0] else None, db if n[1] else None]
-        for i in range(3):
+        want = any(n[1 + 4 * i] or n[2 + 4 * i] for i in range(5))
+        dy, _, gp = K.silu_gate_bwd(g.float().contiguous(), qs, y=yc, want_gparams=want)
+        out = [dy if n[0] else None]
+        for i in range(5):
             sh = shapes[i]
-            out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[2 + 4 * i]) else None,
-                    gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[3 + 4 * i]) else None, None, None]
+            out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[1 + 4 * i]) else None,
+                    gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[2 + 4 * i]) else None, None, None]
         return tuple(out)
 
 

@@ -239,6 +239,10 @@ def _static_params(quant, device):
     return [quant.scale, quant.offset, quant.qmin, quant.qmax]
 
 
+def _active(quant):
+    return quant is not None and quant.enable and quant.qcfg.bitwidth <= 16
+
+
 def _fused_enabled(name):
     """MQB200_FUSED_<NAME>=0 runs that piece of the calibration block op by op (A/B checks)."""
     return os.environ.get(f"MQB200_FUSED_{name}", "1") != "0"
@@ -340,8 +344,11 @@ class QLinear(nn.Linear, _QBase):
     def set_scale_offset(self, act_scale, use_scale_offset_as="parameter"):
         self._set_ranges(act_scale, use_scale_offset_as, self.weight.device)
 
+    def _bias(self):
+        return self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
+
     def forward(self, input_, input_quantized=False):
-        bias = self.bias if not self.use_temporary_parameter else getattr(self, "temp_bias", self.bias)
+        bias = self._bias()
         weight = self._fq_weight()
         if self.input_quantizer is not None and not input_quantized:
             input_ = self.input_quantizer(input_)
@@ -568,22 +575,29 @@ class QSiLU(nn.Module, _QBase):
         return out
 
 
-    def fused_gate(self, a, b, w2):
-        """HFMLP.forward's element-wise core with this module as act_fn (hm:1057-1061):
-            w2.input_quantizer(self(a) * b)
-        as ONE fused kernel (csrc/calib_act.cu).  None when not covered; the caller then goes op by op."""
-        if not _fused_enabled("GATE") or not isinstance(w2, QLinear) or not a.is_cuda or a.dtype != torch.float32 \
-                or b.dtype != torch.float32 or a.shape != b.shape or a.numel() % 4 != 0:
+    def fused_mlp(self, x, w1, w3, w2):
+        """HFMLP.forward (hm:1057-1061) with this module as act_fn, up to w2's GEMM:
+            w2.input_quantizer( self(w1(x)) * w3(x) )
+        as ONE GEMM over the concatenated (fake-quantised) w1 / w3 weights + ONE fused element-wise kernel (csrc/calib_act.cu:
+        both output quantizers, the sigmoid and its quantizer, the products, w2's input quantizer).  None when not covered; the
+        caller then goes module by module."""
+        if not _fused_enabled("GATE") or not all(isinstance(m, QLinear) for m in (w1, w3, w2)) or not x.is_cuda \
+                or x.dtype != torch.float32 or w1.out_features != w3.out_features or w1.out_features % 4 != 0:
             return None
-        if self.input_quantizer is not None and self.input_quantizer.enable and self.input_quantizer.qcfg.bitwidth <= 16:
-            return None                                    # a separate quantizer on a: not the MobileQuant recipe (qm:853-858)
+        if any(_active(m.input_quantizer) for m in (self, w1, w3)) or (w1.bias is None) != (w3.bias is None):
+            return None                                    # quantised by the producer in every MobileQuant recipe (qm:848-858)
         params = []
-        for quant in (self.input2_quantizer, self.output_quantizer, w2.input_quantizer):
-            pq = _static_params(quant, a.device)
+        for quant in (w1.output_quantizer, w3.output_quantizer, self.input2_quantizer, self.output_quantizer, w2.input_quantizer):
+            pq = _static_params(quant, x.device)
             if pq is False:
                 return None
             params += pq
-        return SiluGateFn.apply(a, b, *params)
+        wa, wb = w1._fq_weight(), w3._fq_weight()
+        if wa.dtype != torch.float32 or wb.dtype != torch.float32:
+            return None
+        ba, bb = w1._bias(), w3._bias()
+        y = nn.functional.linear(x, torch.cat((wa, wb), dim=0), None if ba is None else torch.cat((ba, bb), dim=0))
+        return SiluGateFn.apply(y, *params)
 
 
 class QGELU(nn.Module, _QBase):

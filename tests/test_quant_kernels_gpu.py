@@ -287,16 +287,16 @@ def test_attn_probs_fused_matches_chain(cuda, T, hd, bits1, pmin):
             assert abs(r - g) <= tol, (i, r, g, nflip)
 
 
-@pytest.mark.parametrize("on", [(True, True, True), (False, True, True), (True, False, False), (False, False, False)])
+@pytest.mark.parametrize("on", [(True,) * 5, (True, True, False, True, True), (False, False, True, False, False), (False,) * 5])
 def test_silu_gate_fused_matches_chain(cuda, on):
-    """csrc/calib_act.cu silu_gate (forward, backward, the three quantizers' LRL gradients) against the module chain it
-    replaces: w2.input_quantizer(QSiLU(a) * b)."""
+    """csrc/calib_act.cu silu_gate (forward, backward, the five quantizers' LRL gradients) against the module chain it
+    replaces: w2.input_quantizer(QSiLU(fq_a(ya)) * fq_b(yb)), ya | yb side by side in one GEMM result."""
     from mobilequant_b200.quantization.functional import SiluGateFn, StaticFakeQuantFn
     from mobilequant_b200.quantization.qmodule import compute_scale_offset_from_min_max
     torch.manual_seed(5)
-    a0 = torch.randn(3, 257, 64, device=cuda) * 3.0
-    b0 = torch.randn(3, 257, 64, device=cuda) * 2.0
-    W = torch.randn_like(a0)
+    I = 68
+    y0 = torch.randn(3, 257, 2 * I, device=cuda) * torch.tensor([3.0] * I + [2.0] * I, device=cuda)
+    W = torch.randn(3, 257, I, device=cuda)
 
     def qparams(mn, mx, bits, enabled):
         if not enabled:
@@ -306,18 +306,20 @@ def test_silu_gate_fused_matches_chain(cuda, on):
 
     res = []
     for fused in (False, True):
-        a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
-        qs = [qparams(0.0, 1.0, 8, on[0]), qparams(-0.3, 6.0, 8, on[1]), qparams(-9.0, 11.0, 8, on[2])]
+        y = y0.clone().requires_grad_(True)
+        qs = [qparams(-8.0, 9.0, 8, on[0]), qparams(-5.0, 6.0, 8, on[1]), qparams(0.0, 1.0, 8, on[2]), qparams(-0.3, 6.0, 8, on[3]),
+              qparams(-9.0, 11.0, 8, on[4])]
         if fused:
-            out = SiluGateFn.apply(a, b, *[v for q in qs for v in q])
+            out = SiluGateFn.apply(y, *[v for q in qs for v in q])
         else:
-            fq = lambda x, q: x if q[0] is None else StaticFakeQuantFn.apply(x, *q)
-            out = fq(fq(a * fq(torch.sigmoid(a), qs[0]), qs[1]) * b, qs[2])
+            fq = lambda x, q: x if q[0] is None else StaticFakeQuantFn.apply(x.contiguous(), *q)
+            a, b = fq(y[..., :I], qs[0]), fq(y[..., I:], qs[1])
+            out = fq(fq(a * fq(torch.sigmoid(a), qs[2]), qs[3]) * b, qs[4])
         (out * W).sum().backward()
-        res.append((out.detach(), a.grad, b.grad, qs))
-    (o0, ga0, gb0, q0), (o1, ga1, gb1, q1) = res
+        res.append((out.detach(), y.grad, qs))
+    (o0, g0, q0), (o1, g1, q1) = res
     assert torch.equal(o0, o1)
-    assert torch.allclose(ga0, ga1, rtol=1e-5, atol=1e-6) and torch.allclose(gb0, gb1, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(g0, g1, rtol=1e-5, atol=1e-6)
     for r, g in zip(q0, q1):
         if r[0] is None:
             continue
