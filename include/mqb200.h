@@ -108,6 +108,24 @@ int mq_rmsnorm_l2_bwd(void* ctx, const float* x, const float* w, const float* bi
                       float* dw, float* dbias, int64_t rows, int H, float alpha, float eps, const float* const* scales,
                       const float* const* offsets, const float* qmins, const float* qmaxs, float* gparams, void* stream);
 
+/* ---- Calibration Q/K/V post-processing between the projection GEMM and the attention matmuls (hm:470-512 with the QLinear
+ * output quantizers, qm:356-358, and the QMatMul input quantizers, qm:455-458), fused:
+ *   q = fq_3( rope( fq_0(yq) ) ) -> [B, nh, T, hd]    k = fq_4( rope( fq_1(yk) ) ) -> [B, nkv, T, hd]    v = fq_5( fq_2(yv) ) -> [B, nkv, T, hd]
+ * y = [yq | yk | yv]: [rows = B*T, (nh + 2 nkv) * hd] fp32, the result of ONE GEMM over the concatenated projection weights.
+ * rope: (x * cos) + (rotate_half(x) * sin) on the first `rot` dims of a head (hm:338-367; rot % 8 == 0, (hd - rot) % 8 == 0),
+ * cos / sin: [B or 1, T, rot] fp32 (cs_batched != 0: one table per batch row).  scales / offsets: HOST arrays of 6 DEVICE
+ * pointers in the order q_proj / k_proj / v_proj.output_quantizer, qk_bmm.input / input2_quantizer, pv_bmm.input2_quantizer
+ * (NULL pair = disabled); qmins / qmaxs: HOST float[6].
+ * Backward: dy [rows, (nh + 2 nkv) * hd] from dq / dk / dv; gparams (may be NULL) = DEVICE float[12] OVERWRITTEN with
+ * (d/dscale, d/doffset) of the six quantizers in that order (deterministic fixed-order reduction, ctx workspace of `stream`). */
+int mq_qkv_rope_fwd(void* ctx, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cos,
+                    const float* sin, int cs_batched, float* q, float* k, float* v, const float* const* scales,
+                    const float* const* offsets, const float* qmins, const float* qmaxs, void* stream);
+int mq_qkv_rope_bwd(void* ctx, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cos,
+                    const float* sin, int cs_batched, const float* dq, const float* dk, const float* dv, float* dy,
+                    const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs,
+                    float* gparams, void* stream);
+
 /* ---- K8: range statistics, generate_act_range.py:55-69 (per tensor) / :57-63 (per channel) -------------------
  * minmax[0] = min(minmax[0], min x), minmax[1] = max(minmax[1], max x) when accumulate != 0, else overwritten.
  * rows variant: x is [rows, cols]; per_row != 0 reduces over cols (weights, qm:30) else over rows (per-channel

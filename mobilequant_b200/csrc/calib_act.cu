@@ -8,6 +8,11 @@
 //       out = fq_out( w * (alpha * xq / max(||xq||_2, eps)) + bias ),   xq = fq_in(x)
 //     one CTA per row (row statistics through shared memory), dL/dw and dL/dbias accumulated per thread over the rows of a
 //     CTA and folded over CTAs in fixed order by a second tiny kernel.
+//   * Q/K/V post-processing between the (concatenated) projection GEMM and the two attention matmuls (hm:470-512 with the
+//     QLinear output quantizers, qm:356-358, and the QMatMul input quantizers, qm:455-458):
+//       q = fq_qk.in( rope( fq_qproj.out(yq) ) ),  k = fq_qk.in2( rope( fq_kproj.out(yk) ) ),  v = fq_pv.in2( fq_vproj.out(yv) )
+//     read from the [B*T, (nh + 2 nkv) hd] GEMM result, written head-major ([B, nh, T, hd] / [B, nkv, T, hd]): the transposes,
+//     rotate_half / cat and six fake-quant passes of the module graph in one pass each way.
 #include "common.cuh"
 #include "ctx.h"
 #include "fq_math.cuh"
@@ -254,6 +259,149 @@ static int norm_nvt(int H) {
   return chunks <= 1 ? 1 : chunks <= 2 ? 2 : chunks <= 4 ? 4 : 8;
 }
 
+
+struct QkvArgs {
+  const float* y; int64_t rows; int T, nh, nkv, hd, rot;   // y: [rows = B*T, (nh + 2 nkv) * hd]
+  const float *cos, *sin; int cs_batched;                  // [B or 1, T, rot]
+  float *q, *k, *v;                                        // [B, nh, T, hd], [B, nkv, T, hd] x 2  (backward: the incoming gradients)
+  const float *sc[6], *of[6]; float qmin[6], qmax[6];      // q_proj.out, k_proj.out, v_proj.out, qk.input, qk.input2, pv.input2
+  float* dy;                                               // backward: [rows, (nh + 2 nkv) * hd]
+  double* partial; unsigned* ticket; float* gout;          // gout[12] = (d/dscale, d/doffset) of the six quantizers in that order
+};
+
+// One thread per 8-element unit of a head: a rotary unit is 4 dims d_lo.. and their partners d_lo + rot/2.., a pass-through
+// unit 8 consecutive dims (beyond rot, or anywhere in a V head).  Thread (blockIdx.x, threadIdx.x) keeps its unit column and
+// walks rows blockIdx.y, + gridDim.y, ...: its pair of quantizers is fixed.
+struct QkvUnit {
+  int seg, head, hl, nheads, d_lo, d_hi; bool rotary, valid;
+};
+__device__ __forceinline__ QkvUnit qkv_unit(const QkvArgs& p) {
+  QkvUnit n;
+  const int upr = p.hd >> 3;
+  const int u = blockIdx.x * 128 + threadIdx.x;
+  n.valid = u < (p.nh + 2 * p.nkv) * upr;
+  const int uu = n.valid ? u : 0;
+  n.head = uu / upr;
+  const int w = uu - n.head * upr;
+  n.seg = n.head < p.nh ? 0 : (n.head < p.nh + p.nkv ? 1 : 2);
+  n.hl = n.seg == 0 ? n.head : (n.seg == 1 ? n.head - p.nh : n.head - p.nh - p.nkv);
+  n.nheads = n.seg == 0 ? p.nh : p.nkv;
+  n.rotary = n.seg < 2 && w < (p.rot >> 3);
+  n.d_lo = n.rotary ? w * 4 : (n.seg < 2 ? p.rot + (w - (p.rot >> 3)) * 8 : w * 8);
+  n.d_hi = n.rotary ? n.d_lo + (p.rot >> 1) : n.d_lo + 4;
+  return n;
+}
+struct QkvTrig { float clo[4], chi[4], slo[4], shi[4]; };
+__device__ __forceinline__ void qkv_trig(const QkvArgs& p, const QkvUnit& n, int64_t b, int t, QkvTrig& g) {
+  const int64_t cb = ((p.cs_batched ? b : 0) * p.T + t) * p.rot;
+  const float4 c0 = ldg4(p.cos + cb + n.d_lo), c1 = ldg4(p.cos + cb + n.d_hi), s0 = ldg4(p.sin + cb + n.d_lo), s1 = ldg4(p.sin + cb + n.d_hi);
+  g.clo[0] = c0.x; g.clo[1] = c0.y; g.clo[2] = c0.z; g.clo[3] = c0.w; g.chi[0] = c1.x; g.chi[1] = c1.y; g.chi[2] = c1.z; g.chi[3] = c1.w;
+  g.slo[0] = s0.x; g.slo[1] = s0.y; g.slo[2] = s0.z; g.slo[3] = s0.w; g.shi[0] = s1.x; g.shi[1] = s1.y; g.shi[2] = s1.z; g.shi[3] = s1.w;
+}
+__device__ __forceinline__ bool qkv_any_five(const QkvArgs& p) {
+  bool five = false;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) five |= (p.sc[i] != nullptr) && mantissa_all_ones(__ldg(p.sc[i]));
+  return five;
+}
+
+__global__ void __launch_bounds__(128) qkv_rope_fwd_kernel(const QkvArgs p) {
+  const QkvUnit n = qkv_unit(p);
+  if (!n.valid) return;
+  const FqP ql = load_fqp(p.sc[n.seg], p.of[n.seg], p.qmin[n.seg], p.qmax[n.seg]);
+  const FqP qm = load_fqp(p.sc[3 + n.seg], p.of[3 + n.seg], p.qmin[3 + n.seg], p.qmax[3 + n.seg]);
+  float* dst = n.seg == 0 ? p.q : (n.seg == 1 ? p.k : p.v);
+  const int C = (p.nh + 2 * p.nkv) * p.hd;
+  auto body = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+    for (int64_t r = blockIdx.y; r < p.rows; r += gridDim.y) {
+      const int64_t b = r / p.T;
+      const int t = int(r - b * p.T);
+      const float* yr = p.y + r * C + n.head * p.hd;
+      const float4 lo4 = ldg4_stream(yr + n.d_lo), hi4 = ldg4_stream(yr + n.d_hi);
+      const float xlo[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, xhi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+      QkvTrig g;
+      if (n.rotary) qkv_trig(p, n, b, t, g);
+      float olo[4], ohi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = fq_apply<FIVE>(xlo[e], ql), c = fq_apply<FIVE>(xhi[e], ql);
+        float rl = a, rh = c;
+        if (n.rotary) {                                        // (x * cos) + (rotate_half(x) * sin), hm:338-367
+          rl = fadd(fmul(a, g.clo[e]), fmul(-c, g.slo[e]));
+          rh = fadd(fmul(c, g.chi[e]), fmul(a, g.shi[e]));
+        }
+        olo[e] = fq_apply<FIVE>(rl, qm); ohi[e] = fq_apply<FIVE>(rh, qm);
+      }
+      float* dr = dst + ((b * n.nheads + n.hl) * p.T + t) * p.hd;
+      *reinterpret_cast<float4*>(dr + n.d_lo) = make_float4(olo[0], olo[1], olo[2], olo[3]);
+      *reinterpret_cast<float4*>(dr + n.d_hi) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
+    }
+  };
+  dispatch_five(qkv_any_five(p), body);
+}
+
+__global__ void __launch_bounds__(128) qkv_rope_bwd_kernel(const QkvArgs p) {
+  __shared__ float red[32];
+  __shared__ bool s_last;
+  const QkvUnit n = qkv_unit(p);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                        // lin scale, lin offset, mm scale, mm offset of this thread's segment
+  if (n.valid) {
+    const FqP ql = load_fqp(p.sc[n.seg], p.of[n.seg], p.qmin[n.seg], p.qmax[n.seg]);
+    const FqP qm = load_fqp(p.sc[3 + n.seg], p.of[3 + n.seg], p.qmin[3 + n.seg], p.qmax[3 + n.seg]);
+    const float* gsrc = n.seg == 0 ? p.q : (n.seg == 1 ? p.k : p.v);
+    const int C = (p.nh + 2 * p.nkv) * p.hd;
+    auto body = [&](auto five_tag) {
+      constexpr bool FIVE = decltype(five_tag)::value;
+      for (int64_t r = blockIdx.y; r < p.rows; r += gridDim.y) {
+        const int64_t b = r / p.T;
+        const int t = int(r - b * p.T);
+        const float* yr = p.y + r * C + n.head * p.hd;
+        const float* gr = gsrc + ((b * n.nheads + n.hl) * p.T + t) * p.hd;
+        const float4 lo4 = ldg4_stream(yr + n.d_lo), hi4 = ldg4_stream(yr + n.d_hi);
+        const float4 gl4 = ldg4_stream(gr + n.d_lo), gh4 = ldg4_stream(gr + n.d_hi);
+        const float xlo[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, xhi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+        const float glo[4] = {gl4.x, gl4.y, gl4.z, gl4.w}, ghi[4] = {gh4.x, gh4.y, gh4.z, gh4.w};
+        QkvTrig g;
+        if (n.rotary) qkv_trig(p, n, b, t, g);
+        float dlo[4], dhi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = fq_apply<FIVE>(xlo[e], ql), c = fq_apply<FIVE>(xhi[e], ql);
+          float rl = a, rh = c;
+          if (n.rotary) {
+            rl = fadd(fmul(a, g.clo[e]), fmul(-c, g.slo[e]));
+            rh = fadd(fmul(c, g.chi[e]), fmul(a, g.shi[e]));
+          }
+          const FqGrad ml = fq_grad<FIVE>(rl, glo[e], qm), mh = fq_grad<FIVE>(rh, ghi[e], qm);
+          acc[2] += ml.gs + mh.gs; acc[3] += ml.go + mh.go;
+          float ga = ml.gx, gc = mh.gx;
+          if (n.rotary) {                                      // d/da = g_lo*cos_lo + g_hi*sin_hi ; d/dc = g_hi*cos_hi - g_lo*sin_lo
+            ga = fadd(fmul(ml.gx, g.clo[e]), fmul(mh.gx, g.shi[e]));
+            gc = fadd(fmul(mh.gx, g.chi[e]), -fmul(ml.gx, g.slo[e]));
+          }
+          const FqGrad ll = fq_grad<FIVE>(xlo[e], ga, ql), lh = fq_grad<FIVE>(xhi[e], gc, ql);
+          acc[0] += ll.gs + lh.gs; acc[1] += ll.go + lh.go;
+          dlo[e] = ll.gx; dhi[e] = lh.gx;
+        }
+        float* dr = p.dy + r * C + n.head * p.hd;
+        *reinterpret_cast<float4*>(dr + n.d_lo) = make_float4(dlo[0], dlo[1], dlo[2], dlo[3]);
+        *reinterpret_cast<float4*>(dr + n.d_hi) = make_float4(dhi[0], dhi[1], dhi[2], dhi[3]);
+      }
+    };
+    dispatch_five(qkv_any_five(p), body);
+  }
+  if (!p.gout) return;
+  float a12[12];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const bool mine = n.valid && n.seg == s;
+    a12[2 * s] = mine ? acc[0] : 0.f; a12[2 * s + 1] = mine ? acc[1] : 0.f;
+    a12[6 + 2 * s] = mine ? acc[2] : 0.f; a12[6 + 2 * s + 1] = mine ? acc[3] : 0.f;
+  }
+  grid_fold<12>(a12, p.partial, p.ticket, p.gout, red, &s_last, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
+}
+
 }  // namespace mq
 
 using namespace mq;
@@ -375,6 +523,66 @@ int mq_rmsnorm_l2_bwd(void* ctx, const float* x, const float* w, const float* bi
   fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdw, (int)grid, H, dw);
   if (dbias) fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdb, (int)grid, H, dbias);
   return check_launch(c, "mq_rmsnorm_l2_bwd");
+}
+
+static int qkv_check(Ctx* c, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cosp, const float* sinp,
+                     const float* const* scales, const float* const* offsets) {
+  MQ_REQUIRE(c, y && rows >= 0 && T > 0 && rows % T == 0 && nh > 0 && nkv > 0 && scales && offsets, "null pointer or bad shape");
+  MQ_REQUIRE(c, hd % 8 == 0 && rot >= 0 && rot <= hd && rot % 8 == 0, "head_dim and the rotary width must be multiples of 8");
+  MQ_REQUIRE(c, rot == 0 || (cosp && sinp && al16(cosp) && al16(sinp)), "cos / sin tables missing or misaligned");
+  for (int i = 0; i < 6; ++i) MQ_REQUIRE(c, (scales[i] == nullptr) == (offsets[i] == nullptr), "scale and offset come in pairs");
+  return MQ_NO_ERROR;
+}
+static void qkv_fill(QkvArgs& p, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cosp, const float* sinp,
+                     int cs_batched, const float* const* scales, const float* const* offsets, const float* qmins, const float* qmaxs) {
+  p.y = y; p.rows = rows; p.T = T; p.nh = nh; p.nkv = nkv; p.hd = hd; p.rot = rot; p.cos = cosp; p.sin = sinp; p.cs_batched = cs_batched;
+  for (int i = 0; i < 6; ++i) { p.sc[i] = scales[i]; p.of[i] = offsets[i]; p.qmin[i] = qmins[i]; p.qmax[i] = qmaxs[i]; }
+}
+static dim3 qkv_grid(Ctx* c, const QkvArgs& p, int waves) {
+  const int U = (p.nh + 2 * p.nkv) * (p.hd >> 3);
+  const unsigned gx = (unsigned)((U + 127) / 128);
+  int64_t gy = (int64_t(c->sm_count) * waves + gx - 1) / gx;
+  if (gy > p.rows) gy = p.rows;
+  if (gy > 65535) gy = 65535;
+  return dim3(gx, (unsigned)(gy < 1 ? 1 : gy), 1);
+}
+
+int mq_qkv_rope_fwd(void* ctx, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cosp, const float* sinp,
+                    int cs_batched, float* q, float* k, float* v, const float* const* scales, const float* const* offsets,
+                    const float* qmins, const float* qmaxs, void* stream) {
+  MQ_CTX(c, ctx);
+  if (int rc = qkv_check(c, y, rows, T, nh, nkv, hd, rot, cosp, sinp, scales, offsets)) return rc;
+  MQ_REQUIRE(c, q && k && v && qmins && qmaxs && al16(y) && al16(q) && al16(k) && al16(v), "null or misaligned tensor");
+  if (rows == 0) return MQ_NO_ERROR;
+  QkvArgs p{};
+  qkv_fill(p, y, rows, T, nh, nkv, hd, rot, cosp, sinp, cs_batched, scales, offsets, qmins, qmaxs);
+  p.q = q; p.k = k; p.v = v;
+  qkv_rope_fwd_kernel<<<qkv_grid(c, p, 16), 128, 0, (cudaStream_t)stream>>>(p);
+  return check_launch(c, "mq_qkv_rope_fwd");
+}
+
+int mq_qkv_rope_bwd(void* ctx, const float* y, int64_t rows, int T, int nh, int nkv, int hd, int rot, const float* cosp, const float* sinp,
+                    int cs_batched, const float* dq, const float* dk, const float* dv, float* dy, const float* const* scales,
+                    const float* const* offsets, const float* qmins, const float* qmaxs, float* gparams, void* stream) {
+  MQ_CTX(c, ctx);
+  if (int rc = qkv_check(c, y, rows, T, nh, nkv, hd, rot, cosp, sinp, scales, offsets)) return rc;
+  MQ_REQUIRE(c, dq && dk && dv && dy && qmins && qmaxs && al16(y) && al16(dq) && al16(dk) && al16(dv) && al16(dy), "null or misaligned tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    if (gparams) cudaMemsetAsync(gparams, 0, 12 * sizeof(float), st);
+    return MQ_NO_ERROR;
+  }
+  QkvArgs p{};
+  qkv_fill(p, y, rows, T, nh, nkv, hd, rot, cosp, sinp, cs_batched, scales, offsets, qmins, qmaxs);
+  p.q = const_cast<float*>(dq); p.k = const_cast<float*>(dk); p.v = const_cast<float*>(dv); p.dy = dy; p.gout = gparams;
+  if (gparams) {
+    void* wsp = stream_ws(c, st);
+    if (!wsp) return MQ_FAILED_ALLOCATION;
+    p.partial = reinterpret_cast<double*>(wsp);
+    p.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(wsp) + c->ws_bytes - 64);
+  }
+  qkv_rope_bwd_kernel<<<qkv_grid(c, p, 8), 128, 0, st>>>(p);
+  return check_launch(c, "mq_qkv_rope_bwd");
 }
 
 }  // extern "C"

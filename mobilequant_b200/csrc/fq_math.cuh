@@ -105,15 +105,15 @@ __device__ __forceinline__ FqGrad fq_grad(float x, float g, const FqP& q) {
 // gout[NACC]; the ticket resets itself.  `red` = 32 floats of shared memory, `s_last` one shared bool.
 template <int NACC>
 __device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* partial, unsigned* ticket, float* gout, float* red,
-                                          bool* s_last) {
+                                          bool* s_last, unsigned bid = blockIdx.x, unsigned nblk = gridDim.x) {
   float b[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) b[i] = block_reduce(acc[i], OpSum(), red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) partial[NACC * blockIdx.x + i] = b[i];
+    for (int i = 0; i < NACC; ++i) partial[NACC * bid + i] = b[i];
     __threadfence();
-    *s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    *s_last = atomicAdd(ticket, 1u) == nblk - 1;
   }
   __syncthreads();
   if (*s_last && threadIdx.x < 32) {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* part
     double t[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) t[k] = 0.;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32)
+    for (unsigned i = threadIdx.x; i < nblk; i += 32)
 #pragma unroll
       for (int k = 0; k < NACC; ++k) t[k] += vp[NACC * i + k];
 #pragma unroll

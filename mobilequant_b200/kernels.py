@@ -27,6 +27,8 @@ def _protos():
     lib.mq_rmsnorm_l2_supported.argtypes = [c_int]
     lib.mq_rmsnorm_l2_fwd.argtypes = [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P]
     lib.mq_rmsnorm_l2_bwd.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P]
+    lib.mq_qkv_rope_fwd.argtypes = [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P]
+    lib.mq_qkv_rope_bwd.argtypes = [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
     lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
@@ -259,6 +261,35 @@ def rmsnorm_l2_bwd(x, w, bias, nrm, g, alpha, eps, qs, want_dbias=False, want_gp
         check(_launch("rmsnorm_l2_bwd", lib.mq_rmsnorm_l2_bwd, h, ptr(x, F32), ptr(w, F32), ptr(bias), ptr(nrm, F32), ptr(g, F32), ptr(dx), ptr(dw),
                       ptr(dbias), rows, H, float(alpha), float(eps), sc, of, lo, hi, ptr(gp), stream_ptr()), h)
     return dx, dw, dbias, gp
+
+
+def qkv_rope_fwd(y, B, T, nh, nkv, hd, rot, cos, sin, qs):
+    """y [B, T, (nh + 2 nkv) hd] -> q [B, nh, T, hd], k, v [B, nkv, T, hd] (quantise, rotate, quantise; see include/mqb200.h).
+    qs = [q_proj.out, k_proj.out, v_proj.out, qk.input, qk.input2, pv.input2]."""
+    lib = _protos()
+    dev = y.device
+    q = torch.empty((B, nh, T, hd), dtype=F32, device=dev)
+    k = torch.empty((B, nkv, T, hd), dtype=F32, device=dev)
+    v = torch.empty((B, nkv, T, hd), dtype=F32, device=dev)
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(y)
+    with torch.cuda.device(dev):
+        check(_launch("qkv_rope_fwd", lib.mq_qkv_rope_fwd, h, ptr(y, F32), B * T, T, nh, nkv, hd, rot, ptr(cos), ptr(sin),
+                      int(cos is not None and cos.shape[0] > 1), ptr(q), ptr(k), ptr(v), sc, of, lo, hi, stream_ptr()), h)
+    return q, k, v
+
+
+def qkv_rope_bwd(y, B, T, nh, nkv, hd, rot, cos, sin, dq, dk, dv, qs, want_gparams=True):
+    lib = _protos()
+    dy = torch.empty_like(y)
+    gp = torch.empty(12, dtype=F32, device=y.device) if want_gparams else None
+    sc, of, lo, hi = _qarrays(qs)
+    h = _h(y)
+    with torch.cuda.device(y.device):
+        check(_launch("qkv_rope_bwd", lib.mq_qkv_rope_bwd, h, ptr(y, F32), B * T, T, nh, nkv, hd, rot, ptr(cos), ptr(sin),
+                      int(cos is not None and cos.shape[0] > 1), ptr(dq, F32), ptr(dk, F32), ptr(dv, F32), ptr(dy), sc, of, lo, hi, ptr(gp),
+                      stream_ptr()), h)
+    return dy, gp
 
 
 # ---- K8 ---------------------------------------------------------------------------------------------------------

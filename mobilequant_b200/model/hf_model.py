@@ -103,6 +103,11 @@ class HFAttention(nn.Module):
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, **kwargs):
         bsz, q_len, _ = hidden_states.size()
+        fused = getattr(self.qk_bmm, "fused_attention", None)       # Q* modules: the block's attention half in four fused kernels
+        if fused is not None:
+            out = fused(self, hidden_states, attention_mask, position_ids)
+            if out is not None:
+                return self.o_proj(out), None, None
         q = self.q_proj(hidden_states).view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
         k = self.k_proj(hidden_states).view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         v = self.v_proj(hidden_states).view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)

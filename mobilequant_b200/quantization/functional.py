@@ -194,3 +194,36 @@ class RmsNormL2Fn(torch.autograd.Function):
             out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[5 + 4 * i]) else None,
                     gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[6 + 4 * i]) else None, None, None]
         return tuple(out)
+
+
+class QkvRopeFn(torch.autograd.Function):
+    """Everything between the (concatenated) q/k/v projection GEMM and the attention matmuls (hm:470-512): the three QLinear
+    output quantizers, the head split / transpose, RoPE, and the QMatMul input quantizers of q, k and v, as one kernel forward
+    and one backward (csrc/calib_act.cu).  y: [B, T, (nh + 2 nkv) hd]; returns q [B, nh, T, hd], k, v [B, nkv, T, hd].
+    params = (scale, offset, qmin, qmax) x 6 flattened (q_proj.out, k_proj.out, v_proj.out, qk.input, qk.input2, pv.input2)."""
+
+    @staticmethod
+    def forward(ctx, y, cos, sin, nh, nkv, hd, rot, *params):
+        yc = y.detach().contiguous()
+        B, T = yc.shape[0], yc.shape[1]
+        qs, saved, shapes = _pack_q(params)
+        q, k, v = K.qkv_rope_fwd(yc, B, T, nh, nkv, hd, rot, cos, sin, qs)
+        ctx.save_for_backward(yc, cos, sin, *saved)
+        ctx.meta = (B, T, nh, nkv, hd, rot, [None if t is None else (t[2], t[3]) for t in qs], shapes)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        yc, cos, sin, *saved = ctx.saved_tensors
+        B, T, nh, nkv, hd, rot, bounds, shapes = ctx.meta
+        qs = _unpack_q(saved, bounds)
+        n = ctx.needs_input_grad
+        want = any(n[7 + 4 * i] or n[8 + 4 * i] for i in range(6))
+        dy, gp = K.qkv_rope_bwd(yc, B, T, nh, nkv, hd, rot, cos, sin, dq.float().contiguous(), dk.float().contiguous(),
+                                dv.float().contiguous(), qs, want_gparams=want)
+        out = [dy if n[0] else None, None, None, None, None, None, None]
+        for i in range(6):
+            sh = shapes[i]
+            out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[7 + 4 * i]) else None,
+                    gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[8 + 4 * i]) else None, None, None]
+        return tuple(out)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
-from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn
+from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn, QkvRopeFn
 from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
@@ -248,6 +248,26 @@ def _fused_enabled(name):
     return os.environ.get(f"MQB200_FUSED_{name}", "1") != "0"
 
 
+_rope_cache = {}
+
+
+def _rope_tables(builder, position_ids, rot, theta, device):
+    """cos / sin of hm:308-318 for these position ids, built once per (positions, width, base) instead of once per layer call."""
+    key = (id(position_ids), position_ids._version, rot, float(theta), str(device))
+    hit = _rope_cache.get(key)
+    if hit is None or hit[2] is not position_ids:
+        if rot == 0:
+            hit = (None, None, position_ids)
+        else:
+            with torch.no_grad():
+                cos, sin = builder(position_ids, rot, theta, device, torch.float32)
+            hit = (cos.contiguous(), sin.contiguous(), position_ids)      # the reference keeps id() from being reused
+        if len(_rope_cache) > 8:
+            _rope_cache.clear()
+        _rope_cache[key] = hit
+    return hit[0], hit[1]
+
+
 _causal_cache = {}
 
 
@@ -257,17 +277,17 @@ def is_causal_mask(mask, tq, tk):
     mask then counts as not causal)."""
     if mask is None or tq != tk or mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[-2:] != (tq, tk) or mask.dtype != torch.float32:
         return False
-    key = (mask.data_ptr(), tuple(mask.shape), tuple(mask.stride()), mask._version)
+    key = (id(mask), mask._version)
     hit = _causal_cache.get(key)
-    if hit is None:
+    if hit is None or hit[1] is not mask:
         if mask.is_cuda and torch.cuda.is_current_stream_capturing():
             return False
         ref = torch.triu(torch.full((tq, tk), torch.finfo(mask.dtype).min, dtype=mask.dtype, device=mask.device), diagonal=1)
-        hit = bool((mask == ref).all())
-        if len(_causal_cache) > 64:
+        hit = (bool((mask == ref).all()), mask)                            # the reference keeps id() from being reused
+        if len(_causal_cache) > 8:
             _causal_cache.clear()
         _causal_cache[key] = hit
-    return hit
+    return hit[0]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -405,6 +425,47 @@ class QMatMul(nn.Module, _QBase):
         if self.output_quantizer is not None:
             out = self.output_quantizer(out)
         return out
+
+    def fused_attention(self, attn, hidden_states, attention_mask, position_ids):
+        """HFAttention.forward (hm:470-540) up to o_proj's input, with this module as attn.qk_bmm:
+          * q / k / v projections as ONE GEMM over the concatenated fake-quantised weights,
+          * their output quantizers, head split, RoPE and the matmul input quantizers as one kernel (QkvRopeFn),
+          * grouped-query heads addressed through views ([B, nkv, rep*T, hd] x [B, nkv, hd, T]) instead of repeat_kv copies,
+          * the score quantizer / scale / mask / softmax / probability quantizer as one kernel (AttnProbsFn).
+        None when a piece is not covered (the caller then runs the module graph op by op)."""
+        from ..model.hf_model import rope_cos_sin
+        pv, x = attn.pv_bmm, hidden_states
+        lins = (attn.q_proj, attn.k_proj, attn.v_proj)
+        if not _fused_enabled("QKV") or not _fused_enabled("PROBS") or not isinstance(pv, QMatMul) or not all(isinstance(m, QLinear) for m in lins) \
+                or not x.is_cuda or x.dtype != torch.float32 or position_ids is None:
+            return None
+        B, T, _ = x.shape
+        nh, nkv, hd, rot = attn.num_heads, attn.num_key_value_heads, attn.head_dim, attn.rotary_dim
+        if hd % 8 or rot % 8 or (hd - rot) % 8 or nh % nkv or any(_active(m.input_quantizer) for m in lins) \
+                or len({m.bias is None for m in lins}) != 1 or not is_causal_mask(attention_mask, T, T) or not K.attn_probs_supported(T):
+            return None
+        params = []
+        for quant in (lins[0].output_quantizer, lins[1].output_quantizer, lins[2].output_quantizer, self.input_quantizer,
+                      self.input2_quantizer, pv.input2_quantizer, self.output_quantizer, pv.input_quantizer):
+            pq = _static_params(quant, x.device)
+            if pq is False:
+                return None
+            params += pq
+        ws = [m._fq_weight() for m in lins]
+        if any(w.dtype != torch.float32 for w in ws):
+            return None
+        bs = [m._bias() for m in lins]
+        y = nn.functional.linear(x, torch.cat(ws, dim=0), None if bs[0] is None else torch.cat(bs, dim=0))
+        cos, sin = _rope_tables(rope_cos_sin, position_ids, rot, attn.rope_theta, x.device)
+        q, k, v = QkvRopeFn.apply(y, cos, sin, nh, nkv, hd, rot, *params[:24])
+        rep = nh // nkv
+        scores = torch.matmul(q.view(B, nkv, rep * T, hd), k.transpose(2, 3)).view(B, nh, T, T)
+        mul = (torch.ones((), dtype=torch.float32) / torch.tensor(math.sqrt(hd), dtype=torch.float32)).item()
+        probs = AttnProbsFn.apply(scores, mul, *params[24:])
+        out = torch.matmul(probs.view(B, nkv, rep * T, T), v).view(B, nh, T, hd)
+        if pv.output_quantizer is not None:
+            out = pv.output_quantizer(out)
+        return out.transpose(1, 2).contiguous().view(B, T, nh * hd)
 
     def fused_probs(self, q, kt, head_dim, attention_mask, pv_bmm):
         """The attention core of HFAttention.forward (hm:514-534) with this module as qk_bmm:

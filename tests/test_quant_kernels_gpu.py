@@ -372,3 +372,56 @@ def test_rmsnorm_l2_fused_matches_chain(cuda, H, bias, on):
     assert len(gq0) == len(gq1)
     for r, g in zip(gq0, gq1):
         assert abs(r - g) <= 0.03 * abs(r) + 0.05 * max(abs(v) for v in gq0), (gq0, gq1)
+
+
+@pytest.mark.parametrize("nh,nkv,hd,rot,on", [(8, 2, 64, 64, True), (4, 4, 64, 16, True), (6, 3, 80, 32, True), (8, 2, 64, 64, False)])
+def test_qkv_rope_fused_matches_chain(cuda, nh, nkv, hd, rot, on):
+    """csrc/calib_act.cu qkv_rope (forward, dy, the six quantizers' LRL gradients) against the module graph it replaces:
+    output quantizers -> head split / transpose -> RoPE (hm:338-367, partial rotary hm:489-501) -> matmul input quantizers."""
+    from mobilequant_b200.quantization.functional import QkvRopeFn, StaticFakeQuantFn
+    from mobilequant_b200.quantization.qmodule import compute_scale_offset_from_min_max
+    from mobilequant_b200.model.hf_model import rope_cos_sin, apply_rotary_pos_emb
+    torch.manual_seed(nh * hd + rot)
+    B, T = 2, 37
+    y0 = torch.randn(B, T, (nh + 2 * nkv) * hd, device=cuda) * 2.0
+    Wq, Wk, Wv = torch.randn(B, nh, T, hd, device=cuda), torch.randn(B, nkv, T, hd, device=cuda), torch.randn(B, nkv, T, hd, device=cuda)
+    pos = torch.arange(T, device=cuda).unsqueeze(0) + torch.tensor([[0], [3]], device=cuda)
+    cos, sin = rope_cos_sin(pos, rot, 10000.0, cuda, torch.float32)
+
+    def qparams(mn, mx, bits):
+        if not on:
+            return [None, None, 0.0, 0.0]
+        s, o, _, _, lo, hi = compute_scale_offset_from_min_max(mn, mx, bits, False)
+        return [torch.nn.Parameter(s.to(cuda)), torch.nn.Parameter(o.to(cuda)), lo, hi]
+
+    res = []
+    for fused in (False, True):
+        y = y0.clone().requires_grad_(True)
+        qs = [qparams(-6.0, 7.0, 8), qparams(-5.0, 5.5, 8), qparams(-7.0, 6.0, 8), qparams(-8.0, 8.5, 8), qparams(-7.5, 7.0, 8),
+              qparams(-6.5, 6.0, 8)]
+        if fused:
+            q, k, v = QkvRopeFn.apply(y, cos.contiguous(), sin.contiguous(), nh, nkv, hd, rot, *[t for p in qs for t in p])
+        else:
+            fq = lambda x, p: x if p[0] is None else StaticFakeQuantFn.apply(x.contiguous(), *p)
+            yq, yk, yv = y.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
+            q = fq(yq, qs[0]).view(B, T, nh, hd).transpose(1, 2)
+            k = fq(yk, qs[1]).view(B, T, nkv, hd).transpose(1, 2)
+            v = fq(yv, qs[2]).view(B, T, nkv, hd).transpose(1, 2)
+            if rot == hd:
+                q, k = apply_rotary_pos_emb(q, k, cos, sin)
+            else:
+                qr, kr = apply_rotary_pos_emb(q[..., :rot], k[..., :rot], cos, sin)
+                q = torch.cat((qr, q[..., rot:]), dim=-1)
+                k = torch.cat((kr, k[..., rot:]), dim=-1)
+            q, k, v = fq(q, qs[3]), fq(k, qs[4]), fq(v, qs[5])
+        ((q * Wq).sum() + (k * Wk).sum() + (v * Wv).sum()).backward()
+        res.append((q.detach(), k.detach(), v.detach(), y.grad, qs))
+    (q0, k0, v0, g0, p0), (q1, k1, v1, g1, p1) = res
+    assert torch.equal(q0, q1) and torch.equal(k0, k1) and torch.equal(v0, v1)
+    assert torch.allclose(g0, g1, rtol=1e-5, atol=1e-6)
+    for r, g in zip(p0, p1):
+        if r[0] is None:
+            continue
+        for i in (0, 1):
+            ref, got = r[i].grad.item(), g[i].grad.item()
+            assert abs(ref - got) <= 1e-3 * abs(ref) + 2e-2, (i, ref, got)
