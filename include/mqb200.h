@@ -144,11 +144,13 @@ int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_
  *   codes  int8 storage: asymmetric -> uint8 codes, symmetric -> int8 codes; bitwidth 4 with pack4 != 0 packs two
  *          codes per byte (low nibble = even k)
  *   scale_out/offset_out [groups]; colsum int32 [rows] = sum_k code  (zero-point correction of the int GEMM)
- *   wt_out fp32 W' before quantisation (the temp_weight of alg:68, kept for the backward)                       */
+ *   wt_out fp32 W' before quantisation (the temp_weight of alg:68, kept for the backward)
+ *   minmax_out [2 * groups]: the group minima then maxima of W' (before LWC) -- hand it to mq_wprep_bwd as minmax_in and the
+ *          backward skips its own min / max pass over w                                                          */
 int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const float* col_fac, int col_mode,
                  const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
                  mq_qcfg cfg, float* w_fq, void* codes, int pack4, float* scale_out, float* offset_out,
-                 int32_t* colsum, float* wt_out, void* stream);
+                 int32_t* colsum, float* wt_out, float* minmax_out, void* stream);
 
 /* Backward of mq_wprep_fwd: given g = dL/dw_fq produce dL/dcol_fac [cols], dL/drow_fac [rows], dL/dsig_up,
  * dL/dsig_low [groups] (any may be NULL), including the amin/amax paths of qm:264-275 (gradient of a min/max is
@@ -158,7 +160,7 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
 int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_t cols, const float* col_fac,
                  int col_mode, const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
                  mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
-                 float* g_wt, float* scratch, void* stream);
+                 float* g_wt, float* scratch, const float* minmax_in, void* stream);
 
 /* ---- K3/K7: integer GEMM with fused requantisation epilogue == QLinear.forward on codes (qm:341-358) ------------
  * acc = A[M,K] (u8/s8 codes, row-major) x B[N,K]^T (u8/s8 weight codes from mq_wprep_fwd), s32 accumulate on

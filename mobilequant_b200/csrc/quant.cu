@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) wprep_quant_kernel(const float* __restric
                                                            int sym, float* __restrict__ w_fq, uint8_t* __restrict__ codes,
                                                            int pack4, float* __restrict__ scale_out,
                                                            float* __restrict__ offset_out, int32_t* __restrict__ colsum,
-                                                           float* __restrict__ wt_out) {
+                                                           float* __restrict__ wt_out, float* __restrict__ mm_out, int64_t groups) {
   __shared__ int redi[32];
   const int64_t row = blockIdx.x;
   const int64_t g = per_channel ? row : 0;
@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(256) wprep_quant_kernel(const float* __restric
   if (threadIdx.x == 0 && (per_channel || row == 0)) {
     if (scale_out) scale_out[g] = q.s;
     if (offset_out) offset_out[g] = q.o;
+    if (mm_out) { mm_out[g] = row_mn[g]; mm_out[groups + g] = row_mx[g]; }
   }
 }
 
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(256) wprep_quant_v_kernel(const float* __restr
                                                              int per_channel, int bits, int sym, float* __restrict__ w_fq,
                                                              uint8_t* __restrict__ codes, int pack4, float* __restrict__ scale_out,
                                                              float* __restrict__ offset_out, int32_t* __restrict__ colsum,
-                                                             float* __restrict__ wt_out) {
+                                                             float* __restrict__ wt_out, float* __restrict__ mm_out, int64_t groups) {
   __shared__ int redi[32];
   const int64_t row = blockIdx.x;
   const int64_t g = per_channel ? row : 0;
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(256) wprep_quant_v_kernel(const float* __restr
   if (threadIdx.x == 0 && (per_channel || row == 0)) {
     if (scale_out) scale_out[g] = q.s;
     if (offset_out) offset_out[g] = q.o;
+    if (mm_out) { mm_out[g] = row_mn[g]; mm_out[groups + g] = row_mx[g]; }
   }
 }
 
@@ -789,9 +791,10 @@ static int wprep_check(Ctx* c, const float* w, int64_t rows, int64_t cols, const
 int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const float* col_fac, int col_mode,
                  const float* row_fac, int row_mode, const float* sig_up, const float* sig_low, int per_channel,
                  mq_qcfg cfg, float* w_fq, void* codes, int pack4, float* scale_out, float* offset_out, int32_t* colsum,
-                 float* wt_out, void* stream) {
+                 float* wt_out, float* minmax_out, void* stream) {
   MQ_CTX(c, ctx);
   if (int e = wprep_check(c, w, rows, cols, col_fac, col_mode, row_fac, row_mode, cfg)) return e;
+  const int64_t groups = per_channel ? rows : 1;
   MQ_REQUIRE(c, !codes || cfg.bitwidth <= 8, "integer codes are stored in 8 bits");
   MQ_REQUIRE(c, !pack4 || (cfg.bitwidth <= 4 && cols % 2 == 0), "pack4 needs bitwidth <= 4 and even cols");
   cudaStream_t st = (cudaStream_t)stream;
@@ -806,18 +809,18 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
   if (vec)
     wprep_quant_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                          cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
-                                                         scale_out, offset_out, colsum, wt_out);
+                                                         scale_out, offset_out, colsum, wt_out, minmax_out, groups);
   else
     wprep_quant_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                        cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
-                                                       scale_out, offset_out, colsum, wt_out);
+                                                       scale_out, offset_out, colsum, wt_out, minmax_out, groups);
   return check_launch(c, "mq_wprep_fwd");
 }
 
 int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_t cols, const float* col_fac,
                  int col_mode, const float* row_fac, int row_mode, const float* sig_up, const float* sig_low,
                  int per_channel, mq_qcfg cfg, float* g_col_fac, float* g_row_fac, float* g_sig_up, float* g_sig_low,
-                 float* g_wt, float* scratch, void* stream) {
+                 float* g_wt, float* scratch, const float* minmax_in, void* stream) {
   MQ_CTX(c, ctx);
   if (int e = wprep_check(c, w, rows, cols, col_fac, col_mode, row_fac, row_mode, cfg)) return e;
   MQ_REQUIRE(c, g != nullptr, "g is NULL");
@@ -843,9 +846,14 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
   size_t partial_cap = (c->ws_bytes - 64 - size_t(p - ws0)) / sizeof(float);      // (the last 64 bytes are arrival counters)
 
   const bool vec = wprep_vec_ok(cols, w, col_fac, g, g_wt, scratch, 0);
-  if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
-  else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
-  if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
+  if (minmax_in) {                      // group min / max as the forward left them (mq_wprep_fwd minmax_out): no second pass over w
+    row_mn = const_cast<float*>(minmax_in);
+    row_mx = row_mn + (per_channel ? rows : 1);
+  } else {
+    if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+    else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+    if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
+  }
   if (vec)
     wprep_bwd_stats_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                              cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);

@@ -32,9 +32,9 @@ def _protos():
     lib.mq_minmax.argtypes = [_P, _P, c_int64, _P, c_int, _P]
     lib.mq_minmax_2d.argtypes = [_P, _P, c_int64, c_int64, c_int, _P, _P, c_int, _P]
     lib.mq_wprep_fwd.argtypes = [_P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
-                                 _P, _P, c_int, _P, _P, _P, _P, _P]
+                                 _P, _P, c_int, _P, _P, _P, _P, _P, _P]
     lib.mq_wprep_bwd.argtypes = [_P, _P, _P, c_int64, c_int64, _P, c_int, _P, c_int, _P, _P, c_int, mq_qcfg,
-                                 _P, _P, _P, _P, _P, _P, _P]
+                                 _P, _P, _P, _P, _P, _P, _P, _P]
     lib.mq_qgemm.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
                              c_int, _P, c_int64, _P, _P, c_float, c_float, c_float, _P, c_int, _P]
     lib.mq_qgemm_w4a8.argtypes = [_P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_float,
@@ -324,16 +324,20 @@ MODE_NONE, MODE_DIV, MODE_MUL = 0, 1, 2
 
 
 def wprep_fwd(w, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac=None, row_mode=0, sig_up=None,
-              sig_low=None, want_fq=True, want_codes=False, pack4=False, want_wt=False):
-    """Returns dict(w_fq, codes, scale, offset, colsum, wt).  w is [rows, cols] (a norm weight is [1, H])."""
+              sig_low=None, want_fq=True, want_codes=False, pack4=False, want_wt=False, out=None):
+    """Returns dict(w_fq, codes, scale, offset, colsum, wt).  w is [rows, cols] (a norm weight is [1, H]).  `out`: a contiguous
+    fp32 tensor of w's shape that receives w_fq (e.g. a row slice of a buffer several weights share)."""
     lib = _protos()
     w = w.contiguous()
     rows, cols = w.shape
     dev = w.device
     groups = rows if per_channel else 1
-    out = dict(w_fq=torch.empty_like(w) if want_fq else None, codes=None, colsum=None,
+    if out is not None and (out.shape != w.shape or out.dtype != F32 or out.device != w.device or not out.is_contiguous()):
+        raise MQError("wprep_fwd: `out` must be a contiguous fp32 tensor of the weight's shape on its device")
+    w_fq = out if (out is not None and want_fq) else (torch.empty_like(w) if want_fq else None)
+    out = dict(w_fq=w_fq, codes=None, colsum=None,
                scale=torch.empty(groups, dtype=F32, device=dev), offset=torch.empty(groups, dtype=F32, device=dev),
-               wt=torch.empty_like(w) if want_wt else None)
+               wt=torch.empty_like(w) if want_wt else None, minmax=torch.empty(2 * groups, dtype=F32, device=dev))
     if want_codes:
         ncode = rows * cols // 2 if pack4 else rows * cols
         out["codes"] = torch.empty(ncode, dtype=torch.int8 if symmetric else torch.uint8, device=dev)
@@ -345,12 +349,13 @@ def wprep_fwd(w, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac
         check(_launch("wprep_fwd", lib.mq_wprep_fwd, h, ptr(w, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac), int(row_mode),
                                ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(out["w_fq"]),
                                ptr(out["codes"]), int(bool(pack4)), ptr(out["scale"]), ptr(out["offset"]),
-                               ptr(out["colsum"]), ptr(out["wt"]), stream_ptr()), h)
+                               ptr(out["colsum"]), ptr(out["wt"]), ptr(out["minmax"]), stream_ptr()), h)
     return out
 
 
 def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_fac=None, row_mode=0, sig_up=None,
-              sig_low=None, need_col=True, need_row=True, need_sig=True, need_wt=False):
+              sig_low=None, need_col=True, need_row=True, need_sig=True, need_wt=False, minmax=None):
+    """`minmax`: the forward's out["minmax"] (group min / max of the transformed weight); without it they are recomputed."""
     lib = _protos()
     w = w.contiguous(); g = g.contiguous()
     rows, cols = w.shape
@@ -367,7 +372,7 @@ def wprep_bwd(w, g, bits, symmetric, per_channel, col_fac=None, col_mode=0, row_
     with torch.cuda.device(dev):
         check(_launch("wprep_bwd", lib.mq_wprep_bwd, h, ptr(w, F32), ptr(g, F32), rows, cols, ptr(col_fac), int(col_mode), ptr(row_fac),
                                int(row_mode), ptr(sig_up), ptr(sig_low), int(bool(per_channel)), cfg, ptr(g_col),
-                               ptr(g_row), ptr(g_up), ptr(g_low), ptr(g_wt), ptr(scratch), stream_ptr()), h)
+                               ptr(g_row), ptr(g_up), ptr(g_low), ptr(g_wt), ptr(scratch), ptr(minmax), stream_ptr()), h)
     if need_wt:
         return g_col, g_row, g_up, g_low, g_wt
     return g_col, g_row, g_up, g_low

@@ -483,6 +483,14 @@ class _Replay:
         return self.static_out
 
 
+_FP_PASS_SAMPLES = 8          # samples per forward of the e2e FP-target pass
+
+
+def _eager_no_grad(fn, x):
+    with torch.no_grad():
+        return fn(x)
+
+
 def _no_grad_replay(fn, example, device):
     """Forward-only replay unit (FP-target and quant-input refresh passes, alg:471-479,567-573,674-688)."""
     def body(x):
@@ -669,12 +677,23 @@ def e2equant(args, model, dataloader, logger, device=None):
     backbone = LayerList(layers)
 
     if args.epochs > 0:
-        fp_pass = _no_grad_replay(lambda x: backbone(x, attention_mask=attention_mask_batch, position_ids=position_ids)[0], fp_inps[:batch_size], device)
-        for j in my_batches:                                # FP targets of this rank's shard only
-            index = j * batch_size
-            fp_inps[index:index + batch_size] = fp_pass(fp_inps[index:index + batch_size])
+        # FP targets of this rank's shard only.  The float model is the same function of every sample, so the targets are
+        # computed several samples per forward (GEMMs at M = 8 * seqlen instead of seqlen); a ragged tail runs eagerly.
+        mine = [j * batch_size + t for j in my_batches for t in range(batch_size)]
+        chunk = max(batch_size, min(_FP_PASS_SAMPLES, len(mine)))
+        mask_chunk = attention_mask.repeat(chunk, 1, 1, 1) if attention_mask is not None else None
+        run = lambda x, m=mask_chunk: backbone(x, attention_mask=m, position_ids=position_ids)[0]
+        fp_pass = _no_grad_replay(run, fp_inps[:chunk], device)
+        for c0 in range(0, len(mine), chunk):
+            idx = torch.tensor(mine[c0:c0 + chunk], device=device)
+            if len(idx) == chunk:
+                fn = fp_pass
+            else:
+                tail_mask = attention_mask.repeat(len(idx), 1, 1, 1) if attention_mask is not None else None
+                fn = lambda x, m=tail_mask: _eager_no_grad(lambda z: run(z, m), x)
+            fp_inps[idx] = fn(fp_inps[idx])                  # (a replay returns its static output buffer: store before the next call)
             if args.aug_loss:
-                fp_inps_2[index:index + batch_size] = fp_pass(quant_inps[index:index + batch_size])
+                fp_inps_2[idx] = fn(quant_inps[idx])
         del fp_pass
     enable_quant(args, model)
     if args.let:

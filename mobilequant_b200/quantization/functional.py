@@ -38,14 +38,14 @@ class LetLwcWeightQuantFn(torch.autograd.Function):
     every forward)."""
 
     @staticmethod
-    def forward(ctx, w, col_fac, col_mode, row_fac, row_mode, sig_up, sig_low, bits, symmetric, per_channel):
+    def forward(ctx, w, col_fac, col_mode, row_fac, row_mode, sig_up, sig_low, bits, symmetric, per_channel, out=None):
         w2 = w.detach().float().contiguous()
         cf = None if col_fac is None else col_fac.detach().reshape(-1).float().contiguous()
         rf = None if row_fac is None else row_fac.detach().reshape(-1).float().contiguous()
         su = None if sig_up is None else sig_up.detach().reshape(-1).float().contiguous()
         sl = None if sig_low is None else sig_low.detach().reshape(-1).float().contiguous()
-        out = K.wprep_fwd(w2, bits, symmetric, per_channel, cf, col_mode, rf, row_mode, su, sl)
-        ctx.save_for_backward(w2, cf, rf, su, sl)
+        out = K.wprep_fwd(w2, bits, symmetric, per_channel, cf, col_mode, rf, row_mode, su, sl, out=out)
+        ctx.save_for_backward(w2, cf, rf, su, sl, out["minmax"])
         ctx.meta = (col_mode, row_mode, bits, symmetric, per_channel,
                     None if col_fac is None else col_fac.shape, None if row_fac is None else row_fac.shape,
                     None if sig_up is None else sig_up.shape, None if sig_low is None else sig_low.shape, w.dtype)
@@ -54,20 +54,20 @@ class LetLwcWeightQuantFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gs, _go):
-        w2, cf, rf, su, sl = ctx.saved_tensors
+        w2, cf, rf, su, sl, mm = ctx.saved_tensors
         col_mode, row_mode, bits, symmetric, per_channel, cshape, rshape, ushape, lshape, wdtype = ctx.meta
         n = ctx.needs_input_grad
         need_w = n[0]
         if need_w and (col_mode or row_mode):
             raise NotImplementedError("dL/dW through a fused LET transform is never needed (weights are frozen)")
         res = K.wprep_bwd(w2, g.float().contiguous(), bits, symmetric, per_channel, cf, col_mode, rf, row_mode, su, sl,
-                          need_col=n[1], need_row=n[3], need_sig=n[5] or n[6], need_wt=need_w)
+                          need_col=n[1], need_row=n[3], need_sig=n[5] or n[6], need_wt=need_w, minmax=mm)
         g_col, g_row, g_up, g_low = res[:4]
         g_w = res[4].to(wdtype) if need_w else None
         return (g_w, g_col.reshape(cshape) if (n[1] and g_col is not None) else None, None,
                 g_row.reshape(rshape) if (n[3] and g_row is not None) else None, None,
                 g_up.reshape(ushape) if (n[5] and g_up is not None) else None,
-                g_low.reshape(lshape) if (n[6] and g_low is not None) else None, None, None, None)
+                g_low.reshape(lshape) if (n[6] and g_low is not None) else None, None, None, None, None)
 
 
 class AttnProbsFn(torch.autograd.Function):
@@ -227,3 +227,18 @@ class QkvRopeFn(torch.autograd.Function):
             out += [gp[2 * i].reshape(sh[0]) if (sh is not None and n[7 + 4 * i]) else None,
                     gp[2 * i + 1].reshape(sh[1]) if (sh is not None and n[8 + 4 * i]) else None, None, None]
         return tuple(out)
+
+
+class GroupedWeightFn(torch.autograd.Function):
+    """The row-wise concatenation of several fake-quantised weights WITHOUT the copy: each part was written by its weight pass
+    straight into its row slice of `buf` (wprep_fwd(out=...)), so the forward just hands out the buffer and the backward splits
+    the gradient back into per-weight row blocks (contiguous views)."""
+
+    @staticmethod
+    def forward(ctx, buf, *parts):
+        ctx.rows = [p.shape[0] for p in parts]
+        return buf.view_as(buf)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g.split(ctx.rows, dim=0))

@@ -15,7 +15,8 @@ import torch
 import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
-from .functional import StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn, QkvRopeFn
+from .functional import (StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn, QkvRopeFn,
+                         GroupedWeightFn)
 from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
@@ -161,7 +162,7 @@ class Quantizer(nn.Module):
         b = self.qcfg.bitwidth
         return (-2 ** (b - 1), 2 ** (b - 1) - 1) if self.qcfg.is_symmetric else (0, 2 ** b - 1)
 
-    def forward(self, input_, use_scale_offset_as="parameter", let=None):
+    def forward(self, input_, use_scale_offset_as="parameter", let=None, out=None):
         """qm:251-295.  `let` (only passed by QLinear/QRMSNorm under smooth_lm_temporary) fuses the LET transform of
         the raw weight into the same kernel: dict(col_fac, col_mode, row_fac, row_mode)."""
         if not self.enable or self.qcfg.bitwidth > 16:
@@ -183,7 +184,7 @@ class Quantizer(nn.Module):
             lt = let or {}
             y, scale, offset = LetLwcWeightQuantFn.apply(
                 x2, lt.get("col_fac"), lt.get("col_mode", 0), lt.get("row_fac"), lt.get("row_mode", 0), su, sl,
-                self.qcfg.bitwidth, self.qcfg.is_symmetric, self.qcfg.is_per_channel)
+                self.qcfg.bitwidth, self.qcfg.is_symmetric, self.qcfg.is_per_channel, out if x2.shape == x.shape else None)
             self.qmin, self.qmax = self._qrange()
             if self.qcfg.is_per_channel:
                 scale, offset = scale.reshape(-1, 1), offset.reshape(-1, 1)
@@ -241,6 +242,24 @@ def _static_params(quant, device):
 
 def _active(quant):
     return quant is not None and quant.enable and quant.qcfg.bitwidth <= 16
+
+
+def _grouped_weight(mods):
+    """cat([m._fq_weight() for m in mods], 0) for the single GEMM of sibling projections.  After the first call each module's
+    weight pass writes straight into its row slice of one shared buffer (m._wout), so from then on this is a zero-copy view."""
+    ws = [m._fq_weight() for m in mods]
+    buf = getattr(mods[0], "_wgroup", None)
+    if buf is not None and all(getattr(m, "_wout", None) is not None and w.data_ptr() == m._wout.data_ptr() and w.shape == m._wout.shape
+                               for m, w in zip(mods, ws)):
+        return GroupedWeightFn.apply(buf, *ws)
+    if buf is None and all(w.dtype == torch.float32 and w.dim() == 2 for w in ws):
+        buf = torch.empty((sum(w.shape[0] for w in ws), ws[0].shape[1]), dtype=torch.float32, device=ws[0].device)
+        r0 = 0
+        for m, w in zip(mods, ws):
+            m._wout = buf[r0:r0 + w.shape[0]]
+            r0 += w.shape[0]
+        mods[0]._wgroup = buf
+    return torch.cat(ws, dim=0)
 
 
 def _fused_enabled(name):
@@ -333,7 +352,10 @@ class _QBase:
     def _fq_weight_now(self):
         weight, let = self._let_weight(self.weight)
         if self.weight_quantizer is not None:
-            return self.weight_quantizer(weight, let=let) if let is not None else self.weight_quantizer(weight)
+            out = getattr(self, "_wout", None)              # row slice of a buffer shared with sibling projections (_grouped_weight)
+            if out is not None and (out.shape != weight.shape or out.device != weight.device):
+                out = None
+            return self.weight_quantizer(weight, let=let, out=out)
         if let is not None:
             return materialize_let(weight, let)
         return weight
@@ -451,11 +473,10 @@ class QMatMul(nn.Module, _QBase):
             if pq is False:
                 return None
             params += pq
-        ws = [m._fq_weight() for m in lins]
-        if any(w.dtype != torch.float32 for w in ws):
+        if any(m.weight.dtype != torch.float32 for m in lins):
             return None
         bs = [m._bias() for m in lins]
-        y = nn.functional.linear(x, torch.cat(ws, dim=0), None if bs[0] is None else torch.cat(bs, dim=0))
+        y = nn.functional.linear(x, _grouped_weight(lins), None if bs[0] is None else torch.cat(bs, dim=0))
         cos, sin = _rope_tables(rope_cos_sin, position_ids, rot, attn.rope_theta, x.device)
         q, k, v = QkvRopeFn.apply(y, cos, sin, nh, nkv, hd, rot, *params[:24])
         rep = nh // nkv
@@ -653,11 +674,10 @@ class QSiLU(nn.Module, _QBase):
             if pq is False:
                 return None
             params += pq
-        wa, wb = w1._fq_weight(), w3._fq_weight()
-        if wa.dtype != torch.float32 or wb.dtype != torch.float32:
+        if w1.weight.dtype != torch.float32 or w3.weight.dtype != torch.float32:
             return None
         ba, bb = w1._bias(), w3._bias()
-        y = nn.functional.linear(x, torch.cat((wa, wb), dim=0), None if ba is None else torch.cat((ba, bb), dim=0))
+        y = nn.functional.linear(x, _grouped_weight((w1, w3)), None if ba is None else torch.cat((ba, bb), dim=0))
         return SiluGateFn.apply(y, *params)
 
 
