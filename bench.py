@@ -476,8 +476,10 @@ def calib_throughput(model, wq, act, cfg, T, dev, nsamples=96, world=1, rank=0):
     res = {"value": nsamples / dt, "unit": "samples/s", "samples": nsamples, "seconds": dt, "optimizer_steps": steps,
            "learnable_scalars": nlearn, "full_512_sample_run": full,
            "what": "e2equant LET+LWC+LRL, micro-batch 1 per rank, seq %d, 1 epoch, includes FP-target pass, fuse and parameters.pth save" % T,
-           "path": "fused quantizer / weight-prep / AdamW kernels (libmqb200) + library TF32 GEMMs and ATen attention core, whole step "
-                   "replayed as one CUDA graph; 512 samples at this rate: %.1f s (fixed costs included pro rata)" % (512 * dt / nsamples)}
+           "path": "per decoder block: fused QRMSNorm (both quantizers), ONE q|k|v GEMM + fused quantise/RoPE/quantise, fused score-quantise/"
+                   "scale/mask/softmax/quantise, ONE w1|w3 GEMM + fused gated-SiLU core (5 quantizers), fused weight pass (LET+LWC+fake-quant) on a "
+                   "side stream, flat AdamW -- all libmqb200 kernels, forward and backward; the GEMMs themselves are library TF32 (cuBLAS); whole "
+                   "step replayed as one CUDA graph; 512 samples at this rate: %.1f s (fixed costs included pro rata)" % (512 * dt / nsamples)}
     if world > 1:
         res["parallelism"] = "dp%d: samples sharded i %% world == rank, one NCCL SUM all-reduce of the %d learnable-scalar gradients per step" % (world, nlearn)
         res["allreduce_ms_per_step"] = ar_ms
