@@ -229,6 +229,96 @@ __global__ void __launch_bounds__(128) qnorm_pipe_kernel(const NormArgs a) {
   }
 }
 
+// Split-row variant for the prefill (H == 256*NV): TWO warps per row, each keeping half of the row's de-offset integers in
+// registers (half the registers of qnorm_kernel -> twice the resident warps, half the dependent chain per warp); the exact
+// integer statistics and the emitted-code sum meet through shared memory behind a 64-thread named barrier.  Same arithmetic.
+template <bool kLayerNorm, int NV>
+__global__ void __launch_bounds__(128) qnorm_split_kernel(const NormArgs a) {
+  __shared__ unsigned long long s_s2[2][2];
+  __shared__ long long s_s1[2][2];
+  __shared__ int s_cs[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = warp >> 1, hw = warp & 1;
+  const int64_t row = int64_t(blockIdx.x) * 2 + slot;
+  if (row >= a.rows) return;                       // both warps of a row leave together
+  constexpr int H = NV * 256;
+  const float* xr = a.x + row * H + hw * (H / 2);
+  const QParam qi = make_qparam(a.s_in, a.o_in, a.qmax_in);
+  const QParam qo = make_qparam(a.s_out, a.o_out, a.qmax_out);
+  float rr[NV][4];
+  unsigned long long s2 = 0; long long s1 = 0;
+  auto stats = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const float4 v = ldg4_stream(xr + it * 128 + lane * 4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = quant_magic<FIVE>(vv[e], qi);
+        rr[it][e] = __fsub_rn(m, kRoundMagic);
+        const int i = __float_as_int(m) - kRoundMagicBits;          // == int(rr)
+        s2 += (unsigned long long)((long long)i * i);
+        if (kLayerNorm) s1 += i;
+      }
+    }
+  };
+  dispatch_five(qi.five, stats);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    if (kLayerNorm) s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+  }
+  if (lane == 0) { s_s2[slot][hw] = s2; if (kLayerNorm) s_s1[slot][hw] = s1; }
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+  s2 = s_s2[slot][0] + s_s2[slot][1];
+  if (kLayerNorm) s1 = s_s1[slot][0] + s_s1[slot][1];
+  float denom = 1.f, rdenom = 1.f, mean = 0.f, rstd = 1.f;
+  bool five = qo.five | qi.five;
+  if (kLayerNorm) {
+    const double m = (double)s1 / (double)H;
+    const double var = (double)s2 / (double)H - m * m;
+    mean = (float)(m * (double)a.s_in);
+    rstd = (float)(1.0 / sqrt(var * (double)a.s_in * (double)a.s_in + (double)a.eps));
+  } else {
+    denom = fmaxf(fmul(__fsqrt_rn(__ull2float_rn(s2)), a.s_in), 1e-12f);
+    rdenom = __frcp_rn(denom);
+    five |= mantissa_all_ones(denom);
+  }
+  int csum = 0;
+  const bool has_bias = a.bias != nullptr;
+  auto emit = [&](auto five_tag) {
+    constexpr bool FIVE = decltype(five_tag)::value;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int k = hw * (H / 2) + it * 128 + lane * 4;
+      const float4 w = ldg4(a.w_fq + k);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (has_bias) { const float4 b = ldg4(a.bias + k); bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w; }
+      uint32_t packed = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = fmul(rr[it][e], a.s_in);
+        float t;
+        if (kLayerNorm) t = fmul(fmul(fsub(xh, mean), rstd), wv[e]);
+        else t = fmul(wv[e], fmul(a.alpha, div_rn<FIVE>(xh, denom, rdenom)));
+        if (has_bias) t = fadd(t, bv[e]);
+        packed |= (uint32_t)quant_int<FIVE>(t, qo) << (8 * e);
+      }
+      csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+      *reinterpret_cast<uint32_t*>(a.codes + row * H + k) = packed;
+    }
+  };
+  dispatch_five(five, emit);
+  if (a.rowsum) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, d);
+    if (hw == 1 && lane == 0) s_cs[slot] = csum;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+    if (hw == 0 && lane == 0) a.rowsum[row] = csum + s_cs[slot];
+  }
+}
+
 // Few-row variant (decode step: rows == batch): one warp per row leaves a ~3 k-instruction dependent chain on a single
 // warp (17 us per launch for 8 rows); here one 256-thread CTA owns a row, statistics meet through shared memory.  Same
 // arithmetic: the integer sums are exact, so the reduction order does not matter.
@@ -1265,24 +1355,30 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
     else qnorm_row_kernel<false, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
     return check_launch(c, "mq_qnorm");
   }
-  // prefill-sized inputs with H 1024 / 2048: the pipelined persistent kernel (MQB200_QNORM=simple keeps the one-shot kernel)
-  {
-    const char* e = getenv("MQB200_QNORM");
-    if ((H == 2048 || H == 1024) && rows >= 1024 && !(e && e[0] == 's')) {
-      const size_t smem = size_t(H) * 4 * (2 + 4) + 64;
-      const int per_sm = (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024));
-      const unsigned g = (unsigned)std::min<int64_t>((rows + 3) / 4, int64_t(c->sm_count) * per_sm);
+  // prefill-sized inputs with H 1024 / 2048: two warps per row (qnorm_split_kernel).  MQB200_QNORM=simple keeps the one-warp-per-
+  // row kernel, =pipe the persistent bulk-copy pipeline (both measured slower on B200: profiles/r2_qnorm_variants.md)
+  const char* env = getenv("MQB200_QNORM");
+  const char mode = env ? env[0] : 'd';
+  if ((H == 2048 || H == 1024) && rows >= 1024 && mode == 'p') {
+    const size_t smem = size_t(H) * 4 * (2 + 4) + 64;
+    const int per_sm = (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024));
+    const unsigned g = (unsigned)std::min<int64_t>((rows + 3) / 4, int64_t(c->sm_count) * per_sm);
 #define MQ_NORMP(LN, NV)                                                                                                   \
   do {                                                                                                                     \
     static bool attr = false;                                                                                              \
     if (!attr) { cudaFuncSetAttribute(qnorm_pipe_kernel<LN, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
     qnorm_pipe_kernel<LN, NV><<<g, 128, smem, st>>>(a);                                                                    \
   } while (0)
-      if (is_layernorm) { if (H == 2048) MQ_NORMP(true, 16); else MQ_NORMP(true, 8); }
-      else { if (H == 2048) MQ_NORMP(false, 16); else MQ_NORMP(false, 8); }
+    if (is_layernorm) { if (H == 2048) MQ_NORMP(true, 16); else MQ_NORMP(true, 8); }
+    else { if (H == 2048) MQ_NORMP(false, 16); else MQ_NORMP(false, 8); }
 #undef MQ_NORMP
-      return check_launch(c, "mq_qnorm");
-    }
+    return check_launch(c, "mq_qnorm");
+  }
+  if ((H == 2048 || H == 1024) && rows >= 1024 && mode != 's') {
+    const unsigned g2 = (unsigned)((rows + 1) / 2);
+    if (is_layernorm) { if (H == 2048) qnorm_split_kernel<true, 8><<<g2, 128, 0, st>>>(a); else qnorm_split_kernel<true, 4><<<g2, 128, 0, st>>>(a); }
+    else { if (H == 2048) qnorm_split_kernel<false, 8><<<g2, 128, 0, st>>>(a); else qnorm_split_kernel<false, 4><<<g2, 128, 0, st>>>(a); }
+    return check_launch(c, "mq_qnorm");
   }
   unsigned grid = (unsigned)((rows + 3) / 4);
 #define MQ_NORM(LN, NV) qnorm_kernel<LN, NV><<<grid, 128, 0, st>>>(a)
