@@ -507,7 +507,7 @@ def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, w
 
     def body(x, *targets):
         if flat:
-            optimizer.zero_grad()                    # .grad = None: autograd assigns instead of accumulating
+            optimizer.zero_grad()                    # one memset of the flat gradient buffer
         out = forward_fn(x)
         loss = loss_func(targets[0], out)
         for t in targets[1:]:
@@ -517,7 +517,6 @@ def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, w
         loss.backward()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)     # the weight pass's gradient reductions ran on the side stream
-        optimizer.gather_grads()                     # pack the gradients into the flat buffer (memset + multi-tensor copy)
         optimizer.allreduce_grads(world)             # one SUM all-reduce of the flat buffer (no-op on one rank)
         norm = optimizer.step()                      # grad norm, skip-on-non-finite and AdamW on the device
         return loss.detach(), norm

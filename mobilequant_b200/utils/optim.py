@@ -56,10 +56,9 @@ class FlatAdamW:
     """torch.optim.AdamW as the reference constructs it (alg:513, 716-722) + the scaler's grad-norm / skip-on-non-finite
     (optim.py:28-41), executed by ONE fused kernel pair (mq_adamw_step) over a flat parameter buffer.
 
-    Every learnable is re-pointed to a view of `flat` (16-byte aligned slots, grouped by learning-rate group); after a
-    backward pass gather_grads() packs the gradients into `flat_grad`, the buffer the kernel (and the data-parallel
-    all-reduce) reads; the learning rates and the step counter live on the device, which lets a whole training step be
-    replayed as a CUDA graph.
+    Every learnable is re-pointed to a view of `flat` (16-byte aligned slots, grouped by learning-rate group) and its
+    .grad to a view of `flat_grad`, so autograd accumulates straight into the buffer the kernel reads; the learning rates
+    and the step counter live on the device, which lets a whole training step be replayed as a CUDA graph.
     param_groups mirrors the torch attribute for callers that set `param_groups[i]["lr"]`."""
 
     ALIGN = 4      # floats
@@ -89,7 +88,7 @@ class FlatAdamW:
             for p, o, n in self.slots:
                 self.flat[o:o + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + n].view(p.shape)
-                p.grad = None
+                p.grad = self.flat_grad[o:o + n].view(p.shape)
         self.lr_host = torch.tensor([g["lr"] for g in self.param_groups], dtype=torch.float32).pin_memory() \
             if self.device.type == "cuda" else torch.tensor([g["lr"] for g in self.param_groups], dtype=torch.float32)
         self.lr_dev = self.lr_host.to(self.device)
@@ -105,23 +104,10 @@ class FlatAdamW:
         self.lr_dev.copy_(self.lr_host, non_blocking=True)
 
     def zero_grad(self, set_to_none=False):
-        """Detach every .grad: autograd then hands each learnable its gradient tensor as is instead of launching one
-        accumulate kernel per learnable (~1400 two-microsecond adds per TinyLlama step); gather_grads() packs them."""
-        for p, _, _ in self.slots:
-            p.grad = None
-
-    def gather_grads(self):
-        """Pack the learnables' gradients into the flat buffer the fused optimiser kernel (and the all-reduce) reads: one
-        memset (slots without a gradient, alignment padding) + a multi-tensor copy."""
-        import torch
-        self.flat_grad.zero_()
-        dst, src = [], []
+        self.flat_grad.zero_()                  # the views stay attached: autograd accumulates into the flat buffer
         for p, o, n in self.slots:
-            if p.grad is not None:
-                dst.append(self.flat_grad[o:o + n].view(p.shape))
-                src.append(p.grad.detach())
-        if dst:
-            torch._foreach_copy_(dst, src)
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + n].view(p.shape)
 
     def allreduce_grads(self, world):
         """Data-parallel exchange: SUM of the flat gradient buffer over NCCL, then the batch mean (alg:459)."""
