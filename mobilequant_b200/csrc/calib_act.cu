@@ -244,13 +244,23 @@ __global__ void __launch_bounds__(256) rmsnorm_l2_bwd_kernel(const NormCArgs p) 
   if (p.gout) grid_fold<4>(acc, p.partial, p.ticket, p.gout, red, &s_last);
 }
 
-// out[c] = sum over blocks (in block order) of part[blk][c]
+// out[c] = sum over blocks of part[blk][c]: 32 columns x 8 block slices per CTA (slice y takes blocks y, y + 8, ...), the slices
+// meet in shared memory in slice order -- a fixed order, and 8x shorter dependent chains than one thread per column
 __global__ void __launch_bounds__(256) fold_cols_kernel(const float* __restrict__ part, int nblk, int H, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
+  __shared__ float s_p[8][33];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[int64_t(b) * H + c];
-  out[c] = s;
+  if (c < H)
+    for (int b = sy; b < nblk; b += 8) s += part[int64_t(b) * H + c];
+  s_p[sy][cx] = s;
+  __syncthreads();
+  if (sy == 0 && c < H) {
+    float t = s_p[0][cx];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t += s_p[y][cx];
+    out[c] = t;
+  }
 }
 
 static int norm_nvt(int H) {
@@ -520,8 +530,8 @@ int mq_rmsnorm_l2_bwd(void* ctx, const float* x, const float* w, const float* bi
     case 4: rmsnorm_l2_bwd_kernel<4><<<grid, 256, 0, st>>>(p); break;
     default: rmsnorm_l2_bwd_kernel<8><<<grid, 256, 0, st>>>(p); break;
   }
-  fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdw, (int)grid, H, dw);
-  if (dbias) fold_cols_kernel<<<(H + 255) / 256, 256, 0, st>>>(p.pdb, (int)grid, H, dbias);
+  fold_cols_kernel<<<(H + 31) / 32, 256, 0, st>>>(p.pdw, (int)grid, H, dw);
+  if (dbias) fold_cols_kernel<<<(H + 31) / 32, 256, 0, st>>>(p.pdb, (int)grid, H, dbias);
   return check_launch(c, "mq_rmsnorm_l2_bwd");
 }
 

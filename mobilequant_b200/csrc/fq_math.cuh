@@ -101,11 +101,14 @@ __device__ __forceinline__ FqGrad fq_grad(float x, float g, const FqP& q) {
 
 
 // Deterministic grid-wide fold of NACC per-thread float accumulators (quantizer scale / offset gradients): block sums go to
-// double partial[NACC * gridDim.x]; the block whose ticket shows it arrived last adds them in block order and writes
-// gout[NACC]; the ticket resets itself.  `red` = 32 floats of shared memory, `s_last` one shared bool.
+// double partial[NACC * nblk]; the block whose ticket shows it arrived last adds them -- every thread of that block takes the
+// partials bid = tid, tid + blockDim, ... and the threads meet in a fixed shuffle / shared-memory tree, so the order of the
+// additions depends only on the launch geometry -- and writes gout[NACC]; the ticket resets itself.
+// `red` = 32 floats of shared memory, `s_last` one shared bool.  blockDim.x: a multiple of 32, <= 256.
 template <int NACC>
-__device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* partial, unsigned* ticket, float* gout, float* red,
-                                          bool* s_last, unsigned bid = blockIdx.x, unsigned nblk = gridDim.x) {
+__device__ __forceinline__ void grid_fold_to(const float (&acc)[NACC], double* partial, unsigned* ticket, float* const (&outs)[NACC],
+                                             float* red, bool* s_last, unsigned bid = blockIdx.x, unsigned nblk = gridDim.x) {
+  __shared__ double s_fold[8][NACC];
   float b[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) b[i] = block_reduce(acc[i], OpSum(), red);
@@ -116,23 +119,40 @@ __device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* part
     *s_last = atomicAdd(ticket, 1u) == nblk - 1;
   }
   __syncthreads();
-  if (*s_last && threadIdx.x < 32) {
-    __threadfence();
-    const volatile double* vp = partial;
-    double t[NACC];
+  if (!*s_last) return;                                   // block-uniform
+  __threadfence();
+  const volatile double* vp = partial;
+  double t[NACC];
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) t[k] = 0.;
-    for (unsigned i = threadIdx.x; i < nblk; i += 32)
+  for (int k = 0; k < NACC; ++k) t[k] = 0.;
+  for (unsigned i = threadIdx.x; i < nblk; i += blockDim.x)
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) t[k] += vp[NACC * i + k];
+    for (int k = 0; k < NACC; ++k) t[k] += vp[NACC * i + k];
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) t[k] = warp_reduce(t[k], OpSum());
-    if (threadIdx.x == 0) {
+  for (int k = 0; k < NACC; ++k) t[k] = warp_reduce(t[k], OpSum());
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) gout[k] = (float)t[k];
-      *ticket = 0u;
-    }
+    for (int k = 0; k < NACC; ++k) s_fold[wid][k] = t[k];
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      double s = s_fold[0][k];
+      for (int w = 1; w < nw; ++w) s += s_fold[w][k];
+      if (outs[k]) *outs[k] = (float)s;
+    }
+    *ticket = 0u;
+  }
+}
+template <int NACC>
+__device__ __forceinline__ void grid_fold(const float (&acc)[NACC], double* partial, unsigned* ticket, float* gout, float* red,
+                                          bool* s_last, unsigned bid = blockIdx.x, unsigned nblk = gridDim.x) {
+  float* outs[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) outs[k] = gout + k;
+  grid_fold_to<NACC>(acc, partial, ticket, outs, red, s_last, bid, nblk);
 }
 
 }  // namespace mq

@@ -97,29 +97,10 @@ __global__ void __launch_bounds__(256) fq_bwd_kernel(const float* __restrict__ x
     }
   };
   dispatch_five(group == 0 && mantissa_all_ones(s), run);
-  if (partial) {
-    float bs = block_reduce(acc_s, OpSum(), red);
-    float bo = block_reduce(acc_o, OpSum(), red);
-    // the block that arrives last folds the per-block partials in block order (fixed order: deterministic) -- no second launch
-    if (threadIdx.x == 0) {
-      partial[2 * blockIdx.x] = bs; partial[2 * blockIdx.x + 1] = bo;
-      __threadfence();
-      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < 32) {
-      __threadfence();
-      const volatile double* vp = partial;
-      double s2 = 0., o2 = 0.;
-      for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) { s2 += vp[2 * i]; o2 += vp[2 * i + 1]; }
-      s2 = warp_reduce(s2, OpSum());
-      o2 = warp_reduce(o2, OpSum());
-      if (threadIdx.x == 0) {
-        if (gscale) *gscale = (float)s2;
-        if (goffset) *goffset = (float)o2;
-        *ticket = 0u;
-      }
-    }
+  if (partial) {            // the block that arrives last folds the per-block partials in a fixed order -- no second launch
+    const float acc2[2] = {acc_s, acc_o};
+    float* const outs[2] = {gscale, goffset};
+    grid_fold_to<2>(acc2, partial, ticket, outs, red, &s_last);
   }
 }
 
