@@ -216,3 +216,52 @@ def test_calibrate_to_integer_engine_handoff(cuda, tag, tmp_path):
     scale = logits_sim.abs().max().item()
     assert (logits_eng - logits_sim).abs().max().item() < 0.03 * scale
     assert (logits_eng - logits_sim).abs().mean().item() < 3e-3 * scale
+
+
+@pytest.mark.parametrize("tag", ["llama_w8_e2e", "stablelm_w8_omni", "gemma_w8_e2e"])
+def test_fused_block_kernels_match_module_graph(cuda, tag, monkeypatch):
+    """The per-block fused calibration kernels (csrc/calib_attn.cu, csrc/calib_act.cu, grouped GEMMs) against the op-by-op
+    module graph of the same Q* modules: loss and every learnable's gradient at the golden's step-0 point."""
+    from mobilequant_b200.quantization import algorithm as A
+    from mobilequant_b200.model.hf_model import causal_mask_4d
+    g = load_golden(f"model_{tag}.pt")
+    T = g["samples"][0].shape[1]
+    res = []
+    for fused in ("1", "0"):
+        for piece in ("NORM", "QKV", "PROBS", "GATE"):
+            monkeypatch.setenv(f"MQB200_FUSED_{piece}", fused)
+        m = sim_qmodel(g, cuda)
+        args = calib_args(g, "/tmp")
+        layers = m.model.layers
+        emb = m.model.embed_tokens(g["samples"][0].to(cuda))
+        if m.config.normalize_embed:
+            emb = emb * (m.config.hidden_size ** 0.5)
+        mask = causal_mask_4d(1, T, torch.float32, cuda); pos = torch.arange(T, device=cuda).unsqueeze(0)
+        backbone = A.LayerList(layers)
+        A.disable_quant(m)
+        with torch.no_grad():
+            fp_t = backbone(emb, mask, pos)[0]
+        A.enable_quant(args, m)
+        for i, l in enumerate(layers):
+            for k, v in g["let0"][i].items():
+                l.register_parameter(k, torch.nn.Parameter(v.to(cuda)))
+            A.smooth_lm_temporary(l, m.config, True, False)
+        out = backbone(emb, mask, pos)[0]
+        loss = torch.nn.functional.mse_loss(fp_t, out)
+        loss.backward()
+        grads = {f"{i}.{k}": p.grad.detach().clone() for i, l in enumerate(layers) for k, p in l.named_parameters() if p.grad is not None}
+        res.append((fp_t, out.detach(), loss.item(), grads))
+    (t1, o1, l1, g1), (t0, o0, l0, g0) = res
+    assert torch.allclose(t1, t0, rtol=1e-4, atol=1e-4 * t0.abs().max().item())       # float targets: GEMM grouping only
+    assert l1 == pytest.approx(l0, rel=0.02)
+    assert (o1 - o0).abs().mean().item() < 5e-3 * o0.abs().max().item()               # LSB flips of 8-bit codes downstream
+    assert set(g1) == set(g0)
+    lrl_max = max(v.abs().max().item() for k, v in g0.items() if "quantizer.scale" in k)
+    for k, ref in g0.items():
+        got = g1[k]
+        is_lrl = "quantizer.scale" in k or "quantizer.offset" in k
+        if is_lrl and ref.abs().max().item() < 0.05 * lrl_max:
+            assert got.abs().max().item() < 0.1 * lrl_max, (k, got, ref)              # cancellation noise on both sides
+            continue
+        err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        assert err < 0.08, (k, err)
