@@ -431,7 +431,7 @@ def _prefetch_weights(layers, side):
                     w = m._fq_weight_now()
                     ev = torch.cuda.Event()
                     ev.record(side)
-                    m._prepared_weight = (w, ev, side)
+                    m._prepared_weight = (w, ev)
 
 
 def _make_optimizer(groups, wd, device):

@@ -242,38 +242,3 @@ class GroupedWeightFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return (None,) + tuple(g.split(ctx.rows, dim=0))
-
-
-class SideDwLinearFn(torch.autograd.Function):
-    """F.linear whose weight gradient is computed on the side stream that owns the weight pass.
-
-    In calibration the weights are frozen: dL/dW^ is needed only by the weight pass's backward (LET / LWC gradients), which
-    autograd runs on the side stream its forward ran on (algorithm.py:_prefetch_weights).  The dX GEMM stays on the
-    activation stream -- it is the critical path of the backward -- while the dW GEMM (a third of the GEMM work of a step) is
-    issued on the side stream, ordered after the incoming gradient by an event and before the consumer by stream order.
-    Only valid when the consumer of dW runs on `side` (the caller checks)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b, side):
-        ctx.save_for_backward(x, w)
-        ctx.side, ctx.has_b = side, b is not None
-        return torch.nn.functional.linear(x, w, b)
-
-    @staticmethod
-    def backward(ctx, g):
-        x, w = ctx.saved_tensors
-        n = ctx.needs_input_grad
-        side = ctx.side
-        g2 = g.reshape(-1, g.shape[-1])
-        dx = dw = db = None
-        if n[1]:
-            main = torch.cuda.current_stream()
-            side.wait_event(main.record_event())          # g (and x) are complete on the activation stream
-            with torch.cuda.stream(side):
-                dw = g2.t().matmul(x.reshape(-1, x.shape[-1]))
-            g.record_stream(side); x.record_stream(side)
-        if n[0]:
-            dx = g.matmul(w)
-        if ctx.has_b and n[2]:
-            db = g2.sum(0)
-        return dx, dw, db, None

@@ -16,7 +16,7 @@ import torch.nn as nn
 from ..model.hf_model import HFRMSNorm
 from ..model.ops import FMatMul
 from .functional import (StaticFakeQuantFn, LetLwcWeightQuantFn, AttnProbsFn, SiluGateFn, RmsNormL2Fn, QkvRopeFn,
-                         GroupedWeightFn, SideDwLinearFn)
+                         GroupedWeightFn)
 from .. import kernels as K
 
 CLIPMIN = 1e-5   # qm:11
@@ -245,15 +245,13 @@ def _active(quant):
 
 
 def _grouped_weight(mods):
-    """(cat([m._fq_weight() for m in mods], 0), side) for the single GEMM of sibling projections.  After the first call each
-    module's weight pass writes straight into its row slice of one shared buffer (m._wout), so from then on this is a zero-copy
-    view; `side` is then the stream the weight passes ran on (None otherwise: the cat's backward runs on the current stream)."""
+    """cat([m._fq_weight() for m in mods], 0) for the single GEMM of sibling projections.  After the first call each module's
+    weight pass writes straight into its row slice of one shared buffer (m._wout), so from then on this is a zero-copy view."""
     ws = [m._fq_weight() for m in mods]
     buf = getattr(mods[0], "_wgroup", None)
     if buf is not None and all(getattr(m, "_wout", None) is not None and w.data_ptr() == m._wout.data_ptr() and w.shape == m._wout.shape
                                for m, w in zip(mods, ws)):
-        sides = {getattr(m, "_w_side", None) for m in mods}
-        return GroupedWeightFn.apply(buf, *ws), (sides.pop() if len(sides) == 1 else None)
+        return GroupedWeightFn.apply(buf, *ws)
     if buf is None and all(w.dtype == torch.float32 and w.dim() == 2 for w in ws):
         buf = torch.empty((sum(w.shape[0] for w in ws), ws[0].shape[1]), dtype=torch.float32, device=ws[0].device)
         r0 = 0
@@ -261,15 +259,7 @@ def _grouped_weight(mods):
             m._wout = buf[r0:r0 + w.shape[0]]
             r0 += w.shape[0]
         mods[0]._wgroup = buf
-    return torch.cat(ws, dim=0), None
-
-
-def _linear(x, w, b, side):
-    """F.linear; with `side` (the stream on which the consumer of dL/dw runs) the weight-gradient GEMM is taken off the
-    activation stream (functional.py:SideDwLinearFn)."""
-    if side is None or not _fused_enabled("DW_STREAM") or not x.is_cuda or not torch.is_grad_enabled() or not w.requires_grad:
-        return nn.functional.linear(x, w, b)
-    return SideDwLinearFn.apply(x, w, b, side)
+    return torch.cat(ws, dim=0)
 
 
 def _fused_enabled(name):
@@ -351,10 +341,9 @@ class _QBase:
         of the activations, the rest of a step is a chain of small kernels); the stashed tensor is picked up here after waiting
         for its event."""
         pre = getattr(self, "_prepared_weight", None)
-        self._w_side = None
         if pre is not None:
             self._prepared_weight = None
-            w, ev, self._w_side = pre                     # (the stream the weight pass -- and its backward -- runs on)
+            w, ev = pre
             torch.cuda.current_stream().wait_event(ev)
             w.record_stream(torch.cuda.current_stream())
             return w
@@ -405,7 +394,7 @@ class QLinear(nn.Linear, _QBase):
         weight = self._fq_weight()
         if self.input_quantizer is not None and not input_quantized:
             input_ = self.input_quantizer(input_)
-        out = _linear(input_, weight, bias, getattr(self, "_w_side", None))
+        out = nn.functional.linear(input_, weight, bias=bias)
         if self.output_quantizer is not None:
             out = self.output_quantizer(out)
         return out
@@ -487,8 +476,7 @@ class QMatMul(nn.Module, _QBase):
         if any(m.weight.dtype != torch.float32 for m in lins):
             return None
         bs = [m._bias() for m in lins]
-        wcat, side = _grouped_weight(lins)
-        y = _linear(x, wcat, None if bs[0] is None else torch.cat(bs, dim=0), side)
+        y = nn.functional.linear(x, _grouped_weight(lins), None if bs[0] is None else torch.cat(bs, dim=0))
         cos, sin = _rope_tables(rope_cos_sin, position_ids, rot, attn.rope_theta, x.device)
         q, k, v = QkvRopeFn.apply(y, cos, sin, nh, nkv, hd, rot, *params[:24])
         rep = nh // nkv
@@ -689,8 +677,7 @@ class QSiLU(nn.Module, _QBase):
         if w1.weight.dtype != torch.float32 or w3.weight.dtype != torch.float32:
             return None
         ba, bb = w1._bias(), w3._bias()
-        wcat, side = _grouped_weight((w1, w3))
-        y = _linear(x, wcat, None if ba is None else torch.cat((ba, bb), dim=0), side)
+        y = nn.functional.linear(x, _grouped_weight((w1, w3)), None if ba is None else torch.cat((ba, bb), dim=0))
         return SiluGateFn.apply(y, *params)
 
 
