@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "ctx.h"
 #include "fq_math.cuh"
+#include <cstdlib>
 
 namespace mq {
 
@@ -13,6 +14,16 @@ static inline int grid_for(Ctx* c, int64_t work_items, int per_block, int waves 
   int64_t cap = int64_t(c->sm_count) * waves;
   if (need < 1) need = 1;
   return int(need < cap ? need : cap);
+}
+
+// Threads per row-CTA of the weight-pass kernels.  A row is only 8-22 KB: with 256-thread CTAs an SM holds 8 rows (64 KB in flight)
+// and every thread issues one or two loads before the block reduction; narrower CTAs keep up to 32 rows per SM in flight.
+// MQ_WPREP_THREADS overrides (A/B measurements).
+static unsigned wprep_threads(int64_t cols) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MQ_WPREP_THREADS"); forced = e ? atoi(e) : 0; }
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return (unsigned)forced;
+  return cols >= 4096 ? 128u : 64u;
 }
 
 // ================================================================================================================
@@ -736,7 +747,7 @@ int mq_minmax_2d(void* ctx, const float* x, int64_t rows, int64_t cols, int per_
   MQ_REQUIRE(c, x && out_min && out_max && rows > 0 && cols > 0, "null pointer or empty tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (per_row) {
-    minmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(x, cols, out_min, out_max, accumulate);
+    minmax_rows_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(x, cols, out_min, out_max, accumulate);
   } else {
     MQ_REQUIRE(c, size_t(cols) * 2 * sizeof(int) + 64 <= c->ws_bytes, "too many columns for the workspace");
     int* ws = reinterpret_cast<int*>(stream_ws(c, st));
@@ -784,15 +795,15 @@ int mq_wprep_fwd(void* ctx, const float* w, int64_t rows, int64_t cols, const fl
   if (!row_mn) return MQ_FAILED_ALLOCATION;
   float* row_mx = row_mn + rows;
   const bool vec = wprep_vec_ok(cols, w, col_fac, w_fq, wt_out, codes, pack4);
-  if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
-  else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+  if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx);
+  else wprep_rowminmax_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx);
   if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
   if (vec)
-    wprep_quant_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+    wprep_quant_v_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                          cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
                                                          scale_out, offset_out, colsum, wt_out, minmax_out, groups);
   else
-    wprep_quant_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+    wprep_quant_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                        cfg.bitwidth, cfg.is_symmetric, w_fq, (uint8_t*)codes, pack4,
                                                        scale_out, offset_out, colsum, wt_out, minmax_out, groups);
   return check_launch(c, "mq_wprep_fwd");
@@ -831,15 +842,15 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
     row_mn = const_cast<float*>(minmax_in);
     row_mx = row_mn + (per_channel ? rows : 1);
   } else {
-    if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
-    else wprep_rowminmax_kernel<<<(unsigned)rows, 256, 0, st>>>(w, cols, la, row_mn, row_mx);
+    if (vec) wprep_rowminmax_v_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx);
+    else wprep_rowminmax_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, cols, la, row_mn, row_mx);
     if (!per_channel) wprep_fold_kernel<<<1, 256, 0, st>>>(row_mn, row_mx, rows);
   }
   if (vec)
-    wprep_bwd_stats_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+    wprep_bwd_stats_v_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                              cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);
   else
-    wprep_bwd_stats_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
+    wprep_bwd_stats_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low, per_channel,
                                                            cfg.bitwidth, cfg.is_symmetric, row_gs, row_cmn, row_cmx);
   unsigned ggrid = per_channel ? (unsigned)((rows + 255) / 256) : 1u;
   wprep_bwd_group_kernel<<<ggrid, 256, 0, st>>>(row_mn, row_mx, sig_up, sig_low, per_channel, cfg.bitwidth,
@@ -847,11 +858,11 @@ int mq_wprep_bwd(void* ctx, const float* w, const float* g, int64_t rows, int64_
                                                 g_sig_low);
   if (g_col_fac || g_row_fac || g_wt) {
     if (vec)
-      wprep_bwd_apply_v_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
+      wprep_bwd_apply_v_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
                                                                per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
                                                                g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
     else
-      wprep_bwd_apply_kernel<<<(unsigned)rows, 256, 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
+      wprep_bwd_apply_kernel<<<(unsigned)rows, wprep_threads(cols), 0, st>>>(w, g, cols, la, row_mn, row_mx, sig_up, sig_low,
                                                              per_channel, cfg.bitwidth, cfg.is_symmetric, gg,
                                                              g_col_fac ? scratch : nullptr, g_row_fac, g_wt);
   }

@@ -408,10 +408,13 @@ def _use_graphs(device):
 
 
 def _weight_stream(device):
-    """Side stream of the weight pass (MQ_WPREP_STREAM=0 keeps everything on one stream)."""
+    """Side streams of the weight pass (MQ_WPREP_STREAM=0 keeps everything on one stream, MQ_WPREP_STREAMS=n sets their number).
+    One weight's pass is a chain of three to six small dependent kernels (17-46 MB each: launch and tail latency, not bytes,
+    set its pace), so the weights of a block are dealt round-robin onto a few streams and their chains interleave."""
     if device.type != "cuda" or os.environ.get("MQ_WPREP_STREAM", "1") == "0":
         return None
-    return torch.cuda.Stream(device=device)
+    n = max(1, int(os.environ.get("MQ_WPREP_STREAMS", "3")))
+    return [torch.cuda.Stream(device=device) for _ in range(n)]
 
 
 def _prefetch_weights(layers, side):
@@ -423,15 +426,19 @@ def _prefetch_weights(layers, side):
     if side is None:
         return
     main = torch.cuda.current_stream()
-    side.wait_stream(main)                          # LET / LWC parameters of this step are final
-    with torch.cuda.stream(side):
-        for layer in layers:
-            for m in layer.modules():
-                if isinstance(m, (QLinear, QRMSNorm, QLayerNorm)):
+    for s in side:
+        s.wait_stream(main)                         # LET / LWC parameters of this step are final
+    k = 0
+    for layer in layers:
+        for m in layer.modules():
+            if isinstance(m, (QLinear, QRMSNorm, QLayerNorm)):
+                s = side[k % len(side)]
+                k += 1
+                with torch.cuda.stream(s):
                     w = m._fq_weight_now()
                     ev = torch.cuda.Event()
-                    ev.record(side)
-                    m._prepared_weight = (w, ev)
+                    ev.record(s)
+                m._prepared_weight = (w, ev)
 
 
 def _make_optimizer(groups, wd, device):
@@ -515,8 +522,8 @@ def _make_step(args, forward_fn, loss_func, optimizer, loss_scaler, params_fn, w
         if not flat:
             return loss.detach(), _train_step(args, loss, optimizer, loss_scaler, params_fn, world).detach()
         loss.backward()
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)     # the weight pass's gradient reductions ran on the side stream
+        for s in side or ():
+            torch.cuda.current_stream().wait_stream(s)        # the weight pass's gradient reductions ran on the side streams
         optimizer.allreduce_grads(world)             # one SUM all-reduce of the flat buffer (no-op on one rank)
         norm = optimizer.step()                      # grad norm, skip-on-non-finite and AdamW on the device
         return loss.detach(), norm
