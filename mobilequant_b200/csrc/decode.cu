@@ -222,7 +222,8 @@ struct AttnDecArgs {
   float sqk, s_s, o_s, qmax_s, s_p, qmax_p, spv, s_out, o_out;
   const uint32_t* lut;
   uint8_t* out; int32_t* rowsum_out;
-  int CS;                                             // CTAs per cluster == key slices per (sequence, kv head)
+  int CS;                                             // CTAs per cluster == key slices per (sequence, kv head, row group)
+  int RG;                                             // query heads of the kv head handled by one cluster (divides nh / nkv)
   int Tslice;                                         // score slab stride (multiple of 8 >= ceil((pos + 1) / CS))
 };
 
@@ -250,18 +251,18 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(uint32_t addr) {
 }
 
 // reduce R (<= 8) per-thread values over the 256 threads of the block at once; result in every thread
-template <typename T, typename Op>
-__device__ __forceinline__ void block_reduce256_n(T (&v)[8], int R, Op op, T* scratch /* [8 warps][8] */) {
+template <int N, typename T, typename Op>
+__device__ __forceinline__ void block_reduce256_n(T (&v)[N], int R, Op op, T* scratch /* [8 warps][8] */) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) if (r < R) v[r] = warp_reduce(v[r], op);
+  for (int r = 0; r < N; ++r) if (r < R) v[r] = warp_reduce(v[r], op);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) if (r < R) scratch[(threadIdx.x >> 5) * 8 + r] = v[r];
+    for (int r = 0; r < N; ++r) if (r < R) scratch[(threadIdx.x >> 5) * 8 + r] = v[r];
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < N; ++r) {
     if (r < R) {
       T t = scratch[r];
 #pragma unroll
@@ -271,13 +272,17 @@ __device__ __forceinline__ void block_reduce256_n(T (&v)[8], int R, Op op, T* sc
   }
 }
 
-template <int HD>
+// RMAX = query heads per cluster (a.RG <= RMAX).  The per-thread instruction stream of this kernel is a serial chain whose length
+// grows with the number of query heads a thread carries (every loop below is unrolled over them); splitting the heads of a kv
+// head over several clusters shortens the chain and multiplies the CTAs (the K / V slices are then read once per row group,
+// from L2).
+template <int HD, int RMAX>
 __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) {
   constexpr int WPR = HD / 4;                 // 32-bit words per head row
   constexpr int KS = 256 / WPR;               // key sub-slices of the P.V pass inside a CTA
-  constexpr int RMAX = 8;
   extern __shared__ __align__(16) uint8_t smem_dec[];
-  const int R = a.nh / a.nkv;
+  const int Rtot = a.nh / a.nkv;
+  const int R = a.RG;
   DecXchg* s_x = reinterpret_cast<DecXchg*>(smem_dec);                    // first: same offset in every CTA of the cluster
   unsigned long long* s_scr = reinterpret_cast<unsigned long long*>(s_x + 1);   // [8][8] reduction scratch
   uint32_t* s_q = reinterpret_cast<uint32_t*>(s_scr + 64);                // [RMAX][WPR] q codes of the new token
@@ -293,7 +298,9 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   const int CS = a.CS;
   const int cr = (int)cluster_ctarank();
   const int grp = blockIdx.x / CS;
-  const int b = grp / a.nkv, kvh = grp % a.nkv;
+  const int ngrp = Rtot / R, rg = grp % ngrp;           // row group: query heads kvh * Rtot + rg * R + (0 .. R-1)
+  const int b = (grp / ngrp) / a.nkv, kvh = (grp / ngrp) % a.nkv;
+  const bool appender = cr == 0 && rg == 0;             // exactly one CTA per (sequence, kv head) appends the new k / v row
   const int pos = a.pos_dev ? *a.pos_dev : a.pos;
   // a replayed graph increments *pos_dev on the device: a step beyond the position the launch was sized for (cache capacity,
   // score slab, cos / sin tables) must not touch memory.  Every CTA of every cluster sees the same pos: uniform exit.
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   for (int i = tid; i < (R + 2) * WPR; i += 256) {
     const int hh = i / WPR, d = (i % WPR) * 4;
     const bool is_q = hh < R, is_k = hh == R;
-    const uint8_t* src = is_q ? row + (kvh * R + hh) * HD : (is_k ? row + (a.nh + kvh) * HD : row + (a.nh + a.nkv + kvh) * HD);
+    const uint8_t* src = is_q ? row + (kvh * Rtot + rg * R + hh) * HD : (is_k ? row + (a.nh + kvh) * HD : row + (a.nh + a.nkv + kvh) * HD);
     const float s_in = is_q ? a.sq_in : (is_k ? a.sk_in : a.sv_in), o_in = is_q ? a.oq_in : (is_k ? a.ok_in : a.ov_in);
     const QParam& qo = is_q ? qq : (is_k ? qk : qv);
     const uint32_t wx = *reinterpret_cast<const uint32_t*>(src + d);
@@ -342,8 +349,8 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) packed |= (uint32_t)quant_int<true>(o[j], qo) << (8 * j);
     if (is_q) s_q[hh * WPR + (d >> 2)] = packed;
-    else if (is_k) { s_knew[d >> 2] = packed; if (cr == 0) *reinterpret_cast<uint32_t*>(kcache + int64_t(pos) * HD + d) = packed; }
-    else { s_vnew[d >> 2] = packed; if (cr == 0) *reinterpret_cast<uint32_t*>(vcache + int64_t(pos) * HD + d) = packed; }
+    else if (is_k) { s_knew[d >> 2] = packed; if (appender) *reinterpret_cast<uint32_t*>(kcache + int64_t(pos) * HD + d) = packed; }
+    else { s_vnew[d >> 2] = packed; if (appender) *reinterpret_cast<uint32_t*>(vcache + int64_t(pos) * HD + d) = packed; }
   }
   __syncthreads();
   // code sums: q head r -> s_rsq[r], new k row -> s_rsq[RMAX] (and the cache, rank 0)
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
     int sum = 0;
     for (int wd = lane; wd < WPR; wd += 32) sum = (int)__dp4a(hh < R ? s_q[hh * WPR + wd] : s_knew[wd], 0x01010101u, (unsigned)sum);
     sum = warp_reduce(sum, OpSum());
-    if (lane == 0) { if (hh < R) s_rsq[hh] = sum; else { s_rsq[RMAX] = sum; if (cr == 0) rsk[pos] = sum; } }
+    if (lane == 0) { if (hh < R) s_rsq[hh] = sum; else { s_rsq[RMAX] = sum; if (appender) rsk[pos] = sum; } }
   }
   __syncthreads();
 
@@ -365,6 +372,7 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   for (int r = 0; r < RMAX; ++r) mx[r] = -1;
   for (int j = j_lo + tid; j < j_hi; j += 256) {
     const uint4* krow = j == pos ? reinterpret_cast<const uint4*>(s_knew) : reinterpret_cast<const uint4*>(kcache + int64_t(j) * HD);
+    const int rskj = j == pos ? s_rsq[RMAX] : rsk[j];  // issued with the key row's loads, not after the dot products
     int acc[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) acc[r] = 0;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
         for (int r = 0; r < RMAX; ++r)
           if (r < R) acc[r] = (int)__dp4a(kw[e], s_q[r * WPR + w4 * 4 + e], (unsigned)acc[r]);
     }
-    const int colc = -ioq * (j == pos ? s_rsq[RMAX] : rsk[j]) + HD * ioq * iok;
+    const int colc = -ioq * rskj + HD * ioq * iok;
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
       if (r < R) {
@@ -393,8 +401,12 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   if (tid < R) s_x->mx[tid] = mx[tid];
   cluster_sync_all();                                   // #1: slice maxima visible across the cluster
   if (tid < R) {
+    int pm[8];                                          // all peers' loads in flight before the first use (DSMEM latency once)
+#pragma unroll
+    for (int p = 0; p < 8; ++p) pm[p] = p < CS ? ld_peer_s32(map_peer(&s_x->mx[tid], p)) : -1;
     int m = -1;
-    for (int p = 0; p < CS; ++p) m = max(m, ld_peer_s32(map_peer(&s_x->mx[tid], p)));
+#pragma unroll
+    for (int p = 0; p < 8; ++p) m = max(m, pm[p]);
     s_cm[tid] = m;
   }
   __syncthreads();
@@ -418,8 +430,12 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   }
   cluster_sync_all();                                   // #2: slice sums visible
   if (tid < R) {
+    unsigned long long pt[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) pt[p] = p < CS ? ld_peer_u64(map_peer(&s_x->sum[tid], p)) : 0ull;
     unsigned long long t = 0;
-    for (int p = 0; p < CS; ++p) t += ld_peer_u64(map_peer(&s_x->sum[tid], p));
+#pragma unroll
+    for (int p = 0; p < 8; ++p) t += pt[p];
     s_den[tid] = __ull2float_rn(t);
   }
   __syncthreads();
@@ -488,18 +504,22 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
     const int ldo = a.nh * HD;
     for (int i = tid; i < R * HD; i += 256) {
       const int r = i / HD, d = i % HD;
-      int A = 0, psum = 0;
-      for (int p = 0; p < CS; ++p) {
-        A += ld_peer_s32(map_peer(s_red + r * HD + d, p));
-        psum += ld_peer_s32(map_peer(&s_x->ps[r], p));
+      int pa[8], pp[8];                                 // 2 * CS remote loads in flight, then the integer sums
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        pa[p] = p < CS ? ld_peer_s32(map_peer(s_red + r * HD + d, p)) : 0;
+        pp[p] = p < CS ? ld_peer_s32(map_peer(&s_x->ps[r], p)) : 0;
       }
+      int A = 0, psum = 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) { A += pa[p]; psum += pp[p]; }
       A -= iov * psum;
       const int code = quant_int<true>(fmul(__int2float_rn(A), a.spv), qo);
-      a.out[int64_t(b) * ldo + (kvh * R + r) * HD + d] = (uint8_t)code;
+      a.out[int64_t(b) * ldo + (kvh * Rtot + rg * R + r) * HD + d] = (uint8_t)code;
       csum += code;
     }
     if (a.rowsum_out) {
-      int one[8] = {csum, 0, 0, 0, 0, 0, 0, 0};
+      int one[1] = {csum};
       block_reduce256_n(one, 1, OpSum(), reinterpret_cast<int*>(s_scr));
       if (tid == 0) atomicAdd(a.rowsum_out + b, one[0]);
     }
@@ -507,9 +527,9 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   cluster_sync_all();                                   // #4: peers keep their shared memory alive until the leader has read it
 }
 
-static size_t attn_dec_smem(int hd, int R, int Tslice) {
+static size_t attn_dec_smem(int hd, int rmax, int R, int Tslice) {
   const int WPR = hd / 4, KS = 256 / WPR;
-  return sizeof(DecXchg) + 64 * 8 + size_t(8 + 2) * WPR * 4 + 512 * 4 + size_t(KS) * 8 * hd * 4 + 4 * 8 * 4 + size_t(R) * Tslice * 2 + 16;
+  return sizeof(DecXchg) + 64 * 8 + size_t(rmax + 2) * WPR * 4 + 512 * 4 + size_t(KS) * rmax * hd * 4 + 4 * rmax * 4 + size_t(R) * Tslice * 2 + 16;
 }
 
 // =====================================================================================================================
@@ -779,7 +799,14 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
   MQ_REQUIRE(c, a.oq == rintf(a.oq) && a.ok == rintf(a.ok) && a.ov == rintf(a.ov) && a.o_s == rintf(a.o_s) && a.o_out == rintf(a.o_out),
              "integer engine kernels need integral offsets (qm:60)");
   a.lut = lut; a.out = out; a.rowsum_out = rowsum_out;
-  // key slices: one cluster per (sequence, kv head); enough CTAs to fill the machine, at least 64 keys per slice
+  // row groups: RG query heads of a kv head per cluster (MQB200_DEC_RG overrides; measured in profiles/r2_decode_kernels.txt)
+  const int Rtot = nh / nkv;
+  int RG = Rtot >= 2 ? 2 : 1;
+  { const char* e = getenv("MQB200_DEC_RG"); if (e && atoi(e) >= 1 && atoi(e) <= Rtot && Rtot % atoi(e) == 0) RG = atoi(e); }
+  while (Rtot % RG) --RG;
+  const int rmax = RG <= 1 ? 1 : (RG <= 2 ? 2 : (RG <= 4 ? 4 : 8));
+  a.RG = RG;
+  // key slices: one cluster per (sequence, kv head, row group); at least 256 keys per slice
   int CS = 1;
   int cs_max = 8;
   { const char* e = getenv("MQB200_DEC_CS"); if (e && atoi(e) >= 1 && atoi(e) <= 8) cs_max = atoi(e); }   // A/B measurements
@@ -787,33 +814,29 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
   while (CS < cs_max && B * nkv * CS * 2 <= 2 * c->sm_count && (pos_bound + 1) / (CS * 2) >= 256) CS *= 2;
   a.CS = CS;
   a.Tslice = (((pos_bound + 1) + CS - 1) / CS + 7) / 8 * 8;
-  const size_t smem = attn_dec_smem(hd, nh / nkv, a.Tslice);
+  const size_t smem = attn_dec_smem(hd, rmax, RG, a.Tslice);
   MQ_REQUIRE(c, smem <= 227 * 1024, "sequence too long for the decode attention score slab");
   cudaStream_t st = (cudaStream_t)stream;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(B * nkv * CS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(B * nkv * (Rtot / RG) * CS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t le = cudaSuccess;
-#define MQ_DEC(HDV)                                                                                                         \
+#define MQ_DEC2(HDV, RM)                                                                                                    \
   {                                                                                                                         \
     static size_t attr_smem = 48 * 1024;                                                                                    \
-    static bool np_set = false;                                                                                             \
     if (smem > attr_smem) {                                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));  \
       attr_smem = smem;                                                                                                     \
     }                                                                                                                       \
-    if (CS > 8 && !np_set) {                                                                                                \
-      cudaError_t e = cudaFuncSetAttribute(qattn_decode_kernel<HDV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);    \
-      if (e != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));  \
-      np_set = true;                                                                                                        \
-    }                                                                                                                       \
-    le = cudaLaunchKernelEx(&cfg, qattn_decode_kernel<HDV>, a);                                                             \
+    le = cudaLaunchKernelEx(&cfg, qattn_decode_kernel<HDV, RM>, a);                                                         \
   }
+#define MQ_DEC(HDV) { if (rmax == 1) MQ_DEC2(HDV, 1) else if (rmax == 2) MQ_DEC2(HDV, 2) else if (rmax == 4) MQ_DEC2(HDV, 4) else MQ_DEC2(HDV, 8) }
   if (hd == 32) MQ_DEC(32) else if (hd == 64) MQ_DEC(64) else if (hd == 128) MQ_DEC(128) else MQ_DEC(256)
+#undef MQ_DEC2
 #undef MQ_DEC
   if (le != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qattn_decode launch: ") + cudaGetErrorString(le));
   return check_launch(c, "mq_qattn_decode");
