@@ -1,5 +1,6 @@
 // Context management + error reporting of libmqb200 (include/mqb200.h).
 #include "ctx.h"
+#include <cstdlib>
 #include <new>
 
 namespace mq {
@@ -10,6 +11,12 @@ int fail(Ctx* c, int code, const std::string& what) {
   if (code < 0 || code > MQ_INTERNAL_ERROR) code = MQ_INTERNAL_ERROR;
   if (c) c->last_error[code] = what; else g_setup_error[code] = what;
   return code;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MQB200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
 }
 
 void* stream_ws(Ctx* c, cudaStream_t st) {

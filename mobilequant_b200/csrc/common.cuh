@@ -147,6 +147,16 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T* smem /* >= 32 entries *
   return r;
 }
 
+// ---- programmatic dependent launch (decode step: ~200 dependent kernels of 3-15 us per token) -------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running: everything before pdl_wait() (barrier / TMEM set-up, loads of CONSTANT data such as weights and lookup tables)
+// overlaps the predecessor; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+// pdl_trigger() lets the NEXT kernel in the stream be scheduled (it is issued at the top of every decode kernel: a dependent
+// can only start once every CTA of its predecessor has started, so a running kernel never waits for a slot held by a
+// kernel that waits for it).  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- vector ld/st ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ldg4_stream(const float* p) {

@@ -40,6 +40,19 @@ int fail(Ctx* c, int code, const std::string& what);
 void* stream_ws(Ctx* c, cudaStream_t st);      // scratch buffer (ws_bytes) owned by `st`; nullptr when it cannot be allocated
 int check_launch(Ctx* c, const char* what);
 
+// Launch with the programmatic-dependent-launch attribute (common.cuh: pdl_wait / pdl_trigger).  MQB200_PDL=0 launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 }  // namespace mq
 
 #define MQ_CTX(c, p)                               \

@@ -39,6 +39,8 @@ using namespace tc;
 template <int MODE>
 __global__ void __launch_bounds__(128) qgemv_epi_kernel(const GvEpiArgs a) {
   __shared__ int s_sum[4];
+  pdl_trigger();
+  pdl_wait();                                                       // the accumulator comes from the GEMV before this launch
   const int m = blockIdx.y;
   const int NO = MODE == GV_ACTMUL ? a.N / 2 : a.N;                 // output columns
   const int j0 = (blockIdx.x * 128 + threadIdx.x) * 4;
@@ -115,12 +117,22 @@ qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int k = k0; k < k1; ++k) {
+      // The weights are constants: the first ring of weight tiles is requested BEFORE the grid dependency resolves, so a
+      // dependent launch streams them while the kernel that produces x is still running; x follows after pdl_wait().
+      const int npre = min(kGvStages, k1 - k0);
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full_bar[i], L::kWBytes + L::kXBytes);
+        tma_load_2d(smem_w + i * L::kWBytes, &tmap_w, &full_bar[i], (k0 + i) * kGvBK, n0);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i)
+        tma_load_2d(smem_x + i * L::kXBytes, &tmap_x, &full_bar[i], (k0 + i) * kGvBK, 0);      // rows >= B are zero-filled
+      int stage = npre == kGvStages ? 0 : npre; uint32_t phase = npre == kGvStages ? 1 : 0;
+      for (int k = k0 + npre; k < k1; ++k) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], L::kWBytes + L::kXBytes);
         tma_load_2d(smem_w + stage * L::kWBytes, &tmap_w, &full_bar[stage], k * kGvBK, n0);
-        tma_load_2d(smem_x + stage * L::kXBytes, &tmap_x, &full_bar[stage], k * kGvBK, 0);   // rows >= B are zero-filled
+        tma_load_2d(smem_x + stage * L::kXBytes, &tmap_x, &full_bar[stage], k * kGvBK, 0);
         if (++stage == kGvStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -144,6 +156,7 @@ qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
   } else {
     // warps 2..5: TMEM lane quarter (warp & 3) == 32 weight rows; thread = weight row n, registers = batch columns
     const int quarter = warp & 3;
+    pdl_wait();                                 // the accumulator these warps add into is zeroed by an earlier kernel of the chain
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const int n = n0 + quarter * 32 + lane;
@@ -295,6 +308,9 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   float* s_den = reinterpret_cast<float*>(s_cm + RMAX);                   // [RMAX]
   uint16_t* s_c = reinterpret_cast<uint16_t*>(s_den + RMAX);              // [R][Tslice] score codes, then prob codes
 
+  pdl_trigger();                                          // decode chain (common.cuh)
+  for (int i = threadIdx.x; i < 512; i += 256) s_tab[i] = __ldg(a.lut + i);   // constant table: before the grid dependency resolves
+  pdl_wait();                                             // qkv codes (and *pos_dev) come from earlier kernels of the chain
   const int CS = a.CS;
   const int cr = (int)cluster_ctarank();
   const int grp = blockIdx.x / CS;
@@ -315,7 +331,6 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   int32_t* rsk = a.rskc + (int64_t(b) * a.nkv + kvh) * a.Tmax;
   const int half = a.rot / 2;
 
-  for (int i = tid; i < 512; i += 256) s_tab[i] = __ldg(a.lut + i);
 
   // ---- 1. RoPE + requant of the new token (every CTA of the cluster, redundantly: it is a few hundred elements);
   //         heads 0..R-1 = q, R = k, R+1 = v; one thread = 4 head dims; rank 0 appends k / v to the cache
@@ -544,6 +559,8 @@ constexpr int kFgRows = 4;
 template <int BMAX>
 __global__ void __launch_bounds__(256) fgemv_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
                                                     int B, int V, int K) {
+  pdl_trigger();
+  pdl_wait();                                  // x comes from the final norm before this launch
   const int lane = threadIdx.x & 31;
   const int v0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kFgRows;
   if (v0 >= V) return;
@@ -662,7 +679,8 @@ static int launch_qgemv(Ctx* c, const void* x, int x_signed, const void* w, int 
   }
   const uint32_t idesc = make_idesc(2u, w_signed ? 1u : 0u, x_signed ? 1u : 0u, 0u, 0u, kGvBM, BP);
   const int n_tiles = (args.N + kGvBM - 1) / kGvBM;
-  qgemv_kernel<BP><<<n_tiles * args.ksplit, 192, L::kTotal, st>>>(tw, tx, args, idesc);
+  cudaError_t le = launch_pdl(qgemv_kernel<BP>, dim3(n_tiles * args.ksplit), dim3(192), (size_t)L::kTotal, st, tw, tx, args, idesc);
+  if (le != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemv launch: ") + cudaGetErrorString(le));
   return check_launch(c, "mq_qgemv");
 }
 
@@ -742,9 +760,9 @@ int mq_qgemv_epilogue(void* ctx, int32_t* acc, int ldacc, int B, int N, const in
   const int NO = mode == GV_ACTMUL ? N / 2 : N;
   dim3 grid((NO / 4 + 127) / 128, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == GV_QUANT) qgemv_epi_kernel<GV_QUANT><<<grid, 128, 0, st>>>(a);
-  else if (mode == GV_ACTMUL) qgemv_epi_kernel<GV_ACTMUL><<<grid, 128, 0, st>>>(a);
-  else qgemv_epi_kernel<GV_RESID><<<grid, 128, 0, st>>>(a);
+  if (mode == GV_QUANT) launch_pdl(qgemv_epi_kernel<GV_QUANT>, grid, dim3(128), 0, st, a);
+  else if (mode == GV_ACTMUL) launch_pdl(qgemv_epi_kernel<GV_ACTMUL>, grid, dim3(128), 0, st, a);
+  else launch_pdl(qgemv_epi_kernel<GV_RESID>, grid, dim3(128), 0, st, a);
   return check_launch(c, "mq_qgemv_epilogue");
 }
 
@@ -766,8 +784,8 @@ int mq_fgemv(void* ctx, const float* x, const float* w, float* out, int B, int V
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "x and w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((V + 8 * kFgRows - 1) / (8 * kFgRows));
-  if (B <= 8) fgemv_kernel<8><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
-  else fgemv_kernel<16><<<grid, 256, 0, st>>>(x, w, out, B, V, K);
+  if (B <= 8) launch_pdl(fgemv_kernel<8>, dim3(grid), dim3(256), 0, st, x, w, out, B, V, K);
+  else launch_pdl(fgemv_kernel<16>, dim3(grid), dim3(256), 0, st, x, w, out, B, V, K);
   return check_launch(c, "mq_fgemv");
 }
 
@@ -819,10 +837,12 @@ int mq_qattn_decode(void* ctx, const uint8_t* qkv, int ldq, int B, int nh, int n
   cudaStream_t st = (cudaStream_t)stream;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B * nkv * (Rtot / RG) * CS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaSuccess;
 #define MQ_DEC2(HDV, RM)                                                                                                    \
   {                                                                                                                         \

@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(128) qnorm_split_kernel(const NormArgs a) {
 // then normalises those columns: two launches per layer fewer in the decode chain.
 template <bool kLayerNorm, bool FUSE>
 __global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a, const GvEpiArgs e) {
+  pdl_trigger();                                 // decode chain: let the next kernel set itself up (common.cuh)
+  pdl_wait();                                    // x / the GEMV accumulator come from the predecessor
   __shared__ unsigned long long s_s2[8];
   __shared__ long long s_s1[8];
   __shared__ int s_cs[8];
@@ -1351,8 +1353,8 @@ int mq_qnorm(void* ctx, const float* x, int64_t rows, int H, int is_layernorm, f
   NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
   if (rows <= 256 && H <= 8192) {                 // decode-sized inputs: one CTA per row
     const GvEpiArgs none{};
-    if (is_layernorm) qnorm_row_kernel<true, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
-    else qnorm_row_kernel<false, false><<<(unsigned)rows, 256, 0, st>>>(a, none);
+    if (is_layernorm) launch_pdl(qnorm_row_kernel<true, false>, dim3((unsigned)rows), dim3(256), 0, st, a, none);
+    else launch_pdl(qnorm_row_kernel<false, false>, dim3((unsigned)rows), dim3(256), 0, st, a, none);
     return check_launch(c, "mq_qnorm");
   }
   // prefill-sized inputs with H 1024 / 2048: two warps per row (qnorm_split_kernel).  MQB200_QNORM=simple keeps the one-warp-per-
@@ -1409,8 +1411,8 @@ int mq_qnorm_resid(void* ctx, float* x, int rows, int H, int is_layernorm, float
   NormArgs a{x, rows, H, s_in, o_in, qmax_in, w_fq, bias, alpha, eps, s_out, o_out, qmax_out, codes, rowsum};
   GvEpiArgs e{rows, H, acc, ldacc, g_rowsum, g_sxw, g_ow, g_c0, g_bias, g_so, g_oo, g_qgroup, g_qmax, nullptr, (int64_t)H, nullptr,
               nullptr, 1.f, 0.f, 255.f, x, nullptr};
-  if (is_layernorm) qnorm_row_kernel<true, true><<<(unsigned)rows, 256, 0, st>>>(a, e);
-  else qnorm_row_kernel<false, true><<<(unsigned)rows, 256, 0, st>>>(a, e);
+  if (is_layernorm) launch_pdl(qnorm_row_kernel<true, true>, dim3((unsigned)rows), dim3(256), 0, st, a, e);
+  else launch_pdl(qnorm_row_kernel<false, true>, dim3((unsigned)rows), dim3(256), 0, st, a, e);
   return check_launch(c, "mq_qnorm_resid");
 }
 
