@@ -310,13 +310,13 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
 
   pdl_trigger();                                          // decode chain (common.cuh)
   for (int i = threadIdx.x; i < 512; i += 256) s_tab[i] = __ldg(a.lut + i);   // constant table: before the grid dependency resolves
-  pdl_wait();                                             // qkv codes (and *pos_dev) come from earlier kernels of the chain
   const int CS = a.CS;
   const int cr = (int)cluster_ctarank();
   const int grp = blockIdx.x / CS;
   const int ngrp = Rtot / R, rg = grp % ngrp;           // row group: query heads kvh * Rtot + rg * R + (0 .. R-1)
   const int b = (grp / ngrp) / a.nkv, kvh = (grp / ngrp) % a.nkv;
   const bool appender = cr == 0 && rg == 0;             // exactly one CTA per (sequence, kv head) appends the new k / v row
+  // *pos_dev is advanced by the LAST kernel of a decode step, which has completed before any kernel of this step started
   const int pos = a.pos_dev ? *a.pos_dev : a.pos;
   // a replayed graph increments *pos_dev on the device: a step beyond the position the launch was sized for (cache capacity,
   // score slab, cos / sin tables) must not touch memory.  Every CTA of every cluster sees the same pos: uniform exit.
@@ -325,9 +325,16 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   const int per = (Tk + CS - 1) / CS;
   const int j_lo = min(Tk, cr * per), j_hi = min(Tk, j_lo + per);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint8_t* row = a.qkv + int64_t(b) * a.ldq;
   uint8_t* kcache = a.kc + (int64_t(b) * a.nkv + kvh) * a.Tmax * HD;
   uint8_t* vcache = a.vc + (int64_t(b) * a.nkv + kvh) * a.Tmax * HD;
+  // the cache rows of earlier positions were written by earlier decode steps: pull this CTA's K and V slices towards L2 while
+  // the predecessor (the QKV epilogue) is still running
+  for (int64_t off = int64_t(j_lo) * HD + tid * 128; off < int64_t(min(j_hi, pos)) * HD; off += 256 * 128) {
+    prefetch_l2(kcache + off);
+    prefetch_l2(vcache + off);
+  }
+  pdl_wait();                                             // the qkv codes of this step come from earlier kernels of the chain
+  const uint8_t* row = a.qkv + int64_t(b) * a.ldq;
   int32_t* rsk = a.rskc + (int64_t(b) * a.nkv + kvh) * a.Tmax;
   const int half = a.rot / 2;
 

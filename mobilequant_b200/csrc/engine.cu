@@ -328,6 +328,10 @@ __global__ void __launch_bounds__(128) qnorm_split_kernel(const NormArgs a) {
 template <bool kLayerNorm, bool FUSE>
 __global__ void __launch_bounds__(256) qnorm_row_kernel(const NormArgs a, const GvEpiArgs e) {
   pdl_trigger();                                 // decode chain: let the next kernel set itself up (common.cuh)
+  for (int k = threadIdx.x * 4; k < a.H; k += 1024) {       // constants of the second pass: into L1 while the predecessor runs
+    prefetch_l1(a.w_fq + k);
+    if (a.bias) prefetch_l1(a.bias + k);
+  }
   pdl_wait();                                    // x / the GEMV accumulator come from the predecessor
   __shared__ unsigned long long s_s2[8];
   __shared__ long long s_s1[8];
