@@ -85,8 +85,10 @@ class IntEngine:
         # nibbles through shared memory (16 KB read + 32 KB written per k-slice) competes with the tensor core's own operand
         # fetch (96 B/clk of the 128 B/clk shared-memory port), while the scratch copy costs only L2 traffic.
         self.fused_w4 = os.environ.get("MQB200_W4_FUSED", "0") == "1"
-        # decode: the residual epilogues of o_proj / w2 ride on the following row norm (two launches per layer fewer)
-        self.fused_resid_norm = os.environ.get("MQB200_RESID_NORM", "1") != "0"
+        # decode: the residual epilogues of o_proj / w2 as their own launches (default) or riding on the following row norm
+        # (MQB200_RESID_NORM=1, two launches per layer fewer).  With programmatic dependent launch along the chain an extra
+        # launch costs less than the longer norm kernel: measured 1.155 ms (separate) against 1.181 ms (fused) per step.
+        self.fused_resid_norm = os.environ.get("MQB200_RESID_NORM", "0") == "1"
 
     # ---- build ------------------------------------------------------------------------------------------------------
     def _wq(self, w, c, want_fq=False):
