@@ -411,8 +411,9 @@ def decode_throughput(eng, ids, B, T, nsteps):
     peak = peaks.get("hbm_gbs", 6500.0)
     ach = bytes_step / (ms / 1e3) / 1e9
     return {"value": B * 1e3 / ms, "unit": "tok/s", "batch": B, "context": T0, "steps": nsteps, "ms_per_step": ms,
-            "what": "greedy decode, one CUDA-graph replay per token: qnorm, tcgen05 skinny GEMM (split-K, integer red.add) + requant "
-                    "epilogue x4, fused RoPE/append/attention on the int8 KV cache per layer; fp32 lm_head + argmax",
+            "what": "greedy decode, one CUDA-graph replay per token, kernels chained by programmatic dependent launch: qnorm, tcgen05 "
+                    "skinny GEMM (split-K, integer red.add, weight tiles requested ahead of the dependency) + requant epilogue x4, fused "
+                    "RoPE/append/attention on the int8 KV cache per layer; fp32 lm_head + argmax",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "bytes_per_step": bytes_step, "weights_int8": wbytes, "lm_head_fp32": head, "kv_cache_read": kv,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6500 GB/s"}}
