@@ -28,6 +28,11 @@ struct Ctx {
   std::vector<std::pair<cudaStream_t, void*>> ws_by_stream;
   int* counters = nullptr; // zero-initialised arrival counters of the fused skinny-GEMM epilogue (self-resetting)
   int n_counters = 0;
+  // Destination of the latest mq_unpack4: weight codes inside this range are produced by a kernel of the same stream (packed
+  // 4-bit weights expanded into scratch right before the GEMM), so the skinny GEMM must not request them ahead of its grid
+  // dependency (decode.cu: weight-tile prefetch before pdl_wait).
+  const char* unpack_lo = nullptr;
+  const char* unpack_hi = nullptr;
   std::string last_error[6];
 };
 

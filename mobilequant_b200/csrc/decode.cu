@@ -68,6 +68,7 @@ struct QGemvArgs {
   int ksplit;
   int mode;           // GV_NONE: raw accumulator only; else the last CTA of each column group runs that epilogue
   int* counters;      // [column groups] arrival counters (zero on entry, reset by the last CTA)
+  int w_const;        // the weight codes are not written by the preceding kernels of the stream: tiles may be requested early
   GvEpiArgs epi;
 };
 
@@ -119,7 +120,7 @@ qgemv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     if (lane == 0) {
       // The weights are constants: the first ring of weight tiles is requested BEFORE the grid dependency resolves, so a
       // dependent launch streams them while the kernel that produces x is still running; x follows after pdl_wait().
-      const int npre = min(kGvStages, k1 - k0);
+      const int npre = p.w_const ? min(kGvStages, k1 - k0) : 0;
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&full_bar[i], L::kWBytes + L::kXBytes);
         tma_load_2d(smem_w + i * L::kWBytes, &tmap_w, &full_bar[i], (k0 + i) * kGvBK, n0);
@@ -686,7 +687,10 @@ static int launch_qgemv(Ctx* c, const void* x, int x_signed, const void* w, int 
   }
   const uint32_t idesc = make_idesc(2u, w_signed ? 1u : 0u, x_signed ? 1u : 0u, 0u, 0u, kGvBM, BP);
   const int n_tiles = (args.N + kGvBM - 1) / kGvBM;
-  cudaError_t le = launch_pdl(qgemv_kernel<BP>, dim3(n_tiles * args.ksplit), dim3(192), (size_t)L::kTotal, st, tw, tx, args, idesc);
+  QGemvArgs args2 = args;
+  const char* wlo = static_cast<const char*>(w);
+  args2.w_const = !(c->unpack_lo && wlo < c->unpack_hi && wlo + size_t(args.N) * args.K > c->unpack_lo);
+  cudaError_t le = launch_pdl(qgemv_kernel<BP>, dim3(n_tiles * args.ksplit), dim3(192), (size_t)L::kTotal, st, tw, tx, args2, idesc);
   if (le != cudaSuccess) return fail(c, MQ_RUNTIME_ERROR, std::string("mq_qgemv launch: ") + cudaGetErrorString(le));
   return check_launch(c, "mq_qgemv");
 }
@@ -779,6 +783,8 @@ int mq_unpack4(void* ctx, const uint8_t* packed, int64_t n_codes, int is_signed,
   MQ_REQUIRE(c, n_codes % 32 == 0, "the number of codes must be a multiple of 32");
   MQ_REQUIRE(c, (reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "buffers must be 16-byte aligned");
   const int64_t n16 = n_codes / 32;
+  c->unpack_lo = static_cast<const char*>(out);
+  c->unpack_hi = c->unpack_lo + n_codes;
   unpack4_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(packed),
                                                                                  reinterpret_cast<uint4*>(out), n16, is_signed);
   return check_launch(c, "mq_unpack4");
