@@ -471,71 +471,138 @@ __device__ __forceinline__ void qrope_body(const RopeArgs& a, uint8_t* vs) {
     }
     const int b = tok / a.T, t = tok % a.T;
     const uint8_t* row = a.qkv + int64_t(tok) * a.ldq;
-    // cos / sin of this lane's head dims (shared by every head of the token).  Dims beyond the rotary width (partial rotary,
-    // hm:489-501) use cos 1, sin 0 and themselves as partner -- x*1 + x*0 == x exactly -- so the head loops are branch
-    // free; the sign of rotate_half (hm:338-344: cat(-x2, x1)) is folded into sin (fmul(-y, s) == fmul(y, -s)).
-    float cv[WPT][4], sv[WPT][4];
-    int dpart[WPT];
-#pragma unroll
-    for (int wi = 0; wi < WPT; ++wi) {
-      const int d = (sub + wi * LPI) * 4;
-      if (d < a.rot) {
-        const bool neg = d < half;
-        dpart[wi] = neg ? d + half : d - half;
-        const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
-        cv[wi][0] = c.x; cv[wi][1] = c.y; cv[wi][2] = c.z; cv[wi][3] = c.w;
-        sv[wi][0] = neg ? -sn.x : sn.x; sv[wi][1] = neg ? -sn.y : sn.y; sv[wi][2] = neg ? -sn.z : sn.z; sv[wi][3] = neg ? -sn.w : sn.w;
-      } else {
-        dpart[wi] = d;
-        cv[wi][0] = cv[wi][1] = cv[wi][2] = cv[wi][3] = 1.f;
-        sv[wi][0] = sv[wi][1] = sv[wi][2] = sv[wi][3] = 0.f;
+    if (a.rot == HD) {
+      // ---- full rotary width: pair-wise path.  A lane owns 8 dims of the lower half of a head AND their 8 partners in the upper
+      // half (HD / 16 lanes per head), so every code is loaded, unpacked and de-quantised once and both rotated halves come out
+      // of the same registers: out[d] = x[d]*cos[d] + x[d+h]*(-sin[d]),  out[d+h] = x[d+h]*cos[d+h] + x[d]*sin[d+h]
+      // (hm:338-367 with rotate_half = cat(-x2, x1); operation for operation what the generic path below computes).
+      constexpr int LPH = HD / 16, HPW2 = 32 / LPH;
+      const int sub2 = lane % LPH, grp2 = lane / LPH;
+      const int dl = sub2 * 8, dh = dl + HD / 2;
+      float cl[8], ch[8], nsl[8], sh[8];
+      {
+        const float* cr = a.cos + int64_t(t) * a.rot; const float* sr = a.sin + int64_t(t) * a.rot;
+        const float4 c0 = ldg4(cr + dl), c1 = ldg4(cr + dl + 4), c2 = ldg4(cr + dh), c3 = ldg4(cr + dh + 4);
+        const float4 s0 = ldg4(sr + dl), s1 = ldg4(sr + dl + 4), s2 = ldg4(sr + dh), s3 = ldg4(sr + dh + 4);
+        cl[0] = c0.x; cl[1] = c0.y; cl[2] = c0.z; cl[3] = c0.w; cl[4] = c1.x; cl[5] = c1.y; cl[6] = c1.z; cl[7] = c1.w;
+        ch[0] = c2.x; ch[1] = c2.y; ch[2] = c2.z; ch[3] = c2.w; ch[4] = c3.x; ch[5] = c3.y; ch[6] = c3.z; ch[7] = c3.w;
+        nsl[0] = -s0.x; nsl[1] = -s0.y; nsl[2] = -s0.z; nsl[3] = -s0.w; nsl[4] = -s1.x; nsl[5] = -s1.y; nsl[6] = -s1.z; nsl[7] = -s1.w;
+        sh[0] = s2.x; sh[1] = s2.y; sh[2] = s2.z; sh[3] = s2.w; sh[4] = s3.x; sh[5] = s3.y; sh[6] = s3.z; sh[7] = s3.w;
       }
+      const int64_t strideh2 = int64_t(a.T) * HD;
+      auto heads2 = [&](int nheads, const uint8_t* src0, float s_in, float o_in, const QParam& qo, uint8_t* dst0, int32_t* rs0) {
+        constexpr int U = 1;                             // head groups in flight per lane (2 doubles the registers: 128, two CTAs per SM)
+        for (int hh0 = 0; hh0 < nheads; hh0 += U * HPW2) {
+          uint2 wl[U], wh[U];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int hh = hh0 + u * HPW2 + grp2;
+            ok[u] = hh < nheads;
+            const uint8_t* src = src0 + (ok[u] ? hh : 0) * HD;
+            wl[u] = __ldg(reinterpret_cast<const uint2*>(src + dl));
+            wh[u] = __ldg(reinterpret_cast<const uint2*>(src + dh));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int hh = hh0 + u * HPW2 + grp2;
+            float x[8], y[8];
+            { float t4[4]; unpack4(wl[u].x, s_in, o_in, t4); x[0] = t4[0]; x[1] = t4[1]; x[2] = t4[2]; x[3] = t4[3];
+              unpack4(wl[u].y, s_in, o_in, t4); x[4] = t4[0]; x[5] = t4[1]; x[6] = t4[2]; x[7] = t4[3];
+              unpack4(wh[u].x, s_in, o_in, t4); y[0] = t4[0]; y[1] = t4[1]; y[2] = t4[2]; y[3] = t4[3];
+              unpack4(wh[u].y, s_in, o_in, t4); y[4] = t4[0]; y[5] = t4[1]; y[6] = t4[2]; y[7] = t4[3]; }
+            uint32_t pl[2] = {0u, 0u}, ph[2] = {0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float lo = fadd(fmul(x[e], cl[e]), fmul(y[e], nsl[e]));
+              const float hi = fadd(fmul(y[e], ch[e]), fmul(x[e], sh[e]));
+              pl[e >> 2] |= (uint32_t)quant_int<FIVE>(lo, qo) << (8 * (e & 3));
+              ph[e >> 2] |= (uint32_t)quant_int<FIVE>(hi, qo) << (8 * (e & 3));
+            }
+            uint8_t* dst = dst0 + hh * strideh2;
+            if (ok[u]) {
+              *reinterpret_cast<uint2*>(dst + dl) = make_uint2(pl[0], pl[1]);
+              *reinterpret_cast<uint2*>(dst + dh) = make_uint2(ph[0], ph[1]);
+            }
+            int csum = (int)__dp4a(pl[0], 0x01010101u, 0u);
+            csum = (int)__dp4a(pl[1], 0x01010101u, (unsigned)csum);
+            csum = (int)__dp4a(ph[0], 0x01010101u, (unsigned)csum);
+            csum = (int)__dp4a(ph[1], 0x01010101u, (unsigned)csum);
+#pragma unroll
+            for (int dd = LPH >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
+            if (ok[u] && sub2 == 0) rs0[int64_t(hh) * a.T] = csum;
+          }
+        }
+      };
+      heads2(a.nh, row, a.sq_in, a.oq_in, qq, a.q + (int64_t(b) * a.nh * a.T + t) * HD, a.rsq + int64_t(b) * a.nh * a.T + t);
+      heads2(a.nkv, row + a.nh * HD, a.sk_in, a.ok_in, qk, a.k + (int64_t(b) * a.nkv * a.T + t) * HD, a.rsk + int64_t(b) * a.nkv * a.T + t);
+    } else {
+      // cos / sin of this lane's head dims (shared by every head of the token).  Dims beyond the rotary width (partial rotary,
+      // hm:489-501) use cos 1, sin 0 and themselves as partner -- x*1 + x*0 == x exactly -- so the head loops are branch
+      // free; the sign of rotate_half (hm:338-344: cat(-x2, x1)) is folded into sin (fmul(-y, s) == fmul(y, -s)).
+      float cv[WPT][4], sv[WPT][4];
+      int dpart[WPT];
+  #pragma unroll
+      for (int wi = 0; wi < WPT; ++wi) {
+        const int d = (sub + wi * LPI) * 4;
+        if (d < a.rot) {
+          const bool neg = d < half;
+          dpart[wi] = neg ? d + half : d - half;
+          const float4 c = ldg4(a.cos + int64_t(t) * a.rot + d), sn = ldg4(a.sin + int64_t(t) * a.rot + d);
+          cv[wi][0] = c.x; cv[wi][1] = c.y; cv[wi][2] = c.z; cv[wi][3] = c.w;
+          sv[wi][0] = neg ? -sn.x : sn.x; sv[wi][1] = neg ? -sn.y : sn.y; sv[wi][2] = neg ? -sn.z : sn.z; sv[wi][3] = neg ? -sn.w : sn.w;
+        } else {
+          dpart[wi] = d;
+          cv[wi][0] = cv[wi][1] = cv[wi][2] = cv[wi][3] = 1.f;
+          sv[wi][0] = sv[wi][1] = sv[wi][2] = sv[wi][3] = 0.f;
+        }
+      }
+      // ---- q heads, then k heads: HPW heads per iteration, LPI adjacent lanes per head.  src0: codes of head 0 of the kind in
+      // the token's row; dst0 / rs0: head 0 of this token in the output layout (heads are T*HD / T elements apart)
+      const int64_t strideh = int64_t(a.T) * HD;
+      auto heads = [&](int nheads, const uint8_t* src0, float s_in, float o_in, const QParam& qo, uint8_t* dst0, int32_t* rs0) {
+        constexpr int U = 2;                               // heads in flight per lane group: the loop is load-latency bound
+        for (int hh0 = 0; hh0 < nheads; hh0 += U * HPW) {
+          uint32_t wx[U][WPT], wy[U][WPT];
+          bool ok[U];
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int hh = hh0 + u * HPW + grp;
+            ok[u] = hh < nheads;
+            const uint8_t* src = src0 + (ok[u] ? hh : 0) * HD;
+  #pragma unroll
+            for (int wi = 0; wi < WPT; ++wi) {
+              wx[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + (sub + wi * LPI) * 4));
+              wy[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + dpart[wi]));
+            }
+          }
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int hh = hh0 + u * HPW + grp;
+            int csum = 0;
+            uint8_t* dst = dst0 + hh * strideh;
+  #pragma unroll
+            for (int wi = 0; wi < WPT; ++wi) {
+              const int d = (sub + wi * LPI) * 4;
+              float x[4], y[4];
+              unpack4(wx[u][wi], s_in, o_in, x);
+              unpack4(wy[u][wi], s_in, o_in, y);
+              uint32_t packed = 0;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)   // q_embed = q * cos + rotate_half(q) * sin
+                packed |= (uint32_t)quant_int<FIVE>(fadd(fmul(x[j], cv[wi][j]), fmul(y[j], sv[wi][j])), qo) << (8 * j);
+              if (ok[u]) *reinterpret_cast<uint32_t*>(dst + d) = packed;
+              csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
+            }
+  #pragma unroll
+            for (int dd = LPI >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
+            if (ok[u] && sub == 0) rs0[int64_t(hh) * a.T] = csum;
+          }
+        }
+      };
+      heads(a.nh, row, a.sq_in, a.oq_in, qq, a.q + (int64_t(b) * a.nh * a.T + t) * HD, a.rsq + int64_t(b) * a.nh * a.T + t);
+      heads(a.nkv, row + a.nh * HD, a.sk_in, a.ok_in, qk, a.k + (int64_t(b) * a.nkv * a.T + t) * HD, a.rsk + int64_t(b) * a.nkv * a.T + t);
     }
-    // ---- q heads, then k heads: HPW heads per iteration, LPI adjacent lanes per head.  src0: codes of head 0 of the kind in
-    // the token's row; dst0 / rs0: head 0 of this token in the output layout (heads are T*HD / T elements apart)
-    const int64_t strideh = int64_t(a.T) * HD;
-    auto heads = [&](int nheads, const uint8_t* src0, float s_in, float o_in, const QParam& qo, uint8_t* dst0, int32_t* rs0) {
-      constexpr int U = 2;                               // heads in flight per lane group: the loop is load-latency bound
-      for (int hh0 = 0; hh0 < nheads; hh0 += U * HPW) {
-        uint32_t wx[U][WPT], wy[U][WPT];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int hh = hh0 + u * HPW + grp;
-          ok[u] = hh < nheads;
-          const uint8_t* src = src0 + (ok[u] ? hh : 0) * HD;
-#pragma unroll
-          for (int wi = 0; wi < WPT; ++wi) {
-            wx[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + (sub + wi * LPI) * 4));
-            wy[u][wi] = __ldg(reinterpret_cast<const uint32_t*>(src + dpart[wi]));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int hh = hh0 + u * HPW + grp;
-          int csum = 0;
-          uint8_t* dst = dst0 + hh * strideh;
-#pragma unroll
-          for (int wi = 0; wi < WPT; ++wi) {
-            const int d = (sub + wi * LPI) * 4;
-            float x[4], y[4];
-            unpack4(wx[u][wi], s_in, o_in, x);
-            unpack4(wy[u][wi], s_in, o_in, y);
-            uint32_t packed = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)   // q_embed = q * cos + rotate_half(q) * sin
-              packed |= (uint32_t)quant_int<FIVE>(fadd(fmul(x[j], cv[wi][j]), fmul(y[j], sv[wi][j])), qo) << (8 * j);
-            if (ok[u]) *reinterpret_cast<uint32_t*>(dst + d) = packed;
-            csum = (int)__dp4a(packed, 0x01010101u, (unsigned)csum);
-          }
-#pragma unroll
-          for (int dd = LPI >> 1; dd > 0; dd >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, dd);
-          if (ok[u] && sub == 0) rs0[int64_t(hh) * a.T] = csum;
-        }
-      }
-    };
-    heads(a.nh, row, a.sq_in, a.oq_in, qq, a.q + (int64_t(b) * a.nh * a.T + t) * HD, a.rsq + int64_t(b) * a.nh * a.T + t);
-    heads(a.nkv, row + a.nh * HD, a.sk_in, a.ok_in, qk, a.k + (int64_t(b) * a.nkv * a.T + t) * HD, a.rsk + int64_t(b) * a.nkv * a.T + t);
     // ---- v: requant into the smem tile
     const uint8_t* vsrc = row + heads_qk * HD;
     for (int c = lane * 4; c < vw; c += 128) {
