@@ -34,7 +34,7 @@ constexpr int kTN = 128;            // keys per tile (UMMA N of S, K extent of P
 constexpr int kSoftWarps = 16;
 constexpr int kTcThreads = kSoftWarps * 32 + 128;   // 16 softmax warps (4 warpgroups) + one control warpgroup (TMA, MMA, 2 idle)
 constexpr int kCkRing = 8;          // ring of per-key correction vectors (> K ring + S buffers, see the producer)
-constexpr int kRepA = 4, kRepB = 8; // bank replication of the two exp tables
+constexpr int kRepA = 8, kRepB = 16; // bank replication of the two exp tables (32 B / 64 B per entry)
 constexpr int kTabBytes = 256 * (kRepA + kRepB) * 4;
 
 template <int HD>
@@ -50,7 +50,7 @@ struct TcLayout {
   static constexpr int kVOff = kKOff + kKStages * kKBytes;          // [kVStages][kVBytes]
   static constexpr int kPOff = kVOff + kVStages * kVBytes;          // [2 bufs][lo, hi][kPBytes]
   static constexpr int kTabOff = kPOff + 4 * kPBytes;
-  static constexpr int kCkOff = kTabOff + kTabBytes + 8192;         // [kCkRing][128] int (8 KB of slack: the tables are aligned at run time)
+  static constexpr int kCkOff = kTabOff + kTabBytes + 16384;        // [kCkRing][128] int (16 KB of slack: the tables are aligned at run time)
   static constexpr int kXiOff = kCkOff + kCkRing * kTN * 4;         // [4][128] int   (row max / prob-code sums)
   static constexpr int kXsOff = kXiOff + 4 * kTM * 4;               // [4][128] u64   (row sums)
   static constexpr int kBarOff = kXsOff + 4 * kTM * 8;
@@ -90,9 +90,9 @@ qattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* s_k = smem + L::kKOff;
   uint8_t* s_v = smem + L::kVOff;
   uint8_t* s_p = smem + L::kPOff;
-  // exp tables: B (256 x 32 B) on an 8 KB boundary of the shared window, A (256 x 16 B) right behind it on a 4 KB boundary,
+  // exp tables: B (256 x 64 B) on a 16 KB boundary of the shared window, A (256 x 32 B) right behind it on an 8 KB boundary,
   // so that a lookup address is (index field of k) | (table base + bank copy of the lane): one shift + one LOP3
-  const uint32_t tab_addr = (smem_u32(smem + L::kTabOff) + 8191u) & ~8191u;
+  const uint32_t tab_addr = (smem_u32(smem + L::kTabOff) + 16383u) & ~16383u;
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L::kTabOff + (tab_addr - smem_u32(smem + L::kTabOff)));
   int* s_ck = reinterpret_cast<int*>(smem + L::kCkOff);
   int* s_xi = reinterpret_cast<int*>(smem + L::kXiOff);
@@ -127,12 +127,13 @@ qattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     fence_barrier_init();
   }
   if (warp == kSoftWarps + 1) tmem_alloc(tmem_slot, 512);
-  if (warp < kSoftWarps) {                  // exp tables, entries replicated across banks (lane & 3 / lane & 7 picks the copy)
+  if (warp < kSoftWarps) {                  // exp tables, entries replicated across banks (lane & 7 / lane & 15 picks the copy)
     for (int i = threadIdx.x; i < 256; i += kSoftWarps * 32) {
       const uint32_t va = __ldg(a.lut + i), vb = __ldg(a.lut + 256 + i);
-      reinterpret_cast<uint4*>(s_tab)[2 * i] = make_uint4(vb, vb, vb, vb);
-      reinterpret_cast<uint4*>(s_tab)[2 * i + 1] = make_uint4(vb, vb, vb, vb);
-      reinterpret_cast<uint4*>(s_tab)[512 + i] = make_uint4(va, va, va, va);
+#pragma unroll
+      for (int j = 0; j < kRepB / 4; ++j) reinterpret_cast<uint4*>(s_tab)[(kRepB / 4) * i + j] = make_uint4(vb, vb, vb, vb);
+#pragma unroll
+      for (int j = 0; j < kRepA / 4; ++j) reinterpret_cast<uint4*>(s_tab)[256 * (kRepB / 4) + (kRepA / 4) * i + j] = make_uint4(va, va, va, va);
     }
   }
   tc_fence_before();
@@ -263,12 +264,12 @@ qattn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const QParam qp = make_qparam(a.s_p, 0.f, a.qmax_p);
     const QParam qo = make_qparam(a.s_out, a.o_out, 255.f);
     const int iok = (int)a.ok, ioq = (int)a.oq, iov = (int)a.ov;
-    static_assert(kRepA == 4 && kRepB == 8, "lookup addresses hard-code the entry sizes (16 / 32 bytes)");
-    const uint32_t tabB = tab_addr + (lane & (kRepB - 1)) * 4, tabA = tab_addr + 8192u + (lane & (kRepA - 1)) * 4;
+    static_assert(kRepA == 8 && kRepB == 16, "lookup addresses hard-code the entry sizes (32 / 64 bytes)");
+    const uint32_t tabB = tab_addr + (lane & (kRepB - 1)) * 4, tabA = tab_addr + 16384u + (lane & (kRepA - 1)) * 4;
     auto lds32 = [](uint32_t addr) -> uint32_t { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
     auto exp_tab = [&](int k) -> uint32_t {      // E(k) = (A[k >> 8] * B[k & 255]) >> 31; indices masked: discarded lanes stay in range
-      const uint32_t ea = lds32((((uint32_t)k >> 4) & 0xFF0u) | tabA);
-      const uint32_t eb = lds32((((uint32_t)k << 5) & 0x1FE0u) | tabB);
+      const uint32_t ea = lds32((((uint32_t)k >> 3) & 0x1FE0u) | tabA);
+      const uint32_t eb = lds32((((uint32_t)k << 6) & 0x3FC0u) | tabB);
       return (uint32_t)(((unsigned long long)ea * eb) >> 31);
     };
     // hd <= 64: |I| < 2^22, so float(I) comes from the magic-number trick (IADD3 + FADD) instead of I2F
