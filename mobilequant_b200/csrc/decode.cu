@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) qattn_decode_kernel(const AttnDecArgs a) 
   const int pos = a.pos_dev ? *a.pos_dev : a.pos;
   // a replayed graph increments *pos_dev on the device: a step beyond the position the launch was sized for (cache capacity,
   // score slab, cos / sin tables) must not touch memory.  Every CTA of every cluster sees the same pos: uniform exit.
-  if (pos < 0 || pos > a.pos_max) return;
+  if (pos < 0 || pos > a.pos_max) { pdl_wait(); return; }   // (a grid that skips the wait would let ITS dependents overtake the chain)
   const int Tk = pos + 1;
   const int per = (Tk + CS - 1) / CS;
   const int j_lo = min(Tk, cr * per), j_hi = min(Tk, j_lo + per);

@@ -262,6 +262,15 @@ def clear_temp_variable(model):
             m.let = None
 
 
+def _release_weight_buffers(model):
+    """Drop the calibration-time scratch the Q* modules hold on to: the shared buffers sibling projections write their
+    fake-quantised weights into (qmodule.py:_grouped_weight; one fp32 copy of every grouped weight) and prefetched weights."""
+    for m in model.modules():
+        for a in ("_wout", "_wgroup", "_prepared_weight", "_w_side"):
+            if hasattr(m, a):
+                delattr(m, a)
+
+
 def get_lr(max_lr, min_lr, it, warmup_iters, max_iters):
     """alg:296-307: linear warm-up then cosine decay."""
     if it < warmup_iters:
@@ -631,6 +640,7 @@ def omniquant(args, model, dataloader, logger, device=None):
                 logger.info(f"layer {i} iter {epochs} loss:{loss_mean} norm:{norm_mean} max memory_allocated {torch.cuda.max_memory_allocated(device) / 1024**2} ")
             del step
             clear_temp_variable(qlayer)
+            _release_weight_buffers(qlayer)
             del optimizer
         if args.epochs > 0:
             omni_parameters[i] = quant_state_dict(qlayer)
@@ -756,6 +766,7 @@ def e2equant(args, model, dataloader, logger, device=None):
         e2e_parameters[i] = OrderedDict((k, v.clone()) for k, v in quant_state_dict(layers[i]).items())
         smooth_lm_inplace(layers[i], model.config, args.let, args.use_shift)
         _drop_learned(layers[i])
+        _release_weight_buffers(layers[i])
     if rank == 0:
         torch.save(e2e_parameters, os.path.join(args.output_dir, "parameters.pth"))
     step = None
