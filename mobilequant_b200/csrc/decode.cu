@@ -706,7 +706,11 @@ static int qgemv_dispatch(Ctx* c, const void* x_codes, int x_signed, const void*
   const int n_tiles = (args.N + kGvBM - 1) / kGvBM;
   if (args.ksplit <= 0) {
     // fill the machine (two CTAs per SM) but keep at least two 128-byte K slices per CTA
-    args.ksplit = std::max(1, std::min(2 * c->sm_count / n_tiles, std::max(1, k_iters / 2)));
+    // (MQB200_GEMV_FILL / MQB200_GEMV_MINK override the two numbers: A/B measurements)
+    static int fill = -1, mink = -1;
+    if (fill < 0) { const char* e = getenv("MQB200_GEMV_FILL"); fill = e && atoi(e) > 0 ? atoi(e) : 2; }
+    if (mink < 0) { const char* e = getenv("MQB200_GEMV_MINK"); mink = e && atoi(e) > 0 ? atoi(e) : 2; }
+    args.ksplit = std::max(1, std::min(fill * c->sm_count / n_tiles, std::max(1, k_iters / mink)));
   }
   args.ksplit = std::min(args.ksplit, k_iters);
   if (args.B <= 16) return launch_qgemv<16>(c, x_codes, x_signed, w_codes, w_signed, args, st);
