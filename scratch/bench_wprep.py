@@ -32,4 +32,4 @@ for rows, cols, per_ch in [(2048, 2048, False), (11264 // 2, 2048, False), (2048
     tf = graph_time(lambda: K.wprep_fwd(w, 8, False, per_ch, cf, 2, None, 0, su, sl))
     tb = graph_time(lambda: K.wprep_bwd(w, g, 8, False, per_ch, cf, 2, None, 0, su, sl, minmax=out["minmax"]))
     mb = rows * cols * 4 / 1e6
-    print(f"[{rows} x {cols}] per_channel={per_ch}: fwd {tf:.1f} us ({3 * mb / tf / 1e3:.2f} TB/s of 12 B/elem)  bwd {tb:.1f} us ({6 * mb / tb / 1e3:.2f} TB/s of 24 B/elem)")
+    print(f"[{rows} x {cols}] per_channel={per_ch}: fwd {tf:.1f} us ({3 * mb / tf:.2f} TB/s of 12 B/elem)  bwd {tb:.1f} us ({6 * mb / tb:.2f} TB/s of 24 B/elem)")
