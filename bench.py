@@ -36,7 +36,8 @@ def parse():
     p.add_argument("--config", type=int, default=None, choices=[2, 3, 4, 5],
                    help="preset of BASELINE.json:configs -- 2: the default headline run; 3: TinyLlama W4A8 per-channel, batch 32; "
                         "4: stablelm-2-1.6b (calibration leg sharded over the ranks); 5: gemma-2b, seq 2048")
-    p.add_argument("--calib-samples", type=int, default=256)
+    p.add_argument("--calib-samples", type=int, default=512,
+                   help="calibration samples of the calib leg (BASELINE config 2: 512), sharded over the ranks")
     p.add_argument("--layers", type=int, default=None, help="debug: override num_hidden_layers")
     p.add_argument("--no-calib", action="store_true")
     p.add_argument("--no-decode", action="store_true")
